@@ -1,0 +1,130 @@
+/*
+ * tvs.h -- C ABI of the B200-native maximum-likelihood variant-frequency fitter
+ *          ("traversome_b200/libtvs.so").
+ *
+ * The reference (JianjunJin/Traversome v0.1.7.1) is pure Python and has no FFI for this
+ * path; the drop-in boundary is its Python class `ModelFitMaxLike`
+ * (traversome/ModelFitMaxLike.py:61-580).  The entry points below are what that class's
+ * arithmetic is replaced by; `traversome_b200/ModelFitMaxLike.py` is the only caller and
+ * INTEGRATION.md shows the ctypes stub a maintainer would add to the reference.
+ *
+ * Math (traversome/ModelGenerator.py:129-176), for one batch "lane" b (= one bootstrap
+ * replicate and/or one candidate-variant subset):
+ *
+ *     LL_b(theta) = C_b + sum_r w[r,b] * log( (sum_v A[r,v]*theta[v,b]) / (sum_v L[v]*theta[v,b]) )
+ *
+ *   A  R x V  integer read-path x variant occurrence counts (`from_variants`), CSR, shared by all lanes
+ *   L  V      integer variant sizes (`variant_sizes`)
+ *   w  R x B  integer observed records per read path and lane (sum of `num_matched` over the
+ *             lane's bins of that read path)
+ *   C  B      sum over the lane's bins of num_matched*log(num_possible_X)   (constant in theta)
+ *   mask V x B  1 = variant v is in lane b's candidate subset (`within_variant_ids`)
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative TVS_E* code; nothing throws across the
+ *     boundary; `tvs_last_error()` returns a thread-local message for the last failure.
+ *   - array arguments may be HOST or DEVICE pointers unless stated otherwise (copies use
+ *     cudaMemcpyDefault); all per-lane matrices are "lane-minor": element (i, b) at [i*B + b].
+ *   - a handle owns one CUDA stream on one device; calls on one handle are serialised by the
+ *     caller; different handles are independent (re-entrant per handle).
+ *   - there is NO CPU fallback: without a usable CUDA device tvs_create fails with TVS_ECUDA.
+ */
+#ifndef TVS_H_
+#define TVS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tvs_problem* tvs_handle;
+
+enum {
+    TVS_OK = 0,
+    TVS_EINVAL = -1,   /* bad argument (null pointer, negative size, unsorted CSR, ...)          */
+    TVS_ECUDA = -2,    /* CUDA runtime error or no device                                         */
+    TVS_ENOMEM = -3,   /* host or device allocation failed                                        */
+    TVS_ELIMIT = -4,   /* V > 65535, a count A[r,v] > 65535 or a chunk too large for this build   */
+    TVS_ESTATE = -5    /* call order violated (e.g. tvs_fit before tvs_set_lanes)                 */
+};
+
+/* per-lane status written by tvs_fit */
+enum {
+    TVS_CONVERGED = 0,   /* KKT residuals below tol                                               */
+    TVS_MAXITER = 1,     /* max_iter reached; best point so far returned                          */
+    TVS_STALLED = 2,     /* line search could not improve at fp64 resolution; residuals returned  */
+    TVS_INFEASIBLE = 3   /* some read path with w>0 is covered by no variant of the lane's subset
+                            (the reference's objective is -inf: ModelFitMaxLike.py:560-580 guards
+                            it with cover_all_observed_subpaths)                                  */
+};
+
+typedef struct tvs_fit_options {
+    double tol;          /* KKT tolerance: max_v phi_v*|g_v-1| and max_{v: phi_v~0} (g_v-1); <=0 -> 1e-10   */
+    int32_t max_iter;    /* maximum accepted L-BFGS iterations per lane; <=0 -> 1000                        */
+    int32_t history;     /* L-BFGS memory (1..16); <=0 -> 8                                                  */
+    int32_t check_every; /* host polls the device-side "active lanes" counter every k passes; <=0 -> 4      */
+    int32_t reserved;
+} tvs_fit_options;
+
+typedef struct tvs_fit_stats {
+    int64_t passes;          /* fused likelihood/gradient passes launched by the last tvs_fit             */
+    int64_t kernel_launches; /* all kernels launched by the last tvs_fit                                  */
+    double  pass_ms;         /* CUDA-event time spent in the pass kernel (sum over passes)                */
+    double  total_ms;        /* CUDA-event time of the whole tvs_fit on the handle's stream               */
+    int64_t lane_passes;     /* sum over passes of lanes processed (for roofline arithmetic)              */
+} tvs_fit_stats;
+
+/* library / device ------------------------------------------------------------------------- */
+int         tvs_version(void);
+const char* tvs_last_error(void);
+int         tvs_device_count(int* n_out);
+
+/* problem = the shared CSR (replaces the symengine expression build of
+ * ModelFitMaxLike.get_neg_likelihood_of_var_freq, ModelFitMaxLike.py:515-558, and
+ * PathMultinomialModel.get_like_formula's bins x variants loop, ModelGenerator.py:153-169).
+ * row_ptr[R+1], col[nnz], val[nnz] int32 with 0 <= col < V sorted within a row, val >= 1; L[V] int64 > 0. */
+int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz,
+               const int32_t* row_ptr, const int32_t* col, const int32_t* val, const int64_t* L);
+int tvs_destroy(tvs_handle h);
+
+/* lanes (replaces the per-replicate / per-subset rebuild of the objective: traversome.py:515-545,
+ * ModelFitMaxLike.py:349-370).  w[R*B] int32 >= 0; mask[V*B] uint8 or NULL (= all variants);
+ * C[B] or NULL (= 0).  Computes N_b = sum_r w[r,b] on the device. */
+int tvs_set_lanes(tvs_handle h, int64_t B, const int32_t* w, const uint8_t* mask, const double* C);
+
+/* device-side bootstrap: lane b's w[.,b] ~ Multinomial(N, n_obs/N), N = sum n_obs, drawn record by
+ * record with Philox4x32-10(key=(seed, b), counter=draw index) -- the batched equivalent of
+ * `random.choices(records_pool_sorted, k=N)` (traversome.py:1652) for synthetic workloads.
+ * Lane 0 is the unresampled data when keep_lane0 != 0.  mask/C as in tvs_set_lanes. */
+int tvs_resample(tvs_handle h, int64_t B, const int32_t* n_obs, uint64_t seed, int keep_lane0,
+                 const uint8_t* mask, const double* C);
+
+/* copies the current lane weights (R*B int32, lane-minor) to `w_out` (host or device). */
+int tvs_get_weights(tvs_handle h, int32_t* w_out);
+
+/* LL_b(theta[.,b]) for every lane (replaces the lambdified objective, ModelFitMaxLike.py:534-545).
+ * theta need not be normalised; entries outside the lane's mask are ignored.  -inf where the
+ * reference's objective is -inf. */
+int tvs_loglik(tvs_handle h, const double* theta, double* ll_out);
+
+/* maximum-likelihood fit of every lane (replaces minimize_neg_likelihood, ModelFitMaxLike.py:19-58).
+ * theta0[V*B] or NULL (= uniform over the lane's mask).  Outputs (any may be NULL):
+ * theta_out[V*B] (sums to 1 over the mask, 0 outside), ll_out[B] (includes C), kkt_out[2*B]
+ * (complementarity, dual residual), iters_out[B], status_out[B]. */
+int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt,
+            double* theta_out, double* ll_out, double* kkt_out, int32_t* iters_out, int32_t* status_out);
+
+int tvs_last_fit_stats(tvs_handle h, tvs_fit_stats* out);
+
+/* sizes of the handle, for callers that only hold the handle */
+int tvs_dims(tvs_handle h, int64_t* R, int64_t* V, int64_t* nnz, int64_t* B);
+
+/* fp64 FMA peak micro-benchmark (MEASURED_PEAKS.json has no fp64 entry; SURVEY.md 8d asks for one).
+ * Returns TFLOP/s of dependent-chain-free DFMA on `device`. */
+int tvs_measure_fp64_peak(int device, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVS_H_ */

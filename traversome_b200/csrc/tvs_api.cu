@@ -1,0 +1,551 @@
+// libtvs.so -- C ABI (include/tvs.h) over the sm_100a kernels in tvs_kernels.cuh.
+// Host side: CSR validation and chunking, launch geometry, the batched L-BFGS driver loop.
+#include "tvs_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+namespace tvs {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return e == cudaErrorMemoryAllocation ? TVS_ENOMEM : TVS_ECUDA;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+template <class T>
+static int dev_alloc(T** p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    TVS_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
+    return TVS_OK;
+}
+template <class T>
+static void dev_free(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+static void free_csr(Csr& c) {
+    dev_free(c.row_ptr); dev_free(c.ent); dev_free(c.chunk_row0); dev_free(c.ccol_ptr); dev_free(c.ccol_id);
+    dev_free(c.ccol_start); dev_free(c.cent); dev_free(c.invL); dev_free(c.Ld);
+}
+static void free_lanes(Lanes& l) {
+    dev_free(l.w); dev_free(l.mask); dev_free(l.C); dev_free(l.N);
+    l = Lanes();
+}
+static void free_fit(FitState& f) {
+    dev_free(f.z); dev_free(f.zt); dev_free(f.g); dev_free(f.gt); dev_free(f.gh); dev_free(f.d); dev_free(f.x);
+    dev_free(f.theta_io); dev_free(f.gamma); dev_free(f.ll_out); dev_free(f.kkt_out); dev_free(f.iters_out); dev_free(f.status_out);
+    dev_free(f.S); dev_free(f.Y); dev_free(f.rho);
+    dev_free(f.F); dev_free(f.dg); dev_free(f.alpha); dev_free(f.llsum); dev_free(f.kkt); dev_free(f.sumphi);
+    dev_free(f.ls); dev_free(f.iters); dev_free(f.status); dev_free(f.head); dev_free(f.cnt); dev_free(f.done);
+    dev_free(f.tpart); dev_free(f.llpart); dev_free(f.nactive); dev_free(f.tile_active);
+    if (f.h_nactive) cudaFreeHost(f.h_nactive);
+    f = FitState();
+}
+
+// ---------------------------------------------------------------------------------- launch geometry
+struct PassPlan {
+    int lpt = 1; bool xs = false; int tiles = 0; int splits = 1; size_t smem = 0;
+};
+
+template <int LPT, bool XS, bool BW>
+static int plan_one(const tvs_problem* h, int64_t B, PassPlan* out) {
+    const int LT = 32 * LPT;
+    const Csr& c = h->csr;
+    size_t dbl = 0;
+    if (XS) dbl += (size_t)c.V * LT * (BW ? 2 : 1);
+    dbl += (size_t)std::max(c.rows_per_chunk, kWarps) * LT;
+    const size_t smem = dbl * sizeof(double);
+    if (smem > 200 * 1024) return TVS_ELIMIT;
+    auto kern = pass_kernel<LPT, XS, BW>;
+    TVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    TVS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+    if (occ < 1) return TVS_ELIMIT;
+    const int slots = occ * h->sm_count;
+    out->lpt = LPT; out->xs = XS; out->smem = smem;
+    out->tiles = (int)((B + LT - 1) / LT);
+    int s = slots / std::max(out->tiles, 1);
+    s = std::max(1, std::min(s, c.n_chunks));
+    const int forced = env_int("TVS_SPLITS", 0);
+    if (forced > 0) s = std::min(forced, c.n_chunks);
+    out->splits = s;
+    return TVS_OK;
+}
+
+template <bool BW>
+static int make_plan(const tvs_problem* h, int64_t B, PassPlan* out) {
+    int lpt = (B > 32) ? 2 : 1;
+    const int forced = env_int("TVS_LPT", 0);
+    if (forced == 1 || forced == 2) lpt = forced;
+    const bool no_xs = env_int("TVS_NO_XS", 0) != 0;
+    int rc = TVS_ELIMIT;
+    if (!no_xs) {
+        if (lpt == 2) rc = plan_one<2, true, BW>(h, B, out);
+        if (rc != TVS_OK) rc = plan_one<1, true, BW>(h, B, out);
+    }
+    if (rc != TVS_OK && lpt == 2) rc = plan_one<2, false, BW>(h, B, out);
+    if (rc != TVS_OK) rc = plan_one<1, false, BW>(h, B, out);
+    if (rc != TVS_OK && rc != TVS_ECUDA) set_error("no pass-kernel configuration fits (V=%lld)", (long long)h->csr.V);
+    return rc;
+}
+
+template <bool BW>
+static int launch_pass(tvs_problem* h, const PassPlan& pl, const PassArgs& a) {
+    dim3 grid(pl.tiles, pl.splits), block(kThreads);
+    if (pl.lpt == 2 && pl.xs) pass_kernel<2, true, BW><<<grid, block, pl.smem, h->stream>>>(a);
+    else if (pl.lpt == 1 && pl.xs) pass_kernel<1, true, BW><<<grid, block, pl.smem, h->stream>>>(a);
+    else if (pl.lpt == 2) pass_kernel<2, false, BW><<<grid, block, pl.smem, h->stream>>>(a);
+    else pass_kernel<1, false, BW><<<grid, block, pl.smem, h->stream>>>(a);
+    TVS_CUDA(cudaGetLastError());
+    return TVS_OK;
+}
+
+static PassArgs base_args(const tvs_problem* h) {
+    PassArgs a{};
+    const Csr& c = h->csr;
+    a.row_ptr = c.row_ptr; a.ent = c.ent; a.chunk_row0 = c.chunk_row0; a.ccol_ptr = c.ccol_ptr; a.ccol_id = c.ccol_id;
+    a.ccol_start = c.ccol_start; a.cent = c.cent; a.w = h->lanes.w; a.B = h->lanes.B; a.V = (int)c.V;
+    a.n_chunks = c.n_chunks; a.rows_per_chunk = c.rows_per_chunk;
+    return a;
+}
+
+// ------------------------------------------------------------------------------------- fit state
+static int ensure_fit_state(tvs_problem* h, int m, int splits) {
+    FitState& f = h->fs;
+    const int64_t V = h->csr.V, B = h->lanes.B;
+    if (f.V == V && f.B == B && f.m == m && f.splits >= splits) return TVS_OK;
+    free_fit(f);
+    const size_t vb = (size_t)V * B;
+    int rc;
+#define A_(ptr, n) if ((rc = dev_alloc(&f.ptr, (n))) != TVS_OK) { free_fit(f); return rc; }
+    A_(z, vb) A_(zt, vb) A_(g, vb) A_(gt, vb) A_(gh, vb) A_(d, vb) A_(x, vb) A_(theta_io, vb) A_(gamma, B)
+    A_(ll_out, B) A_(kkt_out, 2 * (size_t)B) A_(iters_out, B) A_(status_out, B)
+    A_(S, vb * m) A_(Y, vb * m) A_(rho, (size_t)B * m)
+    A_(F, B) A_(dg, B) A_(alpha, B) A_(llsum, B) A_(kkt, 2 * (size_t)B) A_(sumphi, B)
+    A_(ls, B) A_(iters, B) A_(status, B) A_(head, B) A_(cnt, B) A_(done, B)
+    A_(tpart, vb * splits) A_(llpart, (size_t)B * splits) A_(nactive, 32) A_(tile_active, 1)
+#undef A_
+    if (cudaMallocHost((void**)&f.h_nactive, 16 * sizeof(int32_t)) != cudaSuccess) { free_fit(f); set_error("cudaMallocHost failed"); return TVS_ENOMEM; }
+    f.V = V; f.B = B; f.m = m; f.splits = splits;
+    return TVS_OK;
+}
+
+}  // namespace tvs
+
+using namespace tvs;
+
+// =============================================================================================== API
+extern "C" {
+
+int tvs_version(void) { return 100; }
+const char* tvs_last_error(void) { return g_err; }
+
+int tvs_device_count(int* n_out) {
+    if (!n_out) { set_error("n_out is null"); return TVS_EINVAL; }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *n_out = 0; return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__); }
+    *n_out = n;
+    return TVS_OK;
+}
+
+int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, const int32_t* row_ptr,
+               const int32_t* col, const int32_t* val, const int64_t* L) {
+    if (!out) { set_error("out is null"); return TVS_EINVAL; }
+    *out = nullptr;
+    if (R <= 0 || V <= 0 || nnz < 0 || !row_ptr || (nnz > 0 && (!col || !val)) || !L) {
+        set_error("tvs_create: bad sizes or null arrays (R=%lld V=%lld nnz=%lld)", (long long)R, (long long)V, (long long)nnz);
+        return TVS_EINVAL;
+    }
+    if (V > 65535 || R > 2000000000LL || nnz > 2000000000LL) { set_error("tvs_create: V>65535 or R/nnz>2e9 unsupported"); return TVS_ELIMIT; }
+    if (row_ptr[0] != 0 || row_ptr[R] != nnz) { set_error("tvs_create: row_ptr[0]!=0 or row_ptr[R]!=nnz"); return TVS_EINVAL; }
+    for (int64_t r = 0; r < R; ++r) {
+        if (row_ptr[r + 1] < row_ptr[r]) { set_error("tvs_create: row_ptr not monotone at row %lld", (long long)r); return TVS_EINVAL; }
+        for (int64_t k = row_ptr[r]; k < row_ptr[r + 1]; ++k) {
+            if (col[k] < 0 || col[k] >= V) { set_error("tvs_create: column %d out of range at nnz %lld", col[k], (long long)k); return TVS_EINVAL; }
+            if (k > row_ptr[r] && col[k] <= col[k - 1]) { set_error("tvs_create: columns not strictly increasing in row %lld", (long long)r); return TVS_EINVAL; }
+            if (val[k] < 1) { set_error("tvs_create: count < 1 at nnz %lld", (long long)k); return TVS_EINVAL; }
+            if (val[k] > 65535) { set_error("tvs_create: count %d > 65535 at nnz %lld", val[k], (long long)k); return TVS_ELIMIT; }
+        }
+    }
+    for (int64_t v = 0; v < V; ++v)
+        if (L[v] <= 0) { set_error("tvs_create: variant size L[%lld] <= 0", (long long)v); return TVS_EINVAL; }
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("tvs_create: no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+        return TVS_ECUDA;
+    }
+    if (device < 0 || device >= ndev) { set_error("tvs_create: device %d out of range (0..%d)", device, ndev - 1); return TVS_EINVAL; }
+    TVS_CUDA(cudaSetDevice(device));
+
+    tvs_problem* h = new (std::nothrow) tvs_problem();
+    if (!h) { set_error("out of host memory"); return TVS_ENOMEM; }
+    h->device = device;
+    int rc = TVS_OK;
+    auto fail = [&](int code) { tvs_destroy(h); return code; };
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(TVS_ECUDA);
+    h->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(TVS_ECUDA);
+    cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->evp0); cudaEventCreate(&h->evp1);
+
+    Csr& c = h->csr;
+    c.R = R; c.V = V; c.nnz = nnz;
+    int rpc = env_int("TVS_RC", 128);
+    rpc = std::max(kWarps, std::min(rpc, 4096));
+    c.rows_per_chunk = rpc;
+    c.n_chunks = (int)((R + rpc - 1) / rpc);
+
+    // host build: packed row-major entries, per-chunk column-major entries
+    std::vector<uint32_t> ent((size_t)std::max<int64_t>(nnz, 1)), cent((size_t)std::max<int64_t>(nnz, 1));
+    std::vector<int32_t> chunk_row0(c.n_chunks + 1), ccol_ptr(c.n_chunks + 1), ccol_id, ccol_start;
+    std::vector<int32_t> cnt((size_t)V), pos((size_t)V);
+    for (int64_t k = 0; k < nnz; ++k) ent[k] = (uint32_t)col[k] | ((uint32_t)val[k] << 16);
+    int64_t cursor = 0;
+    for (int ch = 0; ch < c.n_chunks; ++ch) {
+        const int64_t r0 = (int64_t)ch * rpc, r1 = std::min<int64_t>(R, r0 + rpc);
+        chunk_row0[ch] = (int32_t)r0;
+        ccol_ptr[ch] = (int32_t)ccol_id.size();
+        std::fill(cnt.begin(), cnt.end(), 0);
+        for (int64_t k = row_ptr[r0]; k < row_ptr[r1]; ++k) cnt[col[k]]++;
+        for (int64_t v = 0; v < V; ++v)
+            if (cnt[v]) { ccol_id.push_back((int32_t)v); ccol_start.push_back((int32_t)cursor); pos[v] = (int32_t)cursor; cursor += cnt[v]; }
+        for (int64_t r = r0; r < r1; ++r)
+            for (int64_t k = row_ptr[r]; k < row_ptr[r + 1]; ++k)
+                cent[pos[col[k]]++] = (uint32_t)(r - r0) | ((uint32_t)val[k] << 16);
+    }
+    chunk_row0[c.n_chunks] = (int32_t)R;
+    ccol_ptr[c.n_chunks] = (int32_t)ccol_id.size();
+    ccol_start.push_back((int32_t)cursor);
+    c.n_ccol = (int64_t)ccol_id.size();
+    std::vector<double> invL((size_t)V), Ld((size_t)V);
+    for (int64_t v = 0; v < V; ++v) { Ld[v] = (double)L[v]; invL[v] = 1.0 / Ld[v]; }
+
+#define UP_(dst, vec, T)                                                                                  \
+    if ((rc = dev_alloc(&c.dst, (vec).size())) != TVS_OK) return fail(rc);                                \
+    if (cudaMemcpy(c.dst, (vec).data(), (vec).size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) \
+        return fail(cuda_fail(cudaGetLastError(), "upload " #dst, __FILE__, __LINE__));
+    if ((rc = dev_alloc(&c.row_ptr, (size_t)R + 1)) != TVS_OK) return fail(rc);
+    if (cudaMemcpy(c.row_ptr, row_ptr, ((size_t)R + 1) * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(cuda_fail(cudaGetLastError(), "upload row_ptr", __FILE__, __LINE__));
+    UP_(ent, ent, uint32_t) UP_(cent, cent, uint32_t) UP_(chunk_row0, chunk_row0, int32_t) UP_(ccol_ptr, ccol_ptr, int32_t)
+    if (ccol_id.empty()) ccol_id.push_back(0);
+    UP_(ccol_id, ccol_id, int32_t) UP_(ccol_start, ccol_start, int32_t) UP_(invL, invL, double) UP_(Ld, Ld, double)
+#undef UP_
+    *out = h;
+    return TVS_OK;
+}
+
+int tvs_destroy(tvs_handle h) {
+    if (!h) return TVS_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_fit(h->fs); free_lanes(h->lanes); free_csr(h->csr);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->evp0) cudaEventDestroy(h->evp0);
+    if (h->evp1) cudaEventDestroy(h->evp1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return TVS_OK;
+}
+
+int tvs_dims(tvs_handle h, int64_t* R, int64_t* V, int64_t* nnz, int64_t* B) {
+    if (!h) { set_error("null handle"); return TVS_EINVAL; }
+    if (R) *R = h->csr.R;
+    if (V) *V = h->csr.V;
+    if (nnz) *nnz = h->csr.nnz;
+    if (B) *B = h->lanes_set ? h->lanes.B : 0;
+    return TVS_OK;
+}
+
+static int reserve_lanes(tvs_problem* h, int64_t B, bool with_mask, bool with_C) {
+    Lanes& l = h->lanes;
+    const int64_t R = h->csr.R, V = h->csr.V;
+    int rc;
+    if (l.cap_w < R * B) { dev_free(l.w); if ((rc = dev_alloc(&l.w, (size_t)(R * B))) != TVS_OK) return rc; l.cap_w = R * B; }
+    if (with_mask) {
+        if (l.cap_mask < V * B || !l.mask) { dev_free(l.mask); if ((rc = dev_alloc(&l.mask, (size_t)(V * B))) != TVS_OK) return rc; l.cap_mask = V * B; }
+    } else { dev_free(l.mask); l.cap_mask = 0; }
+    if (l.cap_b < B || !l.N) {
+        dev_free(l.N); dev_free(l.C);
+        if ((rc = dev_alloc(&l.N, (size_t)B)) != TVS_OK) return rc;
+        l.cap_b = B;
+    }
+    if (with_C) { if (!l.C && (rc = dev_alloc(&l.C, (size_t)l.cap_b)) != TVS_OK) return rc; }
+    else dev_free(l.C);
+    l.B = B;
+    return TVS_OK;
+}
+
+static int finish_lanes(tvs_problem* h, const uint8_t* mask, const double* C) {
+    Lanes& l = h->lanes;
+    const int64_t V = h->csr.V, B = l.B;
+    if (mask) TVS_CUDA(cudaMemcpyAsync(l.mask, mask, (size_t)(V * B), cudaMemcpyDefault, h->stream));
+    if (C) TVS_CUDA(cudaMemcpyAsync(l.C, C, (size_t)B * sizeof(double), cudaMemcpyDefault, h->stream));
+    lane_sum_kernel<<<(unsigned)((B + 127) / 128), 128, 0, h->stream>>>(l.w, h->csr.R, B, l.N);
+    TVS_CUDA(cudaGetLastError());
+    TVS_CUDA(cudaStreamSynchronize(h->stream));
+    h->lanes_set = true;
+    return TVS_OK;
+}
+
+int tvs_set_lanes(tvs_handle h, int64_t B, const int32_t* w, const uint8_t* mask, const double* C) {
+    if (!h || B <= 0 || !w) { set_error("tvs_set_lanes: null handle/weights or B<=0"); return TVS_EINVAL; }
+    TVS_CUDA(cudaSetDevice(h->device));
+    h->lanes_set = false;
+    int rc = reserve_lanes(h, B, mask != nullptr, C != nullptr);
+    if (rc != TVS_OK) return rc;
+    TVS_CUDA(cudaMemcpyAsync(h->lanes.w, w, (size_t)(h->csr.R * B) * sizeof(int32_t), cudaMemcpyDefault, h->stream));
+    return finish_lanes(h, mask, C);
+}
+
+int tvs_resample(tvs_handle h, int64_t B, const int32_t* n_obs, uint64_t seed, int keep_lane0, const uint8_t* mask,
+                 const double* C) {
+    if (!h || B <= 0 || !n_obs) { set_error("tvs_resample: null handle/n_obs or B<=0"); return TVS_EINVAL; }
+    if (B > 65535) { set_error("tvs_resample: B > 65535 lanes per call unsupported"); return TVS_ELIMIT; }
+    TVS_CUDA(cudaSetDevice(h->device));
+    h->lanes_set = false;
+    const int64_t R = h->csr.R;
+    int rc = reserve_lanes(h, B, mask != nullptr, C != nullptr);
+    if (rc != TVS_OK) return rc;
+    std::vector<int32_t> n((size_t)R);
+    TVS_CUDA(cudaMemcpy(n.data(), n_obs, (size_t)R * sizeof(int32_t), cudaMemcpyDefault));
+    std::vector<int64_t> cum((size_t)R);
+    int64_t tot = 0;
+    for (int64_t r = 0; r < R; ++r) {
+        if (n[r] < 0) { set_error("tvs_resample: negative count at row %lld", (long long)r); return TVS_EINVAL; }
+        tot += n[r]; cum[r] = tot;
+    }
+    if (tot <= 0) { set_error("tvs_resample: no records"); return TVS_EINVAL; }
+    int64_t* d_cum = nullptr; int32_t* d_n = nullptr;
+    if ((rc = dev_alloc(&d_cum, (size_t)R)) != TVS_OK) return rc;
+    if ((rc = dev_alloc(&d_n, (size_t)R)) != TVS_OK) { cudaFree(d_cum); return rc; }
+    cudaMemcpyAsync(d_cum, cum.data(), (size_t)R * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(d_n, n.data(), (size_t)R * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream);
+    cudaMemsetAsync(h->lanes.w, 0, (size_t)(R * B) * sizeof(int32_t), h->stream);
+    const int threads = 256;
+    int bx = (int)std::min<int64_t>((tot + threads - 1) / threads, 64);
+    resample_kernel<<<dim3(bx, (unsigned)B), threads, 0, h->stream>>>(d_cum, R, tot, B, seed, keep_lane0, d_n, h->lanes.w);
+    cudaError_t e = cudaGetLastError();
+    rc = (e == cudaSuccess) ? finish_lanes(h, mask, C) : cuda_fail(e, "resample_kernel", __FILE__, __LINE__);
+    cudaFree(d_cum); cudaFree(d_n);
+    return rc;
+}
+
+int tvs_get_weights(tvs_handle h, int32_t* w_out) {
+    if (!h || !w_out) { set_error("tvs_get_weights: null argument"); return TVS_EINVAL; }
+    if (!h->lanes_set) { set_error("tvs_get_weights: lanes not set"); return TVS_ESTATE; }
+    TVS_CUDA(cudaSetDevice(h->device));
+    TVS_CUDA(cudaMemcpyAsync(w_out, h->lanes.w, (size_t)(h->csr.R * h->lanes.B) * sizeof(int32_t), cudaMemcpyDefault, h->stream));
+    TVS_CUDA(cudaStreamSynchronize(h->stream));
+    return TVS_OK;
+}
+
+int tvs_loglik(tvs_handle h, const double* theta, double* ll_out) {
+    if (!h || !theta || !ll_out) { set_error("tvs_loglik: null argument"); return TVS_EINVAL; }
+    if (!h->lanes_set) { set_error("tvs_loglik: call tvs_set_lanes first"); return TVS_ESTATE; }
+    TVS_CUDA(cudaSetDevice(h->device));
+    const int64_t V = h->csr.V, B = h->lanes.B;
+    PassPlan pl;
+    int rc = make_plan<false>(h, B, &pl);
+    if (rc != TVS_OK) return rc;
+    double *d_theta = nullptr, *d_x = nullptr, *d_den = nullptr, *d_llp = nullptr, *d_out = nullptr;
+    auto cleanup = [&]() { cudaFree(d_theta); cudaFree(d_x); cudaFree(d_den); cudaFree(d_llp); cudaFree(d_out); };
+    if ((rc = dev_alloc(&d_theta, (size_t)(V * B))) != TVS_OK || (rc = dev_alloc(&d_x, (size_t)(V * B))) != TVS_OK ||
+        (rc = dev_alloc(&d_den, (size_t)B)) != TVS_OK || (rc = dev_alloc(&d_llp, (size_t)B * pl.splits)) != TVS_OK ||
+        (rc = dev_alloc(&d_out, (size_t)B)) != TVS_OK) { cleanup(); return rc; }
+    cudaMemcpyAsync(d_theta, theta, (size_t)(V * B) * sizeof(double), cudaMemcpyDefault, h->stream);
+    const unsigned gb = (unsigned)((B + 127) / 128);
+    prep_theta_kernel<<<gb, 128, 0, h->stream>>>(d_theta, h->lanes.mask, h->csr.Ld, (int)V, B, d_x, d_den);
+    PassArgs a = base_args(h);
+    a.x = d_x; a.done = nullptr; a.tpart = nullptr; a.llpart = d_llp;
+    rc = launch_pass<false>(h, pl, a);
+    if (rc == TVS_OK) {
+        finish_loglik_kernel<<<gb, 128, 0, h->stream>>>(d_llp, pl.splits, B, h->lanes.N, h->lanes.C, d_den, d_out);
+        cudaMemcpyAsync(ll_out, d_out, (size_t)B * sizeof(double), cudaMemcpyDefault, h->stream);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "tvs_loglik", __FILE__, __LINE__);
+    }
+    cleanup();
+    return rc;
+}
+
+int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, double* theta_out, double* ll_out,
+            double* kkt_out, int32_t* iters_out, int32_t* status_out) {
+    if (!h) { set_error("tvs_fit: null handle"); return TVS_EINVAL; }
+    if (!h->lanes_set) { set_error("tvs_fit: call tvs_set_lanes or tvs_resample first"); return TVS_ESTATE; }
+    TVS_CUDA(cudaSetDevice(h->device));
+    tvs_fit_options opt{};
+    if (opt_in) opt = *opt_in;
+    if (!(opt.tol > 0.0)) opt.tol = 1e-10;
+    if (opt.max_iter <= 0) opt.max_iter = 1000;
+    if (opt.history <= 0) opt.history = 8;
+    opt.history = std::min(opt.history, kMaxHistory);
+    if (opt.check_every <= 0) opt.check_every = 4;
+    const bool time_passes = (opt.reserved & 1) != 0 || env_int("TVS_TIME_PASSES", 0) != 0;
+
+    const int64_t V = h->csr.V, B = h->lanes.B;
+    const int m = opt.history;
+    PassPlan pl;
+    int rc = make_plan<true>(h, B, &pl);
+    if (rc != TVS_OK) return rc;
+    if ((rc = ensure_fit_state(h, m, pl.splits)) != TVS_OK) return rc;
+    FitState& f = h->fs;
+    cudaStream_t st = h->stream;
+    const size_t vb = (size_t)V * B;
+
+    TVS_CUDA(cudaEventRecord(h->ev0, st));
+    // reset state
+    cudaMemsetAsync(f.z, 0, vb * 8, st); cudaMemsetAsync(f.g, 0, vb * 8, st); cudaMemsetAsync(f.d, 0, vb * 8, st);
+    cudaMemsetAsync(f.gt, 0, vb * 8, st);
+    cudaMemsetAsync(f.F, 0, B * 8, st); cudaMemsetAsync(f.dg, 0, B * 8, st); cudaMemsetAsync(f.alpha, 0, B * 8, st);
+    cudaMemsetAsync(f.llsum, 0, B * 8, st); cudaMemsetAsync(f.kkt, 0, 2 * B * 8, st); cudaMemsetAsync(f.sumphi, 0, B * 8, st);
+    cudaMemsetAsync(f.ls, 0, B * 4, st); cudaMemsetAsync(f.iters, 0xFF, B * 4, st); cudaMemsetAsync(f.status, 0, B * 4, st);
+    cudaMemsetAsync(f.head, 0, B * 4, st); cudaMemsetAsync(f.cnt, 0, B * 4, st); cudaMemsetAsync(f.done, 0, B * 4, st);
+    cudaMemsetAsync(f.rho, 0, (size_t)B * m * 8, st);
+    const double* d_theta0 = nullptr;
+    if (theta0) {
+        cudaMemcpyAsync(f.theta_io, theta0, vb * 8, cudaMemcpyDefault, st);
+        d_theta0 = f.theta_io;
+    }
+    const unsigned gb = (unsigned)((B + 127) / 128);
+    init_z_kernel<<<gb, 128, 0, st>>>(d_theta0, h->lanes.mask, h->csr.Ld, h->csr.invL, (int)V, B, f.zt, f.x);
+
+    PassArgs pa = base_args(h);
+    pa.x = f.x; pa.done = f.done; pa.tpart = f.tpart; pa.llpart = f.llpart;
+    UpdArgs ua{};
+    ua.tpart = f.tpart; ua.llpart = f.llpart; ua.S = pl.splits; ua.invL = h->csr.invL; ua.N = h->lanes.N; ua.mask = h->lanes.mask;
+    ua.z = f.z; ua.zt = f.zt; ua.g = f.g; ua.gt = f.gt; ua.gh = f.gh; ua.d = f.d; ua.x = f.x; ua.Sh = f.S; ua.Yh = f.Y;
+    ua.rho = f.rho; ua.gamma = f.gamma; ua.F = f.F; ua.dg = f.dg; ua.alpha = f.alpha; ua.llsum = f.llsum; ua.kkt = f.kkt;
+    ua.sumphi = f.sumphi; ua.ls = f.ls; ua.iters = f.iters; ua.status = f.status; ua.head = f.head; ua.cnt = f.cnt;
+    ua.done = f.done; ua.V = (int)V; ua.B = B; ua.m = m; ua.max_iter = opt.max_iter; ua.tol = opt.tol;
+    ua.tol_dual = 100.0 * opt.tol;
+
+    const int64_t max_passes = (int64_t)opt.max_iter * 2 + 64;
+    const unsigned ub = (unsigned)((B + 31) / 32);
+    std::vector<cudaEvent_t> pev;      // per-pass events when timing is requested
+    std::vector<cudaEvent_t> polls;    // one event per poll slot (ring of 16)
+    for (int i = 0; i < 16; ++i) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); polls.push_back(e); }
+    int64_t passes = 0, launches = 1, n_polls = 0, polls_checked = 0;
+    bool all_done = false;
+    cudaError_t cerr = cudaSuccess;
+    while (!all_done && passes < max_passes) {
+        for (int k = 0; k < opt.check_every && passes < max_passes; ++k) {
+            if (!pl.xs) { cudaMemsetAsync(f.tpart, 0, vb * pl.splits * 8, st); ++launches; }
+            if (time_passes) { cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); pev.push_back(e0); pev.push_back(e1); cudaEventRecord(e0, st); }
+            rc = launch_pass<true>(h, pl, pa);
+            if (rc != TVS_OK) break;
+            if (time_passes) cudaEventRecord(pev.back(), st);
+            const bool last = (k == opt.check_every - 1) || (passes + 1 == max_passes);
+            ua.nactive = last ? f.nactive + (n_polls % 16) : f.nactive + 31;   // word 31 = scratch between polls
+            if (last) { cudaMemsetAsync(f.nactive + (n_polls % 16), 0, 4, st); ++launches; }
+            lbfgs_update_kernel<<<ub, kUpdWarps * 32, 0, st>>>(ua);
+            ++passes; launches += 2;
+        }
+        if (rc != TVS_OK) break;
+        const int slot = (int)(n_polls % 16);
+        cudaMemcpyAsync(f.h_nactive + slot, f.nactive + slot, 4, cudaMemcpyDeviceToHost, st);
+        cudaEventRecord(polls[slot], st);
+        ++n_polls;
+        // pipelined polling: look at the PREVIOUS batch's counter while this batch runs
+        if (n_polls >= 2) {
+            const int ps = (int)((n_polls - 2) % 16);
+            cerr = cudaEventSynchronize(polls[ps]);
+            if (cerr != cudaSuccess) break;
+            ++polls_checked;
+            if (f.h_nactive[ps] == 0) all_done = true;
+        }
+    }
+    if (rc == TVS_OK && cerr == cudaSuccess) {
+        FinArgs fa{};
+        fa.z = f.z; fa.invL = h->csr.invL; fa.llsum = f.llsum; fa.sumphi = f.sumphi; fa.N = h->lanes.N; fa.C = h->lanes.C;
+        fa.kkt = f.kkt; fa.iters = f.iters; fa.status = f.status; fa.done = f.done; fa.mask = h->lanes.mask;
+        fa.theta_out = theta_out ? f.theta_io : nullptr; fa.ll_out = ll_out ? f.ll_out : nullptr;
+        fa.kkt_out = kkt_out ? f.kkt_out : nullptr; fa.iters_out = iters_out ? f.iters_out : nullptr;
+        fa.status_out = status_out ? f.status_out : nullptr;
+        fa.V = (int)V; fa.B = B;
+        finalize_fit_kernel<<<gb, 128, 0, st>>>(fa);
+        ++launches;
+        if (theta_out) cudaMemcpyAsync(theta_out, f.theta_io, vb * 8, cudaMemcpyDefault, st);
+        if (ll_out) cudaMemcpyAsync(ll_out, f.ll_out, (size_t)B * 8, cudaMemcpyDefault, st);
+        if (kkt_out) cudaMemcpyAsync(kkt_out, f.kkt_out, 2 * (size_t)B * 8, cudaMemcpyDefault, st);
+        if (iters_out) cudaMemcpyAsync(iters_out, f.iters_out, (size_t)B * 4, cudaMemcpyDefault, st);
+        if (status_out) cudaMemcpyAsync(status_out, f.status_out, (size_t)B * 4, cudaMemcpyDefault, st);
+        cudaEventRecord(h->ev1, st);
+        cerr = cudaStreamSynchronize(st);
+    } else {
+        cudaStreamSynchronize(st);
+    }
+    h->stats = tvs_fit_stats{};
+    h->stats.passes = passes; h->stats.kernel_launches = launches; h->stats.lane_passes = passes * B;
+    if (rc == TVS_OK && cerr == cudaSuccess) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        h->stats.total_ms = ms;
+        double pm = 0.0;
+        for (size_t i = 0; i + 1 < pev.size(); i += 2) { float q = 0.f; if (cudaEventElapsedTime(&q, pev[i], pev[i + 1]) == cudaSuccess) pm += q; }
+        h->stats.pass_ms = pm;
+    }
+    for (auto e : pev) cudaEventDestroy(e);
+    for (auto e : polls) cudaEventDestroy(e);
+    if (rc != TVS_OK) return rc;
+    if (cerr != cudaSuccess) return cuda_fail(cerr, "tvs_fit", __FILE__, __LINE__);
+    return TVS_OK;
+}
+
+int tvs_last_fit_stats(tvs_handle h, tvs_fit_stats* out) {
+    if (!h || !out) { set_error("tvs_last_fit_stats: null argument"); return TVS_EINVAL; }
+    *out = h->stats;
+    return TVS_OK;
+}
+
+int tvs_measure_fp64_peak(int device, double* tflops_out) {
+    if (!tflops_out) { set_error("tflops_out is null"); return TVS_EINVAL; }
+    TVS_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    TVS_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    double* d = nullptr;
+    TVS_CUDA(cudaMalloc((void**)&d, (size_t)blocks * threads * 8));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, threads>>>(d, iters, 1.0 + rep);
+        cudaEventRecord(e1);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e, "fp64_peak_kernel", __FILE__, __LINE__); }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+        best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops_out = best;
+    return TVS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// Internal declarations shared by the translation units of libtvs.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/tvs.h"
+
+namespace tvs {
+
+constexpr int kWarps = 8;            // warps per CTA of the pass kernel
+constexpr int kThreads = kWarps * 32;
+constexpr int kMaxHistory = 16;
+constexpr int kUpdWarps = 8;         // warps per CTA of the L-BFGS update kernel (split V)
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+#define TVS_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess) return tvs::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// Read paths are processed in "chunks" of consecutive rows.  Inside a chunk the non-zeros are
+// stored twice: row-major (forward product p = A x) and column-major (transposed product
+// t = A^T (w/p)), so that both products read their dense operand conflict-free from shared memory.
+struct Csr {
+    int64_t R = 0, V = 0, nnz = 0;
+    int n_chunks = 0;
+    int rows_per_chunk = 0;          // upper bound
+    // device arrays
+    int32_t*  row_ptr = nullptr;     // [R+1]
+    uint32_t* ent = nullptr;         // [nnz]  col | val<<16, row-major
+    int32_t*  chunk_row0 = nullptr;  // [n_chunks+1]
+    int32_t*  ccol_ptr = nullptr;    // [n_chunks+1] -> index into ccol_id / ccol_start
+    int32_t*  ccol_id = nullptr;     // [n_ccol] column id of each non-empty (chunk, column)
+    int32_t*  ccol_start = nullptr;  // [n_ccol+1] -> index into cent
+    uint32_t* cent = nullptr;        // [nnz]  local_row | val<<16, column-major within chunk
+    double*   invL = nullptr;        // [V] 1/L_v
+    double*   Ld = nullptr;          // [V] L_v as double
+    int64_t   n_ccol = 0;
+};
+
+struct Lanes {
+    int64_t B = 0;
+    int32_t* w = nullptr;      // [R*B]
+    uint8_t* mask = nullptr;   // [V*B]
+    double*  C = nullptr;      // [B]
+    double*  N = nullptr;      // [B]
+    int64_t  cap_w = 0, cap_mask = 0, cap_b = 0;
+};
+
+struct FitState {               // all device, sized for (V, B, history, splits)
+    int64_t V = 0, B = 0; int m = 0; int splits = 0;
+    double *z = nullptr, *zt = nullptr, *g = nullptr, *gt = nullptr, *gh = nullptr, *d = nullptr, *x = nullptr;
+    double *theta_io = nullptr, *gamma = nullptr;   // theta0 upload / theta_out staging; L-BFGS H0 scale
+    double *ll_out = nullptr, *kkt_out = nullptr; int32_t *iters_out = nullptr, *status_out = nullptr;
+    double *S = nullptr, *Y = nullptr, *rho = nullptr;
+    double *F = nullptr, *dg = nullptr, *alpha = nullptr, *llsum = nullptr, *kkt = nullptr, *sumphi = nullptr;
+    int32_t *ls = nullptr, *iters = nullptr, *status = nullptr, *head = nullptr, *cnt = nullptr, *done = nullptr;
+    double *tpart = nullptr, *llpart = nullptr;
+    int32_t *nactive = nullptr;   // device counter
+    int32_t *tile_active = nullptr;
+    int32_t *h_nactive = nullptr; // pinned host mirror
+    size_t bytes = 0;
+};
+
+}  // namespace tvs
+
+struct tvs_problem {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr;
+    tvs::Csr csr;
+    tvs::Lanes lanes;
+    tvs::FitState fs;
+    tvs_fit_stats stats{};
+    bool lanes_set = false;
+};

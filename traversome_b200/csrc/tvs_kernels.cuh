@@ -1,0 +1,539 @@
+// CUDA kernels of libtvs.so (sm_100a).  Included once by tvs_api.cu.
+//
+// Layout rule for every per-lane matrix: lane-minor, element (i, b) at [i*B + b]; a warp's 32
+// threads are 32 consecutive lanes, so every global access below is a contiguous 128/256-byte
+// segment and every shared-memory access is a conflict-free 64-bit column.
+#pragma once
+#include "tvs_internal.h"
+#include <math.h>
+
+namespace tvs {
+
+// ------------------------------------------------------------------------------------------------
+// Fused likelihood pass:  p = A x ;  rr = w / p ;  ll += w log p ;  t = A^T rr      (per lane)
+//
+// replaces: PathMultinomialModel.get_like_formula (ModelGenerator.py:153-174) evaluated by the
+// lambdified objective (ModelFitMaxLike.py:534-545), once per SLSQP function evaluation.
+//
+// grid = (lane tiles, row splits); CTA (tile, split) walks chunks split, split+S, ...
+//   phase 1 (row-major entries):   warp <- rows of the chunk, thread <- LPT lanes of the tile
+//   phase 2 (column-major entries): warp <- non-empty columns of the chunk, same lanes
+// XS: x tile and t accumulators live in shared memory (V*LT*16 bytes); otherwise x is read from
+// global/L2 and t is accumulated in the CTA's private slice of the partial buffer.
+// ------------------------------------------------------------------------------------------------
+struct PassArgs {
+    const int32_t* row_ptr; const uint32_t* ent;
+    const int32_t* chunk_row0; const int32_t* ccol_ptr; const int32_t* ccol_id; const int32_t* ccol_start;
+    const uint32_t* cent;
+    const int32_t* w; const double* x; const int32_t* done;
+    double* tpart; double* llpart;
+    int64_t B; int V; int n_chunks; int rows_per_chunk;
+};
+
+template <int LPT, bool XS, bool BACKWARD>
+__global__ void __launch_bounds__(kThreads) pass_kernel(const PassArgs a) {
+    constexpr int LT = 32 * LPT;
+    extern __shared__ double smem[];
+    const int t = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int tile = blockIdx.x, split = blockIdx.y, S = gridDim.y;
+    const int64_t B = a.B;
+    const int V = a.V;
+    const int64_t lane0 = (int64_t)tile * LT;
+
+    // lanes of this thread
+    int64_t lane[LPT]; bool lv[LPT];
+#pragma unroll
+    for (int j = 0; j < LPT; ++j) { lane[j] = lane0 + j * 32 + t; lv[j] = lane[j] < B; }
+
+    // skip tiles whose lanes have all finished (uniform over the CTA)
+    if (a.done != nullptr) {
+        int alive = 0;
+#pragma unroll
+        for (int j = 0; j < LPT; ++j) alive |= (lv[j] && a.done[lane[j]] == 0);
+        if (!__syncthreads_or(alive)) return;
+    }
+
+    double* x_s = smem;                                   // [V*LT]        (XS)
+    double* t_s = x_s + (XS ? (size_t)V * LT : 0);        // [V*LT]        (XS && BACKWARD)
+    double* rr_s = t_s + ((XS && BACKWARD) ? (size_t)V * LT : 0);  // [rows_per_chunk*LT]
+
+    if (XS) {
+        for (int i = threadIdx.x; i < V * LT; i += kThreads) {
+            const int v = i / LT, l = i - v * LT;
+            const int64_t b = lane0 + l;
+            x_s[i] = (b < B) ? a.x[(int64_t)v * B + b] : 0.0;
+            if (BACKWARD) t_s[i] = 0.0;
+        }
+        __syncthreads();
+    }
+
+    double ll[LPT];
+#pragma unroll
+    for (int j = 0; j < LPT; ++j) ll[j] = 0.0;
+
+    for (int c = split; c < a.n_chunks; c += S) {
+        const int row0 = a.chunk_row0[c], row1 = a.chunk_row0[c + 1];
+        // ---------------- phase 1: p = A x over the rows of the chunk
+        for (int r = row0 + wi; r < row1; r += kWarps) {
+            const int k0 = __ldg(a.row_ptr + r), k1 = __ldg(a.row_ptr + r + 1);
+            double p[LPT];
+#pragma unroll
+            for (int j = 0; j < LPT; ++j) p[j] = 0.0;
+            for (int k = k0; k < k1; ++k) {
+                const uint32_t e = __ldg(a.ent + k);
+                const int col = e & 0xffffu;
+                const double f = (double)(e >> 16);
+#pragma unroll
+                for (int j = 0; j < LPT; ++j) {
+                    double xv;
+                    if (XS) xv = x_s[col * LT + j * 32 + t];
+                    else xv = lv[j] ? __ldg(a.x + (int64_t)col * B + lane[j]) : 0.0;
+                    p[j] = fma(f, xv, p[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < LPT; ++j) {
+                const int wv = lv[j] ? __ldg(a.w + (int64_t)r * B + lane[j]) : 0;
+                double rr = 0.0;
+                if (wv > 0) {
+                    const double wd = (double)wv;
+                    rr = wd / p[j];
+                    ll[j] = fma(wd, log(p[j]), ll[j]);
+                }
+                if (BACKWARD) rr_s[(r - row0) * LT + j * 32 + t] = rr;
+            }
+        }
+        if (BACKWARD) {
+            __syncthreads();
+            // ------------ phase 2: t += A^T rr over the non-empty columns of the chunk
+            const int c0 = a.ccol_ptr[c], c1 = a.ccol_ptr[c + 1];
+            for (int ci = c0 + wi; ci < c1; ci += kWarps) {
+                const int v = __ldg(a.ccol_id + ci);
+                const int k0 = __ldg(a.ccol_start + ci), k1 = __ldg(a.ccol_start + ci + 1);
+                double acc[LPT];
+#pragma unroll
+                for (int j = 0; j < LPT; ++j) acc[j] = 0.0;
+                for (int k = k0; k < k1; ++k) {
+                    const uint32_t e = __ldg(a.cent + k);
+                    const int rl = e & 0xffffu;
+                    const double f = (double)(e >> 16);
+#pragma unroll
+                    for (int j = 0; j < LPT; ++j) acc[j] = fma(f, rr_s[rl * LT + j * 32 + t], acc[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < LPT; ++j) {
+                    if (XS) t_s[v * LT + j * 32 + t] += acc[j];
+                    else if (lv[j]) a.tpart[((int64_t)split * V + v) * B + lane[j]] += acc[j];
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---------------- epilogue: per-split partials, summed later in fixed split order (deterministic)
+    if (XS && BACKWARD) {
+        for (int i = threadIdx.x; i < V * LT; i += kThreads) {
+            const int v = i / LT, l = i - v * LT;
+            const int64_t b = lane0 + l;
+            if (b < B) a.tpart[((int64_t)split * V + v) * B + b] = t_s[i];
+        }
+    }
+    __syncthreads();
+    double* red = rr_s;  // reuse: [kWarps*LT]; rows_per_chunk >= kWarps is enforced on the host
+#pragma unroll
+    for (int j = 0; j < LPT; ++j) red[wi * LT + j * 32 + t] = ll[j];
+    __syncthreads();
+    if (wi == 0) {
+#pragma unroll
+        for (int j = 0; j < LPT; ++j) {
+            double s = 0.0;
+            for (int q = 0; q < kWarps; ++q) s += red[q * LT + j * 32 + t];
+            if (lv[j]) a.llpart[(int64_t)split * B + lane[j]] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small per-lane kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void lane_sum_kernel(const int32_t* __restrict__ w, int64_t R, int64_t B, double* __restrict__ N) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    long long s = 0;
+    for (int64_t r = 0; r < R; ++r) s += w[r * B + b];
+    N[b] = (double)s;
+}
+
+// z0 from theta0 (or uniform over the mask): phi_v ~ theta_v * L_v, z = sqrt(phi)
+__global__ void init_z_kernel(const double* __restrict__ theta0, const uint8_t* __restrict__ mask,
+                              const double* __restrict__ Ld, const double* __restrict__ invL, int V, int64_t B,
+                              double* __restrict__ zt, double* __restrict__ x) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double s = 0.0;
+    for (int v = 0; v < V; ++v) {
+        const bool m = mask ? mask[(int64_t)v * B + b] != 0 : true;
+        double ph = 0.0;
+        if (m) ph = theta0 ? fmax(theta0[(int64_t)v * B + b], 0.0) * Ld[v] : 1.0;
+        s += ph;
+    }
+    for (int v = 0; v < V; ++v) {
+        const bool m = mask ? mask[(int64_t)v * B + b] != 0 : true;
+        double ph = 0.0;
+        if (m) {
+            ph = theta0 ? fmax(theta0[(int64_t)v * B + b], 0.0) * Ld[v] : 1.0;
+            ph = (s > 0.0) ? ph / s : 0.0;
+            ph = fmax(ph, 1e-12);      // an exact zero inside the subset is a stationary point of the z-parametrisation
+        }
+        const double zz = sqrt(ph);
+        zt[(int64_t)v * B + b] = zz;
+        x[(int64_t)v * B + b] = zz * zz * invL[v];
+    }
+}
+
+// x for tvs_loglik: x_v = mask ? theta_v : 0 ; denom_b = sum_v x_v L_v
+__global__ void prep_theta_kernel(const double* __restrict__ theta, const uint8_t* __restrict__ mask,
+                                  const double* __restrict__ Ld, int V, int64_t B, double* __restrict__ x,
+                                  double* __restrict__ denom) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double s = 0.0;
+    for (int v = 0; v < V; ++v) {
+        const bool m = mask ? mask[(int64_t)v * B + b] != 0 : true;
+        const double th = m ? theta[(int64_t)v * B + b] : 0.0;
+        x[(int64_t)v * B + b] = th;
+        s = fma(th, Ld[v], s);
+    }
+    denom[b] = s;
+}
+
+__global__ void finish_loglik_kernel(const double* __restrict__ llpart, int S, int64_t B, const double* __restrict__ N,
+                                     const double* __restrict__ C, const double* __restrict__ denom, double* __restrict__ out) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double s = 0.0;
+    for (int q = 0; q < S; ++q) s += llpart[(int64_t)q * B + b];
+    out[b] = s - N[b] * log(denom[b]) + (C ? C[b] : 0.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched L-BFGS step in z = sqrt(phi) (one CTA = 32 lanes x kUpdWarps warps that split V).
+//
+// minimise  F(z) = -(1/N) sum_r w_r log( sum_v A_rv z_v^2 / L_v ) + sum_v z_v^2      (no constraints)
+// whose minimisers are exactly the KKT points of the reference's constrained problem
+// (max LL s.t. theta >= 0, sum theta = 1: ModelFitMaxLike.py:27-40) with phi_v = z_v^2 = theta_v L_v / sum(theta L).
+// replaces: scipy SLSQP multistart (ModelFitMaxLike.py:19-58).
+// ------------------------------------------------------------------------------------------------
+struct UpdArgs {
+    const double* tpart; const double* llpart; int S;
+    const double* invL; const double* N; const uint8_t* mask;
+    double *z, *zt, *g, *gt, *gh, *d, *x, *Sh, *Yh, *rho, *gamma;
+    double *F, *dg, *alpha, *llsum, *kkt, *sumphi;
+    int32_t *ls, *iters, *status, *head, *cnt, *done, *nactive;
+    int V; int64_t B; int m; int max_iter; double tol, tol_dual;
+};
+
+__device__ __forceinline__ double blk_sum(double v, double (*red)[32], int wi, int t) {
+    red[wi][t] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < kUpdWarps; ++q) s += red[q][t];
+    __syncthreads();
+    return s;
+}
+__device__ __forceinline__ double blk_max(double v, double (*red)[32], int wi, int t) {
+    red[wi][t] = v;
+    __syncthreads();
+    double s = red[0][t];
+#pragma unroll
+    for (int q = 1; q < kUpdWarps; ++q) s = fmax(s, red[q][t]);
+    __syncthreads();
+    return s;
+}
+
+__global__ void __launch_bounds__(kUpdWarps * 32) lbfgs_update_kernel(const UpdArgs a) {
+    __shared__ double red[kUpdWarps][32];
+    __shared__ double alph[kMaxHistory][32];
+    const int t = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int64_t B = a.B;
+    const int64_t b = (int64_t)blockIdx.x * 32 + t;
+    const bool valid = b < B;
+    const int64_t bb = valid ? b : B - 1;          // clamp so that every thread can load safely
+    const int V = a.V, m = a.m;
+    bool active = valid && a.done[bb] == 0;
+    if (!__syncthreads_or(active)) return;
+
+    const double N = a.N[bb];
+    // ---- A: gather partials of the pass evaluated at zt
+    double llsum = 0.0;
+    for (int q = 0; q < a.S; ++q) llsum += a.llpart[(int64_t)q * B + bb];
+    double sp = 0.0, dgt = 0.0;
+    for (int v = wi; v < V; v += kUpdWarps) {
+        const int64_t i = (int64_t)v * B + bb;
+        double tv = 0.0;
+        for (int q = 0; q < a.S; ++q) tv += a.tpart[((int64_t)q * V + v) * B + bb];
+        const double gh = tv * a.invL[v] / N;
+        const double ztv = a.zt[i];
+        const bool mk = a.mask ? a.mask[i] != 0 : true;
+        const double gtv = mk ? 2.0 * ztv * (1.0 - gh) : 0.0;
+        if (active) { a.gt[i] = gtv; a.gh[i] = gh; }
+        sp = fma(ztv, ztv, sp);
+        dgt = fma(a.d[i], gtv, dgt);
+    }
+    const double sumphi = blk_sum(sp, red, wi, t);
+    dgt = blk_sum(dgt, red, wi, t);
+    double Ft = -llsum / N + sumphi;
+    const bool fin = isfinite(llsum) && isfinite(sumphi) && sumphi > 0.0;
+    if (!fin) Ft = INFINITY;
+
+    const int it = a.iters[bb];
+    const bool first = it < 0;
+    const double F = a.F[bb], dg = a.dg[bb], alpha = a.alpha[bb];
+    bool accept;
+    if (first) accept = fin;
+    else accept = fin && (Ft <= F + 1e-4 * alpha * dg ||
+                          (fabs(Ft - F) <= 1e-14 * fabs(F) && fabs(dgt) <= 0.9 * fabs(dg)));
+    accept = accept && active;
+    bool finished = false;
+    int status = TVS_CONVERGED;
+    if (active && first && !fin) { finished = true; status = TVS_INFEASIBLE; }
+
+    // ---- C: accepted lanes move to zt; curvature pair; KKT residuals
+    double ss = 0.0, yy = 0.0, sy = 0.0, comp = 0.0, dual = -INFINITY;
+    for (int v = wi; v < V; v += kUpdWarps) {
+        const int64_t i = (int64_t)v * B + bb;
+        const double ztv = a.zt[i], gtv = a.gt[i];
+        const double sv = ztv - a.z[i], yv = gtv - a.g[i];
+        ss = fma(sv, sv, ss); yy = fma(yv, yv, yy); sy = fma(sv, yv, sy);
+        const bool mk = a.mask ? a.mask[i] != 0 : true;
+        if (mk) {
+            const double ghn = a.gh[i] * sumphi;           // gradient ratio at the normalised point
+            comp = fmax(comp, ztv * ztv / sumphi * fabs(ghn - 1.0));
+            dual = fmax(dual, ghn - 1.0);
+        }
+    }
+    ss = blk_sum(ss, red, wi, t); yy = blk_sum(yy, red, wi, t); sy = blk_sum(sy, red, wi, t);
+    comp = blk_max(comp, red, wi, t); dual = blk_max(dual, red, wi, t);
+
+    int head = a.head[bb], cnt = a.cnt[bb];
+    const bool store = accept && !first && sy > 1e-10 * sqrt(ss * yy) && sy > 0.0;
+    for (int v = wi; v < V; v += kUpdWarps) {
+        const int64_t i = (int64_t)v * B + bb;
+        if (accept) {
+            const double ztv = a.zt[i], gtv = a.gt[i];
+            if (store) {
+                a.Sh[((int64_t)head * V + v) * B + bb] = ztv - a.z[i];
+                a.Yh[((int64_t)head * V + v) * B + bb] = gtv - a.g[i];
+            }
+            a.z[i] = ztv; a.g[i] = gtv;
+        }
+    }
+    int iters = it;
+    if (accept) {
+        iters = it + 1;
+        if (store) {
+            if (wi == 0) { a.rho[(int64_t)head * B + bb] = 1.0 / sy; a.gamma[bb] = sy / yy; }
+            head = (head + 1) % m; cnt = min(cnt + 1, m);
+        }
+        if (comp <= a.tol && dual <= a.tol_dual) { finished = true; status = TVS_CONVERGED; }
+        else if (iters >= a.max_iter) { finished = true; status = TVS_MAXITER; }
+        if (wi == 0) {
+            a.F[bb] = Ft; a.llsum[bb] = llsum; a.sumphi[bb] = sumphi;
+            a.kkt[2 * bb] = comp; a.kkt[2 * bb + 1] = dual; a.iters[bb] = iters; a.ls[bb] = 0;
+        }
+    }
+    __syncthreads();   // z, g, history visible to the whole CTA
+
+    // ---- D: two-loop recursion -> new direction for accepted, unfinished lanes (computed for all, used by those)
+    const bool newdir = accept && !finished;
+    // q = g  (held in a.d)
+    if (__syncthreads_or(newdir)) {
+        for (int v = wi; v < V; v += kUpdWarps) {
+            const int64_t i = (int64_t)v * B + bb;
+            if (newdir) a.d[i] = a.g[i];
+        }
+        for (int j = 0; j < m; ++j) {                      // newest -> oldest
+            const bool use = newdir && j < cnt;
+            const int slot = ((head - 1 - j) % m + m) % m;
+            double part = 0.0;
+            if (use)
+                for (int v = wi; v < V; v += kUpdWarps)
+                    part = fma(a.Sh[((int64_t)slot * V + v) * B + bb], a.d[(int64_t)v * B + bb], part);
+            const double dot1 = blk_sum(part, red, wi, t);     // every thread reaches the barrier
+            const double aj = use ? a.rho[(int64_t)slot * B + bb] * dot1 : 0.0;
+            if (wi == 0) alph[j][t] = aj;
+            if (use)
+                for (int v = wi; v < V; v += kUpdWarps) {
+                    const int64_t i = (int64_t)v * B + bb;
+                    a.d[i] = fma(-aj, a.Yh[((int64_t)slot * V + v) * B + bb], a.d[i]);
+                }
+        }
+        __syncthreads();
+        const double gamma = (cnt > 0) ? a.gamma[bb] : 1.0;
+        if (newdir)
+            for (int v = wi; v < V; v += kUpdWarps) a.d[(int64_t)v * B + bb] *= gamma;
+        for (int j = m - 1; j >= 0; --j) {                 // oldest -> newest
+            const bool use = newdir && j < cnt;
+            const int slot = ((head - 1 - j) % m + m) % m;
+            double part = 0.0;
+            if (use)
+                for (int v = wi; v < V; v += kUpdWarps)
+                    part = fma(a.Yh[((int64_t)slot * V + v) * B + bb], a.d[(int64_t)v * B + bb], part);
+            const double dot2 = blk_sum(part, red, wi, t);
+            const double beta = use ? a.rho[(int64_t)slot * B + bb] * dot2 : 0.0;
+            if (use) {
+                const double coef = alph[j][t] - beta;
+                for (int v = wi; v < V; v += kUpdWarps) {
+                    const int64_t i = (int64_t)v * B + bb;
+                    a.d[i] = fma(coef, a.Sh[((int64_t)slot * V + v) * B + bb], a.d[i]);
+                }
+            }
+        }
+        // d = -r ; descent check
+        double dgn = 0.0, gg = 0.0;
+        for (int v = wi; v < V; v += kUpdWarps) {
+            const int64_t i = (int64_t)v * B + bb;
+            const double gv = a.g[i];
+            if (newdir) { const double dv = -a.d[i]; a.d[i] = dv; dgn = fma(dv, gv, dgn); }
+            gg = fma(gv, gv, gg);
+        }
+        dgn = blk_sum(dgn, red, wi, t); gg = blk_sum(gg, red, wi, t);
+        double anew = 1.0;
+        if (newdir) {
+            if (!(dgn < 0.0) || cnt == 0) {                // not a descent direction (or no history): steepest descent
+                for (int v = wi; v < V; v += kUpdWarps) { const int64_t i = (int64_t)v * B + bb; a.d[i] = -a.g[i]; }
+                if (!(dgn < 0.0)) cnt = 0;
+                dgn = -gg;
+                anew = fmin(1.0, 1.0 / sqrt(fmax(gg, 1e-300)));
+            }
+            if (gg == 0.0) { finished = true; status = TVS_CONVERGED; }
+            if (wi == 0) { a.dg[bb] = dgn; a.alpha[bb] = anew; }
+        }
+        for (int v = wi; v < V; v += kUpdWarps) {
+            const int64_t i = (int64_t)v * B + bb;
+            if (newdir && !finished) {
+                const double zn = fma(anew, a.d[i], a.z[i]);
+                a.zt[i] = zn; a.x[i] = zn * zn * a.invL[v];
+            }
+        }
+    }
+
+    // ---- E: rejected lanes backtrack along the same direction
+    const bool reject = active && !accept && !finished;
+    if (__syncthreads_or(reject)) {
+        int ls = a.ls[bb] + 1;
+        double anew = alpha;
+        bool stall = false;
+        if (reject) {
+            if (ls > 40) stall = true;
+            else {
+                // safeguarded quadratic interpolation
+                double aq = 0.5 * alpha;
+                if (isfinite(Ft)) {
+                    const double den = 2.0 * (Ft - F - dg * alpha);
+                    if (den > 0.0) aq = -dg * alpha * alpha / den;
+                    aq = fmin(fmax(aq, 0.1 * alpha), 0.5 * alpha);
+                } else aq = 0.1 * alpha;
+                anew = aq;
+            }
+        }
+        for (int v = wi; v < V; v += kUpdWarps) {
+            const int64_t i = (int64_t)v * B + bb;
+            if (reject && !stall) {
+                const double zn = fma(anew, a.d[i], a.z[i]);
+                a.zt[i] = zn; a.x[i] = zn * zn * a.invL[v];
+            }
+        }
+        if (reject && wi == 0) { a.alpha[bb] = anew; a.ls[bb] = ls; }
+        if (stall) { finished = true; status = (comp <= 1e3 * a.tol && dual <= 1e3 * a.tol_dual) ? TVS_CONVERGED : TVS_STALLED; }
+    }
+
+    if (valid && wi == 0) {
+        a.head[bb] = head; a.cnt[bb] = cnt;
+        if (active && finished) { a.status[bb] = status; a.done[bb] = 1; }
+    }
+    if (wi == 0) {
+        const unsigned still = __ballot_sync(0xffffffffu, active && !finished);
+        if (t == 0 && still) atomicAdd(a.nactive, __popc(still));
+    }
+}
+
+// theta_out, ll_out, ... from the last accepted point of every lane
+struct FinArgs {
+    const double *z, *invL, *llsum, *sumphi, *N, *C, *kkt; const int32_t *iters, *status, *done; const uint8_t* mask;
+    double *theta_out, *ll_out, *kkt_out; int32_t *iters_out, *status_out; int V; int64_t B;
+};
+__global__ void finalize_fit_kernel(const FinArgs a) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const int st = a.done[b] ? a.status[b] : TVS_MAXITER;   // still running when the pass budget ran out
+    if (a.theta_out) {
+        double s = 0.0;
+        for (int v = 0; v < a.V; ++v) { const double zz = a.z[(int64_t)v * a.B + b]; s += zz * zz * a.invL[v]; }
+        for (int v = 0; v < a.V; ++v) {
+            const double zz = a.z[(int64_t)v * a.B + b];
+            a.theta_out[(int64_t)v * a.B + b] = (st == TVS_INFEASIBLE) ? nan("") : zz * zz * a.invL[v] / s;
+        }
+    }
+    if (a.ll_out)
+        a.ll_out[b] = (st == TVS_INFEASIBLE) ? -INFINITY
+                                             : a.llsum[b] - a.N[b] * log(a.sumphi[b]) + (a.C ? a.C[b] : 0.0);
+    if (a.kkt_out) { a.kkt_out[2 * b] = a.kkt[2 * b]; a.kkt_out[2 * b + 1] = a.kkt[2 * b + 1]; }
+    if (a.iters_out) a.iters_out[b] = a.iters[b] < 0 ? 0 : a.iters[b];
+    if (a.status_out) a.status_out[b] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device bootstrap: Philox4x32-10, key = (seed_lo, seed_hi), counter = (draw_lo, draw_hi, lane, 0x54565321)
+// record index = floor(u64 * Ntot / 2^64); row = first r with cum[r] > index.
+// replaces: random.choices(records_pool_sorted, k=N) + regrouping by read path (traversome.py:1652-1660)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                               uint32_t* out) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void resample_kernel(const int64_t* __restrict__ cum, int64_t R, int64_t Ntot, int64_t B, uint64_t seed,
+                                int keep_lane0, const int32_t* __restrict__ n_obs, int32_t* __restrict__ w) {
+    // grid.y = lane, grid-stride over draws
+    const int64_t b = blockIdx.y;
+    if (keep_lane0 && b == 0) {
+        for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x)
+            w[r * B] = n_obs[r];
+        return;
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Ntot; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t o[4];
+        philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)b, 0x54565321u, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+        const uint64_t u = ((uint64_t)o[1] << 32) | o[0];
+        const uint64_t idx = __umul64hi(u, (uint64_t)Ntot);
+        int64_t lo = 0, hi = R - 1;                 // first r with cum[r] > idx
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(cum + mid) > (int64_t)idx) hi = mid; else lo = mid + 1;
+        }
+        atomicAdd(w + lo * B + b, 1);
+    }
+}
+
+// fp64 FMA peak: 8 independent chains per thread
+__global__ void fp64_peak_kernel(double* out, int iters, double seed) {
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace tvs
