@@ -1,0 +1,405 @@
+"""``ModelFitMaxLike`` -- drop-in replacement of ``traversome/ModelFitMaxLike.py`` on the GPU.
+
+Same constructor, methods, attributes, log lines and exceptions as the reference class
+(ModelFitMaxLike.py:61-580), but
+
+  * the symengine expression build + LLVM lambdify (``get_neg_likelihood_of_var_freq``, :515-558)
+    becomes an integer CSR build (``traversome_b200.csr``) uploaded once per model;
+  * the scipy SLSQP multistart (``minimize_neg_likelihood``, :19-58) becomes ONE batched call of
+    the CUDA solver (``tvs_fit``), one "lane" per candidate-variant subset, so that all
+    leave-one-out candidates of a backward-selection step are fitted together;
+  * ``n_proc`` is accepted and ignored (lanes replace the Pool/dill workers of :219-262).
+
+There is no CPU fallback: constructing the engine raises when ``libtvs.so`` or a CUDA device is
+missing.
+"""
+from collections import OrderedDict
+from typing import OrderedDict as typingODict
+from typing import Set, Union
+
+import numpy as np
+from loguru import logger
+
+from . import _cabi
+from .csr import ReadPathMatrix, lane_from_bins
+from .utils import Criterion, LogLikeFuncInfo, aic, bic
+
+
+class FitResult(object):
+    """What the reference reads off scipy's OptimizeResult: ``x`` (proportions of the fitted ids in
+    increasing id order), ``fun`` (= -loglike), ``success``."""
+    __slots__ = ("x", "fun", "success", "status", "kkt", "nit")
+
+    def __init__(self, x, fun, success, status, kkt, nit):
+        self.x, self.fun, self.success, self.status, self.kkt, self.nit = x, fun, success, status, kkt, nit
+
+
+def minimize_neg_likelihood(neg_loglike_func, num_variables, verbose, err_queue=None):
+    """Module-level entry point kept for API compatibility (ModelFitMaxLike.py:19-58).
+
+    The reference receives an opaque compiled callable; here the callable returned by
+    ``ModelFitMaxLike.get_neg_likelihood_of_var_freq`` carries its lane description, and the fit is
+    done by the CUDA solver.  Returns a FitResult, or False when the fit failed."""
+    try:
+        fitter = getattr(neg_loglike_func, "tvs_fit", None)
+        if fitter is None:
+            raise TypeError("minimize_neg_likelihood: expected the callable produced by "
+                            "traversome_b200.ModelFitMaxLike.get_neg_likelihood_of_var_freq")
+        res = fitter()
+        return res if res.success else False
+    except Exception as e:
+        if err_queue:
+            err_queue.put(e)
+        else:
+            raise e
+
+
+def prune_model_bins(model):
+    """The in-place pruning get_like_formula performs on the model (ModelGenerator.py:138-151)."""
+    kept = []
+    for bins in model.bins_list:
+        bins.rp_bins[:] = [rp for rp in bins.rp_bins if not (rp.num_possible_X < 1)]
+        if bins.rp_bins:
+            kept.append(bins)
+    model.bins_list[:] = kept
+
+
+class ModelFitMaxLike(object):
+    """Find the variant proportions that maximise the likelihood (batched, on one B200)."""
+
+    # solver settings (class level so that callers of the reference signature need not know them)
+    tol = 1e-10
+    max_iter = 2000
+    history = 8
+
+    def __init__(self,
+                 model,
+                 variant_paths,
+                 variant_subpath_counters,
+                 sbp_to_sbp_id,
+                 repr_to_merged_variants,
+                 be_unidentifiable_to,
+                 loglevel="INFO",
+                 bootstrap_mode=False,
+                 device=0):
+        self.model = model
+        self.variant_paths = variant_paths
+        self.num_put_variants = len(variant_paths)
+        self.all_sub_paths = model.all_sub_paths
+        self.variant_subpath_counters = variant_subpath_counters
+        self.sbp_to_sbp_id = sbp_to_sbp_id
+        self.repr_to_merged_variants = repr_to_merged_variants
+        self.be_unidentifiable_to = be_unidentifiable_to
+        self.loglevel = loglevel
+        self.bootstrap_mode = bootstrap_mode
+        self.device = device
+
+        # to be generated
+        self.variant_percents = None
+        self.observed_sbp_id_set = set()
+
+        # res without model selection
+        self.pe_neg_loglike_obj = None
+        self.pe_best_proportions = None
+
+        self.__warning_sent = False
+        self._engine = None
+        self._lane = None            # (w[R] int32, C, N) of this model
+        self._shuffle = np.random.shuffle   # ModelFitMaxLike.py:203; tests may pin the permutation
+        self.n_gpu_fits = 0          # lanes fitted so far (diagnostics)
+
+    # ------------------------------------------------------------------ engine / lanes
+    def _ensure_engine(self):
+        if self._engine is not None:
+            return self._engine
+        prune_model_bins(self.model)
+        matrix = ReadPathMatrix(self.num_put_variants)
+        w_map, C, N = lane_from_bins(self.model.bins_list, matrix)
+        if matrix.R == 0:
+            raise Exception("Likelihood maximization failed.")   # nothing to fit
+        row_ptr, col, val = matrix.arrays()
+        w = np.zeros(matrix.R, dtype=np.int32)
+        for r, n in w_map.items():
+            w[r] = n
+        self._matrix = matrix
+        self._lane = (w, float(C), int(N))
+        self._engine = _cabi.Engine(row_ptr, col, val, np.asarray(self.model.variant_sizes, dtype=np.int64),
+                                    n_variants=self.num_put_variants, device=self.device)
+        return self._engine
+
+    def close(self):
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+
+    def _fit_subsets(self, subsets):
+        """One GPU call: lane b = ML fit restricted to subsets[b] (sets of representative ids).
+        Returns a list of FitResult (x ordered by increasing variant id)."""
+        eng = self._ensure_engine()
+        w, C, N = self._lane
+        B = len(subsets)
+        mask = np.zeros((self.num_put_variants, B), dtype=np.uint8)
+        for b, ids in enumerate(subsets):
+            mask[sorted(ids), b] = 1
+        eng.set_lanes(np.repeat(w[:, None], B, axis=1), mask=mask, C=np.full(B, C))
+        out = eng.fit(tol=self.tol, max_iter=self.max_iter, history=self.history)
+        self.n_gpu_fits += B
+        results = []
+        for b, ids in enumerate(subsets):
+            order = sorted(ids)
+            status = int(out["status"][b])
+            ok = status in (_cabi.CONVERGED, _cabi.STALLED) and np.isfinite(out["loglike"][b])
+            results.append(FitResult(x=np.array(out["theta"][order, b], dtype=np.float64),
+                                     fun=-float(out["loglike"][b]), success=bool(ok), status=status,
+                                     kkt=tuple(out["kkt"][b]), nit=int(out["iters"][b])))
+        return results
+
+    # ------------------------------------------------------------------ public API
+    def point_estimate(self,
+                       chosen_ids: set = None,
+                       criterion=Criterion.BIC):
+        if chosen_ids:
+            chosen_ids = {self.be_unidentifiable_to[variant_id] for variant_id in chosen_ids}
+        else:
+            chosen_ids = {variant_id for variant_id in self.repr_to_merged_variants}
+        self.variant_percents = ["P" + str(variant_id) if variant_id in chosen_ids else False
+                                 for variant_id in range(self.num_put_variants)]
+        if self.bootstrap_mode:
+            logger.debug("Generating the likelihood function .. ")
+        else:
+            logger.info("Generating the likelihood function .. ")
+        self.pe_neg_loglike_obj = self.get_neg_likelihood_of_var_freq(within_variant_ids=chosen_ids)
+        if self.bootstrap_mode:
+            logger.debug("Maximizing the likelihood function .. ")
+        else:
+            logger.info("Maximizing the likelihood function .. ")
+        success_run = minimize_neg_likelihood(
+            neg_loglike_func=self.pe_neg_loglike_obj.loglike_func,
+            num_variables=len(chosen_ids),
+            verbose=self.loglevel in ("TRACE", "ALL"))
+        if success_run:
+            use_prop, echo_prop, this_like, this_criteria = \
+                self.__summarize_like_and_criteria(success_run, chosen_ids, criterion, self.pe_neg_loglike_obj)
+            return use_prop, this_like, this_criteria
+        else:
+            raise Exception("Likelihood maximization failed.")
+
+    def reverse_model_selection(self,
+                                n_proc,
+                                criterion=Criterion.BIC,
+                                chosen_ids: Union[typingODict[int, bool], Set] = None,
+                                random_size: int = 20,
+                                user_fixed_ids: Union[list, tuple, set, None] = None):
+        """Backward stepwise selection by AIC/BIC (ModelFitMaxLike.py:140-322).
+
+        Decision logic identical to the reference; every chunk of leave-one-out candidates
+        (``random_size`` of them) is fitted as one batch of GPU lanes instead of sequentially /
+        through Pool workers.  ``n_proc`` is ignored."""
+        if random_size != 0 and n_proc > random_size and not self.__warning_sent:
+            self.__warning_sent = True
+        diff_tolerance = 1e-6
+        if chosen_ids:
+            chosen_ids = {self.be_unidentifiable_to[variant_id] for variant_id in chosen_ids}
+        else:
+            chosen_ids = {variant_id for variant_id in self.repr_to_merged_variants}
+        chosen_ids = set(chosen_ids)
+        self.variant_percents = ["P" + str(variant_id) if variant_id in chosen_ids else False
+                                 for variant_id in range(self.num_put_variants)]
+        logger.debug("Test variants {}".format(list(chosen_ids)))
+
+        if user_fixed_ids:
+            indispensable_ids = {u_id: True for u_id in user_fixed_ids}
+        else:
+            indispensable_ids = {}
+
+        previous_prop, previous_echo, previous_like, previous_criteria = \
+            self.__compute_like_and_criteria_batch([chosen_ids], criterion)[0]
+        self.__drop_zero_variants(chosen_ids, previous_prop, previous_echo, diff_tolerance, indispensable_ids)
+
+        while len(chosen_ids) > 1:
+            logger.debug("Trying dropping {} variant(s) ..".format(self.num_put_variants - len(chosen_ids) + 1))
+            chosen_ids_sorted = sorted(chosen_ids)
+            chosen_rd_list = list(range(len(chosen_ids_sorted)))
+            self._shuffle(chosen_rd_list)
+            changed = False
+            rs = random_size if random_size > 0 else len(chosen_rd_list)
+            for go_rd_sp in range(0, len(chosen_rd_list), rs):
+                this_rd_ids = chosen_rd_list[go_rd_sp: go_rd_sp + rs]
+                test_id_res = OrderedDict()
+                # -- which candidates of this chunk get a fit (same screening as __test_one_drop, :349-370)
+                to_fit = []
+                for rd_id in this_rd_ids:
+                    var_id = chosen_ids_sorted[rd_id]
+                    label = ", ".join([self.__str_rep_id(_c_i) for _c_i in chosen_ids_sorted])
+                    if var_id not in indispensable_ids:
+                        testing_ids = chosen_ids - {var_id}
+                        if self.cover_all_observed_subpaths(testing_ids):
+                            logger.debug("Test variants [{}] - {}".format(label, self.__str_rep_id(var_id)))
+                            to_fit.append((var_id, testing_ids))
+                        else:
+                            indispensable_ids[var_id] = True
+                            logger.debug("Test variants [{}] - {}: skipped for necessary subpath(s) (case *)"
+                                         .format(label, self.__str_rep_id(var_id)))
+                    else:
+                        logger.debug("Test variants [{}] - {}: skipped for necessary subpath(s) (case **)"
+                                     .format(label, self.__str_rep_id(var_id)))
+                # -- one batch of lanes for the whole chunk
+                if to_fit:
+                    batch = self.__compute_like_and_criteria_batch([ids for _, ids in to_fit], criterion)
+                    for (var_id, _), res_list in zip(to_fit, batch):
+                        test_id_res[var_id] = {"prop": res_list[0], "echo": res_list[1], "loglike": res_list[2],
+                                               criterion: res_list[3]}
+                if test_id_res:
+                    best_drop_id, best_val = sorted([[_go_var_, test_id_res[_go_var_][criterion]]
+                                                     for _go_var_ in test_id_res],
+                                                    key=lambda x: x[1])[0]
+                    if best_val < previous_criteria:
+                        previous_criteria = best_val
+                        previous_like = test_id_res[best_drop_id]["loglike"]
+                        previous_prop = test_id_res[best_drop_id]["prop"]
+                        previous_echo = test_id_res[best_drop_id]["echo"]
+                        chosen_ids.remove(best_drop_id)
+                        log = logger.debug if self.bootstrap_mode else logger.info
+                        log("Drop {}".format(self.__str_rep_id(best_drop_id)))
+                        log("Proportions: " + ", ".join(["%s:%.4f" % (_id, _p) for _id, _p, in previous_echo.items()]))
+                        log("Log-likelihood: %s" % previous_like)
+                        self.__drop_zero_variants(
+                            chosen_ids, previous_prop, previous_echo, diff_tolerance, indispensable_ids)
+                        changed = True
+                        break
+            if not changed:
+                self.__echo_res(previous_echo, previous_like)
+                return previous_prop, previous_like, previous_criteria
+        self.__echo_res(previous_echo, previous_like)
+        return previous_prop, previous_like, previous_criteria
+
+    # ------------------------------------------------------------------ helpers (reference-private names kept)
+    def __echo_res(self, previous_echo, previous_like):
+        if self.bootstrap_mode:
+            logger.info(f"{self.bootstrap_mode} Proportions: " +
+                        ", ".join(["%s:%.4f" % (_id, _p) for _id, _p, in previous_echo.items()]))
+            logger.debug("Log-likelihood: %s" % previous_like)
+        else:
+            logger.info("Proportions: " + ", ".join(["%s:%.4f" % (_id, _p) for _id, _p, in previous_echo.items()]))
+            logger.info("Log-likelihood: %s" % previous_like)
+
+    def __drop_zero_variants(self, chosen_ids, representative_props, echo_props, diff_tolerance, indispensable_ids):
+        """|prop| < 1e-6 -> dropped without refit (ModelFitMaxLike.py:333-347)."""
+        for var_id in list(chosen_ids):
+            if var_id in indispensable_ids:
+                continue
+            if abs(representative_props[var_id] - 0.) < diff_tolerance:
+                chosen_ids.remove(var_id)
+                for cid_var_id in self.repr_to_merged_variants[var_id]:
+                    del representative_props[cid_var_id]
+                del echo_props[self.__str_rep_id(var_id)]
+                if self.bootstrap_mode:
+                    logger.debug("Drop {}".format(self.__str_rep_id(var_id)))
+                else:
+                    logger.info("Drop {}".format(self.__str_rep_id(var_id)))
+
+    def __compute_like_and_criteria_batch(self, id_sets, criteria):
+        """Batched __compute_like_and_criteria (ModelFitMaxLike.py:448-459): one lane per id set."""
+        logger.debug("Generating the likelihood function .. ")
+        for ids in id_sets:
+            if self.bootstrap_mode:
+                logger.debug("Maximizing the likelihood function for {} variants".format(len(ids)))
+            else:
+                logger.info("Maximizing the likelihood function for {} variants".format(len(ids)))
+        results = self._fit_subsets(id_sets)
+        _w, _C, sample_size = self._lane
+        out = []
+        for ids, res in zip(id_sets, results):
+            info = LogLikeFuncInfo(loglike_func=None, variable_size=self.__variable_size(ids), sample_size=sample_size)
+            out.append(self.__summarize_like_and_criteria(res if res.success else False, ids, criteria, info))
+        return out
+
+    def __variable_size(self, ids):
+        # ModelGenerator.py:125-126,175: an empty subset or the full set counts every variant
+        if not ids or set(ids) == set(range(self.num_put_variants)):
+            return self.num_put_variants
+        return len(ids)
+
+    def __summarize_like_and_criteria(self, success_run, chosen_id_set, criteria, neg_loglike_func_obj):
+        if success_run:
+            this_like = -success_run.fun
+            use_prop, echo_prop = self.__summarize_run_prop(success_run, chosen_id_set)
+            logger.debug("Proportions: " + ", ".join(["%s:%.4f" % (_id, _p) for _id, _p, in echo_prop.items()]))
+            logger.debug("Log-likelihood: %s" % this_like)
+            if criteria == "AIC":
+                logger.debug("len_param: %s" % neg_loglike_func_obj.variable_size)
+                this_criteria = aic(loglike=this_like, len_param=neg_loglike_func_obj.variable_size)
+                logger.debug("%s: %s" % (criteria, this_criteria))
+            elif criteria == "BIC":
+                logger.debug("len_param: %s" % neg_loglike_func_obj.variable_size)
+                logger.debug("len_data: %s" % neg_loglike_func_obj.sample_size)
+                this_criteria = bic(loglike=this_like, len_param=neg_loglike_func_obj.variable_size,
+                                    len_data=neg_loglike_func_obj.sample_size)
+                logger.debug("%s: %s" % (criteria, this_criteria))
+            else:
+                raise Exception("Invalid criterion {}".format(criteria))
+            return use_prop, echo_prop, this_like, this_criteria
+        else:
+            raise Exception("Likelihood maximization failed.")
+
+    def __summarize_run_prop(self, success_run, within_var_ids):
+        """Split a representative's proportion evenly over its unidentifiable group (:499-510)."""
+        prop_dict = {}
+        representatives = [rep_id for rep_id in sorted(within_var_ids) if rep_id in self.repr_to_merged_variants]
+        echo_prop = OrderedDict()
+        for go, this_prop in enumerate(success_run.x):
+            this_prop = float(this_prop)
+            echo_prop[self.__str_rep_id(representatives[go])] = this_prop
+            unidentifiable_var_ids = self.repr_to_merged_variants[representatives[go]]
+            this_prop /= len(unidentifiable_var_ids)
+            for cid_var_id in unidentifiable_var_ids:
+                prop_dict[cid_var_id] = this_prop
+        use_prop = OrderedDict([(_id, prop_dict[_id]) for _id in sorted(prop_dict)])
+        return use_prop, echo_prop
+
+    def __str_rep_id(self, rep_id):
+        return "+".join([f"cid_{_cid_var_id}" for _cid_var_id in self.repr_to_merged_variants[rep_id]])
+
+    def get_neg_likelihood_of_var_freq(self, within_variant_ids: set = None, scipy_style=True):
+        """LogLikeFuncInfo whose ``loglike_func`` evaluates -LL on the GPU (replaces the
+        symengine.lambdify'd callable of ModelFitMaxLike.py:515-558).  scipy_style: one array
+        argument, returns a length-1 array; otherwise positional floats."""
+        eng = self._ensure_engine()
+        w, C, N = self._lane
+        if within_variant_ids is None:
+            within_variant_ids = set(range(self.num_put_variants))
+        ids = sorted(within_variant_ids)
+        variable_size = self.__variable_size(set(ids))
+        owner = self
+
+        def neg_loglike(*args):
+            x = np.asarray(args[0] if scipy_style else args, dtype=np.float64).reshape(-1)
+            theta = np.zeros((owner.num_put_variants, 1), dtype=np.float64)
+            theta[ids, 0] = x
+            mask = np.zeros((owner.num_put_variants, 1), dtype=np.uint8)
+            mask[ids, 0] = 1
+            eng.set_lanes(w[:, None], mask=mask, C=np.array([C]))
+            with np.errstate(invalid="ignore"):
+                return -eng.loglik(theta)
+
+        neg_loglike.tvs_fit = lambda: owner._fit_subsets([set(ids)])[0]
+        return LogLikeFuncInfo(loglike_func=neg_loglike, variable_size=variable_size, sample_size=N)
+
+    def update_observed_sp_ids(self):
+        self.observed_sbp_id_set = set()
+        for go_sp, (this_sub_path, this_sub_path_info) in enumerate(self.all_sub_paths.items()):
+            if this_sub_path_info.mapped_records:
+                self.observed_sbp_id_set.add(go_sp)
+            else:
+                logger.trace("Drop subpath without observation: {}: {}".format(go_sp, this_sub_path))
+
+    def cover_all_observed_subpaths(self, variant_ids):
+        """Every observed read path must occur in >=1 variant of the set (ModelFitMaxLike.py:568-580)."""
+        if not self.observed_sbp_id_set:
+            self.update_observed_sp_ids()
+        model_sp_ids = set()
+        for go_var in variant_ids:
+            for sub_path in self.variant_subpath_counters[self.variant_paths[go_var]]:
+                if sub_path in self.sbp_to_sbp_id:
+                    model_sp_ids.add(self.sbp_to_sbp_id[sub_path])
+        return self.observed_sbp_id_set.issubset(model_sp_ids)

@@ -1,0 +1,204 @@
+"""ctypes binding of ``libtvs.so`` (C ABI declared in ``include/tvs.h``).
+
+There is deliberately no CPU fallback: if the shared library is missing, or no CUDA device is
+usable, every entry point raises.  Build the library with ``python __graft_entry__.py build`` or
+``traversome_b200/csrc/build.sh``.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_uint8, c_uint64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtvs.so")
+
+# every symbol include/tvs.h declares (tests check that the library exports all of them)
+SYMBOLS = (
+    "tvs_version", "tvs_last_error", "tvs_device_count", "tvs_create", "tvs_destroy", "tvs_set_lanes",
+    "tvs_resample", "tvs_get_weights", "tvs_loglik", "tvs_fit", "tvs_last_fit_stats", "tvs_dims",
+    "tvs_measure_fp64_peak",
+)
+
+TVS_OK, TVS_EINVAL, TVS_ECUDA, TVS_ENOMEM, TVS_ELIMIT, TVS_ESTATE = 0, -1, -2, -3, -4, -5
+CONVERGED, MAXITER, STALLED, INFEASIBLE = 0, 1, 2, 3
+_ERRNAMES = {-1: "TVS_EINVAL", -2: "TVS_ECUDA", -3: "TVS_ENOMEM", -4: "TVS_ELIMIT", -5: "TVS_ESTATE"}
+
+
+class TvsError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("%s: %s" % (_ERRNAMES.get(code, str(code)), message))
+        self.code = code
+
+
+class FitOptions(ctypes.Structure):
+    _fields_ = [("tol", c_double), ("max_iter", c_int32), ("history", c_int32), ("check_every", c_int32),
+                ("reserved", c_int32)]
+
+
+class FitStats(ctypes.Structure):
+    _fields_ = [("passes", c_int64), ("kernel_launches", c_int64), ("pass_ms", c_double), ("total_ms", c_double),
+                ("lane_passes", c_int64)]
+
+
+_lib = None
+
+
+def load():
+    """Load libtvs.so once; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("traversome_b200: %s not found -- build it with `python __graft_entry__.py build` "
+                          "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.tvs_version.restype = c_int
+    lib.tvs_last_error.restype = c_char_p
+    lib.tvs_device_count.argtypes = [POINTER(c_int)]
+    lib.tvs_create.argtypes = [POINTER(c_void_p), c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.tvs_destroy.argtypes = [c_void_p]
+    lib.tvs_set_lanes.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
+    lib.tvs_resample.argtypes = [c_void_p, c_int64, c_void_p, c_uint64, c_int, c_void_p, c_void_p]
+    lib.tvs_get_weights.argtypes = [c_void_p, c_void_p]
+    lib.tvs_loglik.argtypes = [c_void_p, c_void_p, c_void_p]
+    lib.tvs_fit.argtypes = [c_void_p, c_void_p, POINTER(FitOptions), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.tvs_last_fit_stats.argtypes = [c_void_p, POINTER(FitStats)]
+    lib.tvs_dims.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]
+    lib.tvs_measure_fp64_peak.argtypes = [c_int, POINTER(c_double)]
+    for name in SYMBOLS:
+        fn = getattr(lib, name)
+        if name not in ("tvs_last_error",):
+            fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def _check(code):
+    if code != TVS_OK:
+        raise TvsError(code, load().tvs_last_error().decode("utf-8", "replace"))
+
+
+def device_count():
+    n = c_int(0)
+    lib = load()
+    rc = lib.tvs_device_count(ctypes.byref(n))
+    if rc != TVS_OK:
+        return 0
+    return n.value
+
+
+def _ptr(a):
+    """host numpy array / torch tensor (cpu or cuda) / raw int address / None -> void*"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return c_void_p(a.data_ptr())
+    raise TypeError("unsupported buffer type %r" % type(a))
+
+
+def _as(a, dtype):
+    """C-contiguous host array of dtype (no copy when already so); torch tensors pass through."""
+    if a is None or hasattr(a, "data_ptr") or isinstance(a, int):
+        return a
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Engine(object):
+    """One shared CSR on one GPU + the current batch of lanes.  Thin, typed wrapper over the C ABI."""
+
+    def __init__(self, row_ptr, col, val, variant_sizes, n_variants=None, device=0):
+        lib = load()
+        self._lib = lib
+        self._h = c_void_p(None)
+        self.row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
+        self.col = np.ascontiguousarray(col, dtype=np.int32)
+        self.val = np.ascontiguousarray(val, dtype=np.int32)
+        self.L = np.ascontiguousarray(variant_sizes, dtype=np.int64)
+        self.R = int(self.row_ptr.shape[0] - 1)
+        self.V = int(self.L.shape[0] if n_variants is None else n_variants)
+        self.nnz = int(self.col.shape[0])
+        self.B = 0
+        self.device = int(device)
+        _check(lib.tvs_create(ctypes.byref(self._h), self.device, self.R, self.V, self.nnz, _ptr(self.row_ptr),
+                              _ptr(self.col), _ptr(self.val), _ptr(self.L)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.tvs_destroy(self._h)
+            self._h = c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- lanes
+    def set_lanes(self, w, mask=None, C=None, B=None):
+        """w [R,B] int32 lane-minor; mask [V,B] uint8 or None; C [B] float64 or None."""
+        w = _as(w, np.int32)
+        if B is None:
+            B = int(w.shape[1]) if w.ndim == 2 else int(w.size // self.R)
+        mask = _as(mask, np.uint8)
+        C = _as(C, np.float64)
+        self._keep = (w, mask, C)
+        _check(self._lib.tvs_set_lanes(self._h, int(B), _ptr(w), _ptr(mask), _ptr(C)))
+        self.B = int(B)
+
+    def resample(self, B, n_obs, seed, keep_lane0=False, mask=None, C=None):
+        n_obs = _as(n_obs, np.int32)
+        mask = _as(mask, np.uint8)
+        C = _as(C, np.float64)
+        _check(self._lib.tvs_resample(self._h, int(B), _ptr(n_obs), c_uint64(int(seed)), int(bool(keep_lane0)),
+                                      _ptr(mask), _ptr(C)))
+        self.B = int(B)
+
+    def get_weights(self):
+        out = np.empty((self.R, self.B), dtype=np.int32)
+        _check(self._lib.tvs_get_weights(self._h, _ptr(out)))
+        return out
+
+    # ---- evaluation / fit
+    def loglik(self, theta):
+        theta = _as(theta, np.float64)
+        out = np.empty(self.B, dtype=np.float64)
+        _check(self._lib.tvs_loglik(self._h, _ptr(theta), _ptr(out)))
+        return out
+
+    def fit(self, theta0=None, tol=0.0, max_iter=0, history=0, check_every=0, time_passes=False, out=None):
+        """Returns dict(theta [V,B], loglike [B], kkt [B,2], iters [B], status [B]).
+        `out` may hold preallocated (e.g. pinned) arrays under the same keys."""
+        opt = FitOptions(float(tol), int(max_iter), int(history), int(check_every), 1 if time_passes else 0)
+        theta0 = _as(theta0, np.float64)
+        o = out if out is not None else {}
+        theta = o.get("theta") if o.get("theta") is not None else np.empty((self.V, self.B), dtype=np.float64)
+        ll = o.get("loglike") if o.get("loglike") is not None else np.empty(self.B, dtype=np.float64)
+        kkt = o.get("kkt") if o.get("kkt") is not None else np.empty((self.B, 2), dtype=np.float64)
+        iters = o.get("iters") if o.get("iters") is not None else np.empty(self.B, dtype=np.int32)
+        status = o.get("status") if o.get("status") is not None else np.empty(self.B, dtype=np.int32)
+        _check(self._lib.tvs_fit(self._h, _ptr(theta0), ctypes.byref(opt), _ptr(theta), _ptr(ll), _ptr(kkt),
+                                 _ptr(iters), _ptr(status)))
+        return {"theta": theta, "loglike": ll, "kkt": kkt, "iters": iters, "status": status}
+
+    def last_fit_stats(self):
+        st = FitStats()
+        _check(self._lib.tvs_last_fit_stats(self._h, ctypes.byref(st)))
+        return {"passes": st.passes, "kernel_launches": st.kernel_launches, "pass_ms": st.pass_ms,
+                "total_ms": st.total_ms, "lane_passes": st.lane_passes}
+
+
+def measure_fp64_peak(device=0):
+    v = c_double(0.0)
+    _check(load().tvs_measure_fp64_peak(int(device), ctypes.byref(v)))
+    return v.value
