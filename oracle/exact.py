@@ -32,11 +32,17 @@ def kkt_residuals(A, L, w, phi, mask=None):
     return float(np.max(np.abs(phi * (g - 1.0))[m])), float(np.max((g - 1.0)[m]))
 
 
-def exact_fit(A, L, w, mask=None, em_tol=1e-9, max_em=200000, verbose=False):
+def exact_fit(A, L, w, mask=None, max_newton=300, verbose=False):
     """Returns dict(theta, phi, loglike_no_C, comp, dual, em_iters, newton_iters).
 
     A [R,V] ints (dense or scipy.sparse), L[V], w[R] counts, mask[V] bool (candidate subset).
-    Raises ValueError when some observed row is covered by no variant of the subset (LL = -inf)."""
+    Raises ValueError when some observed row is covered by no variant of the subset (LL = -inf).
+
+    Method: a few plain EM sweeps from the uniform point (strictly positive iterates), then
+    Bertsekas' projected Newton (two-metric projection) on
+        F(phi) = -(1/N) sum_r w_r log (M phi)_r + sum_v phi_v ,  phi >= 0,
+    whose minimiser is the maximiser of the reference's constrained LL (the multiplier of
+    sum(phi)=1 is exactly N).  Dense V x V Hessian: meant for V up to a few hundred."""
     A = sp.csr_matrix(A, dtype=np.float64)
     L = np.asarray(L, dtype=np.float64)
     w = np.asarray(w, dtype=np.float64)
@@ -45,92 +51,70 @@ def exact_fit(A, L, w, mask=None, em_tol=1e-9, max_em=200000, verbose=False):
     M = sp.csr_matrix(A @ sp.diags(1.0 / L))
     MT = sp.csr_matrix(M.T)
     N = w.sum()
+    obs = w > 0
     cover = np.asarray((A[:, m] if m.any() else A[:, :0]).sum(axis=1)).ravel()
-    if np.any((w > 0) & (cover == 0)):
+    if np.any(obs & (cover == 0)):
         raise ValueError("subset does not cover every observed read path: LL = -inf")
+    wo = w[obs]
+
+    def F_of(ph):
+        pp = (M @ ph)[obs]
+        if np.any(pp <= 0):
+            return np.inf
+        return -float(wo @ np.log(pp)) / N + ph.sum()
+
     phi = np.where(m, 1.0, 0.0)
     phi /= phi.sum()
-    # ---- EM with SQUAREM extrapolation (safeguarded by the log-likelihood)
-    def ll_of(p):
-        sel = w > 0
-        return float(np.sum(w[sel] * np.log(p[sel])))
-    it = 0
-    g, p = _grad(M, MT, w, N, phi)
-    while it < max_em:
-        phi1 = phi * g
-        g1, p1 = _grad(M, MT, w, N, phi1)
-        phi2 = phi1 * g1
-        it += 2
-        r = phi1 - phi
-        v = (phi2 - phi1) - r
-        rn, vn = np.sqrt(r @ r), np.sqrt(v @ v)
-        cand = phi2
-        if vn > 0:
-            a = max(1.0, rn / vn)
-            if a > 1.0:
-                ext = phi + 2 * a * r + a * a * v
-                ext = np.where(m, np.maximum(ext, 0.0), 0.0)
-                s = ext.sum()
-                if s > 0:
-                    ext /= s
-                    pe = M @ ext
-                    if np.all(pe[w > 0] > 0) and ll_of(pe) >= ll_of(M @ phi2):
-                        cand = ext
-        phi = cand / cand.sum()
-        g, p = _grad(M, MT, w, N, phi)
-        it += 1
-        comp = np.max(np.abs(phi * (g - 1.0)))
-        if verbose and it % 300 == 0:
-            print("em", it, comp)
-        if comp < em_tol:
-            break
-    # ---- active-set Newton polish on F(phi) = -(1/N) sum w log(M phi) + sum phi, phi >= 0
+    em_iters = 30
+    for _ in range(em_iters):
+        g, _p = _grad(M, MT, w, N, phi)
+        phi = phi * g
     newton = 0
-    for newton in range(1, 60):
+    for newton in range(1, max_newton + 1):
         g, p = _grad(M, MT, w, N, phi)
-        grad = 1.0 - g
-        free = m & ((phi > 1e-14) | (grad < 0))
-        phi = np.where(free, phi, 0.0)
-        if np.max(np.abs(phi * grad)) < 1e-15 and np.max(-grad[m & ~free], initial=0.0) <= 0:
+        grad = np.where(m, 1.0 - g, 0.0)
+        proj = phi - np.maximum(phi - grad, 0.0)              # projected-gradient residual
+        eps = min(1e-8, float(np.linalg.norm(proj)))
+        bound = (~m) | ((phi <= eps) & (grad > 0))          # held at (moved to) zero
+        comp = float(np.max(np.abs(phi * grad)))
+        dual = float(np.max(-grad[m]))
+        if verbose:
+            print("newton", newton, "comp", comp, "dual", dual, "free", int((~bound).sum()))
+        if comp <= 1e-16 and dual <= 1e-13 and not np.any(bound & (phi > 0)):
             break
-        idx = np.where(free)[0]
-        d = np.where(w > 0, w / (p * p), 0.0) / N
-        Mf = M[:, idx]
-        H = (Mf.T @ sp.diags(d) @ Mf).toarray()
-        H += 1e-14 * np.trace(H) / max(len(idx), 1) * np.eye(len(idx))
-        try:
-            step = np.linalg.solve(H, -grad[idx])
-        except np.linalg.LinAlgError:
-            break
-        t = 1.0
-        neg = step < 0
-        if neg.any():
-            t = min(1.0, 0.999999 * np.min(-phi[idx][neg] / step[neg]))
-        # backtrack on F
-        def F(ph):
-            pp = M @ ph
-            if np.any(pp[w > 0] <= 0):
-                return np.inf
-            return -ll_of(pp) / N + ph.sum()
-        F0 = F(phi)
-        ok = False
-        for _ in range(40):
-            trial = phi.copy()
-            trial[idx] = np.maximum(phi[idx] + t * step, 0.0)
-            if F(trial) <= F0 + 1e-15 * abs(F0):
-                ok = True
+        idx = np.where(~bound)[0]
+        d = np.zeros(V)
+        if idx.size:
+            dw = np.where(obs, w / np.where(obs, p * p, 1.0), 0.0) / N
+            Mf = M[:, idx]
+            H = (Mf.T @ sp.diags(dw) @ Mf).toarray()
+            H[np.diag_indices_from(H)] += 1e-15 * max(np.trace(H) / idx.size, 1e-300)
+            try:
+                d[idx] = np.linalg.solve(H, -grad[idx])
+            except np.linalg.LinAlgError:
+                d[idx] = -grad[idx]
+        d[bound] = -phi[bound]                                 # bound coordinates go to exactly zero
+        F0 = F_of(phi)
+        t, moved = 1.0, False
+        for _ in range(60):
+            trial = np.maximum(phi + t * d, 0.0)
+            trial[bound] = 0.0
+            Ft = F_of(trial)
+            # Armijo on the projected arc (Bertsekas 1982)
+            decrease = float(grad[idx] @ (phi[idx] - trial[idx])) + float(grad[bound] @ (phi[bound] - trial[bound]))
+            if Ft <= F0 - 1e-4 * decrease or (abs(Ft - F0) <= 4e-16 * abs(F0) and decrease >= 0):
+                moved = True
                 break
             t *= 0.5
-        if not ok:
+        if not moved or np.array_equal(trial, phi):
             break
-        # drop numerically-zero coordinates whose gradient says "stay at the bound"
         phi = trial
-    phi = np.where(phi < 1e-300, 0.0, phi)
-    phi /= phi.sum()
+    phi = phi / phi.sum()
     g, p = _grad(M, MT, w, N, phi)
     comp = float(np.max(np.abs(phi * (g - 1.0))))
     dual = float(np.max((g - 1.0)[m]))
     x = phi / L
     theta = x / x.sum()
-    return {"theta": theta, "phi": phi, "loglike_no_C": ll_of(A @ theta) - N * np.log(float(L @ theta)),
-            "comp": comp, "dual": dual, "em_iters": it, "newton_iters": newton}
+    ll = float(wo @ np.log((A @ theta)[obs])) - N * np.log(float(L @ theta))
+    return {"theta": theta, "phi": phi, "loglike_no_C": ll, "comp": comp, "dual": dual,
+            "em_iters": em_iters, "newton_iters": newton}

@@ -87,7 +87,9 @@ def test_exact_fit_vs_reference_synthetic_point_estimates(synthetic_small):
             for cid, p in fit["prop"]:
                 assert abs(got[cid] - p) < 5e-4
             ll = r["loglike_no_C"] + C
-            assert abs((ll - fit["loglike"]) / fit["loglike"]) < 1e-9
+            # the reference's SLSQP (ftol 1e-5) stops up to ~1e-4 LL units BELOW the maximum: on case k8 its own
+            # answer is 1.7e-9 relative under the exact optimum -- never above it.
+            assert abs((ll - fit["loglike"]) / fit["loglike"]) < 1e-8
             assert ll >= fit["loglike"] - 1e-8
 
 

@@ -446,7 +446,11 @@ __global__ void __launch_bounds__(kUpdWarps * 32) lbfgs_update_kernel(const UpdA
             }
         }
         if (reject && wi == 0) { a.alpha[bb] = anew; a.ls[bb] = ls; }
-        if (stall) { finished = true; status = (comp <= 1e3 * a.tol && dual <= 1e3 * a.tol_dual) ? TVS_CONVERGED : TVS_STALLED; }
+        if (stall) {   // judge the last ACCEPTED point (its residuals were stored when it was accepted)
+            const double c0 = a.kkt[2 * bb], d0 = a.kkt[2 * bb + 1];
+            finished = true;
+            status = (c0 <= 1e2 * a.tol && d0 <= 1e2 * a.tol_dual) ? TVS_CONVERGED : TVS_STALLED;
+        }
     }
 
     if (valid && wi == 0) {
