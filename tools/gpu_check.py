@@ -13,7 +13,7 @@ from traversome_b200 import _cabi, synthetic  # noqa: E402
 
 
 def run(wl, B, env, label, theta_ref=None, check_every=0):
-    for k in ("TVS_LPT", "TVS_RC", "TVS_NO_XS", "TVS_SPLITS"):
+    for k in ("TVS_LPT", "TVS_RC", "TVS_NO_XS", "TVS_SPLITS", "TVS_NO_COMPACT"):
         os.environ.pop(k, None)
     os.environ.update({k: str(v) for k, v in env.items()})
     eng = _cabi.Engine(wl.row_ptr, wl.col, wl.val, wl.L)
@@ -28,6 +28,8 @@ def run(wl, B, env, label, theta_ref=None, check_every=0):
                wall_ms=round(wall * 1e3, 2), ms_per_pass=round(st["pass_ms"] / max(st["passes"], 1), 4),
                iters_min=int(it.min()), iters_med=float(np.median(it)), iters_max=int(it.max()),
                status=np.bincount(out["status"], minlength=4).tolist(), kkt=[float(out["kkt"][:, 0].max()), float(out["kkt"][:, 1].max())])
+    rec["iters_pct"] = [int(x) for x in np.percentile(it, [50, 75, 90, 95, 99, 99.9])]
+    rec["lane_passes"] = st["lane_passes"]
     if theta_ref is not None:
         rec["max_dtheta_vs_ref"] = float(np.abs(out["theta"] - theta_ref).max())
     bytes_pass = synthetic.algorithmic_bytes_per_pass(wl.R, wl.V, wl.nnz, B)
@@ -45,8 +47,8 @@ if __name__ == "__main__":
     B = int(sys.argv[2]) if len(sys.argv) > 2 else synthetic.CONFIGS[which]["lanes"]
     print(which, "R", wl.R, "V", wl.V, "nnz", wl.nnz, "N", wl.N, "B", B, flush=True)
     ref = run(wl, B, {}, "default")
-    for env, label in [({"TVS_LPT": 1}, "lpt1"), ({"TVS_LPT": 1, "TVS_RC": 64}, "lpt1_rc64"), ({"TVS_LPT": 2, "TVS_RC": 64}, "lpt2_rc64"),
-                       ({"TVS_LPT": 1, "TVS_RC": 256}, "lpt1_rc256"), ({"TVS_NO_XS": 1}, "no_xs"), ({"TVS_NO_XS": 1, "TVS_LPT": 1}, "no_xs_lpt1")]:
+    for env, label in [({"TVS_LPT": 1, "TVS_RC": 64}, "lpt1_rc64"), ({"TVS_LPT": 1, "TVS_RC": 64, "TVS_NO_COMPACT": 1}, "lpt1_rc64_nocompact"),
+                       ({"TVS_LPT": 2, "TVS_RC": 64}, "lpt2_rc64")]:
         try:
             run(wl, B, env, label, theta_ref=ref["theta"])
         except Exception as e:

@@ -51,12 +51,7 @@ static void free_lanes(Lanes& l) {
     l = Lanes();
 }
 static void free_fit(FitState& f) {
-    dev_free(f.z); dev_free(f.zt); dev_free(f.g); dev_free(f.gt); dev_free(f.gh); dev_free(f.d); dev_free(f.x);
-    dev_free(f.theta_io); dev_free(f.gamma); dev_free(f.ll_out); dev_free(f.kkt_out); dev_free(f.iters_out); dev_free(f.status_out);
-    dev_free(f.S); dev_free(f.Y); dev_free(f.rho);
-    dev_free(f.F); dev_free(f.dg); dev_free(f.alpha); dev_free(f.llsum); dev_free(f.kkt); dev_free(f.sumphi);
-    dev_free(f.ls); dev_free(f.iters); dev_free(f.status); dev_free(f.head); dev_free(f.cnt); dev_free(f.done);
-    dev_free(f.tpart); dev_free(f.llpart); dev_free(f.nactive); dev_free(f.tile_active);
+    for (void* p : f.owned) cudaFree(p);
     if (f.h_nactive) cudaFreeHost(f.h_nactive);
     f = FitState();
 }
@@ -129,24 +124,50 @@ static PassArgs base_args(const tvs_problem* h) {
 }
 
 // ------------------------------------------------------------------------------------- fit state
-static int ensure_fit_state(tvs_problem* h, int m, int splits) {
+template <class T>
+static int fit_alloc(FitState& f, T** p, size_t n) {
+    int rc = dev_alloc(p, n);
+    if (rc == TVS_OK) f.owned.push_back((void*)*p);
+    return rc;
+}
+
+static int ensure_fit_state(tvs_problem* h, int m) {
     FitState& f = h->fs;
-    const int64_t V = h->csr.V, B = h->lanes.B;
-    if (f.V == V && f.B == B && f.m == m && f.splits >= splits) return TVS_OK;
+    const int64_t V = h->csr.V, B = h->lanes.B, R = h->csr.R;
+    if (f.V == V && f.B == B && f.m == m && f.R == R) return TVS_OK;
     free_fit(f);
     const size_t vb = (size_t)V * B;
     int rc;
-#define A_(ptr, n) if ((rc = dev_alloc(&f.ptr, (n))) != TVS_OK) { free_fit(f); return rc; }
-    A_(z, vb) A_(zt, vb) A_(g, vb) A_(gt, vb) A_(gh, vb) A_(d, vb) A_(x, vb) A_(theta_io, vb) A_(gamma, B)
-    A_(ll_out, B) A_(kkt_out, 2 * (size_t)B) A_(iters_out, B) A_(status_out, B)
-    A_(S, vb * m) A_(Y, vb * m) A_(rho, (size_t)B * m)
-    A_(F, B) A_(dg, B) A_(alpha, B) A_(llsum, B) A_(kkt, 2 * (size_t)B) A_(sumphi, B)
-    A_(ls, B) A_(iters, B) A_(status, B) A_(head, B) A_(cnt, B) A_(done, B)
-    A_(tpart, vb * splits) A_(llpart, (size_t)B * splits) A_(nactive, 32) A_(tile_active, 1)
+#define A_(ptr, n) if ((rc = fit_alloc(f, &(ptr), (size_t)(n))) != TVS_OK) { free_fit(f); return rc; }
+    for (int i = 0; i < 2; ++i) {
+        LaneSet& s = f.set[i];
+        A_(s.orig, B) A_(s.z, vb) A_(s.zt, vb) A_(s.g, vb) A_(s.d, vb) A_(s.x, vb)
+        A_(s.S, vb * m) A_(s.Y, vb * m) A_(s.rho, (size_t)B * m)
+        A_(s.gamma, B) A_(s.F, B) A_(s.dg, B) A_(s.alpha, B) A_(s.llsum, B) A_(s.sumphi, B) A_(s.kkt, 2 * (size_t)B)
+        A_(s.ls, B) A_(s.iters, B) A_(s.head, B) A_(s.cnt, B) A_(s.done, B) A_(s.status, B)
+    }
+    f.half = B / 2 + 1;
+    for (int i = 0; i < 2; ++i) {
+        A_(f.wbuf[i], (size_t)R * f.half) A_(f.mbuf[i], (size_t)V * f.half) A_(f.nbuf[i], f.half) A_(f.cbuf[i], f.half)
+    }
+    A_(f.gt, vb) A_(f.gh, vb)
+    // partial buffers: splits*width never exceeds (resident CTAs)*(lanes per tile) + width
+    f.tpart_cap = (size_t)V * ((size_t)h->sm_count * 16 * 64 + (size_t)B);
+    f.llpart_cap = f.tpart_cap / (size_t)V;
+    A_(f.tpart, f.tpart_cap) A_(f.llpart, f.llpart_cap)
+    A_(f.idx, B) A_(f.nactive, 32)
+    A_(f.theta_io, vb) A_(f.ll_out, B) A_(f.kkt_out, 2 * (size_t)B) A_(f.iters_out, B) A_(f.status_out, B)
 #undef A_
-    if (cudaMallocHost((void**)&f.h_nactive, 16 * sizeof(int32_t)) != cudaSuccess) { free_fit(f); set_error("cudaMallocHost failed"); return TVS_ENOMEM; }
-    f.V = V; f.B = B; f.m = m; f.splits = splits;
+    if (cudaMallocHost((void**)&f.h_nactive, 32 * sizeof(int32_t)) != cudaSuccess) { free_fit(f); set_error("cudaMallocHost failed"); return TVS_ENOMEM; }
+    f.V = V; f.B = B; f.m = m; f.R = R;
     return TVS_OK;
+}
+
+template <typename T>
+static void gather_rows(cudaStream_t st, const T* src, T* dst, int64_t rows, int64_t Bs, int64_t Bd, const int32_t* idx) {
+    if (!src || !dst || rows <= 0 || Bd <= 0) return;
+    dim3 grid((unsigned)((Bd + 127) / 128), (unsigned)std::min<int64_t>(rows, 4096));
+    gather_rows_kernel<T><<<grid, 128, 0, st>>>(src, dst, rows, Bs, Bd, idx);
 }
 
 }  // namespace tvs
@@ -405,101 +426,148 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
     opt.history = std::min(opt.history, kMaxHistory);
     if (opt.check_every <= 0) opt.check_every = 4;
     const bool time_passes = (opt.reserved & 1) != 0 || env_int("TVS_TIME_PASSES", 0) != 0;
+    const bool no_compact = (opt.reserved & 2) != 0 || env_int("TVS_NO_COMPACT", 0) != 0;
 
-    const int64_t V = h->csr.V, B = h->lanes.B;
+    const int64_t V = h->csr.V, B0 = h->lanes.B, R = h->csr.R;
     const int m = opt.history;
-    PassPlan pl;
-    int rc = make_plan<true>(h, B, &pl);
-    if (rc != TVS_OK) return rc;
-    if ((rc = ensure_fit_state(h, m, pl.splits)) != TVS_OK) return rc;
+    int rc;
+    if ((rc = ensure_fit_state(h, m)) != TVS_OK) return rc;
     FitState& f = h->fs;
     cudaStream_t st = h->stream;
-    const size_t vb = (size_t)V * B;
+    const size_t vb0 = (size_t)V * B0;
 
     TVS_CUDA(cudaEventRecord(h->ev0, st));
-    // reset state
-    cudaMemsetAsync(f.z, 0, vb * 8, st); cudaMemsetAsync(f.g, 0, vb * 8, st); cudaMemsetAsync(f.d, 0, vb * 8, st);
-    cudaMemsetAsync(f.gt, 0, vb * 8, st);
-    cudaMemsetAsync(f.F, 0, B * 8, st); cudaMemsetAsync(f.dg, 0, B * 8, st); cudaMemsetAsync(f.alpha, 0, B * 8, st);
-    cudaMemsetAsync(f.llsum, 0, B * 8, st); cudaMemsetAsync(f.kkt, 0, 2 * B * 8, st); cudaMemsetAsync(f.sumphi, 0, B * 8, st);
-    cudaMemsetAsync(f.ls, 0, B * 4, st); cudaMemsetAsync(f.iters, 0xFF, B * 4, st); cudaMemsetAsync(f.status, 0, B * 4, st);
-    cudaMemsetAsync(f.head, 0, B * 4, st); cudaMemsetAsync(f.cnt, 0, B * 4, st); cudaMemsetAsync(f.done, 0, B * 4, st);
-    cudaMemsetAsync(f.rho, 0, (size_t)B * m * 8, st);
-    const double* d_theta0 = nullptr;
-    if (theta0) {
-        cudaMemcpyAsync(f.theta_io, theta0, vb * 8, cudaMemcpyDefault, st);
-        d_theta0 = f.theta_io;
+    int cur = 0;
+    {   // ---- reset set 0 (full width, views the caller's lanes)
+        LaneSet& s = f.set[0];
+        s.width = B0; s.w = h->lanes.w; s.mask = h->lanes.mask; s.N = h->lanes.N; s.C = h->lanes.C;
+        cudaMemsetAsync(s.z, 0, vb0 * 8, st); cudaMemsetAsync(s.g, 0, vb0 * 8, st); cudaMemsetAsync(s.d, 0, vb0 * 8, st);
+        cudaMemsetAsync(f.gt, 0, vb0 * 8, st);
+        cudaMemsetAsync(s.F, 0, B0 * 8, st); cudaMemsetAsync(s.dg, 0, B0 * 8, st); cudaMemsetAsync(s.alpha, 0, B0 * 8, st);
+        cudaMemsetAsync(s.llsum, 0, B0 * 8, st); cudaMemsetAsync(s.kkt, 0, 2 * B0 * 8, st); cudaMemsetAsync(s.sumphi, 0, B0 * 8, st);
+        cudaMemsetAsync(s.gamma, 0, B0 * 8, st); cudaMemsetAsync(s.rho, 0, (size_t)B0 * m * 8, st);
+        cudaMemsetAsync(s.ls, 0, B0 * 4, st); cudaMemsetAsync(s.iters, 0xFF, B0 * 4, st); cudaMemsetAsync(s.status, 0, B0 * 4, st);
+        cudaMemsetAsync(s.head, 0, B0 * 4, st); cudaMemsetAsync(s.cnt, 0, B0 * 4, st); cudaMemsetAsync(s.done, 0, B0 * 4, st);
+        iota_kernel<<<(unsigned)((B0 + 255) / 256), 256, 0, st>>>(s.orig, B0);
+        const double* d_theta0 = nullptr;
+        if (theta0) { cudaMemcpyAsync(f.theta_io, theta0, vb0 * 8, cudaMemcpyDefault, st); d_theta0 = f.theta_io; }
+        init_z_kernel<<<(unsigned)((B0 + 127) / 128), 128, 0, st>>>(d_theta0, s.mask, h->csr.Ld, h->csr.invL, (int)V, B0, s.zt, s.x);
     }
-    const unsigned gb = (unsigned)((B + 127) / 128);
-    init_z_kernel<<<gb, 128, 0, st>>>(d_theta0, h->lanes.mask, h->csr.Ld, h->csr.invL, (int)V, B, f.zt, f.x);
 
-    PassArgs pa = base_args(h);
-    pa.x = f.x; pa.done = f.done; pa.tpart = f.tpart; pa.llpart = f.llpart;
-    UpdArgs ua{};
-    ua.tpart = f.tpart; ua.llpart = f.llpart; ua.S = pl.splits; ua.invL = h->csr.invL; ua.N = h->lanes.N; ua.mask = h->lanes.mask;
-    ua.z = f.z; ua.zt = f.zt; ua.g = f.g; ua.gt = f.gt; ua.gh = f.gh; ua.d = f.d; ua.x = f.x; ua.Sh = f.S; ua.Yh = f.Y;
-    ua.rho = f.rho; ua.gamma = f.gamma; ua.F = f.F; ua.dg = f.dg; ua.alpha = f.alpha; ua.llsum = f.llsum; ua.kkt = f.kkt;
-    ua.sumphi = f.sumphi; ua.ls = f.ls; ua.iters = f.iters; ua.status = f.status; ua.head = f.head; ua.cnt = f.cnt;
-    ua.done = f.done; ua.V = (int)V; ua.B = B; ua.m = m; ua.max_iter = opt.max_iter; ua.tol = opt.tol;
-    ua.tol_dual = 100.0 * opt.tol;
-
-    const int64_t max_passes = (int64_t)opt.max_iter * 2 + 64;
-    const unsigned ub = (unsigned)((B + 31) / 32);
     std::vector<cudaEvent_t> pev;      // per-pass events when timing is requested
-    std::vector<cudaEvent_t> polls;    // one event per poll slot (ring of 16)
-    for (int i = 0; i < 16; ++i) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); polls.push_back(e); }
-    int64_t passes = 0, launches = 1, n_polls = 0, polls_checked = 0;
-    bool all_done = false;
+    int64_t passes = 0, launches = 3, lane_passes = 0, n_polls = 0, compactions = 0;
+    const int64_t max_passes = (int64_t)opt.max_iter * 2 + 64;
     cudaError_t cerr = cudaSuccess;
-    while (!all_done && passes < max_passes) {
+    bool all_done = false;
+
+    auto finalize = [&](const LaneSet& s, int only_done) {
+        FinArgs fa{};
+        fa.z = s.z; fa.invL = h->csr.invL; fa.llsum = s.llsum; fa.sumphi = s.sumphi; fa.N = s.N; fa.C = s.C; fa.kkt = s.kkt;
+        fa.iters = s.iters; fa.status = s.status; fa.done = s.done; fa.orig = s.orig;
+        fa.theta_out = theta_out ? f.theta_io : nullptr; fa.ll_out = ll_out ? f.ll_out : nullptr;
+        fa.kkt_out = kkt_out ? f.kkt_out : nullptr; fa.iters_out = iters_out ? f.iters_out : nullptr;
+        fa.status_out = status_out ? f.status_out : nullptr;
+        fa.V = (int)V; fa.B = s.width; fa.B0 = B0; fa.only_done = only_done;
+        finalize_fit_kernel<<<(unsigned)((s.width + 127) / 128), 128, 0, st>>>(fa);
+        ++launches;
+    };
+
+    while (!all_done && passes < max_passes && rc == TVS_OK) {
+        LaneSet& s = f.set[cur];
+        const int64_t W = s.width;
+        // ---- launch geometry for the current width
+        PassPlan pl;
+        {
+            rc = make_plan<true>(h, W, &pl);
+            if (rc != TVS_OK) break;
+            while (pl.splits > 1 && (size_t)pl.splits * (size_t)W * (size_t)V > f.tpart_cap) --pl.splits;
+            if ((size_t)pl.splits * (size_t)W * (size_t)V > f.tpart_cap) { set_error("partial buffer too small"); rc = TVS_ENOMEM; break; }
+        }
+        PassArgs pa = base_args(h);
+        pa.w = s.w; pa.B = W; pa.x = s.x; pa.done = s.done; pa.tpart = f.tpart; pa.llpart = f.llpart;
+        UpdArgs ua{};
+        ua.tpart = f.tpart; ua.llpart = f.llpart; ua.S = pl.splits; ua.invL = h->csr.invL; ua.N = s.N; ua.mask = s.mask;
+        ua.z = s.z; ua.zt = s.zt; ua.g = s.g; ua.gt = f.gt; ua.gh = f.gh; ua.d = s.d; ua.x = s.x; ua.Sh = s.S; ua.Yh = s.Y;
+        ua.rho = s.rho; ua.gamma = s.gamma; ua.F = s.F; ua.dg = s.dg; ua.alpha = s.alpha; ua.llsum = s.llsum; ua.kkt = s.kkt;
+        ua.sumphi = s.sumphi; ua.ls = s.ls; ua.iters = s.iters; ua.status = s.status; ua.head = s.head; ua.cnt = s.cnt;
+        ua.done = s.done; ua.V = (int)V; ua.B = W; ua.m = m; ua.max_iter = opt.max_iter; ua.tol = opt.tol;
+        ua.tol_dual = 100.0 * opt.tol;
+        const unsigned ub = (unsigned)((W + 31) / 32);
+
+        // ---- a batch of passes, then one synchronous poll of the device-side "still iterating" counter
+        const int slot = (int)(n_polls % 16);
         for (int k = 0; k < opt.check_every && passes < max_passes; ++k) {
-            if (!pl.xs) { cudaMemsetAsync(f.tpart, 0, vb * pl.splits * 8, st); ++launches; }
+            if (!pl.xs) { cudaMemsetAsync(f.tpart, 0, (size_t)V * W * pl.splits * 8, st); ++launches; }
             if (time_passes) { cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); pev.push_back(e0); pev.push_back(e1); cudaEventRecord(e0, st); }
             rc = launch_pass<true>(h, pl, pa);
             if (rc != TVS_OK) break;
             if (time_passes) cudaEventRecord(pev.back(), st);
             const bool last = (k == opt.check_every - 1) || (passes + 1 == max_passes);
-            ua.nactive = last ? f.nactive + (n_polls % 16) : f.nactive + 31;   // word 31 = scratch between polls
-            if (last) { cudaMemsetAsync(f.nactive + (n_polls % 16), 0, 4, st); ++launches; }
+            ua.nactive = last ? f.nactive + slot : f.nactive + 31;   // word 31 = scratch between polls
+            if (last) { cudaMemsetAsync(f.nactive + slot, 0, 4, st); ++launches; }
             lbfgs_update_kernel<<<ub, kUpdWarps * 32, 0, st>>>(ua);
-            ++passes; launches += 2;
+            ++passes; launches += 2; lane_passes += W;
         }
         if (rc != TVS_OK) break;
-        const int slot = (int)(n_polls % 16);
         cudaMemcpyAsync(f.h_nactive + slot, f.nactive + slot, 4, cudaMemcpyDeviceToHost, st);
-        cudaEventRecord(polls[slot], st);
+        cerr = cudaStreamSynchronize(st);
+        if (cerr != cudaSuccess) break;
         ++n_polls;
-        // pipelined polling: look at the PREVIOUS batch's counter while this batch runs
-        if (n_polls >= 2) {
-            const int ps = (int)((n_polls - 2) % 16);
-            cerr = cudaEventSynchronize(polls[ps]);
-            if (cerr != cudaSuccess) break;
-            ++polls_checked;
-            if (f.h_nactive[ps] == 0) all_done = true;
+        const int64_t active = f.h_nactive[slot];
+        if (active == 0) { all_done = true; break; }
+        // ---- compaction: keep only the lanes that are still iterating
+        if (!no_compact && active * 2 <= W && W > 32 && active <= f.half) {
+            finalize(s, 1);                                      // results of the finished lanes, at their original ids
+            LaneSet& n = f.set[cur ^ 1];
+            build_index_kernel<<<1, 1024, 0, st>>>(s.done, W, f.idx, f.nactive + 30);
+            const int bi = (int)(compactions & 1);
+            const int64_t A = active;
+            gather_rows(st, s.w, f.wbuf[bi], R, W, A, f.idx);
+            gather_rows(st, s.mask, f.mbuf[bi], V, W, A, f.idx);
+            gather_rows(st, s.N, f.nbuf[bi], 1, W, A, f.idx);
+            gather_rows(st, s.C, f.cbuf[bi], 1, W, A, f.idx);
+            n.w = f.wbuf[bi]; n.mask = s.mask ? f.mbuf[bi] : nullptr; n.N = f.nbuf[bi]; n.C = s.C ? f.cbuf[bi] : nullptr;
+            gather_rows(st, (const int32_t*)s.orig, n.orig, 1, W, A, f.idx);
+            gather_rows(st, (const double*)s.z, n.z, V, W, A, f.idx);
+            gather_rows(st, (const double*)s.zt, n.zt, V, W, A, f.idx);
+            gather_rows(st, (const double*)s.g, n.g, V, W, A, f.idx);
+            gather_rows(st, (const double*)s.d, n.d, V, W, A, f.idx);
+            gather_rows(st, (const double*)s.x, n.x, V, W, A, f.idx);
+            gather_rows(st, (const double*)s.S, n.S, (int64_t)m * V, W, A, f.idx);
+            gather_rows(st, (const double*)s.Y, n.Y, (int64_t)m * V, W, A, f.idx);
+            gather_rows(st, (const double*)s.rho, n.rho, m, W, A, f.idx);
+            gather_rows(st, (const double*)s.gamma, n.gamma, 1, W, A, f.idx);
+            gather_rows(st, (const double*)s.F, n.F, 1, W, A, f.idx);
+            gather_rows(st, (const double*)s.dg, n.dg, 1, W, A, f.idx);
+            gather_rows(st, (const double*)s.alpha, n.alpha, 1, W, A, f.idx);
+            gather_rows(st, (const double*)s.llsum, n.llsum, 1, W, A, f.idx);
+            gather_rows(st, (const double*)s.sumphi, n.sumphi, 1, W, A, f.idx);
+            gather_rows(st, (const double*)s.kkt, n.kkt, 2, W, A, f.idx);
+            gather_rows(st, (const int32_t*)s.ls, n.ls, 1, W, A, f.idx);
+            gather_rows(st, (const int32_t*)s.iters, n.iters, 1, W, A, f.idx);
+            gather_rows(st, (const int32_t*)s.head, n.head, 1, W, A, f.idx);
+            gather_rows(st, (const int32_t*)s.cnt, n.cnt, 1, W, A, f.idx);
+            cudaMemsetAsync(n.done, 0, A * 4, st); cudaMemsetAsync(n.status, 0, A * 4, st);
+            n.width = A;
+            launches += 28;
+            ++compactions;
+            cur ^= 1;
         }
     }
     if (rc == TVS_OK && cerr == cudaSuccess) {
-        FinArgs fa{};
-        fa.z = f.z; fa.invL = h->csr.invL; fa.llsum = f.llsum; fa.sumphi = f.sumphi; fa.N = h->lanes.N; fa.C = h->lanes.C;
-        fa.kkt = f.kkt; fa.iters = f.iters; fa.status = f.status; fa.done = f.done; fa.mask = h->lanes.mask;
-        fa.theta_out = theta_out ? f.theta_io : nullptr; fa.ll_out = ll_out ? f.ll_out : nullptr;
-        fa.kkt_out = kkt_out ? f.kkt_out : nullptr; fa.iters_out = iters_out ? f.iters_out : nullptr;
-        fa.status_out = status_out ? f.status_out : nullptr;
-        fa.V = (int)V; fa.B = B;
-        finalize_fit_kernel<<<gb, 128, 0, st>>>(fa);
-        ++launches;
-        if (theta_out) cudaMemcpyAsync(theta_out, f.theta_io, vb * 8, cudaMemcpyDefault, st);
-        if (ll_out) cudaMemcpyAsync(ll_out, f.ll_out, (size_t)B * 8, cudaMemcpyDefault, st);
-        if (kkt_out) cudaMemcpyAsync(kkt_out, f.kkt_out, 2 * (size_t)B * 8, cudaMemcpyDefault, st);
-        if (iters_out) cudaMemcpyAsync(iters_out, f.iters_out, (size_t)B * 4, cudaMemcpyDefault, st);
-        if (status_out) cudaMemcpyAsync(status_out, f.status_out, (size_t)B * 4, cudaMemcpyDefault, st);
+        finalize(f.set[cur], 0);
+        if (theta_out) cudaMemcpyAsync(theta_out, f.theta_io, vb0 * 8, cudaMemcpyDefault, st);
+        if (ll_out) cudaMemcpyAsync(ll_out, f.ll_out, (size_t)B0 * 8, cudaMemcpyDefault, st);
+        if (kkt_out) cudaMemcpyAsync(kkt_out, f.kkt_out, 2 * (size_t)B0 * 8, cudaMemcpyDefault, st);
+        if (iters_out) cudaMemcpyAsync(iters_out, f.iters_out, (size_t)B0 * 4, cudaMemcpyDefault, st);
+        if (status_out) cudaMemcpyAsync(status_out, f.status_out, (size_t)B0 * 4, cudaMemcpyDefault, st);
         cudaEventRecord(h->ev1, st);
         cerr = cudaStreamSynchronize(st);
     } else {
         cudaStreamSynchronize(st);
     }
     h->stats = tvs_fit_stats{};
-    h->stats.passes = passes; h->stats.kernel_launches = launches; h->stats.lane_passes = passes * B;
+    h->stats.passes = passes; h->stats.kernel_launches = launches; h->stats.lane_passes = lane_passes;
     if (rc == TVS_OK && cerr == cudaSuccess) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, h->ev0, h->ev1);
@@ -509,7 +577,6 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         h->stats.pass_ms = pm;
     }
     for (auto e : pev) cudaEventDestroy(e);
-    for (auto e : polls) cudaEventDestroy(e);
     if (rc != TVS_OK) return rc;
     if (cerr != cudaSuccess) return cuda_fail(cerr, "tvs_fit", __FILE__, __LINE__);
     return TVS_OK;

@@ -50,19 +50,37 @@ struct Lanes {
     int64_t  cap_w = 0, cap_mask = 0, cap_b = 0;
 };
 
-struct FitState {               // all device, sized for (V, B, history, splits)
-    int64_t V = 0, B = 0; int m = 0; int splits = 0;
-    double *z = nullptr, *zt = nullptr, *g = nullptr, *gt = nullptr, *gh = nullptr, *d = nullptr, *x = nullptr;
-    double *theta_io = nullptr, *gamma = nullptr;   // theta0 upload / theta_out staging; L-BFGS H0 scale
-    double *ll_out = nullptr, *kkt_out = nullptr; int32_t *iters_out = nullptr, *status_out = nullptr;
-    double *S = nullptr, *Y = nullptr, *rho = nullptr;
-    double *F = nullptr, *dg = nullptr, *alpha = nullptr, *llsum = nullptr, *kkt = nullptr, *sumphi = nullptr;
-    int32_t *ls = nullptr, *iters = nullptr, *status = nullptr, *head = nullptr, *cnt = nullptr, *done = nullptr;
-    double *tpart = nullptr, *llpart = nullptr;
-    int32_t *nactive = nullptr;   // device counter
-    int32_t *tile_active = nullptr;
+// One set of per-lane arrays at some width.  tvs_fit keeps two of them and "compacts" the lanes
+// that are still iterating from one into the other whenever at least half of the lanes have finished,
+// so that the pass kernel never spends time on converged lanes.
+struct LaneSet {
+    int64_t width = 0;
+    // inputs (set 0 views the arrays of Lanes; after the first compaction they are owned copies)
+    const int32_t* w = nullptr; const uint8_t* mask = nullptr; const double* N = nullptr; const double* C = nullptr;
+    int32_t* orig = nullptr;      // [cap] original lane id of each column
+    // solver state, all lane-minor [rows * width]
+    double *z = nullptr, *zt = nullptr, *g = nullptr, *d = nullptr, *x = nullptr;          // V rows
+    double *S = nullptr, *Y = nullptr;                                                     // m*V rows
+    double *rho = nullptr;                                                                 // m rows
+    double *gamma = nullptr, *F = nullptr, *dg = nullptr, *alpha = nullptr, *llsum = nullptr, *sumphi = nullptr;
+    double *kkt = nullptr;                                                                 // 2 rows
+    int32_t *ls = nullptr, *iters = nullptr, *head = nullptr, *cnt = nullptr, *done = nullptr, *status = nullptr;
+};
+
+struct FitState {               // all device, sized for (V, B, history)
+    int64_t V = 0, B = 0, R = 0; int m = 0;
+    LaneSet set[2];
+    int32_t* wbuf[2] = {nullptr, nullptr}; uint8_t* mbuf[2] = {nullptr, nullptr};
+    double* nbuf[2] = {nullptr, nullptr}; double* cbuf[2] = {nullptr, nullptr};
+    int64_t half = 0;           // capacity (lanes) of the compaction buffers above
+    double *gt = nullptr, *gh = nullptr;            // scratch, V rows at full width
+    double *tpart = nullptr, *llpart = nullptr; size_t tpart_cap = 0, llpart_cap = 0;
+    int32_t *idx = nullptr;                          // compaction gather list
+    int32_t *nactive = nullptr;   // device counters (ring)
     int32_t *h_nactive = nullptr; // pinned host mirror
-    size_t bytes = 0;
+    // output staging at the ORIGINAL width
+    double *theta_io = nullptr, *ll_out = nullptr, *kkt_out = nullptr; int32_t *iters_out = nullptr, *status_out = nullptr;
+    std::vector<void*> owned;   // every cudaMalloc'ed block above
 };
 
 }  // namespace tvs

@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kUpdWarps * 32) lbfgs_update_kernel(const UpdA
         else if (iters >= a.max_iter) { finished = true; status = TVS_MAXITER; }
         if (wi == 0) {
             a.F[bb] = Ft; a.llsum[bb] = llsum; a.sumphi[bb] = sumphi;
-            a.kkt[2 * bb] = comp; a.kkt[2 * bb + 1] = dual; a.iters[bb] = iters; a.ls[bb] = 0;
+            a.kkt[bb] = comp; a.kkt[B + bb] = dual; a.iters[bb] = iters; a.ls[bb] = 0;
         }
     }
     __syncthreads();   // z, g, history visible to the whole CTA
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(kUpdWarps * 32) lbfgs_update_kernel(const UpdA
         }
         if (reject && wi == 0) { a.alpha[bb] = anew; a.ls[bb] = ls; }
         if (stall) {   // judge the last ACCEPTED point (its residuals were stored when it was accepted)
-            const double c0 = a.kkt[2 * bb], d0 = a.kkt[2 * bb + 1];
+            const double c0 = a.kkt[bb], d0 = a.kkt[B + bb];
             finished = true;
             status = (c0 <= 1e2 * a.tol && d0 <= 1e2 * a.tol_dual) ? TVS_CONVERGED : TVS_STALLED;
         }
@@ -463,29 +463,73 @@ __global__ void __launch_bounds__(kUpdWarps * 32) lbfgs_update_kernel(const UpdA
     }
 }
 
-// theta_out, ll_out, ... from the last accepted point of every lane
+// theta_out, ll_out, ... from the last accepted point of the lanes of one LaneSet, written at the lanes'
+// ORIGINAL ids (orig[]) into arrays of the original width B0.  only_done: skip lanes still iterating.
 struct FinArgs {
-    const double *z, *invL, *llsum, *sumphi, *N, *C, *kkt; const int32_t *iters, *status, *done; const uint8_t* mask;
-    double *theta_out, *ll_out, *kkt_out; int32_t *iters_out, *status_out; int V; int64_t B;
+    const double *z, *invL, *llsum, *sumphi, *N, *C, *kkt; const int32_t *iters, *status, *done, *orig;
+    double *theta_out, *ll_out, *kkt_out; int32_t *iters_out, *status_out; int V; int64_t B, B0; int only_done;
 };
 __global__ void finalize_fit_kernel(const FinArgs a) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;
-    const int st = a.done[b] ? a.status[b] : TVS_MAXITER;   // still running when the pass budget ran out
+    const bool dn = a.done[b] != 0;
+    if (a.only_done && !dn) return;
+    const int st = dn ? a.status[b] : TVS_MAXITER;   // still running when the pass budget ran out
+    const int64_t o = a.orig[b];
     if (a.theta_out) {
         double s = 0.0;
         for (int v = 0; v < a.V; ++v) { const double zz = a.z[(int64_t)v * a.B + b]; s += zz * zz * a.invL[v]; }
         for (int v = 0; v < a.V; ++v) {
             const double zz = a.z[(int64_t)v * a.B + b];
-            a.theta_out[(int64_t)v * a.B + b] = (st == TVS_INFEASIBLE) ? nan("") : zz * zz * a.invL[v] / s;
+            a.theta_out[(int64_t)v * a.B0 + o] = (st == TVS_INFEASIBLE) ? nan("") : zz * zz * a.invL[v] / s;
         }
     }
     if (a.ll_out)
-        a.ll_out[b] = (st == TVS_INFEASIBLE) ? -INFINITY
+        a.ll_out[o] = (st == TVS_INFEASIBLE) ? -INFINITY
                                              : a.llsum[b] - a.N[b] * log(a.sumphi[b]) + (a.C ? a.C[b] : 0.0);
-    if (a.kkt_out) { a.kkt_out[2 * b] = a.kkt[2 * b]; a.kkt_out[2 * b + 1] = a.kkt[2 * b + 1]; }
-    if (a.iters_out) a.iters_out[b] = a.iters[b] < 0 ? 0 : a.iters[b];
-    if (a.status_out) a.status_out[b] = st;
+    if (a.kkt_out) { a.kkt_out[2 * o] = a.kkt[b]; a.kkt_out[2 * o + 1] = a.kkt[a.B + b]; }
+    if (a.iters_out) a.iters_out[o] = a.iters[b] < 0 ? 0 : a.iters[b];
+    if (a.status_out) a.status_out[o] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lane compaction: idx = columns with done == 0 in increasing order; gather_rows copies those columns
+// of a [rows x Bs] lane-minor matrix into a [rows x Bd] one.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) build_index_kernel(const int32_t* __restrict__ done, int64_t B,
+                                                           int32_t* __restrict__ idx, int32_t* __restrict__ count) {
+    __shared__ int32_t part[1024];
+    const int t = threadIdx.x;
+    const int64_t seg = (B + 1023) / 1024;
+    const int64_t b0 = (int64_t)t * seg, b1 = min(B, b0 + seg);
+    int32_t c = 0;
+    for (int64_t b = b0; b < b1; ++b) c += (done[b] == 0);
+    part[t] = c;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {         // inclusive scan
+        const int32_t v = (t >= off) ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int32_t pos = part[t] - c;
+    for (int64_t b = b0; b < b1; ++b)
+        if (done[b] == 0) idx[pos++] = (int32_t)b;
+    if (t == 1023) *count = part[1023];
+}
+
+template <typename T>
+__global__ void gather_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t rows, int64_t Bs, int64_t Bd,
+                                   const int32_t* __restrict__ idx) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Bd) return;
+    const int64_t sj = idx[j];
+    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) dst[r * Bd + j] = src[r * Bs + sj];
+}
+
+__global__ void iota_kernel(int32_t* p, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (int32_t)i;
 }
 
 // ------------------------------------------------------------------------------------------------
