@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- bootstrap ML fits/sec of the B200 path (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = the maximum-likelihood fit of one batch of B bootstrap replicates (lanes) of the
+workload (BASELINE.json configs[1]: 64 candidate variants x 20k read paths, B = 1,000 replicates per
+GPU), every lane iterated to the KKT tolerance 1e-10.  `value` = lanes fitted per second by the
+whole job with the replicate weights already resident in HBM; `e2e` = the same fit driven through
+the public API with the weights in pinned HOST memory (H2D of the weights and D2H of the results
+inside the timed region).  Weak scaling: every rank fits its own B replicates (different seeds) of
+the same read-path x variant matrix; there is no data-path collective, results are gathered once.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "bootstrap ML fits/sec"
+UNIT = "replicate-fits/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as h:
+            d = json.load(h)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json: torch copy_ read+write)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def _cpu_fit_one(args):
+    """One lane through the restated reference driver (oracle/slsqp_port.py): returns (seconds, loglike)."""
+    A_data, A_idx, A_ptr, shape, L, w, seed = args
+    import scipy.sparse as sp
+    from oracle import slsqp_port
+    A = sp.csr_matrix((A_data, A_idx, A_ptr), shape=shape)
+    fun, n = slsqp_port.neg_loglike_closure(A, L, w, 0.0)
+    try:                                   # one BLAS thread per worker process: no oversubscription
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=1)
+    except Exception:
+        limiter = None
+    t0 = time.perf_counter()
+    res = slsqp_port.minimize_neg_likelihood_port(fun, n, rng=np.random.default_rng(seed))
+    dt = time.perf_counter() - t0
+    if limiter is not None:
+        limiter.restore_original_limits()
+    return dt, (-float(res.fun) if res is not False else float("nan"))
+
+
+def cpu_reference_rate(wl, lanes, n_proc, seed=0):
+    """lane-fits/s of the reference's CPU path on `lanes` bootstrap lanes using n_proc processes."""
+    from traversome_b200 import synthetic
+    A = wl.scipy_csr()
+    w = synthetic.bootstrap_weights(wl.n_obs, lanes, seed=seed + 17, keep_lane0=False)
+    jobs = [(A.data, A.indices, A.indptr, A.shape, wl.L, w[:, b].copy(), seed * 1000 + b) for b in range(lanes)]
+    t0 = time.perf_counter()
+    if n_proc <= 1:
+        res = [_cpu_fit_one(j) for j in jobs]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(n_proc) as pool:
+            res = pool.map(_cpu_fit_one, jobs, chunksize=1)
+    wall = time.perf_counter() - t0
+    return lanes / wall, wall, [r[1] for r in res]
+
+
+def run_reference(args, wl):
+    """`--impl reference`: the reference's own CPU implementation of the path (restated driver, see
+    oracle/slsqp_port.py) on all host cores; each step = a bounded sample of the workload's lanes."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    lanes_per_step = max(cores * 8, 16)
+    for _ in range(args.warmup):
+        cpu_reference_rate(wl, max(cores, 2), cores, seed=99)
+    times, lls = [], []
+    for k in range(args.steps):
+        rate, wall, ll = cpu_reference_rate(wl, lanes_per_step, cores, seed=k)
+        times.append(wall)
+        lls += ll
+    total = float(np.sum(times))
+    value = lanes_per_step * args.steps / total
+    sample = "%d bootstrap lanes per step of %s (full workload: %d lanes/GPU), %d processes" % (
+        lanes_per_step, args.workload, args.lanes, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, wl),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "note": "restated reference driver (scipy SLSQP multistart, ftol 1e-5, 6 successes) + numpy closure "
+                                     "of the reference objective; omits the reference's symengine build + LLVM JIT per fit"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, wl):
+    return {"workload": "%s: %d variants x %d read paths (nnz %d, %d reads), %d bootstrap replicates per GPU, "
+                        "full-candidate-set ML fit to KKT 1e-10" % (args.workload, wl.V, wl.R, wl.nnz, wl.N, args.lanes),
+            "lanes_per_gpu": args.lanes, "V": wl.V, "R": wl.R, "nnz": wl.nnz,
+            "l2": "L2 flushed between timed steps (256 MiB write); within a step the solver re-reads its own weights",
+            "parallelism": "lanes sharded over ranks, no data-path collective"}
+
+
+# ------------------------------------------------------------------------------------------------- ours
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    from traversome_b200 import synthetic
+    if args.lanes <= 0:
+        args.lanes = synthetic.CONFIGS[args.workload]["lanes"]
+    wl = synthetic.make_config(args.workload)
+
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from traversome_b200 import _cabi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B = args.lanes
+    eng = _cabi.Engine(wl.row_ptr, wl.col, wl.val, wl.L, device=local_rank)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    # every rank: its own B bootstrap replicates, drawn on the device (lane 0 of rank 0 = the observed data)
+    eng.resample(B, wl.n_obs, seed=2024 + 7919 * rank, keep_lane0=(rank == 0))
+    w_host = torch.empty((wl.R, B), dtype=torch.int32, pin_memory=True)
+    w_host.numpy()[:] = eng.get_weights()
+    outs = {"theta": torch.empty((wl.V, B), dtype=torch.float64, pin_memory=True).numpy(),
+            "loglike": torch.empty(B, dtype=torch.float64, pin_memory=True).numpy(),
+            "kkt": torch.empty((B, 2), dtype=torch.float64, pin_memory=True).numpy(),
+            "iters": torch.empty(B, dtype=torch.int32, pin_memory=True).numpy(),
+            "status": torch.empty(B, dtype=torch.int32, pin_memory=True).numpy()}
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        flush.zero_()
+        eng.fit(out=outs)
+    # ---- timed: device-resident weights
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    dev_ms, launches, passes, lane_passes = [], 0, 0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        out = eng.fit(out=outs)
+        st = eng.last_fit_stats()
+        dev_ms.append(st["total_ms"])
+        launches += st["kernel_launches"]
+        passes += st["passes"]
+        lane_passes += st["lane_passes"]
+    barrier()
+    wall = time.perf_counter() - t0
+    converged = int((out["status"] == _cabi.CONVERGED).sum())
+    iters_mean = float(out["iters"].mean())
+    # ---- timed: end to end through the public API, weights in pinned host memory
+    e2e_ms = []
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        eng.set_lanes(w_host, B=B)            # H2D of this step's weights
+        eng.fit(out=outs)                     # D2H of theta / loglike / kkt / iters / status into pinned memory
+        e2e_ms.append(1e3 * (time.perf_counter() - t1))
+    barrier()
+    clocks = sampler.stop()
+    # ---- one extra (untimed) step with per-launch CUDA events for the roofline of the dominant kernel
+    flush.zero_()
+    eng.fit(out=outs, time_passes=True)
+    stp = eng.last_fit_stats()
+
+    step_ms = float(np.sum(dev_ms)) / args.steps
+    e2e_step_ms = float(np.sum(e2e_ms)) / args.steps
+    if world > 1:
+        t = torch.tensor([step_ms, e2e_step_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms, e2e_step_ms = float(t[0]), float(t[1])
+        c = torch.tensor([converged, launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        converged, launches = int(c[0]), int(c[1])
+    if rank == 0:
+        total_lanes = B * world
+        value = total_lanes / (step_ms * 1e-3)
+        peak, peak_src = measured_peaks()
+        # algorithmic bytes of the pass-kernel launches of the profiled step (SURVEY.md 8d figure, per launch width)
+        alg_bytes = (8.0 * wl.nnz + 4.0 * (wl.R + 1)) * stp["passes"] + (4.0 * wl.R + 16.0 * wl.V) * stp["lane_passes"]
+        pass_s = stp["pass_ms"] * 1e-3
+        achieved = alg_bytes / pass_s / 1e9 if pass_s > 0 else 0.0
+        flops = 4.0 * wl.nnz * stp["lane_passes"] + 6.0 * wl.R * stp["lane_passes"]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args, wl),
+            "e2e": {"value": total_lanes / (e2e_step_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(wl.R) * B * 4,
+                    "d2h_bytes_per_step": int(wl.V) * B * 8 + B * (8 + 16 + 4 + 4)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "pass_kernel (fused A x, w/p, w log p, A^T(w/p))",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                         "traffic": 77.3e6, "traffic_note": "dram read+write per full-width launch, ncu --set full (profiles/)",
+                         "avg_launch_us": 1e3 * stp["pass_ms"] / max(stp["passes"], 1), "launches_profiled": stp["passes"],
+                         "fp64_tflops_achieved": flops / pass_s / 1e12 if pass_s > 0 else 0.0,
+                         "pass_share_of_step": stp["pass_ms"] / stp["total_ms"] if stp["total_ms"] > 0 else None},
+            "solver": {"converged_lanes": converged, "lanes": total_lanes, "mean_iters": iters_mean,
+                       "passes_per_step": passes / args.steps, "lane_passes_per_step": lane_passes / args.steps,
+                       "wall_ms_per_step": 1e3 * wall / args.steps},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = 1
+            n_sample = 24
+            rate, wall_cpu, lls = cpu_reference_rate(wl, n_sample, cores, seed=5)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "%d of the %d bootstrap lanes, one process (the reference's default -p 1; its bootstrap loop is "
+                          "serial), %.1f s of CPU work" % (n_sample, B, wall_cpu),
+                "note": "restated reference driver (scipy SLSQP multistart) + numpy closure of the reference objective; "
+                        "omits the reference's symengine build + LLVM JIT, i.e. faster than the true reference"}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
