@@ -73,6 +73,8 @@ typedef struct tvs_fit_stats {
     double  pass_ms;         /* CUDA-event time spent in the pass kernel (sum over passes)                */
     double  total_ms;        /* CUDA-event time of the whole tvs_fit on the handle's stream               */
     int64_t lane_passes;     /* sum over passes of lanes processed (for roofline arithmetic)              */
+    double  update_ms;       /* CUDA-event time spent in the L-BFGS update kernel (when timing is requested) */
+    int64_t compactions;     /* lane compactions performed                                                */
 } tvs_fit_stats;
 
 /* library / device ------------------------------------------------------------------------- */

@@ -38,7 +38,7 @@ class FitOptions(ctypes.Structure):
 
 class FitStats(ctypes.Structure):
     _fields_ = [("passes", c_int64), ("kernel_launches", c_int64), ("pass_ms", c_double), ("total_ms", c_double),
-                ("lane_passes", c_int64)]
+                ("lane_passes", c_int64), ("update_ms", c_double), ("compactions", c_int64)]
 
 
 _lib = None
@@ -195,7 +195,8 @@ class Engine(object):
         st = FitStats()
         _check(self._lib.tvs_last_fit_stats(self._h, ctypes.byref(st)))
         return {"passes": st.passes, "kernel_launches": st.kernel_launches, "pass_ms": st.pass_ms,
-                "total_ms": st.total_ms, "lane_passes": st.lane_passes}
+                "total_ms": st.total_ms, "lane_passes": st.lane_passes, "update_ms": st.update_ms,
+                "compactions": st.compactions}
 
 
 def measure_fp64_peak(device=0):

@@ -80,6 +80,7 @@ static int plan_one(const tvs_problem* h, int64_t B, PassPlan* out) {
     out->tiles = (int)((B + LT - 1) / LT);
     int s = slots / std::max(out->tiles, 1);
     s = std::max(1, std::min(s, c.n_chunks));
+    s = std::min(s, env_int("TVS_MAX_SPLITS", 1024));
     const int forced = env_int("TVS_SPLITS", 0);
     if (forced > 0) s = std::min(forced, c.n_chunks);
     out->splits = s;
@@ -144,6 +145,7 @@ static int ensure_fit_state(tvs_problem* h, int m) {
         A_(s.orig, B) A_(s.z, vb) A_(s.zt, vb) A_(s.g, vb) A_(s.d, vb) A_(s.x, vb)
         A_(s.S, vb * m) A_(s.Y, vb * m) A_(s.rho, (size_t)B * m)
         A_(s.gamma, B) A_(s.F, B) A_(s.dg, B) A_(s.alpha, B) A_(s.llsum, B) A_(s.sumphi, B) A_(s.kkt, 2 * (size_t)B)
+        A_(s.gram, (size_t)B * ((2 * m + 1) * (2 * m + 2) / 2))
         A_(s.ls, B) A_(s.iters, B) A_(s.head, B) A_(s.cnt, B) A_(s.done, B) A_(s.status, B)
     }
     f.half = B / 2 + 1;
@@ -154,7 +156,7 @@ static int ensure_fit_state(tvs_problem* h, int m) {
     // partial buffers: splits*width never exceeds (resident CTAs)*(lanes per tile) + width
     f.tpart_cap = (size_t)V * ((size_t)h->sm_count * 16 * 64 + (size_t)B);
     f.llpart_cap = f.tpart_cap / (size_t)V;
-    A_(f.tpart, f.tpart_cap) A_(f.llpart, f.llpart_cap)
+    A_(f.tpart, f.tpart_cap) A_(f.llpart, f.llpart_cap) A_(f.t_red, vb) A_(f.ll_red, B)
     A_(f.idx, B) A_(f.nactive, 32)
     A_(f.theta_io, vb) A_(f.ll_out, B) A_(f.kkt_out, 2 * (size_t)B) A_(f.iters_out, B) A_(f.status_out, B)
 #undef A_
@@ -424,6 +426,8 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
     if (opt.max_iter <= 0) opt.max_iter = 1000;
     if (opt.history <= 0) opt.history = 8;
     opt.history = std::min(opt.history, kMaxHistory);
+    const bool upd_v1 = env_int("TVS_UPD_V1", 0) != 0;       // the plain two-loop update kernel (any history)
+    if (!upd_v1) opt.history = (opt.history <= 4) ? 4 : 8;    // the vector-free kernel is instantiated for 4 and 8
     if (opt.check_every <= 0) opt.check_every = 4;
     const bool time_passes = (opt.reserved & 1) != 0 || env_int("TVS_TIME_PASSES", 0) != 0;
     const bool no_compact = (opt.reserved & 2) != 0 || env_int("TVS_NO_COMPACT", 0) != 0;
@@ -436,6 +440,8 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
     cudaStream_t st = h->stream;
     const size_t vb0 = (size_t)V * B0;
 
+    TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(VlLayout<4>::doubles * 8)));
+    TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(VlLayout<8>::doubles * 8)));
     TVS_CUDA(cudaEventRecord(h->ev0, st));
     int cur = 0;
     {   // ---- reset set 0 (full width, views the caller's lanes)
@@ -446,6 +452,8 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         cudaMemsetAsync(s.F, 0, B0 * 8, st); cudaMemsetAsync(s.dg, 0, B0 * 8, st); cudaMemsetAsync(s.alpha, 0, B0 * 8, st);
         cudaMemsetAsync(s.llsum, 0, B0 * 8, st); cudaMemsetAsync(s.kkt, 0, 2 * B0 * 8, st); cudaMemsetAsync(s.sumphi, 0, B0 * 8, st);
         cudaMemsetAsync(s.gamma, 0, B0 * 8, st); cudaMemsetAsync(s.rho, 0, (size_t)B0 * m * 8, st);
+        cudaMemsetAsync(s.gram, 0, (size_t)B0 * ((2 * m + 1) * (2 * m + 2) / 2) * 8, st);
+        cudaMemsetAsync(s.S, 0, vb0 * m * 8, st); cudaMemsetAsync(s.Y, 0, vb0 * m * 8, st);
         cudaMemsetAsync(s.ls, 0, B0 * 4, st); cudaMemsetAsync(s.iters, 0xFF, B0 * 4, st); cudaMemsetAsync(s.status, 0, B0 * 4, st);
         cudaMemsetAsync(s.head, 0, B0 * 4, st); cudaMemsetAsync(s.cnt, 0, B0 * 4, st); cudaMemsetAsync(s.done, 0, B0 * 4, st);
         iota_kernel<<<(unsigned)((B0 + 255) / 256), 256, 0, st>>>(s.orig, B0);
@@ -454,7 +462,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         init_z_kernel<<<(unsigned)((B0 + 127) / 128), 128, 0, st>>>(d_theta0, s.mask, h->csr.Ld, h->csr.invL, (int)V, B0, s.zt, s.x);
     }
 
-    std::vector<cudaEvent_t> pev;      // per-pass events when timing is requested
+    std::vector<cudaEvent_t> pev, uev; // per-pass / per-update events when timing is requested
     int64_t passes = 0, launches = 3, lane_passes = 0, n_polls = 0, compactions = 0;
     const int64_t max_passes = (int64_t)opt.max_iter * 2 + 64;
     cudaError_t cerr = cudaSuccess;
@@ -486,7 +494,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         PassArgs pa = base_args(h);
         pa.w = s.w; pa.B = W; pa.x = s.x; pa.done = s.done; pa.tpart = f.tpart; pa.llpart = f.llpart;
         UpdArgs ua{};
-        ua.tpart = f.tpart; ua.llpart = f.llpart; ua.S = pl.splits; ua.invL = h->csr.invL; ua.N = s.N; ua.mask = s.mask;
+        ua.tpart = f.t_red; ua.llpart = f.ll_red; ua.S = 1; ua.invL = h->csr.invL; ua.N = s.N; ua.mask = s.mask;
         ua.z = s.z; ua.zt = s.zt; ua.g = s.g; ua.gt = f.gt; ua.gh = f.gh; ua.d = s.d; ua.x = s.x; ua.Sh = s.S; ua.Yh = s.Y;
         ua.rho = s.rho; ua.gamma = s.gamma; ua.F = s.F; ua.dg = s.dg; ua.alpha = s.alpha; ua.llsum = s.llsum; ua.kkt = s.kkt;
         ua.sumphi = s.sumphi; ua.ls = s.ls; ua.iters = s.iters; ua.status = s.status; ua.head = s.head; ua.cnt = s.cnt;
@@ -502,11 +510,16 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
             rc = launch_pass<true>(h, pl, pa);
             if (rc != TVS_OK) break;
             if (time_passes) cudaEventRecord(pev.back(), st);
+            reduce_partials_kernel<<<(unsigned)(((int64_t)(V + 1) * W + 255) / 256), 256, 0, st>>>(f.tpart, f.llpart, pl.splits, (int)V, W,
+                                                                                                  f.t_red, f.ll_red);
             const bool last = (k == opt.check_every - 1) || (passes + 1 == max_passes);
             ua.nactive = last ? f.nactive + slot : f.nactive + 31;   // word 31 = scratch between polls
             if (last) { cudaMemsetAsync(f.nactive + slot, 0, 4, st); ++launches; }
-            lbfgs_update_kernel<<<ub, kUpdWarps * 32, 0, st>>>(ua);
-            ++passes; launches += 2; lane_passes += W;
+            if (upd_v1) lbfgs_update_kernel<<<ub, kUpdWarps * 32, 0, st>>>(ua);
+            else if (m == 4) lbfgs_update_vl_kernel<4><<<ub, kUpdWarps * 32, VlLayout<4>::doubles * 8, st>>>(ua, s.gram);
+            else lbfgs_update_vl_kernel<8><<<ub, kUpdWarps * 32, VlLayout<8>::doubles * 8, st>>>(ua, s.gram);
+            if (time_passes) { cudaEvent_t e2; cudaEventCreate(&e2); uev.push_back(pev.back()); uev.push_back(e2); cudaEventRecord(e2, st); }
+            ++passes; launches += 3; lane_passes += W;
         }
         if (rc != TVS_OK) break;
         cudaMemcpyAsync(f.h_nactive + slot, f.nactive + slot, 4, cudaMemcpyDeviceToHost, st);
@@ -543,6 +556,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
             gather_rows(st, (const double*)s.llsum, n.llsum, 1, W, A, f.idx);
             gather_rows(st, (const double*)s.sumphi, n.sumphi, 1, W, A, f.idx);
             gather_rows(st, (const double*)s.kkt, n.kkt, 2, W, A, f.idx);
+            gather_rows(st, (const double*)s.gram, n.gram, (int64_t)((2 * m + 1) * (2 * m + 2) / 2), W, A, f.idx);
             gather_rows(st, (const int32_t*)s.ls, n.ls, 1, W, A, f.idx);
             gather_rows(st, (const int32_t*)s.iters, n.iters, 1, W, A, f.idx);
             gather_rows(st, (const int32_t*)s.head, n.head, 1, W, A, f.idx);
@@ -575,7 +589,12 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         double pm = 0.0;
         for (size_t i = 0; i + 1 < pev.size(); i += 2) { float q = 0.f; if (cudaEventElapsedTime(&q, pev[i], pev[i + 1]) == cudaSuccess) pm += q; }
         h->stats.pass_ms = pm;
+        double um = 0.0;
+        for (size_t i = 0; i + 1 < uev.size(); i += 2) { float q = 0.f; if (cudaEventElapsedTime(&q, uev[i], uev[i + 1]) == cudaSuccess) um += q; }
+        h->stats.update_ms = um;
+        h->stats.compactions = compactions;
     }
+    for (size_t i = 1; i < uev.size(); i += 2) cudaEventDestroy(uev[i]);
     for (auto e : pev) cudaEventDestroy(e);
     if (rc != TVS_OK) return rc;
     if (cerr != cudaSuccess) return cuda_fail(cerr, "tvs_fit", __FILE__, __LINE__);

@@ -64,6 +64,7 @@ struct LaneSet {
     double *rho = nullptr;                                                                 // m rows
     double *gamma = nullptr, *F = nullptr, *dg = nullptr, *alpha = nullptr, *llsum = nullptr, *sumphi = nullptr;
     double *kkt = nullptr;                                                                 // 2 rows
+    double *gram = nullptr;                                                                // (2m+1)(2m+2)/2 rows (vector-free L-BFGS)
     int32_t *ls = nullptr, *iters = nullptr, *head = nullptr, *cnt = nullptr, *done = nullptr, *status = nullptr;
 };
 
@@ -75,6 +76,7 @@ struct FitState {               // all device, sized for (V, B, history)
     int64_t half = 0;           // capacity (lanes) of the compaction buffers above
     double *gt = nullptr, *gh = nullptr;            // scratch, V rows at full width
     double *tpart = nullptr, *llpart = nullptr; size_t tpart_cap = 0, llpart_cap = 0;
+    double *t_red = nullptr, *ll_red = nullptr;     // partials summed over the row splits
     int32_t *idx = nullptr;                          // compaction gather list
     int32_t *nactive = nullptr;   // device counters (ring)
     int32_t *h_nactive = nullptr; // pinned host mirror
