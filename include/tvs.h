@@ -95,6 +95,14 @@ int tvs_destroy(tvs_handle h);
  * C[B] or NULL (= 0).  Computes N_b = sum_r w[r,b] on the device. */
 int tvs_set_lanes(tvs_handle h, int64_t B, const int32_t* w, const uint8_t* mask, const double* C);
 
+/* same, for batches in which many lanes share one weight column (all candidate subsets of one
+ * replicate in a backward-selection step, ModelFitMaxLike.py:206-262): w_cols[R*n_cols] int32
+ * (element (r, c) at [r*n_cols + c]) holds the DISTINCT weight columns and lane b uses column
+ * col_of_lane[b]; the R x B lane-minor matrix is expanded on the device, so only R*n_cols integers
+ * cross PCIe. */
+int tvs_set_lanes_indexed(tvs_handle h, int64_t B, int64_t n_cols, const int32_t* w_cols, const int32_t* col_of_lane,
+                          const uint8_t* mask, const double* C);
+
 /* device-side bootstrap: lane b's w[.,b] ~ Multinomial(N, n_obs/N), N = sum n_obs, drawn record by
  * record with Philox4x32-10(key=(seed, b), counter=draw index) -- the batched equivalent of
  * `random.choices(records_pool_sorted, k=N)` (traversome.py:1652) for synthetic workloads.

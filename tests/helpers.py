@@ -104,3 +104,45 @@ def resample_reference(n_obs, B, seed, keep_lane0):
         rows = np.searchsorted(cum, idx, side="right")
         w[:, b] = np.bincount(rows, minlength=R)
     return w
+
+
+class OracleEngine(object):
+    """CPU stand-in for traversome_b200._cabi.Engine, backed by the oracle's exact solver.  TEST ONLY:
+    lets the host-side logic above the C ABI (lane batching, lock-step selection, sharding + gather)
+    run in `-m "not gpu"` tests; injected through LaneContext.engine_factory."""
+
+    def __init__(self, row_ptr, col, val, variant_sizes, n_variants=None, device=0):
+        import scipy.sparse as sp
+        self.R = len(row_ptr) - 1
+        self.V = int(n_variants if n_variants is not None else len(variant_sizes))
+        self.A = sp.csr_matrix((np.asarray(val, np.float64), np.asarray(col), np.asarray(row_ptr)), shape=(self.R, self.V))
+        self.L = np.asarray(variant_sizes, np.float64)
+        self.calls = 0
+
+    def set_lanes_indexed(self, w_cols, col_of_lane, mask=None, C=None):
+        self.w = np.asarray(w_cols)[:, np.asarray(col_of_lane)]
+        self.mask = np.ones((self.V, self.w.shape[1]), np.uint8) if mask is None else np.asarray(mask)
+        self.C = np.zeros(self.w.shape[1]) if C is None else np.asarray(C)
+        self.B = self.w.shape[1]
+
+    def fit(self, tol=0.0, max_iter=0, history=0, **_kw):
+        from oracle import exact
+        self.calls += 1
+        B = self.B
+        out = {"theta": np.zeros((self.V, B)), "loglike": np.zeros(B), "kkt": np.zeros((B, 2)),
+               "iters": np.zeros(B, np.int32), "status": np.zeros(B, np.int32)}
+        for b in range(B):
+            try:
+                r = exact.exact_fit(self.A, self.L, self.w[:, b], mask=self.mask[:, b].astype(bool))
+            except ValueError:
+                out["status"][b] = 3
+                out["loglike"][b] = -np.inf
+                out["theta"][:, b] = np.nan
+                continue
+            out["theta"][:, b] = r["theta"]
+            out["loglike"][b] = r["loglike_no_C"] + self.C[b]
+            out["kkt"][b] = (r["comp"], r["dual"])
+        return out
+
+    def close(self):
+        pass

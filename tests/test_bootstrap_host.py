@@ -1,0 +1,153 @@
+"""CPU: host logic of the batched bootstrap / model-selection drivers (decision replay, tally,
+lock-step batching), with the GPU engine replaced by the oracle-backed stand-in of tests/helpers.py."""
+import numpy as np
+import pytest
+
+from tests.helpers import OracleEngine, fit_context, model_from_tables
+from traversome_b200 import bootstrap
+from traversome_b200.ModelFitMaxLike import ModelFitMaxLike
+from traversome_b200.lanes import LaneContext, LaneSharder
+
+
+def _ctx(L):
+    ctx = LaneContext(len(L), L)
+    ctx.engine_factory = OracleEngine
+    return ctx
+
+
+def _golden_selection(case, criterion):
+    for fit in case["fits"]:
+        if fit["kind"] == "reverse_model_selection" and fit["criterion"] == criterion:
+            return fit
+    raise KeyError(criterion)
+
+
+@pytest.mark.parametrize("criterion", ["BIC", "AIC"])
+def test_reverse_model_selection_decisions_match_reference(synthetic_small, criterion):
+    """Same chosen variant set as the reference's own run (golden), proportions within the
+    reference's SLSQP spread, criterion value within 1e-9 relative."""
+    for case in synthetic_small["cases"]:
+        model = model_from_tables(case["variant_sizes"], case["bins_list"])
+        kw = fit_context(model, case["be_unidentifiable_to"], case["repr_to_merged_variants"])
+        fitter = ModelFitMaxLike(context=_ctx(case["variant_sizes"]), **kw)
+        prop, like, crit = fitter.reverse_model_selection(n_proc=1, criterion=criterion)
+        ref = _golden_selection(case, criterion)
+        assert sorted(prop) == [cid for cid, _ in ref["prop"]], case["name"]
+        for cid, p in ref["prop"]:
+            assert abs(prop[cid] - p) < 5e-4
+        assert abs(like - ref["loglike"]) < 1e-8 * abs(ref["loglike"])
+        assert abs(crit - ref["criterion_value"]) < 1e-8 * abs(ref["criterion_value"])
+        assert like >= ref["loglike"] - 1e-7            # the exact optimum is never worse than SLSQP's
+
+
+def test_point_estimate_matches_reference_and_failure_mode(synthetic_small):
+    for case in synthetic_small["cases"]:
+        model = model_from_tables(case["variant_sizes"], case["bins_list"])
+        kw = fit_context(model, case["be_unidentifiable_to"], case["repr_to_merged_variants"])
+        fitter = ModelFitMaxLike(context=_ctx(case["variant_sizes"]), **kw)
+        for fit in case["fits"]:
+            if fit["kind"] != "point_estimate":
+                continue
+            chosen = set(fit["chosen_ids"]) if fit["chosen_ids"] else None
+            if "error" in fit:
+                with pytest.raises(Exception, match="Likelihood maximization failed."):
+                    fitter.point_estimate(chosen_ids=chosen, criterion=fit["criterion"])
+                continue
+            prop, like, crit = fitter.point_estimate(chosen_ids=chosen, criterion=fit["criterion"])
+            assert list(prop) == [cid for cid, _ in fit["prop"]]
+            for cid, p in fit["prop"]:
+                assert abs(prop[cid] - p) < 5e-4
+            assert abs(crit - fit["criterion_value"]) < 1e-8 * abs(fit["criterion_value"])
+
+
+def test_lock_step_selection_equals_serial(synthetic_small):
+    """All replicates' coroutines advanced together give exactly the serial results, in fewer engine calls."""
+    case = synthetic_small["cases"][2]
+    L = case["variant_sizes"]
+    rng = np.random.default_rng(0)
+    models = []
+    for k in range(5):                      # 5 "replicates": resampled num_matched of the same bins
+        bins = [dict(b, rp_bins=[dict(rp, num_matched=int(rng.poisson(rp["num_matched"])) + 1) for rp in b["rp_bins"]])
+                for b in case["bins_list"]]
+        models.append(model_from_tables(L, bins))
+    serial = []
+    for m in models:
+        kw = fit_context(m, case["be_unidentifiable_to"], case["repr_to_merged_variants"])
+        f = ModelFitMaxLike(context=_ctx(L), **kw)
+        f._shuffle = lambda x: None
+        serial.append(f.reverse_model_selection(n_proc=1))
+    ctx = _ctx(L)
+    fitters = []
+    for m in models:
+        kw = fit_context(m, case["be_unidentifiable_to"], case["repr_to_merged_variants"])
+        f = ModelFitMaxLike(context=ctx, **kw)
+        f._shuffle = lambda x: None
+        fitters.append(f)
+    batched = bootstrap.run_selections(fitters)
+    for (p0, l0, c0), (p1, l1, c1) in zip(serial, batched):
+        assert list(p0) == list(p1)
+        assert all(abs(p0[k] - p1[k]) < 1e-9 for k in p0) and abs(l0 - l1) < 1e-9 * abs(l0) and abs(c0 - c1) < 1e-9 * abs(c0)
+    assert ctx.n_batches < sum(1 for _ in models) * 3      # far fewer engine calls than serial fits
+    assert ctx.n_lanes_fitted == sum(f.n_gpu_fits for f in fitters)
+
+
+def test_support_tally_matches_reference_tables(plastome):
+    """summarize_replicates / check_bs_threshold on the reference's own replicate results reproduce its
+    support table (final.result.tab) -- traversome.py:561-617."""
+    reps = [dict((int(c), p) for c, p in fit["prop"]) for fit in plastome["fits"][1:]]
+    raw = dict((int(c), p) for c, p in plastome["final"]["variant_proportions"])
+    count_unique = {}
+    for v in reps:
+        assert bootstrap.check_bs_threshold(count_unique, v, len(reps), 0.95)
+    s = bootstrap.summarize_replicates(reps, raw, plastome["final"]["res_loglike"], plastome["final"]["res_criterion"])
+    got = [[list(k), s.vp_unique_results[k]["support"]] for k in s.vp_unique_results_sorted]
+    assert got == plastome["final"]["support"]
+    top = s.vp_unique_results[s.vp_unique_results_sorted[0]]
+    assert top["raw_like"] == plastome["final"]["res_loglike"] and top["raw_criterion"] == plastome["final"]["res_criterion"]
+    std = np.std(np.array(top["values"]), axis=0, ddof=1)      # traversome.py output_result writes the sample std
+    line = plastome["output_tables"]["final.result.tab"].strip().split("\n")[1].split("\t")
+    assert [float(x) for x in line[-1].split(",")] == [round(float(x), 4) for x in std] or \
+        all(abs(float(a) - b) < 1.01e-4 for a, b in zip(line[-1].split(","), std))
+
+
+def test_bs_threshold_early_stop_index():
+    count = {}
+    seq = [{0: 1.0}, {1: 1.0}, {0: .5, 1: .5}, {0: 1.0}]
+    flags = [bootstrap.check_bs_threshold(count, v, 4, 0.95) for v in seq]
+    assert flags == [True, False, False, False]
+    count = {}
+    assert all(bootstrap.check_bs_threshold(count, {0: 1.0}, 10, 0.95) for _ in range(10))
+
+
+def test_do_subsampling_on_plastome_replicates(plastome):
+    """cfg1 end to end above the C ABI (engine = oracle stand-in): 100 replicate models of the reference run ->
+    identical support table; every replicate's proportions within the reference's own tolerance."""
+    L = plastome["variant_sizes"]
+    models = [model_from_tables(L, m["bins_list"]) for m in plastome["models"]]
+    ctx = _ctx(L)
+    kw0 = fit_context(models[0], plastome["be_unidentifiable_to"], plastome["repr_to_merged_variants"])
+    full = ModelFitMaxLike(context=ctx, **kw0)
+    raw = full.reverse_model_selection(n_proc=1)
+    shared = {k: kw0[k] for k in ("variant_paths", "variant_subpath_counters", "repr_to_merged_variants", "be_unidentifiable_to")}
+    reps = []
+    for m in models[1:]:
+        kw = fit_context(m, plastome["be_unidentifiable_to"], plastome["repr_to_merged_variants"])
+        reps.append((m, kw["sbp_to_sbp_id"]))
+    s = bootstrap.do_subsampling(reps, shared, full, raw, n_replicate=100, threshold=0.95)
+    assert s.bs_eligible and s.n_replicates_run == 100
+    got = [[list(k), s.vp_unique_results[k]["support"]] for k in s.vp_unique_results_sorted]
+    assert got == plastome["final"]["support"]
+    for v_prop, fit in zip(s.variant_proportions_reps, plastome["fits"][1:]):
+        for cid, p in fit["prop"]:
+            assert abs(v_prop[cid] - p) < 5e-4
+    assert ctx.n_batches <= 6            # 1 (full) + a handful of lock-step rounds for 100 replicates
+
+
+def test_shard_bounds_cover_all_lanes():
+    for B in (1, 2, 7, 64, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [LaneSharder.bounds(B, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,191 @@
+"""GPU (-m gpu): the reference-facing boundary -- ``ModelFitMaxLike`` (point_estimate,
+reverse_model_selection, get_neg_likelihood_of_var_freq) and the batched bootstrap driver -- running on
+the CUDA solver through the C ABI, against the reference's own results (tests/golden) and the oracle.
+
+north_star tolerances: LL 1e-9 relative and frequencies 1e-6 absolute against the exact optimum of the
+reference's objective (oracle/exact.py; SURVEY.md 8c explains why the reference's raw SLSQP output, which
+scatters by ~3e-4 between its own restarts, cannot be the 1e-6 target); selected models and the
+bootstrap support table identical to the reference's.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import exact, loglik
+from tests.helpers import fit_context, hexf, model_from_tables
+from traversome_b200 import _cabi, bootstrap
+from traversome_b200.ModelFitMaxLike import ModelFitMaxLike
+from traversome_b200.lanes import LaneContext, LaneRequest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu(lib_built):
+    if _cabi.device_count() < 1:
+        pytest.fail("no CUDA device: -m gpu tests must run on the B200 box")
+    return True
+
+
+def _selection(case, criterion):
+    return [f for f in case["fits"] if f["kind"] == "reverse_model_selection" and f["criterion"] == criterion][0]
+
+
+@pytest.mark.parametrize("criterion", ["BIC", "AIC"])
+def test_reverse_model_selection_matches_reference(gpu, synthetic_small, criterion):
+    for case in synthetic_small["cases"]:
+        L = case["variant_sizes"]
+        model = model_from_tables(L, case["bins_list"])
+        kw = fit_context(model, case["be_unidentifiable_to"], case["repr_to_merged_variants"])
+        fitter = ModelFitMaxLike(**kw)
+        prop, like, crit = fitter.reverse_model_selection(n_proc=1, criterion=criterion)
+        ref = _selection(case, criterion)
+        assert sorted(prop) == [cid for cid, _ in ref["prop"]], case["name"]            # identical model
+        for cid, p in ref["prop"]:
+            assert abs(prop[cid] - p) < 5e-4                                             # reference's SLSQP spread
+        assert abs(like - ref["loglike"]) < 1e-8 * abs(ref["loglike"])
+        assert like >= ref["loglike"] - 1e-7
+        # against the exact optimum of the selected model: the north_star tolerances
+        A, w, C, N = loglik.rows_from_bins(L, case["bins_list"])
+        groups = {int(k): v for k, v in case["repr_to_merged_variants"]}
+        reps = sorted({int(dict(case["be_unidentifiable_to"])[cid]) for cid in prop})
+        mask = np.zeros(len(L), bool)
+        mask[reps] = True
+        r = exact.exact_fit(A, L, w, mask=mask)
+        for rep in reps:
+            for member in groups[rep]:
+                assert abs(prop[member] - r["theta"][rep] / len(groups[rep])) < 1e-6
+        assert abs(like - (r["loglike_no_C"] + C)) < 1e-9 * abs(like)
+        # the criterion is the one of the last accepted FIT (zero-proportion drops do not refit, :333-347)
+        assert abs(crit - ref["criterion_value"]) < 1e-8 * abs(crit)
+        fitter.close()
+
+
+def test_point_estimate_and_failure_mode(gpu, synthetic_small):
+    for case in synthetic_small["cases"]:
+        model = model_from_tables(case["variant_sizes"], case["bins_list"])
+        kw = fit_context(model, case["be_unidentifiable_to"], case["repr_to_merged_variants"])
+        fitter = ModelFitMaxLike(**kw)
+        for fit in case["fits"]:
+            if fit["kind"] != "point_estimate":
+                continue
+            chosen = set(fit["chosen_ids"]) if fit["chosen_ids"] else None
+            if "error" in fit:
+                with pytest.raises(Exception, match="Likelihood maximization failed."):
+                    fitter.point_estimate(chosen_ids=chosen, criterion=fit["criterion"])
+                continue
+            prop, like, crit = fitter.point_estimate(chosen_ids=chosen, criterion=fit["criterion"])
+            assert list(prop) == [cid for cid, _ in fit["prop"]]
+            for cid, p in fit["prop"]:
+                assert abs(prop[cid] - p) < 5e-4
+            assert abs(like - fit["loglike"]) < 1e-8 * abs(like) and like >= fit["loglike"] - 1e-7
+            assert abs(crit - fit["criterion_value"]) < 1e-8 * abs(crit)
+        fitter.close()
+
+
+def test_neg_loglike_callable_matches_known_answers(gpu, plastome, synthetic_small):
+    """get_neg_likelihood_of_var_freq().loglike_func == the reference's lambdified objective (known answers
+    from get_like_formula(floats, math.log), ModelGenerator.py:110-178)."""
+    cases = [(plastome["variant_sizes"], plastome["models"][0]["bins_list"], plastome["known_answer_ll"],
+              plastome["be_unidentifiable_to"], plastome["repr_to_merged_variants"])]
+    cases += [(c["variant_sizes"], c["bins_list"], c["known_answer_ll"], c["be_unidentifiable_to"], c["repr_to_merged_variants"])
+              for c in synthetic_small["cases"]]
+    for L, bins, kas, unid, groups in cases:
+        model = model_from_tables(L, bins)
+        fitter = ModelFitMaxLike(**fit_context(model, unid, groups))
+        for ka in kas:
+            ids = sorted(ka["subset"]) if ka["subset"] else list(range(len(L)))
+            info = fitter.get_neg_likelihood_of_var_freq(within_variant_ids=set(ids))
+            theta = np.array([hexf(t) for t in ka["theta"]])
+            got = -float(info.loglike_func(theta[ids])[0])
+            ref = hexf(ka["loglike"])
+            assert info.variable_size == ka["variable_size"] and info.sample_size == ka["sample_size"]
+            if math.isinf(ref):
+                assert math.isinf(got) and got < 0
+            else:
+                assert abs(got - ref) < 1e-9 * abs(ref)
+        fitter.close()
+
+
+def test_cfg1_bootstrap_flow_on_gpu(gpu, plastome):
+    """BASELINE.json configs[0]: whole-data selection + 100 bootstrap replicates of the reference run, all
+    replicates in lock step on the GPU: same chosen model in every replicate, same support table,
+    %.4f proportions of bootstraps.replicates.tab reproduced (up to the reference's own SLSQP noise)."""
+    L = plastome["variant_sizes"]
+    models = [model_from_tables(L, m["bins_list"]) for m in plastome["models"]]
+    kw0 = fit_context(models[0], plastome["be_unidentifiable_to"], plastome["repr_to_merged_variants"])
+    full = ModelFitMaxLike(**kw0)
+    raw = full.reverse_model_selection(n_proc=1)
+    assert abs(raw[0][0] - 23 / 35.) < 1e-9 and abs(raw[0][1] - 12 / 35.) < 1e-9
+    assert abs(raw[1] - plastome["final"]["res_loglike"]) < 1e-9 * abs(raw[1])
+    assert abs(raw[2] - plastome["final"]["res_criterion"]) < 1e-9 * abs(raw[2])
+    shared = {k: kw0[k] for k in ("variant_paths", "variant_subpath_counters", "repr_to_merged_variants", "be_unidentifiable_to")}
+    reps = []
+    for m in models[1:]:
+        kw = fit_context(m, plastome["be_unidentifiable_to"], plastome["repr_to_merged_variants"])
+        reps.append((m, kw["sbp_to_sbp_id"]))
+    s = bootstrap.do_subsampling(reps, shared, full, raw, n_replicate=100, threshold=0.95)
+    assert s.bs_eligible and s.n_replicates_run == 100
+    got = [[list(k), s.vp_unique_results[k]["support"]] for k in s.vp_unique_results_sorted]
+    assert got == plastome["final"]["support"]
+    ctx = full._ensure_lane()
+    assert ctx.n_batches <= 6
+    tab = plastome["output_tables"]["bootstraps.replicates.tab"].strip().split("\n")[1:]
+    for line, v_prop, fit, m in zip(tab, s.variant_proportions_reps, plastome["fits"][1:], plastome["models"][1:]):
+        ref4 = [float(x) for x in line.split("\t")[1:]]
+        assert all(abs(round(v_prop[c], 4) - ref4[c]) <= 1.01e-4 for c in (0, 1))
+        A, w, C, N = loglik.rows_from_bins(L, m["bins_list"])
+        r = exact.exact_fit(A, L, w)
+        assert abs(v_prop[0] - r["theta"][0]) < 1e-6 and abs(v_prop[1] - r["theta"][1]) < 1e-6
+    full.close()
+
+
+def test_indexed_lanes_equal_expanded_lanes(gpu):
+    from traversome_b200 import synthetic
+    wl = synthetic.make_workload(10, 500, 0.3, seed=4)
+    cols = synthetic.bootstrap_weights(wl.n_obs, 3, seed=1)
+    idx = np.array([0, 2, 2, 1, 0, 1, 2], np.int32)
+    mask = np.ones((wl.V, idx.size), np.uint8)
+    mask[3, 2] = 0
+    mask[5, 4] = 0
+    with _cabi.Engine(wl.row_ptr, wl.col, wl.val, wl.L) as eng:
+        eng.set_lanes_indexed(cols, idx, mask=mask)
+        assert np.array_equal(eng.get_weights(), cols[:, idx])
+        a = eng.fit()
+        eng.set_lanes(cols[:, idx], mask=mask)
+        b = eng.fit()
+    assert np.array_equal(a["theta"], b["theta"], equal_nan=True) and np.array_equal(a["loglike"], b["loglike"])
+    assert np.array_equal(a["status"], b["status"]) and (a["status"] == _cabi.CONVERGED).sum() >= 5
+    with pytest.raises(_cabi.TvsError):
+        with _cabi.Engine(wl.row_ptr, wl.col, wl.val, wl.L) as eng:
+            eng.set_lanes_indexed(cols, np.array([0, 3], np.int32))
+
+
+def test_lane_context_batches_mixed_replicates_and_subsets(gpu):
+    from traversome_b200 import synthetic
+    wl = synthetic.make_workload(12, 900, 0.3, seed=9)
+    ctx = LaneContext(wl.V, wl.L)
+    ctx.matrix._sigs = [tuple((int(c), int(v)) for c, v in zip(wl.col[a:b], wl.val[a:b]))
+                        for a, b in zip(wl.row_ptr[:-1], wl.row_ptr[1:])]
+    ctx.matrix._row_of = {s: i for i, s in enumerate(ctx.matrix._sigs)}
+    W = synthetic.bootstrap_weights(wl.n_obs, 4, seed=2)
+    cols = [ctx.add_weights(W[:, j]) for j in range(4)]
+    reqs = [LaneRequest(cols[j], 10.0 * j, set(range(wl.V)) - ({k} if k >= 0 else set())) for j in range(4) for k in (-1, 0, 5)]
+    res = ctx.fit(reqs)
+    A = wl.scipy_csr()
+    n_ok = 0
+    for rq, fr in zip(reqs, res):
+        m = np.zeros(wl.V, bool)
+        m[rq.ids] = True
+        j = cols.index(rq.col)
+        try:
+            r = exact.exact_fit(A, wl.L, W[:, j], mask=m)
+        except ValueError:                      # the subset leaves an observed read path uncovered
+            assert not fr.success and fr.status == _cabi.INFEASIBLE
+            continue
+        n_ok += 1
+        assert fr.success and np.abs(fr.x - r["theta"][rq.ids]).max() < 1e-6
+        assert abs(-fr.fun - (r["loglike_no_C"] + rq.C)) < 1e-9 * abs(fr.fun)
+    assert n_ok >= 4
+    ctx.close()

@@ -20,18 +20,8 @@ from typing import Set, Union
 import numpy as np
 from loguru import logger
 
-from . import _cabi
-from .csr import ReadPathMatrix, lane_from_bins
+from .lanes import FitResult, LaneContext, LaneRequest  # noqa: F401  (FitResult re-exported)
 from .utils import Criterion, LogLikeFuncInfo, aic, bic
-
-
-class FitResult(object):
-    """What the reference reads off scipy's OptimizeResult: ``x`` (proportions of the fitted ids in
-    increasing id order), ``fun`` (= -loglike), ``success``."""
-    __slots__ = ("x", "fun", "success", "status", "kkt", "nit")
-
-    def __init__(self, x, fun, success, status, kkt, nit):
-        self.x, self.fun, self.success, self.status, self.kkt, self.nit = x, fun, success, status, kkt, nit
 
 
 def minimize_neg_likelihood(neg_loglike_func, num_variables, verbose, err_queue=None):
@@ -81,7 +71,8 @@ class ModelFitMaxLike(object):
                  be_unidentifiable_to,
                  loglevel="INFO",
                  bootstrap_mode=False,
-                 device=0):
+                 device=0,
+                 context=None):
         self.model = model
         self.variant_paths = variant_paths
         self.num_put_variants = len(variant_paths)
@@ -103,55 +94,42 @@ class ModelFitMaxLike(object):
         self.pe_best_proportions = None
 
         self.__warning_sent = False
-        self._engine = None
-        self._lane = None            # (w[R] int32, C, N) of this model
+        # `context` = the CSR + GPU engine; shared by the models of every bootstrap replicate when the
+        # caller batches them (traversome_b200.bootstrap), otherwise private to this object
+        self._context = context
+        self._own_context = context is None
+        self._lane = None            # (weight column id, C, N) of this model inside the context
         self._shuffle = np.random.shuffle   # ModelFitMaxLike.py:203; tests may pin the permutation
         self.n_gpu_fits = 0          # lanes fitted so far (diagnostics)
 
-    # ------------------------------------------------------------------ engine / lanes
-    def _ensure_engine(self):
-        if self._engine is not None:
-            return self._engine
-        prune_model_bins(self.model)
-        matrix = ReadPathMatrix(self.num_put_variants)
-        w_map, C, N = lane_from_bins(self.model.bins_list, matrix)
-        if matrix.R == 0:
-            raise Exception("Likelihood maximization failed.")   # nothing to fit
-        row_ptr, col, val = matrix.arrays()
-        w = np.zeros(matrix.R, dtype=np.int32)
-        for r, n in w_map.items():
-            w[r] = n
-        self._matrix = matrix
-        self._lane = (w, float(C), int(N))
-        self._engine = _cabi.Engine(row_ptr, col, val, np.asarray(self.model.variant_sizes, dtype=np.int64),
-                                    n_variants=self.num_put_variants, device=self.device)
-        return self._engine
+    # ------------------------------------------------------------------ context / lanes
+    def _ensure_lane(self):
+        if self._lane is None:
+            prune_model_bins(self.model)
+            if self._context is None:
+                self._context = LaneContext(self.num_put_variants, self.model.variant_sizes, device=self.device,
+                                            tol=self.tol, max_iter=self.max_iter, history=self.history)
+            self._lane = self._context.add_model(self.model)
+        return self._context
 
     def close(self):
-        if self._engine is not None:
-            self._engine.close()
-            self._engine = None
+        if self._context is not None and self._own_context:
+            self._context.close()
+
+    def lane_requests(self, subsets):
+        """Lane descriptions of ML fits restricted to subsets[b] (sets of representative ids)."""
+        self._ensure_lane()
+        col, C, _N = self._lane
+        return [LaneRequest(col, C, ids) for ids in subsets]
 
     def _fit_subsets(self, subsets):
-        """One GPU call: lane b = ML fit restricted to subsets[b] (sets of representative ids).
-        Returns a list of FitResult (x ordered by increasing variant id)."""
-        eng = self._ensure_engine()
-        w, C, N = self._lane
-        B = len(subsets)
-        mask = np.zeros((self.num_put_variants, B), dtype=np.uint8)
-        for b, ids in enumerate(subsets):
-            mask[sorted(ids), b] = 1
-        eng.set_lanes(np.repeat(w[:, None], B, axis=1), mask=mask, C=np.full(B, C))
-        out = eng.fit(tol=self.tol, max_iter=self.max_iter, history=self.history)
-        self.n_gpu_fits += B
-        results = []
-        for b, ids in enumerate(subsets):
-            order = sorted(ids)
-            status = int(out["status"][b])
-            ok = status in (_cabi.CONVERGED, _cabi.STALLED) and np.isfinite(out["loglike"][b])
-            results.append(FitResult(x=np.array(out["theta"][order, b], dtype=np.float64),
-                                     fun=-float(out["loglike"][b]), success=bool(ok), status=status,
-                                     kkt=tuple(out["kkt"][b]), nit=int(out["iters"][b])))
+        """One GPU call: lane b = ML fit restricted to subsets[b].  Returns a list of FitResult
+        (x ordered by increasing variant id)."""
+        ctx = self._ensure_lane()
+        if ctx.matrix.R == 0:
+            raise Exception("Likelihood maximization failed.")   # nothing to fit
+        results = ctx.fit(self.lane_requests(subsets))
+        self.n_gpu_fits += len(subsets)
         return results
 
     # ------------------------------------------------------------------ public API
@@ -195,6 +173,19 @@ class ModelFitMaxLike(object):
         Decision logic identical to the reference; every chunk of leave-one-out candidates
         (``random_size`` of them) is fitted as one batch of GPU lanes instead of sequentially /
         through Pool workers.  ``n_proc`` is ignored."""
+        steps = self.selection_steps(n_proc, criterion, chosen_ids, random_size, user_fixed_ids)
+        try:
+            subsets = next(steps)
+            while True:
+                subsets = steps.send(self._fit_subsets(subsets))
+        except StopIteration as stop:
+            return stop.value
+
+    def selection_steps(self, n_proc, criterion=Criterion.BIC, chosen_ids=None, random_size=20, user_fixed_ids=None):
+        """reverse_model_selection as a coroutine: yields the list of candidate subsets whose fits it
+        needs next, is sent the list of FitResult, and returns (prop, loglike, criterion) through
+        StopIteration.  `traversome_b200.bootstrap` advances the coroutines of all replicates in lock
+        step so that their candidate lanes share one GPU batch."""
         if random_size != 0 and n_proc > random_size and not self.__warning_sent:
             self.__warning_sent = True
         diff_tolerance = 1e-6
@@ -212,8 +203,9 @@ class ModelFitMaxLike(object):
         else:
             indispensable_ids = {}
 
+        first_sets = [set(chosen_ids)]
         previous_prop, previous_echo, previous_like, previous_criteria = \
-            self.__compute_like_and_criteria_batch([chosen_ids], criterion)[0]
+            self.__summarize_batch(first_sets, (yield first_sets), criterion)[0]
         self.__drop_zero_variants(chosen_ids, previous_prop, previous_echo, diff_tolerance, indispensable_ids)
 
         while len(chosen_ids) > 1:
@@ -245,7 +237,8 @@ class ModelFitMaxLike(object):
                                      .format(label, self.__str_rep_id(var_id)))
                 # -- one batch of lanes for the whole chunk
                 if to_fit:
-                    batch = self.__compute_like_and_criteria_batch([ids for _, ids in to_fit], criterion)
+                    id_sets = [ids for _, ids in to_fit]
+                    batch = self.__summarize_batch(id_sets, (yield id_sets), criterion)
                     for (var_id, _), res_list in zip(to_fit, batch):
                         test_id_res[var_id] = {"prop": res_list[0], "echo": res_list[1], "loglike": res_list[2],
                                                criterion: res_list[3]}
@@ -298,7 +291,7 @@ class ModelFitMaxLike(object):
                 else:
                     logger.info("Drop {}".format(self.__str_rep_id(var_id)))
 
-    def __compute_like_and_criteria_batch(self, id_sets, criteria):
+    def __summarize_batch(self, id_sets, results, criteria):
         """Batched __compute_like_and_criteria (ModelFitMaxLike.py:448-459): one lane per id set."""
         logger.debug("Generating the likelihood function .. ")
         for ids in id_sets:
@@ -306,8 +299,7 @@ class ModelFitMaxLike(object):
                 logger.debug("Maximizing the likelihood function for {} variants".format(len(ids)))
             else:
                 logger.info("Maximizing the likelihood function for {} variants".format(len(ids)))
-        results = self._fit_subsets(id_sets)
-        _w, _C, sample_size = self._lane
+        _col, _C, sample_size = self._lane
         out = []
         for ids, res in zip(id_sets, results):
             info = LogLikeFuncInfo(loglike_func=None, variable_size=self.__variable_size(ids), sample_size=sample_size)
@@ -364,23 +356,18 @@ class ModelFitMaxLike(object):
         """LogLikeFuncInfo whose ``loglike_func`` evaluates -LL on the GPU (replaces the
         symengine.lambdify'd callable of ModelFitMaxLike.py:515-558).  scipy_style: one array
         argument, returns a length-1 array; otherwise positional floats."""
-        eng = self._ensure_engine()
-        w, C, N = self._lane
+        ctx = self._ensure_lane()
+        _col, _C, N = self._lane
         if within_variant_ids is None:
             within_variant_ids = set(range(self.num_put_variants))
         ids = sorted(within_variant_ids)
         variable_size = self.__variable_size(set(ids))
         owner = self
+        request = self.lane_requests([ids])[0]
 
         def neg_loglike(*args):
             x = np.asarray(args[0] if scipy_style else args, dtype=np.float64).reshape(-1)
-            theta = np.zeros((owner.num_put_variants, 1), dtype=np.float64)
-            theta[ids, 0] = x
-            mask = np.zeros((owner.num_put_variants, 1), dtype=np.uint8)
-            mask[ids, 0] = 1
-            eng.set_lanes(w[:, None], mask=mask, C=np.array([C]))
-            with np.errstate(invalid="ignore"):
-                return -eng.loglik(theta)
+            return ctx.loglik(request, x)
 
         neg_loglike.tvs_fit = lambda: owner._fit_subsets([set(ids)])[0]
         return LogLikeFuncInfo(loglike_func=neg_loglike, variable_size=variable_size, sample_size=N)

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libtvs.so")
 # every symbol include/tvs.h declares (tests check that the library exports all of them)
 SYMBOLS = (
     "tvs_version", "tvs_last_error", "tvs_device_count", "tvs_create", "tvs_destroy", "tvs_set_lanes",
-    "tvs_resample", "tvs_get_weights", "tvs_loglik", "tvs_fit", "tvs_last_fit_stats", "tvs_dims",
+    "tvs_set_lanes_indexed", "tvs_resample", "tvs_get_weights", "tvs_loglik", "tvs_fit", "tvs_last_fit_stats", "tvs_dims",
     "tvs_measure_fp64_peak",
 )
 
@@ -59,6 +59,7 @@ def load():
     lib.tvs_create.argtypes = [POINTER(c_void_p), c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.tvs_destroy.argtypes = [c_void_p]
     lib.tvs_set_lanes.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
+    lib.tvs_set_lanes_indexed.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.tvs_resample.argtypes = [c_void_p, c_int64, c_void_p, c_uint64, c_int, c_void_p, c_void_p]
     lib.tvs_get_weights.argtypes = [c_void_p, c_void_p]
     lib.tvs_loglik.argtypes = [c_void_p, c_void_p, c_void_p]
@@ -155,6 +156,17 @@ class Engine(object):
         self._keep = (w, mask, C)
         _check(self._lib.tvs_set_lanes(self._h, int(B), _ptr(w), _ptr(mask), _ptr(C)))
         self.B = int(B)
+
+    def set_lanes_indexed(self, w_cols, col_of_lane, mask=None, C=None):
+        """w_cols [R,n_cols] int32 distinct weight columns; lane b uses column col_of_lane[b]."""
+        w_cols = _as(w_cols, np.int32)
+        col_of_lane = _as(col_of_lane, np.int32)
+        B = int(col_of_lane.shape[0])
+        n_cols = int(w_cols.shape[1]) if w_cols.ndim == 2 else int(w_cols.size // self.R)
+        mask = _as(mask, np.uint8)
+        C = _as(C, np.float64)
+        _check(self._lib.tvs_set_lanes_indexed(self._h, B, n_cols, _ptr(w_cols), _ptr(col_of_lane), _ptr(mask), _ptr(C)))
+        self.B = B
 
     def resample(self, B, n_obs, seed, keep_lane0=False, mask=None, C=None):
         n_obs = _as(n_obs, np.int32)

@@ -1,0 +1,205 @@
+"""Bootstrap / jackknife replicates as batch lanes (replaces the serial loop of
+``Traversome.do_subsampling``, traversome.py:501-617, "TODO parallelize bootstrap if necessary").
+
+The reference runs, per replicate, resample -> bins -> PathMultinomialModel -> a complete backward
+model selection, one after the other.  Here every replicate's selection is a coroutine
+(``ModelFitMaxLike.selection_steps``); all coroutines advance in lock step and the candidate
+subsets they ask for in one step -- lanes (replicate, subset) -- are fitted by ONE call of the CUDA
+solver on a shared ``LaneContext`` (sharded over the GPUs of the box when the context has a
+``LaneSharder``).  The decision logic inside each replicate is the reference's, untouched, so the
+selected models and the support table are those of the serial loop.
+
+The replicate models themselves (resampling of records and the per-replicate bin statistics,
+traversome.py:1636-1699 and :1305-1384) are inputs here: SURVEY.md section 8(f) item 1.
+"""
+from collections import OrderedDict
+
+import numpy as np
+from loguru import logger
+
+from .ModelFitMaxLike import ModelFitMaxLike
+from .lanes import LaneContext
+from .utils import Criterion
+
+
+def run_selections(fitters, criterion=Criterion.BIC, n_proc=1, random_size=20, user_fixed_ids=None, chosen_ids=None):
+    """Backward model selection of every fitter (one per replicate), lock step.
+
+    fitters: ModelFitMaxLike objects built on ONE shared LaneContext.  Returns a list of
+    (prop, loglike, criterion) -- or the Exception a replicate raised (the reference would have
+    propagated it out of its serial loop at that replicate)."""
+    if not fitters:
+        return []
+    ctx = fitters[0]._ensure_lane()
+    for f in fitters:
+        if f._ensure_lane() is not ctx:
+            raise ValueError("run_selections: all fitters must share one LaneContext")
+    steps = [f.selection_steps(n_proc, criterion, chosen_ids, random_size, user_fixed_ids) for f in fitters]
+    results = [None] * len(fitters)
+    pending = {}                                  # replicate -> subsets it waits for
+    for i, st in enumerate(steps):
+        try:
+            pending[i] = next(st)
+        except StopIteration as stop:             # cannot happen before the first fit, kept for symmetry
+            results[i] = stop.value
+        except Exception as e:
+            results[i] = e
+    n_rounds = 0
+    while pending:
+        order = sorted(pending)
+        requests, owner = [], []
+        for i in order:
+            rq = fitters[i].lane_requests(pending[i])
+            requests += rq
+            owner += [i] * len(rq)
+        fitted = ctx.fit(requests)
+        n_rounds += 1
+        pos = 0
+        for i in order:
+            n = len(pending[i])
+            mine = fitted[pos:pos + n]
+            pos += n
+            fitters[i].n_gpu_fits += n
+            try:
+                pending[i] = steps[i].send(mine)
+            except StopIteration as stop:
+                results[i] = stop.value
+                del pending[i]
+            except Exception as e:
+                results[i] = e
+                del pending[i]
+    logger.debug("run_selections: {} replicates, {} lock-step rounds, {} lanes".format(
+        len(fitters), n_rounds, ctx.n_lanes_fitted))
+    return results
+
+
+def check_bs_threshold(count_unique, new_v_prop, n_reps, threshold):
+    """Traversome._check_bs_threshold (traversome.py:629-644): False when even if every remaining
+    replicate agreed with the current leader its support would stay below `threshold`."""
+    tuple_v_chosen = tuple(sorted(list(new_v_prop.keys())))
+    count_unique[tuple_v_chosen] = count_unique.get(tuple_v_chosen, 0) + 1
+    counts = count_unique.values()
+    current_max = max(counts)
+    remaining = n_reps - sum(counts)
+    return not (float(current_max + remaining) / n_reps < threshold)
+
+
+def sorting_cid(variant_proportions_reps):
+    """Traversome.__sorting_cid (traversome.py:619-627): a universal candidate-id order, first seen
+    by decreasing proportion inside each replicate."""
+    cid_sorter = {}
+    for v_prop in variant_proportions_reps:
+        sorted_res = sorted(list(v_prop.items()), key=lambda x: (-x[1], x[0]))
+        for cid_, _p in sorted_res:
+            if cid_ not in cid_sorter:
+                cid_sorter[cid_] = len(cid_sorter)
+    return cid_sorter
+
+
+class BootstrapSummary(object):
+    """What do_subsampling leaves on the Traversome object (traversome.py:557-617)."""
+
+    def __init__(self):
+        self.variant_proportions_reps = []
+        self.bs_eligible = True
+        self.cid_sorter = {}
+        self.vp_unique_results = {}
+        self.vp_unique_results_sorted = []
+        self.variant_proportions_best = None
+        self.n_replicates_run = 0
+
+
+def summarize_replicates(variant_proportions_reps, raw_variant_proportions, raw_loglike, raw_criterion, bs_eligible=True,
+                         refit=None):
+    """The tally of traversome.py:561-617.  `refit(chosen_ids: set) -> (prop, loglike, criterion)`
+    is the whole-dataset point estimate used to re-evaluate supported solutions (:592-598)."""
+    out = BootstrapSummary()
+    out.variant_proportions_reps = list(variant_proportions_reps)
+    out.bs_eligible = bs_eligible
+    if not out.variant_proportions_reps:
+        return out
+    num_reps = len(out.variant_proportions_reps)
+    out.cid_sorter = sorting_cid(out.variant_proportions_reps)
+    for go_r, v_prop in enumerate(out.variant_proportions_reps):
+        sorted_res = sorted(list(v_prop.items()), key=lambda x: out.cid_sorter[x[0]])
+        tuple_v_chosen, tuple_v_props = zip(*sorted_res)
+        if tuple_v_chosen not in out.vp_unique_results:
+            out.vp_unique_results[tuple_v_chosen] = {"rep_ids": [], "support": None, "values": []}
+        out.vp_unique_results[tuple_v_chosen]["rep_ids"].append(go_r)
+        out.vp_unique_results[tuple_v_chosen]["values"].append(tuple_v_props)
+    for res_info in out.vp_unique_results.values():
+        res_info["support"] = len(res_info["rep_ids"]) / float(num_reps)
+    raw_res = tuple(sorted(raw_variant_proportions.keys(), key=lambda x: (out.cid_sorter.get(x, 0), x)))
+    out.vp_unique_results_sorted = sorted(
+        out.vp_unique_results, key=lambda x: (-out.vp_unique_results[x]["support"], x != raw_res, x))
+    if bs_eligible and (len(out.vp_unique_results_sorted) > 1 or out.vp_unique_results_sorted[0] != raw_res):
+        logger.info("Re-evaluate the supported models using whole dataset ..")
+    for go_s, tuple_v_chosen in enumerate(out.vp_unique_results_sorted):
+        chosen_dict = out.vp_unique_results[tuple_v_chosen]
+        if tuple_v_chosen == raw_res:
+            raw_prop, raw_like, raw_crit = raw_variant_proportions, raw_loglike, raw_criterion
+        elif bs_eligible and (chosen_dict["support"] > 0.05 or go_s == 0) and refit is not None:
+            raw_prop, raw_like, raw_crit = refit(set(tuple_v_chosen))
+        else:
+            values = np.average(chosen_dict["values"], axis=0)
+            raw_prop = {c_id: values[go_c] for go_c, c_id in enumerate(tuple_v_chosen)}
+            raw_like, raw_crit = "*", "*"
+        chosen_dict["raw_prop"] = raw_prop
+        chosen_dict["raw_like"] = raw_like
+        chosen_dict["raw_criterion"] = raw_crit
+        if go_s == 0 and tuple_v_chosen != raw_res and chosen_dict["support"] > 0.05:
+            out.variant_proportions_best = raw_prop
+    return out
+
+
+def do_subsampling(replicate_models, fit_kwargs, full_fit, raw_result, criterion=Criterion.BIC, n_replicate=None,
+                   threshold=0.95, n_proc=1, user_fixed_ids=None, context=None, batch=None):
+    """Batched ``Traversome.do_subsampling``.
+
+    replicate_models  iterable of (model, sbp_to_sbp_id) per replicate, in the reference's order
+                      (what traversome.py:520-539 builds for replicate go_bs).
+    fit_kwargs        the constructor arguments shared by all replicates: variant_paths,
+                      variant_subpath_counters, repr_to_merged_variants, be_unidentifiable_to, loglevel.
+    full_fit          the ModelFitMaxLike of the whole dataset (self.max_like_fit), used by the
+                      re-evaluation of supported solutions exactly like traversome.py:592-598.
+    raw_result        (variant_proportions, res_loglike, res_criterion) of the whole-dataset selection.
+    batch             replicates advanced together (default: all).  The reference's early stop
+                      (--bs-threshold) is applied after each batch at the index where the serial loop
+                      would have stopped, so the surviving replicates are the same.
+    """
+    replicate_models = list(replicate_models)
+    n_replicate = len(replicate_models) if n_replicate is None else int(n_replicate)
+    n_digit = len(str(n_replicate))
+    ctx = context if context is not None else full_fit._ensure_lane()
+    count_unique = {}
+    reps = []
+    bs_eligible = True
+    batch = n_replicate if not batch else int(batch)
+    go_bs = 0
+    while go_bs < n_replicate and bs_eligible:
+        chunk = replicate_models[go_bs: go_bs + batch]
+        fitters = [ModelFitMaxLike(model=model, sbp_to_sbp_id=sbp_to_sbp_id, bootstrap_mode=f"BS{go_bs + k + 1: 0{n_digit}d}",
+                                   context=ctx, **fit_kwargs)
+                   for k, (model, sbp_to_sbp_id) in enumerate(chunk)]
+        for f in fitters:
+            f._shuffle = full_fit._shuffle
+        results = run_selections(fitters, criterion=criterion, n_proc=n_proc, user_fixed_ids=user_fixed_ids)
+        for res in results:
+            if isinstance(res, Exception):
+                raise res                          # the serial loop would have raised at this replicate
+            v_prop = res[0]
+            reps.append(v_prop)
+            if not check_bs_threshold(count_unique, v_prop, n_replicate, threshold):
+                if go_bs < n_replicate - 1:
+                    logger.info("Sampling terminates due to divergence in bootstraps (see '--bs-threshold'). "
+                                "No convincing support can be found given the dataset and parameters. ")
+                bs_eligible = False
+                break
+            go_bs += 1
+    logger.info("Summarizing the replicates ..")
+    raw_prop, raw_like, raw_crit = raw_result
+    summary = summarize_replicates(
+        reps, raw_prop, raw_like, raw_crit, bs_eligible=bs_eligible,
+        refit=lambda ids: full_fit.point_estimate(chosen_ids=ids, criterion=criterion))
+    summary.n_replicates_run = len(reps)
+    return summary

@@ -344,6 +344,30 @@ int tvs_set_lanes(tvs_handle h, int64_t B, const int32_t* w, const uint8_t* mask
     return finish_lanes(h, mask, C);
 }
 
+int tvs_set_lanes_indexed(tvs_handle h, int64_t B, int64_t n_cols, const int32_t* w_cols, const int32_t* col_of_lane,
+                          const uint8_t* mask, const double* C) {
+    if (!h || B <= 0 || n_cols <= 0 || !w_cols || !col_of_lane) { set_error("tvs_set_lanes_indexed: null argument or B/n_cols<=0"); return TVS_EINVAL; }
+    TVS_CUDA(cudaSetDevice(h->device));
+    h->lanes_set = false;
+    const int64_t R = h->csr.R;
+    std::vector<int32_t> idx((size_t)B);
+    TVS_CUDA(cudaMemcpy(idx.data(), col_of_lane, (size_t)B * sizeof(int32_t), cudaMemcpyDefault));
+    for (int64_t b = 0; b < B; ++b)
+        if (idx[b] < 0 || idx[b] >= n_cols) { set_error("tvs_set_lanes_indexed: col_of_lane[%lld]=%d out of range", (long long)b, idx[b]); return TVS_EINVAL; }
+    int rc = reserve_lanes(h, B, mask != nullptr, C != nullptr);
+    if (rc != TVS_OK) return rc;
+    int32_t *d_cols = nullptr, *d_idx = nullptr;
+    if ((rc = dev_alloc(&d_cols, (size_t)(R * n_cols))) != TVS_OK) return rc;
+    if ((rc = dev_alloc(&d_idx, (size_t)B)) != TVS_OK) { cudaFree(d_cols); return rc; }
+    cudaMemcpyAsync(d_cols, w_cols, (size_t)(R * n_cols) * sizeof(int32_t), cudaMemcpyDefault, h->stream);
+    cudaMemcpyAsync(d_idx, idx.data(), (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream);
+    gather_rows(h->stream, (const int32_t*)d_cols, h->lanes.w, R, n_cols, B, d_idx);
+    cudaError_t e = cudaGetLastError();
+    rc = (e == cudaSuccess) ? finish_lanes(h, mask, C) : cuda_fail(e, "expand weight columns", __FILE__, __LINE__);
+    cudaFree(d_cols); cudaFree(d_idx);
+    return rc;
+}
+
 int tvs_resample(tvs_handle h, int64_t B, const int32_t* n_obs, uint64_t seed, int keep_lane0, const uint8_t* mask,
                  const double* C) {
     if (!h || B <= 0 || !n_obs) { set_error("tvs_resample: null handle/n_obs or B<=0"); return TVS_EINVAL; }
