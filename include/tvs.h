@@ -134,6 +134,10 @@ int tvs_dims(tvs_handle h, int64_t* R, int64_t* V, int64_t* nnz, int64_t* B);
  * Returns TFLOP/s of dependent-chain-free DFMA on `device`. */
 int tvs_measure_fp64_peak(int device, double* tflops_out);
 
+/* self-test of the device reciprocal / logarithm used inside the likelihood pass (they replace the
+ * IEEE division and libdevice log there): log_out[i] = log(p[i]), rcp_out[i] = 1/p[i], host arrays. */
+int tvs_selftest_math(int device, int64_t n, const double* p, double* log_out, double* rcp_out);
+
 #ifdef __cplusplus
 }
 #endif

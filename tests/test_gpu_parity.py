@@ -193,6 +193,27 @@ def test_edge_cases(gpu):
             eng.fit()                                    # lanes not set -> TVS_ESTATE
 
 
+def test_device_log_and_reciprocal_are_within_2_ulp(gpu):
+    """The pass kernel replaces IEEE division and libdevice log by MUFU-seeded Newton / an atanh series."""
+    rng = np.random.default_rng(0)
+    p = np.concatenate([10.0 ** rng.uniform(-300, 300, 200000), 10.0 ** rng.uniform(-12, 0, 400000),
+                        1.0 + rng.uniform(-1e-3, 1e-3, 100000), 2.0 ** rng.integers(-1000, 1000, 1000).astype(np.float64),
+                        np.nextafter(2.0 ** rng.integers(-50, 50, 1000).astype(np.float64), 0.0),
+                        np.array([np.sqrt(2.0), np.sqrt(0.5), 1.0, 0.5, 2.0, 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308])])
+    lg, rc = _cabi.selftest_math(p)
+    ref_l = np.log(p)
+    ref_r = 1.0 / p
+    ulp_l = np.abs(lg - ref_l) / np.maximum(np.spacing(np.abs(ref_l)), 5e-324)
+    # near p = 1 the result is tiny: the contract is ABSOLUTE accuracy (terms of a sum of magnitude >= 1e3)
+    bad_l = (ulp_l > 2) & (np.abs(lg - ref_l) > 2.3e-16)
+    assert not bad_l.any(), (p[bad_l][:5], lg[bad_l][:5], ref_l[bad_l][:5])
+    ulp_r = np.abs(rc - ref_r) / np.spacing(np.abs(ref_r))
+    fin = np.isfinite(ref_r) & (np.abs(ref_r) > 1e-300)
+    assert ulp_r[fin].max() <= 2
+    z = _cabi.selftest_math(np.array([0.0, -1.0, np.inf]))
+    assert z[0][0] == -np.inf and np.isnan(z[0][1]) and z[0][2] == np.inf and z[1][0] == np.inf
+
+
 # --------------------------------------------------------------------------------------- resampling
 def test_device_resample_is_bit_exact_vs_numpy_philox(gpu):
     wl = synthetic.make_workload(8, 300, 0.3, seed=21)

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libtvs.so")
 SYMBOLS = (
     "tvs_version", "tvs_last_error", "tvs_device_count", "tvs_create", "tvs_destroy", "tvs_set_lanes",
     "tvs_set_lanes_indexed", "tvs_resample", "tvs_get_weights", "tvs_loglik", "tvs_fit", "tvs_last_fit_stats", "tvs_dims",
-    "tvs_measure_fp64_peak",
+    "tvs_measure_fp64_peak", "tvs_selftest_math",
 )
 
 TVS_OK, TVS_EINVAL, TVS_ECUDA, TVS_ENOMEM, TVS_ELIMIT, TVS_ESTATE = 0, -1, -2, -3, -4, -5
@@ -67,6 +67,7 @@ def load():
     lib.tvs_last_fit_stats.argtypes = [c_void_p, POINTER(FitStats)]
     lib.tvs_dims.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]
     lib.tvs_measure_fp64_peak.argtypes = [c_int, POINTER(c_double)]
+    lib.tvs_selftest_math.argtypes = [c_int, c_int64, c_void_p, c_void_p, c_void_p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("tvs_last_error",):
@@ -215,3 +216,12 @@ def measure_fp64_peak(device=0):
     v = c_double(0.0)
     _check(load().tvs_measure_fp64_peak(int(device), ctypes.byref(v)))
     return v.value
+
+
+def selftest_math(p, device=0):
+    """(log(p), 1/p) computed by the device routines of the likelihood pass."""
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    lg = np.empty_like(p)
+    rc = np.empty_like(p)
+    _check(load().tvs_selftest_math(int(device), p.size, _ptr(p), _ptr(lg), _ptr(rc)))
+    return lg, rc

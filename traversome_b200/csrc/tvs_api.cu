@@ -1,6 +1,7 @@
 // libtvs.so -- C ABI (include/tvs.h) over the sm_100a kernels in tvs_kernels.cuh.
 // Host side: CSR validation and chunking, launch geometry, the batched L-BFGS driver loop.
 #include "tvs_kernels.cuh"
+#include "tvs_pass2.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -45,6 +46,7 @@ static void dev_free(T*& p) {
 static void free_csr(Csr& c) {
     dev_free(c.row_ptr); dev_free(c.ent); dev_free(c.chunk_row0); dev_free(c.ccol_ptr); dev_free(c.ccol_id);
     dev_free(c.ccol_start); dev_free(c.cent); dev_free(c.invL); dev_free(c.Ld);
+    dev_free(c.col32); dev_free(c.fval); dev_free(c.crow32); dev_free(c.cfval);
 }
 static void free_lanes(Lanes& l) {
     dev_free(l.w); dev_free(l.mask); dev_free(l.C); dev_free(l.N);
@@ -59,7 +61,89 @@ static void free_fit(FitState& f) {
 // ---------------------------------------------------------------------------------- launch geometry
 struct PassPlan {
     int lpt = 1; bool xs = false; int tiles = 0; int splits = 1; size_t smem = 0;
+    bool v2 = false;      // pass2_kernel<lpt, BW> (lpt = lanes per thread)
+    int v3_warps = 0;     // > 0: pass3_kernel<lpt, v3_warps, BW> (entries staged in shared memory)
 };
+
+static int splits_for(const tvs_problem* h, int slots, int tiles) {
+    const Csr& c = h->csr;
+    int s = slots / std::max(tiles, 1);
+    s = std::max(1, std::min(s, c.n_chunks));
+    s = std::min(s, env_int("TVS_MAX_SPLITS", 1024));
+    const int forced = env_int("TVS_SPLITS", 0);
+    if (forced > 0) s = std::min(forced, c.n_chunks);
+    return s;
+}
+
+// pass2_kernel: K lanes per thread, x/t tiles in shared memory.  Fails with TVS_ELIMIT when the tiles do not fit.
+template <int K, bool BW>
+static int plan_v2(const tvs_problem* h, int64_t B, PassPlan* out) {
+    const int LT = 32 * K;
+    const Csr& c = h->csr;
+    if (B % K != 0) return TVS_ELIMIT;
+    const size_t dbl = (size_t)c.V * LT * (BW ? 2 : 1) + (size_t)std::max(c.rows_per_chunk, kWarps2) * LT;
+    const size_t smem = dbl * sizeof(double);
+    if (smem > 220 * 1024) return TVS_ELIMIT;
+    auto kern = pass2_kernel<K, BW>;
+    TVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    TVS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads2, smem));
+    if (occ < 1) return TVS_ELIMIT;
+    out->v2 = true; out->lpt = K; out->xs = true; out->smem = smem;
+    out->tiles = (int)((B + LT - 1) / LT);
+    out->splits = splits_for(h, occ * h->sm_count, out->tiles);
+    return TVS_OK;
+}
+
+// pass3_kernel: pass2 + cp.async staging of each chunk's entries (needs max_chunk_nnz * 36 bytes more).
+template <int K, int NW, bool BW>
+static int plan_v3(const tvs_problem* h, int64_t B, PassPlan* out) {
+    const int LT = 32 * K;
+    const Csr& c = h->csr;
+    if (B % K != 0 || c.rows_per_chunk < NW) return TVS_ELIMIT;
+    const Pass3Smem L = pass3_layout((int)c.V, LT, c.rows_per_chunk, std::max(c.max_chunk_nnz, 1), BW, NW);
+    if (L.total > 225 * 1024) return TVS_ELIMIT;
+    auto kern = pass3_kernel<K, NW, BW>;
+    TVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    int occ = 0;
+    TVS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, L.total));
+    if (occ < 1) return TVS_ELIMIT;
+    out->v2 = true; out->v3_warps = NW; out->lpt = K; out->xs = true; out->smem = L.total;
+    out->tiles = (int)((B + LT - 1) / LT);
+    out->splits = splits_for(h, occ * h->sm_count, out->tiles);
+    return TVS_OK;
+}
+
+template <bool BW>
+static int make_plan_v2(const tvs_problem* h, int64_t B, PassPlan* out) {
+    // cheapest K by (padded lanes) x (relative cost per lane of the K-lane inner loops)
+    const double rel[3] = {1.0, 0.70, 0.55};
+    const int forced = env_int("TVS_K", 0);
+    double best = 1e300;
+    PassPlan bp;
+    int rc_any = TVS_ELIMIT;
+    for (int ki = 0; ki < 3; ++ki) {
+        const int K = 1 << ki;
+        if (forced && forced != K) continue;
+        PassPlan p;
+        int rc = TVS_ELIMIT;
+        if (env_int("TVS_NO_STAGE", 0) == 0) {
+            if (env_int("TVS_NW", 16) == 32)
+                rc = (K == 1) ? plan_v3<1, 32, BW>(h, B, &p) : (K == 2) ? plan_v3<2, 32, BW>(h, B, &p) : plan_v3<4, 32, BW>(h, B, &p);
+            else
+                rc = (K == 1) ? plan_v3<1, 16, BW>(h, B, &p) : (K == 2) ? plan_v3<2, 16, BW>(h, B, &p) : plan_v3<4, 16, BW>(h, B, &p);
+            if (rc == TVS_ECUDA) return rc;
+        }
+        if (rc != TVS_OK) rc = (K == 1) ? plan_v2<1, BW>(h, B, &p) : (K == 2) ? plan_v2<2, BW>(h, B, &p) : plan_v2<4, BW>(h, B, &p);
+        if (rc == TVS_ECUDA) return rc;
+        if (rc != TVS_OK) continue;
+        rc_any = TVS_OK;
+        const double cost = (double)p.tiles * 32 * K * rel[ki];
+        if (cost < best) { best = cost; bp = p; }
+    }
+    if (rc_any == TVS_OK) *out = bp;
+    return rc_any;
+}
 
 template <int LPT, bool XS, bool BW>
 static int plan_one(const tvs_problem* h, int64_t B, PassPlan* out) {
@@ -78,17 +162,16 @@ static int plan_one(const tvs_problem* h, int64_t B, PassPlan* out) {
     const int slots = occ * h->sm_count;
     out->lpt = LPT; out->xs = XS; out->smem = smem;
     out->tiles = (int)((B + LT - 1) / LT);
-    int s = slots / std::max(out->tiles, 1);
-    s = std::max(1, std::min(s, c.n_chunks));
-    s = std::min(s, env_int("TVS_MAX_SPLITS", 1024));
-    const int forced = env_int("TVS_SPLITS", 0);
-    if (forced > 0) s = std::min(forced, c.n_chunks);
-    out->splits = s;
+    out->splits = splits_for(h, slots, out->tiles);
     return TVS_OK;
 }
 
 template <bool BW>
 static int make_plan(const tvs_problem* h, int64_t B, PassPlan* out) {
+    if (env_int("TVS_PASS_V1", 0) == 0) {
+        const int rc2 = make_plan_v2<BW>(h, B, out);
+        if (rc2 == TVS_OK || rc2 == TVS_ECUDA) return rc2;       // otherwise: tiles too large for shared memory
+    }
     int lpt = (B > 32) ? 2 : 1;
     const int forced = env_int("TVS_LPT", 0);
     if (forced == 1 || forced == 2) lpt = forced;
@@ -107,6 +190,28 @@ static int make_plan(const tvs_problem* h, int64_t B, PassPlan* out) {
 template <bool BW>
 static int launch_pass(tvs_problem* h, const PassPlan& pl, const PassArgs& a) {
     dim3 grid(pl.tiles, pl.splits), block(kThreads);
+    if (pl.v3_warps == 16) {
+        if (pl.lpt == 4) pass3_kernel<4, 16, BW><<<grid, 512, pl.smem, h->stream>>>(a);
+        else if (pl.lpt == 2) pass3_kernel<2, 16, BW><<<grid, 512, pl.smem, h->stream>>>(a);
+        else pass3_kernel<1, 16, BW><<<grid, 512, pl.smem, h->stream>>>(a);
+        TVS_CUDA(cudaGetLastError());
+        return TVS_OK;
+    }
+    if (pl.v3_warps == 32) {
+        if (pl.lpt == 4) pass3_kernel<4, 32, BW><<<grid, 1024, pl.smem, h->stream>>>(a);
+        else if (pl.lpt == 2) pass3_kernel<2, 32, BW><<<grid, 1024, pl.smem, h->stream>>>(a);
+        else pass3_kernel<1, 32, BW><<<grid, 1024, pl.smem, h->stream>>>(a);
+        TVS_CUDA(cudaGetLastError());
+        return TVS_OK;
+    }
+    if (pl.v2) {
+        dim3 block2(kThreads2);
+        if (pl.lpt == 4) pass2_kernel<4, BW><<<grid, block2, pl.smem, h->stream>>>(a);
+        else if (pl.lpt == 2) pass2_kernel<2, BW><<<grid, block2, pl.smem, h->stream>>>(a);
+        else pass2_kernel<1, BW><<<grid, block2, pl.smem, h->stream>>>(a);
+        TVS_CUDA(cudaGetLastError());
+        return TVS_OK;
+    }
     if (pl.lpt == 2 && pl.xs) pass_kernel<2, true, BW><<<grid, block, pl.smem, h->stream>>>(a);
     else if (pl.lpt == 1 && pl.xs) pass_kernel<1, true, BW><<<grid, block, pl.smem, h->stream>>>(a);
     else if (pl.lpt == 2) pass_kernel<2, false, BW><<<grid, block, pl.smem, h->stream>>>(a);
@@ -121,6 +226,7 @@ static PassArgs base_args(const tvs_problem* h) {
     a.row_ptr = c.row_ptr; a.ent = c.ent; a.chunk_row0 = c.chunk_row0; a.ccol_ptr = c.ccol_ptr; a.ccol_id = c.ccol_id;
     a.ccol_start = c.ccol_start; a.cent = c.cent; a.w = h->lanes.w; a.B = h->lanes.B; a.V = (int)c.V;
     a.n_chunks = c.n_chunks; a.rows_per_chunk = c.rows_per_chunk;
+    a.col32 = c.col32; a.fval = c.fval; a.crow32 = c.crow32; a.cfval = c.cfval; a.stage_cap = std::max(c.max_chunk_nnz, 1);
     return a;
 }
 
@@ -148,7 +254,7 @@ static int ensure_fit_state(tvs_problem* h, int m) {
         A_(s.gram, (size_t)B * ((2 * m + 1) * (2 * m + 2) / 2))
         A_(s.ls, B) A_(s.iters, B) A_(s.head, B) A_(s.cnt, B) A_(s.done, B) A_(s.status, B)
     }
-    f.half = B / 2 + 1;
+    f.half = B / 2 + 4;            // +3: compacted widths are padded to a multiple of 4 (vector loads of w)
     for (int i = 0; i < 2; ++i) {
         A_(f.wbuf[i], (size_t)R * f.half) A_(f.mbuf[i], (size_t)V * f.half) A_(f.nbuf[i], f.half) A_(f.cbuf[i], f.half)
     }
@@ -157,7 +263,7 @@ static int ensure_fit_state(tvs_problem* h, int m) {
     f.tpart_cap = (size_t)V * ((size_t)h->sm_count * 16 * 64 + (size_t)B);
     f.llpart_cap = f.tpart_cap / (size_t)V;
     A_(f.tpart, f.tpart_cap) A_(f.llpart, f.llpart_cap) A_(f.t_red, vb) A_(f.ll_red, B)
-    A_(f.idx, B) A_(f.nactive, 32)
+    A_(f.idx, B + 4) A_(f.nactive, 32)
     A_(f.theta_io, vb) A_(f.ll_out, B) A_(f.kkt_out, 2 * (size_t)B) A_(f.iters_out, B) A_(f.status_out, B)
 #undef A_
     if (cudaMallocHost((void**)&f.h_nactive, 32 * sizeof(int32_t)) != cudaSuccess) { free_fit(f); set_error("cudaMallocHost failed"); return TVS_ENOMEM; }
@@ -235,8 +341,8 @@ int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, c
 
     Csr& c = h->csr;
     c.R = R; c.V = V; c.nnz = nnz;
-    int rpc = env_int("TVS_RC", 128);
-    rpc = std::max(kWarps, std::min(rpc, 4096));
+    int rpc = env_int("TVS_RC", 64);
+    rpc = std::max(kWarps2, std::min(rpc, 4096));
     c.rows_per_chunk = rpc;
     c.n_chunks = (int)((R + rpc - 1) / rpc);
 
@@ -260,6 +366,17 @@ int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, c
     }
     chunk_row0[c.n_chunks] = (int32_t)R;
     ccol_ptr[c.n_chunks] = (int32_t)ccol_id.size();
+    std::vector<int32_t> col32v((size_t)std::max<int64_t>(nnz, 1)), crow32v((size_t)std::max<int64_t>(nnz, 1));
+    std::vector<double> fvalv((size_t)std::max<int64_t>(nnz, 1)), cfvalv((size_t)std::max<int64_t>(nnz, 1));
+    for (int64_t k = 0; k < nnz; ++k) {
+        col32v[k] = col[k]; fvalv[k] = (double)val[k];
+        crow32v[k] = (int32_t)(cent[k] & 0xffffu); cfvalv[k] = (double)(cent[k] >> 16);
+    }
+    c.max_chunk_nnz = 0;
+    for (int ch = 0; ch < c.n_chunks; ++ch) {
+        const int64_t r0 = (int64_t)ch * rpc, r1 = std::min<int64_t>(R, r0 + rpc);
+        c.max_chunk_nnz = std::max(c.max_chunk_nnz, (int)(row_ptr[r1] - row_ptr[r0]));
+    }
     ccol_start.push_back((int32_t)cursor);
     c.n_ccol = (int64_t)ccol_id.size();
     std::vector<double> invL((size_t)V), Ld((size_t)V);
@@ -272,6 +389,7 @@ int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, c
     if ((rc = dev_alloc(&c.row_ptr, (size_t)R + 1)) != TVS_OK) return fail(rc);
     if (cudaMemcpy(c.row_ptr, row_ptr, ((size_t)R + 1) * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess)
         return fail(cuda_fail(cudaGetLastError(), "upload row_ptr", __FILE__, __LINE__));
+    UP_(col32, col32v, int32_t) UP_(fval, fvalv, double) UP_(crow32, crow32v, int32_t) UP_(cfval, cfvalv, double)
     UP_(ent, ent, uint32_t) UP_(cent, cent, uint32_t) UP_(chunk_row0, chunk_row0, int32_t) UP_(ccol_ptr, ccol_ptr, int32_t)
     if (ccol_id.empty()) ccol_id.push_back(0);
     UP_(ccol_id, ccol_id, int32_t) UP_(ccol_start, ccol_start, int32_t) UP_(invL, invL, double) UP_(Ld, Ld, double)
@@ -466,6 +584,9 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
 
     TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(VlLayout<4>::doubles * 8)));
     TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(VlLayout<8>::doubles * 8)));
+    TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Vl2Layout<4>::doubles * 8)));
+    TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Vl2Layout<8>::doubles * 8)));
+    const bool upd_v2 = env_int("TVS_UPD_V2", 0) != 0;        // the 32-lane x 8-warp vector-free kernel
     TVS_CUDA(cudaEventRecord(h->ev0, st));
     int cur = 0;
     {   // ---- reset set 0 (full width, views the caller's lanes)
@@ -487,6 +608,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
     }
 
     std::vector<cudaEvent_t> pev, uev; // per-pass / per-update events when timing is requested
+    std::vector<int64_t> pass_width;   // width of every pass (TVS_DUMP_PASSES)
     int64_t passes = 0, launches = 3, lane_passes = 0, n_polls = 0, compactions = 0;
     const int64_t max_passes = (int64_t)opt.max_iter * 2 + 64;
     cudaError_t cerr = cudaSuccess;
@@ -523,7 +645,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         ua.rho = s.rho; ua.gamma = s.gamma; ua.F = s.F; ua.dg = s.dg; ua.alpha = s.alpha; ua.llsum = s.llsum; ua.kkt = s.kkt;
         ua.sumphi = s.sumphi; ua.ls = s.ls; ua.iters = s.iters; ua.status = s.status; ua.head = s.head; ua.cnt = s.cnt;
         ua.done = s.done; ua.V = (int)V; ua.B = W; ua.m = m; ua.max_iter = opt.max_iter; ua.tol = opt.tol;
-        ua.tol_dual = 100.0 * opt.tol;
+        ua.tol_dual = (double)env_int("TVS_DUAL_MULT", 100) * opt.tol;
         const unsigned ub = (unsigned)((W + 31) / 32);
 
         // ---- a batch of passes, then one synchronous poll of the device-side "still iterating" counter
@@ -539,11 +661,15 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
             const bool last = (k == opt.check_every - 1) || (passes + 1 == max_passes);
             ua.nactive = last ? f.nactive + slot : f.nactive + 31;   // word 31 = scratch between polls
             if (last) { cudaMemsetAsync(f.nactive + slot, 0, 4, st); ++launches; }
+            const unsigned ub2 = (unsigned)((W + kU2Lanes - 1) / kU2Lanes);
             if (upd_v1) lbfgs_update_kernel<<<ub, kUpdWarps * 32, 0, st>>>(ua);
+            else if (!upd_v2 && m == 4) lbfgs_update_vl2_kernel<4><<<ub2, kU2Threads, Vl2Layout<4>::doubles * 8, st>>>(ua, s.gram);
+            else if (!upd_v2) lbfgs_update_vl2_kernel<8><<<ub2, kU2Threads, Vl2Layout<8>::doubles * 8, st>>>(ua, s.gram);
             else if (m == 4) lbfgs_update_vl_kernel<4><<<ub, kUpdWarps * 32, VlLayout<4>::doubles * 8, st>>>(ua, s.gram);
             else lbfgs_update_vl_kernel<8><<<ub, kUpdWarps * 32, VlLayout<8>::doubles * 8, st>>>(ua, s.gram);
             if (time_passes) { cudaEvent_t e2; cudaEventCreate(&e2); uev.push_back(pev.back()); uev.push_back(e2); cudaEventRecord(e2, st); }
             ++passes; launches += 3; lane_passes += W;
+            if (time_passes) pass_width.push_back(W);
         }
         if (rc != TVS_OK) break;
         cudaMemcpyAsync(f.h_nactive + slot, f.nactive + slot, 4, cudaMemcpyDeviceToHost, st);
@@ -553,12 +679,13 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         const int64_t active = f.h_nactive[slot];
         if (active == 0) { all_done = true; break; }
         // ---- compaction: keep only the lanes that are still iterating
-        if (!no_compact && active * 2 <= W && W > 32 && active <= f.half) {
+        if (!no_compact && active * 2 <= W && W > 32 && active + 3 <= f.half) {
             finalize(s, 1);                                      // results of the finished lanes, at their original ids
             LaneSet& n = f.set[cur ^ 1];
             build_index_kernel<<<1, 1024, 0, st>>>(s.done, W, f.idx, f.nactive + 30);
             const int bi = (int)(compactions & 1);
-            const int64_t A = active;
+            // new width: survivors + up to 3 padding lanes (index -1 -> zeros, flagged done, no original id)
+            const int64_t A = (active + 3) & ~(int64_t)3;
             gather_rows(st, s.w, f.wbuf[bi], R, W, A, f.idx);
             gather_rows(st, s.mask, f.mbuf[bi], V, W, A, f.idx);
             gather_rows(st, s.N, f.nbuf[bi], 1, W, A, f.idx);
@@ -586,6 +713,10 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
             gather_rows(st, (const int32_t*)s.head, n.head, 1, W, A, f.idx);
             gather_rows(st, (const int32_t*)s.cnt, n.cnt, 1, W, A, f.idx);
             cudaMemsetAsync(n.done, 0, A * 4, st); cudaMemsetAsync(n.status, 0, A * 4, st);
+            if (A > active) {
+                cudaMemsetAsync(n.done + active, 1, (A - active) * 4, st);
+                cudaMemsetAsync(n.orig + active, 0xFF, (A - active) * 4, st);
+            }
             n.width = A;
             launches += 28;
             ++compactions;
@@ -617,6 +748,14 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         for (size_t i = 0; i + 1 < uev.size(); i += 2) { float q = 0.f; if (cudaEventElapsedTime(&q, uev[i], uev[i + 1]) == cudaSuccess) um += q; }
         h->stats.update_ms = um;
         h->stats.compactions = compactions;
+        if (time_passes && env_int("TVS_DUMP_PASSES", 0)) {
+            for (size_t i = 0; i + 1 < pev.size(); i += 2) {
+                float q = 0.f, u = 0.f;
+                cudaEventElapsedTime(&q, pev[i], pev[i + 1]);
+                cudaEventElapsedTime(&u, uev[i], uev[i + 1]);
+                fprintf(stderr, "pass %zu width %lld pass_us %.1f update_us %.1f\n", i / 2, (long long)pass_width[i / 2], q * 1e3, u * 1e3);
+            }
+        }
     }
     for (size_t i = 1; i < uev.size(); i += 2) cudaEventDestroy(uev[i]);
     for (auto e : pev) cudaEventDestroy(e);
@@ -628,6 +767,23 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
 int tvs_last_fit_stats(tvs_handle h, tvs_fit_stats* out) {
     if (!h || !out) { set_error("tvs_last_fit_stats: null argument"); return TVS_EINVAL; }
     *out = h->stats;
+    return TVS_OK;
+}
+
+int tvs_selftest_math(int device, int64_t n, const double* p, double* log_out, double* rcp_out) {
+    if (n <= 0 || !p || !log_out || !rcp_out) { set_error("tvs_selftest_math: bad argument"); return TVS_EINVAL; }
+    TVS_CUDA(cudaSetDevice(device));
+    double *d_p = nullptr, *d_l = nullptr, *d_r = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&d_p, (size_t)n)) != TVS_OK || (rc = dev_alloc(&d_l, (size_t)n)) != TVS_OK || (rc = dev_alloc(&d_r, (size_t)n)) != TVS_OK) {
+        cudaFree(d_p); cudaFree(d_l); cudaFree(d_r); return rc;
+    }
+    cudaMemcpy(d_p, p, (size_t)n * 8, cudaMemcpyDefault);
+    selftest_math_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_p, n, d_l, d_r);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) { cudaMemcpy(log_out, d_l, (size_t)n * 8, cudaMemcpyDefault); cudaMemcpy(rcp_out, d_r, (size_t)n * 8, cudaMemcpyDefault); }
+    cudaFree(d_p); cudaFree(d_l); cudaFree(d_r);
+    if (e != cudaSuccess) return cuda_fail(e, "selftest_math_kernel", __FILE__, __LINE__);
     return TVS_OK;
 }
 

@@ -28,6 +28,8 @@ struct PassArgs {
     const int32_t* w; const double* x; const int32_t* done;
     double* tpart; double* llpart;
     int64_t B; int V; int n_chunks; int rows_per_chunk;
+    // decoded entries (pass3_kernel): column / chunk-local row as int32, count as double
+    const int32_t* col32; const double* fval; const int32_t* crow32; const double* cfval; int stage_cap;
 };
 
 template <int LPT, bool XS, bool BACKWARD>
@@ -767,6 +769,296 @@ __global__ void __launch_bounds__(kUpdWarps * 32) lbfgs_update_vl_kernel(const U
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Same update, latency-oriented geometry (profiles/r1_v2_summary.md: the 32-lane x 8-warp kernel above
+// takes ~65 us at ANY width because each warp walks V/8 variants one dependent global round trip at a
+// time and only B/32 CTAs exist).  Here a CTA owns 8 lanes and 32 "variant slots": thread = (lane l,
+// slot vs), a warp = 4 slots x 8 lanes (each slot row is a 64-byte segment of the lane-minor arrays), so
+// with 32 slots a sweep over V = 64 is two round trips and B/8 CTAs are resident.
+// ------------------------------------------------------------------------------------------------
+constexpr int kU2Lanes = 8;
+constexpr int kU2Slots = 32;
+constexpr int kU2Threads = kU2Lanes * kU2Slots;
+constexpr int kU2Warps = kU2Threads / 32;
+
+template <int M>
+struct Vl2Layout {
+    static constexpr int NB = 2 * M + 1;
+    static constexpr int NG = NB * (NB + 1) / 2;
+    static constexpr int NACC = 6 * M + 9;
+    // Gs[NG][8] dl[NB][8] acc[NACC+4][8] part[W][NACC+4][8]
+    static constexpr size_t doubles = (size_t)(NG + NB + (NACC + 4) + (size_t)kU2Warps * (NACC + 4)) * kU2Lanes + 4 * kU2Lanes;
+};
+
+// sums (or maxima for q >= first_max) of vals[0..n) over the 64 slots of each lane -> acc[q][l]
+template <int N>
+__device__ __forceinline__ void cta_reduce(double* vals, int first_max, double* part, double (*acc)[kU2Lanes], int w, int t, int l) {
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+        double v = vals[q];
+        const double o1 = __shfl_xor_sync(0xffffffffu, v, 8);
+        v = (q >= first_max) ? fmax(v, o1) : v + o1;
+        const double o2 = __shfl_xor_sync(0xffffffffu, v, 16);
+        v = (q >= first_max) ? fmax(v, o2) : v + o2;
+        if (t < kU2Lanes) part[((size_t)w * N + q) * kU2Lanes + l] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N * kU2Lanes; i += kU2Threads) {
+        const int q = i / kU2Lanes, ll = i - q * kU2Lanes;
+        double r = part[(size_t)q * kU2Lanes + ll];
+        for (int ww = 1; ww < kU2Warps; ++ww) {
+            const double o = part[((size_t)ww * N + q) * kU2Lanes + ll];
+            r = (q >= first_max) ? fmax(r, o) : r + o;
+        }
+        acc[q][ll] = r;
+    }
+    __syncthreads();
+}
+
+template <int M>
+__global__ void __launch_bounds__(kU2Threads) lbfgs_update_vl2_kernel(const UpdArgs a, double* __restrict__ Gm) {
+    constexpr int NB = Vl2Layout<M>::NB, NG = Vl2Layout<M>::NG, NACC = Vl2Layout<M>::NACC;
+    constexpr int GI = 2 * M;
+    constexpr int NR = NACC + 2;                                  // + comp, dual (max-reduced)
+    extern __shared__ double sm2[];
+    double (*Gs)[kU2Lanes] = reinterpret_cast<double (*)[kU2Lanes]>(sm2);                                   // [NG]
+    double (*dl)[kU2Lanes] = reinterpret_cast<double (*)[kU2Lanes]>(sm2 + (size_t)NG * kU2Lanes);           // [NB]
+    double (*acc)[kU2Lanes] = reinterpret_cast<double (*)[kU2Lanes]>(sm2 + (size_t)(NG + NB) * kU2Lanes);   // [NACC+4]
+    double* part = sm2 + (size_t)(NG + NB + NACC + 4) * kU2Lanes;                                           // [W][NACC+4][8]
+    double (*misc)[kU2Lanes] = reinterpret_cast<double (*)[kU2Lanes]>(part + (size_t)kU2Warps * (NACC + 4) * kU2Lanes);   // [4]
+
+    const int tid = threadIdx.x, t = tid & 31, w = tid >> 5;
+    const int l = tid & (kU2Lanes - 1), vs = tid >> 3;
+    const int64_t B = a.B;
+    const int64_t b = (int64_t)blockIdx.x * kU2Lanes + l;
+    const bool valid = b < B;
+    const int64_t bb = valid ? b : B - 1;
+    const int V = a.V;
+    const bool active = valid && a.done[bb] == 0;
+    if (!__syncthreads_or(active)) return;
+
+    for (int q = vs; q < NG; q += kU2Slots) Gs[q][l] = Gm[(int64_t)q * B + bb];
+
+    const double N = a.N[bb];
+    // ---- A: gather the partials of the pass evaluated at zt
+    double llsum = 0.0;
+    for (int q = 0; q < a.S; ++q) llsum += a.llpart[(int64_t)q * B + bb];
+    double r2[2] = {0.0, 0.0};                                  // sum phi, d.gt
+    for (int v = vs; v < V; v += kU2Slots) {
+        const int64_t i = (int64_t)v * B + bb;
+        double tv = 0.0;
+        for (int q = 0; q < a.S; ++q) tv += a.tpart[((int64_t)q * V + v) * B + bb];
+        const double gh = tv * a.invL[v] / N;
+        const double ztv = a.zt[i];
+        const bool mk = a.mask ? a.mask[i] != 0 : true;
+        const double gtv = mk ? 2.0 * ztv * (1.0 - gh) : 0.0;
+        if (active) { a.gt[i] = gtv; a.gh[i] = gh; }
+        r2[0] = fma(ztv, ztv, r2[0]);
+        r2[1] = fma(a.d[i], gtv, r2[1]);
+    }
+    cta_reduce<2>(r2, 2, part, acc, w, t, l);
+    const double sumphi = acc[0][l], dgt = acc[1][l];
+    double Ft = -llsum / N + sumphi;
+    const bool fin = isfinite(llsum) && isfinite(sumphi) && sumphi > 0.0;
+    if (!fin) Ft = INFINITY;
+
+    const int it = a.iters[bb];
+    const bool first = it < 0;
+    const double F = a.F[bb], dg = a.dg[bb], alpha = a.alpha[bb];
+    bool accept;
+    if (first) accept = fin;
+    else accept = fin && (Ft <= F + 1e-4 * alpha * dg ||
+                          (fabs(Ft - F) <= 1e-14 * fabs(F) && fabs(dgt) <= 0.9 * fabs(dg)));
+    accept = accept && active;
+    bool finished = false;
+    int status = TVS_CONVERGED;
+    if (active && first && !fin) { finished = true; status = TVS_INFEASIBLE; }
+
+    // ---- B: one sweep: dot products of the new vectors (s, y, g_new) with the whole basis + KKT residuals
+    __syncthreads();                                            // acc is rewritten below
+    if (__syncthreads_or(accept)) {
+        double ac[NR];
+#pragma unroll
+        for (int q = 0; q < NR; ++q) ac[q] = 0.0;
+        ac[NACC + 1] = -INFINITY;
+        if (accept) {
+            for (int v = vs; v < V; v += kU2Slots) {
+                const int64_t i = (int64_t)v * B + bb;
+                const double ztv = a.zt[i], gn = a.gt[i], go = a.g[i];
+                const double sv = ztv - a.z[i], yv = gn - go;
+#pragma unroll
+                for (int k = 0; k < M; ++k) {
+                    const double Sk = a.Sh[((int64_t)k * V + v) * B + bb], Yk = a.Yh[((int64_t)k * V + v) * B + bb];
+                    ac[k] = fma(sv, Sk, ac[k]);                 ac[M + k] = fma(sv, Yk, ac[M + k]);
+                    ac[2 * M + k] = fma(yv, Sk, ac[2 * M + k]); ac[3 * M + k] = fma(yv, Yk, ac[3 * M + k]);
+                    ac[4 * M + k] = fma(gn, Sk, ac[4 * M + k]); ac[5 * M + k] = fma(gn, Yk, ac[5 * M + k]);
+                }
+                ac[6 * M + 0] = fma(sv, sv, ac[6 * M + 0]); ac[6 * M + 1] = fma(sv, yv, ac[6 * M + 1]);
+                ac[6 * M + 2] = fma(yv, yv, ac[6 * M + 2]); ac[6 * M + 3] = fma(gn, gn, ac[6 * M + 3]);
+                ac[6 * M + 4] = fma(sv, gn, ac[6 * M + 4]); ac[6 * M + 5] = fma(yv, gn, ac[6 * M + 5]);
+                ac[6 * M + 6] = fma(sv, go, ac[6 * M + 6]); ac[6 * M + 7] = fma(yv, go, ac[6 * M + 7]);
+                ac[6 * M + 8] = fma(gn, go, ac[6 * M + 8]);
+                const bool mk = a.mask ? a.mask[i] != 0 : true;
+                if (mk) {
+                    const double ghn = a.gh[i] * sumphi;
+                    ac[NACC] = fmax(ac[NACC], ztv * ztv / sumphi * fabs(ghn - 1.0));
+                    ac[NACC + 1] = fmax(ac[NACC + 1], ghn - 1.0);
+                }
+            }
+        }
+        cta_reduce<NR>(ac, NACC, part, acc, w, t, l);
+    }
+    const double ss = acc[6 * M + 0][l], sy = acc[6 * M + 1][l], yy = acc[6 * M + 2][l], gg = acc[6 * M + 3][l];
+    const double comp = acc[NACC][l], dual = acc[NACC + 1][l];
+
+    int head = a.head[bb], cnt = a.cnt[bb];
+    const bool store = accept && !first && sy > 1e-10 * sqrt(ss * yy) && sy > 0.0;
+    // ---- C: move accepted lanes, write the new curvature pair into ring slot `head`
+    if (accept) {
+        for (int v = vs; v < V; v += kU2Slots) {
+            const int64_t i = (int64_t)v * B + bb;
+            const double ztv = a.zt[i], gtv = a.gt[i];
+            if (store) {
+                a.Sh[((int64_t)head * V + v) * B + bb] = ztv - a.z[i];
+                a.Yh[((int64_t)head * V + v) * B + bb] = gtv - a.g[i];
+            }
+            a.z[i] = ztv; a.g[i] = gtv;
+        }
+    }
+    int iters = it;
+    if (accept) {
+        iters = it + 1;
+        if (comp <= a.tol && dual <= a.tol_dual) { finished = true; status = TVS_CONVERGED; }
+        else if (iters >= a.max_iter) { finished = true; status = TVS_MAXITER; }
+    }
+    const bool newdir = accept && !finished;
+    double anew = 1.0;
+
+    // ---- D: scalar phase, one thread per lane: Gram update, two-loop on coefficients
+    if (vs == 0 && accept) {
+#pragma unroll
+        for (int k = 0; k < M; ++k) { Gs[tri_idx(GI, k)][l] = acc[4 * M + k][l]; Gs[tri_idx(GI, M + k)][l] = acc[5 * M + k][l]; }
+        Gs[tri_idx(GI, GI)][l] = gg;
+        if (store) {
+            const int h = head;
+            for (int k = 0; k < M; ++k) {
+                Gs[tri_idx(h, k)][l] = acc[k][l];             Gs[tri_idx(h, M + k)][l] = acc[M + k][l];
+                Gs[tri_idx(M + h, k)][l] = acc[2 * M + k][l]; Gs[tri_idx(M + h, M + k)][l] = acc[3 * M + k][l];
+            }
+            Gs[tri_idx(h, h)][l] = ss; Gs[tri_idx(h, M + h)][l] = sy; Gs[tri_idx(M + h, M + h)][l] = yy;
+            Gs[tri_idx(GI, h)][l] = acc[6 * M + 4][l]; Gs[tri_idx(GI, M + h)][l] = acc[6 * M + 5][l];
+            head = (h + 1) % M; cnt = min(cnt + 1, M);
+        }
+        double dgn = -gg;
+        if (newdir) {
+            double u[NB];
+            double* al = part;                                   // [M][8] scratch (the partials are consumed)
+#pragma unroll
+            for (int k = 0; k < NB; ++k) { dl[k][l] = 0.0; u[k] = -Gs[tri_idx(k, GI)][l]; }
+            dl[GI][l] = -1.0;
+            for (int j = 0; j < cnt; ++j) {                       // newest -> oldest
+                const int sl = ((head - 1 - j) % M + M) % M;
+                double us = 0.0;
+#pragma unroll
+                for (int k = 0; k < NB; ++k) us = (k == sl) ? u[k] : us;
+                const double aj = us / Gs[tri_idx(sl, M + sl)][l];
+                al[j * kU2Lanes + l] = aj;
+                dl[M + sl][l] -= aj;
+#pragma unroll
+                for (int k = 0; k < NB; ++k) u[k] = fma(-aj, Gs[tri_idx(k, M + sl)][l], u[k]);
+            }
+            if (cnt > 0) {
+                const int sl = ((head - 1) % M + M) % M;
+                const double gamma = Gs[tri_idx(sl, M + sl)][l] / Gs[tri_idx(M + sl, M + sl)][l];
+#pragma unroll
+                for (int k = 0; k < NB; ++k) { dl[k][l] *= gamma; u[k] *= gamma; }
+            }
+            for (int j = cnt - 1; j >= 0; --j) {                  // oldest -> newest
+                const int sl = ((head - 1 - j) % M + M) % M;
+                double uy = 0.0;
+#pragma unroll
+                for (int k = 0; k < NB; ++k) uy = (k == M + sl) ? u[k] : uy;
+                const double cf = al[j * kU2Lanes + l] - uy / Gs[tri_idx(sl, M + sl)][l];
+                dl[sl][l] += cf;
+#pragma unroll
+                for (int k = 0; k < NB; ++k) u[k] = fma(cf, Gs[tri_idx(k, sl)][l], u[k]);
+            }
+            dgn = u[GI];
+            if (!(dgn < 0.0) || cnt == 0) {                       // not a descent direction / no history
+#pragma unroll
+                for (int k = 0; k < NB; ++k) dl[k][l] = 0.0;
+                dl[GI][l] = -1.0;
+                if (!(dgn < 0.0)) cnt = 0;
+                dgn = -gg;
+                anew = fmin(1.0, 1.0 / sqrt(fmax(gg, 1e-300)));
+            }
+            if (gg == 0.0) { finished = true; status = TVS_CONVERGED; }
+        }
+        a.F[bb] = Ft; a.llsum[bb] = llsum; a.sumphi[bb] = sumphi;
+        a.kkt[bb] = comp; a.kkt[B + bb] = dual; a.iters[bb] = iters; a.ls[bb] = 0;
+        a.dg[bb] = dgn; a.alpha[bb] = anew;
+        a.head[bb] = head; a.cnt[bb] = cnt;
+        misc[0][l] = anew; misc[1][l] = finished ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (accept) { anew = misc[0][l]; finished = misc[1][l] != 0.0; }
+
+    // ---- E: d = sum_k delta_k b_k ; next trial point
+    if (newdir && !finished) {
+        for (int v = vs; v < V; v += kU2Slots) {
+            const int64_t i = (int64_t)v * B + bb;
+            double dv = dl[GI][l] * a.g[i];
+#pragma unroll
+            for (int k = 0; k < M; ++k) {
+                dv = fma(dl[k][l], a.Sh[((int64_t)k * V + v) * B + bb], dv);
+                dv = fma(dl[M + k][l], a.Yh[((int64_t)k * V + v) * B + bb], dv);
+            }
+            a.d[i] = dv;
+            const double zn = fma(anew, dv, a.z[i]);
+            a.zt[i] = zn; a.x[i] = zn * zn * a.invL[v];
+        }
+    }
+    if (accept)
+        for (int q = vs; q < NG; q += kU2Slots) Gm[(int64_t)q * B + bb] = Gs[q][l];
+
+    // ---- F: rejected lanes backtrack along the stored direction
+    const bool reject = active && !accept && !finished;
+    if (reject) {
+        const int ls = a.ls[bb] + 1;
+        double ar = alpha;
+        bool stall = false;
+        if (ls > 40) stall = true;
+        else {
+            double aq = 0.5 * alpha;
+            if (isfinite(Ft)) {
+                const double den = 2.0 * (Ft - F - dg * alpha);
+                if (den > 0.0) aq = -dg * alpha * alpha / den;
+                aq = fmin(fmax(aq, 0.1 * alpha), 0.5 * alpha);
+            } else aq = 0.1 * alpha;
+            ar = aq;
+        }
+        if (!stall) {
+            for (int v = vs; v < V; v += kU2Slots) {
+                const int64_t i = (int64_t)v * B + bb;
+                const double zn = fma(ar, a.d[i], a.z[i]);
+                a.zt[i] = zn; a.x[i] = zn * zn * a.invL[v];
+            }
+        }
+        if (vs == 0) { a.alpha[bb] = ar; a.ls[bb] = ls; }
+        if (stall) {
+            const double c0 = a.kkt[bb], d0 = a.kkt[B + bb];
+            finished = true;
+            status = (c0 <= 1e2 * a.tol && d0 <= 1e2 * a.tol_dual) ? TVS_CONVERGED : TVS_STALLED;
+        }
+    }
+
+    if (vs == 0 && active && finished) { a.status[bb] = status; a.done[bb] = 1; }
+    if (w == 0) {
+        const unsigned still = __ballot_sync(0xffffffffu, t < kU2Lanes && active && !finished);
+        if (t == 0 && still) atomicAdd(a.nactive, __popc(still));
+    }
+}
+
 // theta_out, ll_out, ... from the last accepted point of the lanes of one LaneSet, written at the lanes'
 // ORIGINAL ids (orig[]) into arrays of the original width B0.  only_done: skip lanes still iterating.
 struct FinArgs {
@@ -780,6 +1072,7 @@ __global__ void finalize_fit_kernel(const FinArgs a) {
     if (a.only_done && !dn) return;
     const int st = dn ? a.status[b] : TVS_MAXITER;   // still running when the pass budget ran out
     const int64_t o = a.orig[b];
+    if (o < 0) return;                                // padding lane of a compacted set
     if (a.theta_out) {
         double s = 0.0;
         for (int v = 0; v < a.V; ++v) { const double zz = a.z[(int64_t)v * a.B + b]; s += zz * zz * a.invL[v]; }
@@ -819,7 +1112,10 @@ __global__ void __launch_bounds__(1024) build_index_kernel(const int32_t* __rest
     int32_t pos = part[t] - c;
     for (int64_t b = b0; b < b1; ++b)
         if (done[b] == 0) idx[pos++] = (int32_t)b;
-    if (t == 1023) *count = part[1023];
+    if (t == 1023) {
+        *count = part[1023];
+        for (int q = 0; q < 3; ++q) idx[part[1023] + q] = -1;     // padding entries (see gather_rows_kernel)
+    }
 }
 
 template <typename T>
@@ -827,8 +1123,8 @@ __global__ void gather_rows_kernel(const T* __restrict__ src, T* __restrict__ ds
                                    const int32_t* __restrict__ idx) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= Bd) return;
-    const int64_t sj = idx[j];
-    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) dst[r * Bd + j] = src[r * Bs + sj];
+    const int64_t sj = idx[j];                              // -1: padding lane -> zeros
+    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) dst[r * Bd + j] = (sj >= 0) ? src[r * Bs + sj] : T(0);
 }
 
 __global__ void iota_kernel(int32_t* p, int64_t n) {

@@ -1,0 +1,473 @@
+// pass2_kernel -- second-generation fused likelihood pass (sm_100a).  Included by tvs_api.cu.
+//
+//     p = A x ;  rr = w / p ;  ll += w log p ;  t = A^T rr            (per lane)
+//
+// replaces: PathMultinomialModel.get_like_formula (ModelGenerator.py:153-174) evaluated by the
+// lambdified objective (ModelFitMaxLike.py:534-545), once per optimiser function evaluation.
+//
+// What changed against pass_kernel (profiles/r1_v1_summary.md: issue-bound, 310 warp instructions
+// per (row, 32 lanes) of which 13 were useful DFMA):
+//   * K consecutive lanes per thread (K = 1, 2, 4): one entry decode / address computation feeds K
+//     FMAs, the x / rr operands come from shared memory as 128-bit loads (conflict-free layout),
+//     the weights from global memory as one K*4-byte load per thread.
+//   * 1/p from `rcp.approx.ftz.f64` + two Newton steps (5 instructions instead of the ~40 of an
+//     IEEE division) and log p from an inlined atanh series on the reduced mantissa (no table: the
+//     binding resource of the sparse product is shared-memory operand bandwidth, so the logarithm
+//     is kept on the fp64 pipe).  Both are accurate to ~1 ulp; tests/test_gpu_parity.py pins them.
+//   * 16 warps per CTA.
+// Lane l of a tile lives at slot(l) inside every shared-memory row so that the two 16-byte halves
+// of a thread's K = 4 lanes are each contiguous across the warp.
+#pragma once
+#include "tvs_internal.h"
+#include <math.h>
+
+namespace tvs {
+
+constexpr int kWarps2 = 16;
+constexpr int kThreads2 = kWarps2 * 32;
+
+// coefficients of atanh(s)/s - 1 = s^2/3 + s^4/5 + ... in constant memory: DFMA reads them as c[][] operands
+__constant__ double kLogC[12] = {1.0 / 3.0, 1.0 / 5.0, 1.0 / 7.0, 1.0 / 9.0, 1.0 / 11.0, 1.0 / 13.0, 1.0 / 15.0, 1.0 / 17.0, 1.0 / 19.0,
+                                 6.93147180369123816490e-01 /* ln2_hi, 32 significant bits */, 1.90821492927058770002e-10 /* ln2_lo */, 0.0};
+
+__device__ __forceinline__ bool is_pos_normal(double p) {       // finite, normal, > 0 (one integer compare)
+    return (unsigned)(__double2hiint(p) - 0x00100000) < 0x7fe00000u;
+}
+
+__device__ __forceinline__ double fast_rcp(double p) {          // p finite, normal, > 0
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));        // MUFU.RCP64H, ~2^-20
+    double e = fma(-p, r, 1.0);
+    r = fma(r, e, r);                                            // ~2^-40
+    e = fma(-p, r, 1.0);
+    return fma(r, e, r);                                         // ~1 ulp
+}
+
+// natural logarithm for finite normal p > 0: p = 2^e m, m in [sqrt(1/2), sqrt(2)),
+// log m = 2 atanh(s), s = (m-1)/(m+1), |s| <= 0.1716.
+__device__ __forceinline__ double fast_log_pos(double p) {
+    int hi = __double2hiint(p);
+    const int lo = __double2loint(p);
+    int e = (hi >> 20) - 1023;
+    int mh = (hi & 0x000fffff) | 0x3ff00000;
+    if (mh >= 0x3ff6a09f) { mh -= 0x00100000; e += 1; }
+    const double m = __hiloint2double(mh, lo);
+    const double u = fast_rcp(m + 1.0);
+    const double s = (m - 1.0) * u;
+    const double s2 = s * s;
+    double q = kLogC[8];
+    q = fma(q, s2, kLogC[7]);
+    q = fma(q, s2, kLogC[6]);
+    q = fma(q, s2, kLogC[5]);
+    q = fma(q, s2, kLogC[4]);
+    q = fma(q, s2, kLogC[3]);
+    q = fma(q, s2, kLogC[2]);
+    q = fma(q, s2, kLogC[1]);
+    q = fma(q, s2, kLogC[0]);
+    const double ed = (double)e;
+    const double two_s = s + s;
+    const double tail = fma(two_s * s2, q, ed * kLogC[10]);      // + e * ln2_lo
+    return fma(ed, kLogC[9], two_s + tail);                      // e * ln2_hi is exact
+}
+
+__device__ __forceinline__ double log_any(double p) {           // -inf at 0, nan below, slow path for odd inputs
+    if (is_pos_normal(p)) return fast_log_pos(p);
+    return log(p);
+}
+
+__global__ void selftest_math_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ lg, double* __restrict__ rc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    lg[i] = log_any(p[i]);
+    rc[i] = is_pos_normal(p[i]) ? fast_rcp(p[i]) : 1.0 / p[i];
+}
+
+template <int K>
+__device__ __forceinline__ int lane_slot(int l) {               // position of tile lane l inside a shared row
+    if (K == 4) return ((l >> 1) & 1) * 64 + (l >> 2) * 2 + (l & 1);
+    return l;
+}
+
+template <int K> struct WVec;
+template <> struct WVec<1> { int v[1]; };
+template <> struct __align__(8) WVec<2> { int v[2]; };
+template <> struct __align__(16) WVec<4> { int v[4]; };
+
+template <int K>
+__device__ __forceinline__ void lds_lanes(const double* row, int t, double* out) {   // out[K] = lanes K*t .. K*t+K-1
+    if (K == 1) out[0] = row[t];
+    else if (K == 2) { const double2 a = reinterpret_cast<const double2*>(row)[t]; out[0] = a.x; out[1] = a.y; }
+    else {
+        const double2 a = reinterpret_cast<const double2*>(row)[t];
+        const double2 b = reinterpret_cast<const double2*>(row)[32 + t];
+        out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+    }
+}
+template <int K>
+__device__ __forceinline__ void sts_lanes(double* row, int t, const double* in) {
+    if (K == 1) row[t] = in[0];
+    else if (K == 2) reinterpret_cast<double2*>(row)[t] = make_double2(in[0], in[1]);
+    else {
+        reinterpret_cast<double2*>(row)[t] = make_double2(in[0], in[1]);
+        reinterpret_cast<double2*>(row)[32 + t] = make_double2(in[2], in[3]);
+    }
+}
+
+// grid = (lane tiles, row splits); CTA (tile, split) walks chunks split, split+S, ...
+// requires: B % K == 0 (vector loads of w), V*LT doubles of x (and t) fit in shared memory.
+template <int K, bool BACKWARD>
+__global__ void __launch_bounds__(kThreads2, 1) pass2_kernel(const PassArgs a) {
+    constexpr int LT = 32 * K;
+    extern __shared__ __align__(16) double smem2[];
+    const int t = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int tile = blockIdx.x, split = blockIdx.y, S = gridDim.y;
+    const int64_t B = a.B;
+    const int V = a.V;
+    const int64_t lane0 = (int64_t)tile * LT;
+    const int64_t mylane = lane0 + K * t;                 // first of this thread's K lanes (B % K == 0)
+    const bool lv = mylane < B;
+
+    if (a.done != nullptr) {                              // skip tiles whose lanes have all finished
+        int alive = 0;
+        if (lv) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) alive |= (a.done[mylane + j] == 0);
+        }
+        if (!__syncthreads_or(alive)) return;
+    }
+
+    double* x_s = smem2;                                            // [V][LT]
+    double* t_s = x_s + (size_t)V * LT;                             // [V][LT]   (BACKWARD)
+    double* rr_s = t_s + (BACKWARD ? (size_t)V * LT : 0);           // [rows_per_chunk][LT]
+
+    for (int i = threadIdx.x; i < V * LT; i += kThreads2) {
+        const int v = i / LT, l = i - v * LT;
+        const int64_t b = lane0 + l;
+        // 1.0 for padding and finished lanes: they stay on the fast rcp/log path, their results are never read
+        const bool live = b < B && (a.done == nullptr || a.done[b] == 0);
+        x_s[v * LT + lane_slot<K>(l)] = live ? a.x[(int64_t)v * B + b] : 1.0;
+        if (BACKWARD) t_s[i] = 0.0;
+    }
+    __syncthreads();
+
+    double ll[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) ll[j] = 0.0;
+
+    for (int c = split; c < a.n_chunks; c += S) {
+        const int row0 = a.chunk_row0[c], row1 = a.chunk_row0[c + 1];
+        // ---------------- phase 1: p = A x over the rows of the chunk
+        for (int r = row0 + wi; r < row1; r += kWarps2) {
+            const int k0 = __ldg(a.row_ptr + r), k1 = __ldg(a.row_ptr + r + 1);
+            WVec<K> wv;
+            if (lv) wv = *reinterpret_cast<const WVec<K>*>(a.w + (int64_t)r * B + mylane);
+            else {
+#pragma unroll
+                for (int j = 0; j < K; ++j) wv.v[j] = 0;
+            }
+            double p[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) p[j] = 0.0;
+#pragma unroll 2
+            for (int k = k0; k < k1; ++k) {
+                const uint32_t e = __ldg(a.ent + k);
+                const double f = (double)(e >> 16);
+                double xv[K];
+                lds_lanes<K>(x_s + (e & 0xffffu) * LT, t, xv);
+#pragma unroll
+                for (int j = 0; j < K; ++j) p[j] = fma(f, xv[j], p[j]);
+            }
+            double rr[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const double wd = (double)wv.v[j];
+                const bool on = wv.v[j] > 0;
+                double rcp, lg;
+                if (is_pos_normal(p[j])) { rcp = fast_rcp(p[j]); lg = fast_log_pos(p[j]); }
+                else { rcp = 1.0 / p[j]; lg = log(p[j]); }
+                rr[j] = on ? wd * rcp : 0.0;
+                ll[j] = on ? fma(wd, lg, ll[j]) : ll[j];
+            }
+            if (BACKWARD) sts_lanes<K>(rr_s + (r - row0) * LT, t, rr);
+        }
+        if (BACKWARD) {
+            __syncthreads();
+            // ------------ phase 2: t += A^T rr over the non-empty columns of the chunk
+            const int c0 = a.ccol_ptr[c], c1 = a.ccol_ptr[c + 1];
+            for (int ci = c0 + wi; ci < c1; ci += kWarps2) {
+                const int v = __ldg(a.ccol_id + ci);
+                const int k0 = __ldg(a.ccol_start + ci), k1 = __ldg(a.ccol_start + ci + 1);
+                double acc[K];
+                lds_lanes<K>(t_s + v * LT, t, acc);
+#pragma unroll 2
+                for (int k = k0; k < k1; ++k) {
+                    const uint32_t e = __ldg(a.cent + k);
+                    const double f = (double)(e >> 16);
+                    double rv[K];
+                    lds_lanes<K>(rr_s + (e & 0xffffu) * LT, t, rv);
+#pragma unroll
+                    for (int j = 0; j < K; ++j) acc[j] = fma(f, rv[j], acc[j]);
+                }
+                sts_lanes<K>(t_s + v * LT, t, acc);
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---------------- epilogue: per-split partials, summed later in fixed split order (deterministic)
+    if (BACKWARD) {
+        for (int i = threadIdx.x; i < V * LT; i += kThreads2) {
+            const int v = i / LT, l = i - v * LT;
+            const int64_t b = lane0 + l;
+            if (b < B) a.tpart[((int64_t)split * V + v) * B + b] = t_s[v * LT + lane_slot<K>(l)];
+        }
+    }
+    __syncthreads();
+    double* red = rr_s;                                   // [kWarps2][LT]; rows_per_chunk >= kWarps2 enforced on the host
+    sts_lanes<K>(red + wi * LT, t, ll);
+    __syncthreads();
+    if (wi == 0) {
+        double s[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) s[j] = 0.0;
+        for (int q = 0; q < kWarps2; ++q) {
+            double v[K];
+            lds_lanes<K>(red + q * LT, t, v);
+#pragma unroll
+            for (int j = 0; j < K; ++j) s[j] += v[j];
+        }
+        if (lv) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) a.llpart[(int64_t)split * B + mylane + j] = s[j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass3_kernel: pass2 + the CSR entries of each chunk staged in shared memory by cp.async
+// (profiles/r1_v2_summary.md: pass2 stalls on the dependent LDG(entry) -> LDS(x) -> DFMA chain).
+//   * entries are stored decoded in global memory (column / local row as int32, count as double), so
+//     the inner loops are  LDS.32 (broadcast) + LDS.64 (broadcast) + K/2 x LDS.128 + K x DFMA;
+//   * the row-major entries of the NEXT chunk and the column-major entries of THIS chunk are in flight
+//     while phase 1 runs (double buffer / single buffer);
+//   * the weights of a warp's next row are loaded one row ahead (the only HBM stream of the pass).
+// shared: x_s[V][LT] t_s[V][LT] rr_s[RC][LT] | f1[2][cap] f2[cap] (double) | c1[2][cap] c2[cap] rp[2][RC+1]
+//         cs[V+1] cid[V] (int32)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src));
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+struct Pass3Smem {            // byte offsets from the start of dynamic shared memory
+    size_t x, t, rr, f1, f2, c1, c2, rp, cs, cid, total;
+};
+__host__ __device__ inline Pass3Smem pass3_layout(int V, int LT, int RC, int cap, bool backward, int nw) {
+    Pass3Smem L;
+    size_t o = 0;
+    L.x = o; o += (size_t)V * LT * 8;
+    L.t = o; o += backward ? (size_t)V * LT * 8 : 0;
+    L.rr = o; o += (size_t)(RC > nw ? RC : nw) * LT * 8;
+    L.f1 = o; o += (size_t)2 * cap * 8;
+    L.f2 = o; o += backward ? (size_t)cap * 8 : 0;
+    L.c1 = o; o += (size_t)2 * cap * 4;
+    L.c2 = o; o += backward ? (size_t)cap * 4 : 0;
+    L.rp = o; o += (size_t)2 * (RC + 1) * 4;
+    L.cs = o; o += backward ? (size_t)(V + 1) * 4 : 0;
+    L.cid = o; o += backward ? (size_t)V * 4 : 0;
+    L.total = (o + 15) & ~(size_t)15;
+    return L;
+}
+
+template <int K, int NW, bool BACKWARD>
+__global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
+    constexpr int LT = 32 * K;
+    constexpr int NT = NW * 32;
+    extern __shared__ __align__(16) unsigned char smem3[];
+    const int t = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int tile = blockIdx.x, split = blockIdx.y, S = gridDim.y;
+    const int64_t B = a.B;
+    const int V = a.V, RC = a.rows_per_chunk, cap = a.stage_cap;
+    const int64_t lane0 = (int64_t)tile * LT;
+    const int64_t mylane = lane0 + K * t;
+    const bool lv = mylane < B;
+
+    if (a.done != nullptr) {
+        int alive = 0;
+        if (lv) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) alive |= (a.done[mylane + j] == 0);
+        }
+        if (!__syncthreads_or(alive)) return;
+    }
+
+    const Pass3Smem L = pass3_layout(V, LT, RC, cap, BACKWARD, NW);
+    double* x_s = reinterpret_cast<double*>(smem3 + L.x);
+    double* t_s = reinterpret_cast<double*>(smem3 + L.t);
+    double* rr_s = reinterpret_cast<double*>(smem3 + L.rr);
+    double* f1_s = reinterpret_cast<double*>(smem3 + L.f1);
+    double* f2_s = reinterpret_cast<double*>(smem3 + L.f2);
+    int* c1_s = reinterpret_cast<int*>(smem3 + L.c1);
+    int* c2_s = reinterpret_cast<int*>(smem3 + L.c2);
+    int* rp_s = reinterpret_cast<int*>(smem3 + L.rp);
+    int* cs_s = reinterpret_cast<int*>(smem3 + L.cs);
+    int* cid_s = reinterpret_cast<int*>(smem3 + L.cid);
+
+    // row-major entries + row pointers of chunk c -> buffer `buf`
+    auto stage_rows = [&](int c, int buf) {
+        const int r0 = a.chunk_row0[c], r1 = a.chunk_row0[c + 1];
+        const int e0 = a.row_ptr[r0], n = a.row_ptr[r1] - e0;
+        for (int i = threadIdx.x; i < n; i += NT) {
+            cp_async8(f1_s + (size_t)buf * cap + i, a.fval + e0 + i);
+            cp_async4(c1_s + (size_t)buf * cap + i, a.col32 + e0 + i);
+        }
+        for (int i = threadIdx.x; i <= r1 - r0; i += NT) cp_async4(rp_s + buf * (RC + 1) + i, a.row_ptr + r0 + i);
+    };
+    // column-major entries + column starts / ids of chunk c
+    auto stage_cols = [&](int c) {
+        const int c0 = a.ccol_ptr[c], c1 = a.ccol_ptr[c + 1];
+        const int e0 = a.ccol_start[c0], n = a.ccol_start[c1] - e0;
+        for (int i = threadIdx.x; i < n; i += NT) {
+            cp_async8(f2_s + i, a.cfval + e0 + i);
+            cp_async4(c2_s + i, a.crow32 + e0 + i);
+        }
+        for (int i = threadIdx.x; i <= c1 - c0; i += NT) cp_async4(cs_s + i, a.ccol_start + c0 + i);
+        for (int i = threadIdx.x; i < c1 - c0; i += NT) cp_async4(cid_s + i, a.ccol_id + c0 + i);
+    };
+
+    int c = split, buf = 0;
+    if (c < a.n_chunks) stage_rows(c, 0);
+    cp_async_commit();
+
+    for (int i = threadIdx.x; i < V * LT; i += NT) {
+        const int v = i / LT, l = i - v * LT;
+        const int64_t b = lane0 + l;
+        const bool live = b < B && (a.done == nullptr || a.done[b] == 0);
+        x_s[v * LT + lane_slot<K>(l)] = live ? a.x[(int64_t)v * B + b] : 1.0;
+        if (BACKWARD) t_s[i] = 0.0;
+    }
+
+    double ll[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) ll[j] = 0.0;
+
+    for (; c < a.n_chunks; c += S, buf ^= 1) {
+        const int row0 = a.chunk_row0[c], row1 = a.chunk_row0[c + 1];
+        cp_async_wait_all();
+        __syncthreads();                                   // entries of chunk c (and x_s on the first trip) visible
+        if (BACKWARD) stage_cols(c);
+        if (c + S < a.n_chunks) stage_rows(c + S, buf ^ 1);
+        cp_async_commit();
+        // ---------------- phase 1: p = A x over the rows of the chunk
+        const double* f1 = f1_s + (size_t)buf * cap;
+        const int* c1 = c1_s + (size_t)buf * cap;
+        const int* rp = rp_s + buf * (RC + 1);
+        const int e0 = rp[0];
+        WVec<K> wnext;
+        {
+            const int r = row0 + wi;
+            if (lv && r < row1) wnext = *reinterpret_cast<const WVec<K>*>(a.w + (int64_t)r * B + mylane);
+            else {
+#pragma unroll
+                for (int j = 0; j < K; ++j) wnext.v[j] = 0;
+            }
+        }
+        for (int r = row0 + wi; r < row1; r += NW) {
+            const WVec<K> wv = wnext;
+            if (lv && r + NW < row1) wnext = *reinterpret_cast<const WVec<K>*>(a.w + (int64_t)(r + NW) * B + mylane);
+            const int k0 = rp[r - row0] - e0, k1 = rp[r - row0 + 1] - e0;
+            double p[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) p[j] = 0.0;
+#pragma unroll 4
+            for (int k = k0; k < k1; ++k) {
+                const double f = f1[k];
+                double xv[K];
+                lds_lanes<K>(x_s + c1[k] * LT, t, xv);
+#pragma unroll
+                for (int j = 0; j < K; ++j) p[j] = fma(f, xv[j], p[j]);
+            }
+            bool fast = true;
+#pragma unroll
+            for (int j = 0; j < K; ++j) fast = fast && is_pos_normal(p[j]);
+            double rr[K];
+            if (fast) {
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const double wd = (double)wv.v[j];
+                    const bool on = wv.v[j] > 0;
+                    rr[j] = on ? wd * fast_rcp(p[j]) : 0.0;
+                    ll[j] = on ? fma(wd, fast_log_pos(p[j]), ll[j]) : ll[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const double wd = (double)wv.v[j];
+                    const bool on = wv.v[j] > 0;
+                    rr[j] = on ? wd / p[j] : 0.0;
+                    ll[j] = on ? fma(wd, log(p[j]), ll[j]) : ll[j];
+                }
+            }
+            if (BACKWARD) sts_lanes<K>(rr_s + (r - row0) * LT, t, rr);
+        }
+        if (BACKWARD) {
+            cp_async_wait_all();
+            __syncthreads();                               // rr_s complete, column-major entries landed
+            // ------------ phase 2: t += A^T rr over the non-empty columns of the chunk
+            const int ncol = a.ccol_ptr[c + 1] - a.ccol_ptr[c];
+            const int ce0 = cs_s[0];
+            for (int ci = wi; ci < ncol; ci += NW) {
+                const int v = cid_s[ci];
+                const int k0 = cs_s[ci] - ce0, k1 = cs_s[ci + 1] - ce0;
+                double acc[K];
+                lds_lanes<K>(t_s + v * LT, t, acc);
+#pragma unroll 4
+                for (int k = k0; k < k1; ++k) {
+                    const double f = f2_s[k];
+                    double rv[K];
+                    lds_lanes<K>(rr_s + c2_s[k] * LT, t, rv);
+#pragma unroll
+                    for (int j = 0; j < K; ++j) acc[j] = fma(f, rv[j], acc[j]);
+                }
+                sts_lanes<K>(t_s + v * LT, t, acc);
+            }
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    // ---------------- epilogue
+    if (BACKWARD) {
+        for (int i = threadIdx.x; i < V * LT; i += NT) {
+            const int v = i / LT, l = i - v * LT;
+            const int64_t b = lane0 + l;
+            if (b < B) a.tpart[((int64_t)split * V + v) * B + b] = t_s[v * LT + lane_slot<K>(l)];
+        }
+    }
+    double* red = rr_s;                                   // [NW][LT]
+    sts_lanes<K>(red + wi * LT, t, ll);
+    __syncthreads();
+    if (wi == 0) {
+        double s[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) s[j] = 0.0;
+        for (int q = 0; q < NW; ++q) {
+            double v[K];
+            lds_lanes<K>(red + q * LT, t, v);
+#pragma unroll
+            for (int j = 0; j < K; ++j) s[j] += v[j];
+        }
+        if (lv) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) a.llpart[(int64_t)split * B + mylane + j] = s[j];
+        }
+    }
+}
+
+}  // namespace tvs
