@@ -6,7 +6,7 @@
 
 A "step" = the maximum-likelihood fit of one batch of B bootstrap replicates (lanes) of the
 workload (BASELINE.json configs[1]: 64 candidate variants x 20k read paths, B = 1,000 replicates per
-GPU), every lane iterated to the KKT tolerance 1e-10.  `value` = lanes fitted per second by the
+GPU), every lane iterated to the KKT tolerance 1e-9 (the library default).  `value` = lanes fitted per second by the
 whole job with the replicate weights already resident in HBM; `e2e` = the same fit driven through
 the public API with the weights in pinned HOST memory (H2D of the weights and D2H of the results
 inside the timed region).  Weak scaling: every rank fits its own B replicates (different seeds) of
@@ -161,7 +161,7 @@ def run_reference(args, wl):
 
 def workload_config(args, wl):
     return {"workload": "%s: %d variants x %d read paths (nnz %d, %d reads), %d bootstrap replicates per GPU, "
-                        "full-candidate-set ML fit to KKT 1e-10" % (args.workload, wl.V, wl.R, wl.nnz, wl.N, args.lanes),
+                        "full-candidate-set ML fit to KKT 1e-9" % (args.workload, wl.V, wl.R, wl.nnz, wl.N, args.lanes),
             "lanes_per_gpu": args.lanes, "V": wl.V, "R": wl.R, "nnz": wl.nnz,
             "l2": "L2 flushed between timed steps (256 MiB write); within a step the solver re-reads its own weights",
             "parallelism": "lanes sharded over ranks, no data-path collective"}
@@ -254,10 +254,17 @@ def main():
         e2e_ms.append(1e3 * (time.perf_counter() - t1))
     barrier()
     clocks = sampler.stop()
-    # ---- one extra (untimed) step with per-launch CUDA events for the roofline of the dominant kernel
-    flush.zero_()
-    eng.fit(out=outs, time_passes=True)
-    stp = eng.last_fit_stats()
+    # ---- the same steps once more with CUDA events around every launch of the dominant kernel (the events
+    #      cost ~1 ms per step, so they are kept out of the steps that produce `value`)
+    prof = {"pass_ms": 0.0, "update_ms": 0.0, "total_ms": 0.0, "passes": 0, "lane_passes": 0}
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        eng.fit(out=outs, time_passes=True)
+        stp = eng.last_fit_stats()
+        for k in prof:
+            prof[k] += stp[k]
+    fp64_peak = _cabi.measure_fp64_peak(local_rank)
 
     step_ms = float(np.sum(dev_ms)) / args.steps
     e2e_step_ms = float(np.sum(e2e_ms)) / args.steps
@@ -272,11 +279,14 @@ def main():
         total_lanes = B * world
         value = total_lanes / (step_ms * 1e-3)
         peak, peak_src = measured_peaks()
-        # algorithmic bytes of the pass-kernel launches of the profiled step (SURVEY.md 8d figure, per launch width)
-        alg_bytes = (8.0 * wl.nnz + 4.0 * (wl.R + 1)) * stp["passes"] + (4.0 * wl.R + 16.0 * wl.V) * stp["lane_passes"]
-        pass_s = stp["pass_ms"] * 1e-3
+        # algorithmic bytes of the pass-kernel launches of the profiled steps (SURVEY.md 8d figure at each launch's width)
+        alg_bytes = (8.0 * wl.nnz + 4.0 * (wl.R + 1)) * prof["passes"] + (4.0 * wl.R + 16.0 * wl.V) * prof["lane_passes"]
+        pass_s = prof["pass_ms"] * 1e-3
         achieved = alg_bytes / pass_s / 1e9 if pass_s > 0 else 0.0
-        flops = 4.0 * wl.nnz * stp["lane_passes"] + 6.0 * wl.R * stp["lane_passes"]
+        flops = 4.0 * wl.nnz * prof["lane_passes"] + 6.0 * wl.R * prof["lane_passes"]
+        # shared-memory operand bytes: every FMA of the two sparse products reads one 8-byte operand from shared memory
+        smem_bytes = 2.0 * 8.0 * wl.nnz * prof["lane_passes"]
+        sm_count, smem_bw = 148, 128.0 * 1.965e9          # 128 B/clk/SM at the 1965 MHz boost clock
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -286,14 +296,24 @@ def main():
                     "d2h_bytes_per_step": int(wl.V) * B * 8 + B * (8 + 16 + 4 + 4)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "pass_kernel (fused A x, w/p, w log p, A^T(w/p))",
+            "roofline": {"bound": "hbm", "kernel": "pass3_kernel (fused p = A x, w/p, w log p, t = A^T(w/p))",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                         "traffic": 77.3e6, "traffic_note": "dram read+write per full-width launch, ncu --set full (profiles/)",
-                         "avg_launch_us": 1e3 * stp["pass_ms"] / max(stp["passes"], 1), "launches_profiled": stp["passes"],
-                         "fp64_tflops_achieved": flops / pass_s / 1e12 if pass_s > 0 else 0.0,
-                         "pass_share_of_step": stp["pass_ms"] / stp["total_ms"] if stp["total_ms"] > 0 else None},
+                         "traffic": 76.0e6,
+                         "traffic_note": "dram read+write of ONE full-width (1000-lane) launch, ncu --set full (profiles/r1_v3_summary.md); "
+                                         "algorithmic bytes of that launch: 74.3e6",
+                         "avg_launch_us": 1e3 * prof["pass_ms"] / max(prof["passes"], 1), "launches_profiled": prof["passes"],
+                         "pass_share_of_step": prof["pass_ms"] / prof["total_ms"] if prof["total_ms"] > 0 else None,
+                         "binding_roof_note": "at this lane count the pass is NOT HBM-bound (SURVEY F8): the weights are L2-resident (72 MB) "
+                                              "and every FMA of the sparse products needs an 8-byte shared-memory operand; see fp64 / smem below",
+                         "fp64": {"achieved_tflops": flops / pass_s / 1e12 if pass_s > 0 else 0.0, "peak_tflops": fp64_peak,
+                                  "frac": (flops / pass_s / 1e12 / fp64_peak) if pass_s > 0 and fp64_peak > 0 else None,
+                                  "peak_source": "tvs_measure_fp64_peak (DFMA micro-benchmark on this GPU)"},
+                         "smem_operand": {"achieved_gbs": smem_bytes / pass_s / 1e9 if pass_s > 0 else 0.0,
+                                          "peak_gbs": sm_count * smem_bw / 1e9,
+                                          "frac": (smem_bytes / pass_s) / (sm_count * smem_bw) if pass_s > 0 else None,
+                                          "peak_source": "128 B/clk/SM x 148 SMs x 1.965 GHz (B300_MICROARCH.md shared-memory figure)"}},
             "solver": {"converged_lanes": converged, "lanes": total_lanes, "mean_iters": iters_mean,
-                       "passes_per_step": passes / args.steps, "lane_passes_per_step": lane_passes / args.steps,
+                       "kkt_tol": 1e-9, "passes_per_step": passes / args.steps, "lane_passes_per_step": lane_passes / args.steps,
                        "wall_ms_per_step": 1e3 * wall / args.steps},
         }
         if world == 1 and not args.no_cpu_baseline:

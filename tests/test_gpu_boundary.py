@@ -117,7 +117,7 @@ def test_cfg1_bootstrap_flow_on_gpu(gpu, plastome):
     kw0 = fit_context(models[0], plastome["be_unidentifiable_to"], plastome["repr_to_merged_variants"])
     full = ModelFitMaxLike(**kw0)
     raw = full.reverse_model_selection(n_proc=1)
-    assert abs(raw[0][0] - 23 / 35.) < 1e-9 and abs(raw[0][1] - 12 / 35.) < 1e-9
+    assert abs(raw[0][0] - 23 / 35.) < 1e-7 and abs(raw[0][1] - 12 / 35.) < 1e-7
     assert abs(raw[1] - plastome["final"]["res_loglike"]) < 1e-9 * abs(raw[1])
     assert abs(raw[2] - plastome["final"]["res_criterion"]) < 1e-9 * abs(raw[2])
     shared = {k: kw0[k] for k in ("variant_paths", "variant_subpath_counters", "repr_to_merged_variants", "be_unidentifiable_to")}

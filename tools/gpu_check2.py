@@ -36,11 +36,16 @@ if __name__ == "__main__":
     wl = synthetic.make_config(which)
     B = int(sys.argv[2]) if len(sys.argv) > 2 else synthetic.CONFIGS[which]["lanes"]
     print(which, "R", wl.R, "V", wl.V, "nnz", wl.nnz, "B", B, flush=True)
-    ref = run(wl, B, {"TVS_PASS_V1": 1, "TVS_RC": 128}, "v1")
-    for env, label in [({"TVS_NO_STAGE": 1, "TVS_K": 4}, "v2_k4"), ({"TVS_K": 4}, "v3_k4"), ({"TVS_K": 4, "TVS_NW": 32}, "v3_k4_nw32"),
-                       ({"TVS_K": 2}, "v3_k2"), ({"TVS_K": 2, "TVS_NW": 32}, "v3_k2_nw32"), ({"TVS_K": 1}, "v3_k1"), ({}, "v3_auto"),
-                       ({"TVS_NO_COMPACT": 1, "TVS_K": 4}, "v3_k4_nocompact")]:
+    import itertools
+    ref = None
+    combos = [({}, "auto")]
+    for spec in sys.argv[3:]:
+        env = dict(kv.split("=") for kv in spec.split(","))
+        combos.append((env, spec))
+    for env, label in combos:
         try:
-            run(wl, B, env, label, theta_ref=ref["theta"])
+            out = run(wl, B, env, label, theta_ref=None if ref is None else ref["theta"])
+            if ref is None:
+                ref = out
         except Exception as e:
             print(label, "FAILED", e, flush=True)

@@ -58,7 +58,7 @@ class ModelFitMaxLike(object):
     """Find the variant proportions that maximise the likelihood (batched, on one B200)."""
 
     # solver settings (class level so that callers of the reference signature need not know them)
-    tol = 1e-10
+    tol = 1e-9      # KKT tolerance; observed |theta error| <= ~20 x tol (DESIGN.md section 2)
     max_iter = 2000
     history = 8
 

@@ -47,6 +47,7 @@ static void free_csr(Csr& c) {
     dev_free(c.row_ptr); dev_free(c.ent); dev_free(c.chunk_row0); dev_free(c.ccol_ptr); dev_free(c.ccol_id);
     dev_free(c.ccol_start); dev_free(c.cent); dev_free(c.invL); dev_free(c.Ld);
     dev_free(c.col32); dev_free(c.fval); dev_free(c.crow32); dev_free(c.cfval);
+    if (c.desc) { cudaFree(c.desc); c.desc = nullptr; }
 }
 static void free_lanes(Lanes& l) {
     dev_free(l.w); dev_free(l.mask); dev_free(l.C); dev_free(l.N);
@@ -227,6 +228,7 @@ static PassArgs base_args(const tvs_problem* h) {
     a.ccol_start = c.ccol_start; a.cent = c.cent; a.w = h->lanes.w; a.B = h->lanes.B; a.V = (int)c.V;
     a.n_chunks = c.n_chunks; a.rows_per_chunk = c.rows_per_chunk;
     a.col32 = c.col32; a.fval = c.fval; a.crow32 = c.crow32; a.cfval = c.cfval; a.stage_cap = std::max(c.max_chunk_nnz, 1);
+    a.desc = (const ChunkDesc*)c.desc; a.logc = make_log_coef();
     return a;
 }
 
@@ -389,6 +391,21 @@ int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, c
     if ((rc = dev_alloc(&c.row_ptr, (size_t)R + 1)) != TVS_OK) return fail(rc);
     if (cudaMemcpy(c.row_ptr, row_ptr, ((size_t)R + 1) * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess)
         return fail(cuda_fail(cudaGetLastError(), "upload row_ptr", __FILE__, __LINE__));
+    std::vector<ChunkDesc> descv((size_t)c.n_chunks);
+    for (int ch = 0; ch < c.n_chunks; ++ch) {
+        ChunkDesc& d = descv[ch];
+        d.row0 = chunk_row0[ch]; d.nrows = chunk_row0[ch + 1] - chunk_row0[ch];
+        d.e0 = row_ptr[d.row0]; d.nent = row_ptr[d.row0 + d.nrows] - d.e0;
+        d.c0 = ccol_ptr[ch]; d.ncol = ccol_ptr[ch + 1] - ccol_ptr[ch];
+        d.ce0 = ccol_start[d.c0]; d.ncent = ccol_start[d.c0 + d.ncol] - d.ce0;
+    }
+    {
+        ChunkDesc* dd = nullptr;
+        if ((rc = dev_alloc(&dd, descv.size())) != TVS_OK) return fail(rc);
+        c.desc = dd;
+        if (cudaMemcpy(dd, descv.data(), descv.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice) != cudaSuccess)
+            return fail(cuda_fail(cudaGetLastError(), "upload desc", __FILE__, __LINE__));
+    }
     UP_(col32, col32v, int32_t) UP_(fval, fvalv, double) UP_(crow32, crow32v, int32_t) UP_(cfval, cfvalv, double)
     UP_(ent, ent, uint32_t) UP_(cent, cent, uint32_t) UP_(chunk_row0, chunk_row0, int32_t) UP_(ccol_ptr, ccol_ptr, int32_t)
     if (ccol_id.empty()) ccol_id.push_back(0);
@@ -564,7 +581,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
     TVS_CUDA(cudaSetDevice(h->device));
     tvs_fit_options opt{};
     if (opt_in) opt = *opt_in;
-    if (!(opt.tol > 0.0)) opt.tol = 1e-10;
+    if (!(opt.tol > 0.0)) opt.tol = 1e-9;
     if (opt.max_iter <= 0) opt.max_iter = 1000;
     if (opt.history <= 0) opt.history = 8;
     opt.history = std::min(opt.history, kMaxHistory);
@@ -640,7 +657,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         PassArgs pa = base_args(h);
         pa.w = s.w; pa.B = W; pa.x = s.x; pa.done = s.done; pa.tpart = f.tpart; pa.llpart = f.llpart;
         UpdArgs ua{};
-        ua.tpart = f.t_red; ua.llpart = f.ll_red; ua.S = 1; ua.invL = h->csr.invL; ua.N = s.N; ua.mask = s.mask;
+        ua.invL = h->csr.invL; ua.N = s.N; ua.mask = s.mask;
         ua.z = s.z; ua.zt = s.zt; ua.g = s.g; ua.gt = f.gt; ua.gh = f.gh; ua.d = s.d; ua.x = s.x; ua.Sh = s.S; ua.Yh = s.Y;
         ua.rho = s.rho; ua.gamma = s.gamma; ua.F = s.F; ua.dg = s.dg; ua.alpha = s.alpha; ua.llsum = s.llsum; ua.kkt = s.kkt;
         ua.sumphi = s.sumphi; ua.ls = s.ls; ua.iters = s.iters; ua.status = s.status; ua.head = s.head; ua.cnt = s.cnt;
@@ -656,11 +673,25 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
             rc = launch_pass<true>(h, pl, pa);
             if (rc != TVS_OK) break;
             if (time_passes) cudaEventRecord(pev.back(), st);
-            reduce_partials_kernel<<<(unsigned)(((int64_t)(V + 1) * W + 255) / 256), 256, 0, st>>>(f.tpart, f.llpart, pl.splits, (int)V, W,
-                                                                                                  f.t_red, f.ll_red);
             const bool last = (k == opt.check_every - 1) || (passes + 1 == max_passes);
-            ua.nactive = last ? f.nactive + slot : f.nactive + 31;   // word 31 = scratch between polls
-            if (last) { cudaMemsetAsync(f.nactive + slot, 0, 4, st); ++launches; }
+            const bool legacy_upd = upd_v1 || upd_v2;
+            const bool pre_reduce = legacy_upd || pl.splits > env_int("TVS_FUSE_SPLITS", 24);   // many splits: sum them with full parallelism first
+            if (pre_reduce) {
+                reduce_partials_kernel<<<(unsigned)(((int64_t)(V + 1) * W + 255) / 256), 256, 0, st>>>(f.tpart, f.llpart, pl.splits, (int)V, W,
+                                                                                                      f.t_red, f.ll_red);
+                ua.tpart = f.t_red; ua.llpart = f.ll_red; ua.S = 1;
+                ++launches;
+            } else {
+                ua.tpart = f.tpart; ua.llpart = f.llpart; ua.S = pl.splits;
+            }
+            if (legacy_upd) {           // the older update kernels need a memset of the poll counter
+                ua.nactive = last ? f.nactive + slot : f.nactive + 31;   // word 31 = scratch between polls
+                if (last) { cudaMemsetAsync(f.nactive + slot, 0, 4, st); ++launches; }
+            } else {                    // vl2: counters are reset one launch ahead
+                ua.nactive = last ? f.nactive + slot : f.nactive + 31;
+                ua.nreset = (k == 0 && !last) ? f.nactive + slot : nullptr;
+                if (k == 0 && last) { cudaMemsetAsync(f.nactive + slot, 0, 4, st); ++launches; }
+            }
             const unsigned ub2 = (unsigned)((W + kU2Lanes - 1) / kU2Lanes);
             if (upd_v1) lbfgs_update_kernel<<<ub, kUpdWarps * 32, 0, st>>>(ua);
             else if (!upd_v2 && m == 4) lbfgs_update_vl2_kernel<4><<<ub2, kU2Threads, Vl2Layout<4>::doubles * 8, st>>>(ua, s.gram);
@@ -668,7 +699,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
             else if (m == 4) lbfgs_update_vl_kernel<4><<<ub, kUpdWarps * 32, VlLayout<4>::doubles * 8, st>>>(ua, s.gram);
             else lbfgs_update_vl_kernel<8><<<ub, kUpdWarps * 32, VlLayout<8>::doubles * 8, st>>>(ua, s.gram);
             if (time_passes) { cudaEvent_t e2; cudaEventCreate(&e2); uev.push_back(pev.back()); uev.push_back(e2); cudaEventRecord(e2, st); }
-            ++passes; launches += 3; lane_passes += W;
+            ++passes; launches += 2; lane_passes += W;
             if (time_passes) pass_width.push_back(W);
         }
         if (rc != TVS_OK) break;
@@ -779,7 +810,7 @@ int tvs_selftest_math(int device, int64_t n, const double* p, double* log_out, d
         cudaFree(d_p); cudaFree(d_l); cudaFree(d_r); return rc;
     }
     cudaMemcpy(d_p, p, (size_t)n * 8, cudaMemcpyDefault);
-    selftest_math_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_p, n, d_l, d_r);
+    selftest_math_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_p, n, d_l, d_r, make_log_coef());
     cudaError_t e = cudaDeviceSynchronize();
     if (e == cudaSuccess) { cudaMemcpy(log_out, d_l, (size_t)n * 8, cudaMemcpyDefault); cudaMemcpy(rcp_out, d_r, (size_t)n * 8, cudaMemcpyDefault); }
     cudaFree(d_p); cudaFree(d_l); cudaFree(d_r);

@@ -41,6 +41,7 @@ struct Csr {
     int32_t*  crow32 = nullptr;      // [nnz]  chunk-local row, column-major within chunk
     double*   cfval = nullptr;       // [nnz]  count as double, column-major within chunk
     int       max_chunk_nnz = 0;     // largest number of entries in one chunk
+    void*     desc = nullptr;        // [n_chunks] ChunkDesc (tvs_kernels.cuh)
     double*   invL = nullptr;        // [V] 1/L_v
     double*   Ld = nullptr;          // [V] L_v as double
     int64_t   n_ccol = 0;

@@ -21,6 +21,9 @@ namespace tvs {
 // XS: x tile and t accumulators live in shared memory (V*LT*16 bytes); otherwise x is read from
 // global/L2 and t is accumulated in the CTA's private slice of the partial buffer.
 // ------------------------------------------------------------------------------------------------
+struct LogCoef { double c[11]; };                  // see tvs_pass2.cuh
+struct __align__(16) ChunkDesc { int row0, nrows, e0, nent, c0, ncol, ce0, ncent; };   // one per chunk of rows
+
 struct PassArgs {
     const int32_t* row_ptr; const uint32_t* ent;
     const int32_t* chunk_row0; const int32_t* ccol_ptr; const int32_t* ccol_id; const int32_t* ccol_start;
@@ -30,6 +33,8 @@ struct PassArgs {
     int64_t B; int V; int n_chunks; int rows_per_chunk;
     // decoded entries (pass3_kernel): column / chunk-local row as int32, count as double
     const int32_t* col32; const double* fval; const int32_t* crow32; const double* cfval; int stage_cap;
+    const ChunkDesc* desc;
+    LogCoef logc;
 };
 
 template <int LPT, bool XS, bool BACKWARD>
@@ -258,6 +263,7 @@ struct UpdArgs {
     double *F, *dg, *alpha, *llsum, *kkt, *sumphi;
     int32_t *ls, *iters, *status, *head, *cnt, *done, *nactive;
     int V; int64_t B; int m; int max_iter; double tol, tol_dual;
+    int32_t* nreset;     // counter zeroed by this launch for a LATER launch of the same poll group (or null)
 };
 
 __device__ __forceinline__ double blk_sum(double v, double (*red)[32], int wi, int t) {
@@ -776,6 +782,21 @@ __global__ void __launch_bounds__(kUpdWarps * 32) lbfgs_update_vl_kernel(const U
 // slot vs), a warp = 4 slots x 8 lanes (each slot row is a 64-byte segment of the lane-minor arrays), so
 // with 32 slots a sweep over V = 64 is two round trips and B/8 CTAs are resident.
 // ------------------------------------------------------------------------------------------------
+// sum_q src[q*stride], q = 0..S-1, 8 independent loads in flight, added in order
+__device__ __forceinline__ double sum_splits(const double* __restrict__ src, int S, int64_t stride) {
+    double s0 = 0.0;
+    int q = 0;
+    for (; q + 8 <= S; q += 8) {
+        double v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = src[(int64_t)(q + i) * stride];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s0 += v[i];
+    }
+    for (; q < S; ++q) s0 += src[(int64_t)q * stride];
+    return s0;
+}
+
 constexpr int kU2Lanes = 8;
 constexpr int kU2Slots = 32;
 constexpr int kU2Threads = kU2Lanes * kU2Slots;
@@ -835,19 +856,18 @@ __global__ void __launch_bounds__(kU2Threads) lbfgs_update_vl2_kernel(const UpdA
     const int64_t bb = valid ? b : B - 1;
     const int V = a.V;
     const bool active = valid && a.done[bb] == 0;
+    if (a.nreset != nullptr && blockIdx.x == 0 && tid == 0) *a.nreset = 0;
     if (!__syncthreads_or(active)) return;
 
     for (int q = vs; q < NG; q += kU2Slots) Gs[q][l] = Gm[(int64_t)q * B + bb];
 
     const double N = a.N[bb];
-    // ---- A: gather the partials of the pass evaluated at zt
-    double llsum = 0.0;
-    for (int q = 0; q < a.S; ++q) llsum += a.llpart[(int64_t)q * B + bb];
+    // ---- A: sum the per-split partials of the pass evaluated at zt in FIXED split order (bitwise reproducible)
+    const double llsum = sum_splits(a.llpart + bb, a.S, B);
     double r2[2] = {0.0, 0.0};                                  // sum phi, d.gt
     for (int v = vs; v < V; v += kU2Slots) {
         const int64_t i = (int64_t)v * B + bb;
-        double tv = 0.0;
-        for (int q = 0; q < a.S; ++q) tv += a.tpart[((int64_t)q * V + v) * B + bb];
+        const double tv = sum_splits(a.tpart + i, a.S, (int64_t)V * B);
         const double gh = tv * a.invL[v] / N;
         const double ztv = a.zt[i];
         const bool mk = a.mask ? a.mask[i] != 0 : true;

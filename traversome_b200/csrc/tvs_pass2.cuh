@@ -26,9 +26,16 @@ namespace tvs {
 constexpr int kWarps2 = 16;
 constexpr int kThreads2 = kWarps2 * 32;
 
-// coefficients of atanh(s)/s - 1 = s^2/3 + s^4/5 + ... in constant memory: DFMA reads them as c[][] operands
-__constant__ double kLogC[12] = {1.0 / 3.0, 1.0 / 5.0, 1.0 / 7.0, 1.0 / 9.0, 1.0 / 11.0, 1.0 / 13.0, 1.0 / 15.0, 1.0 / 17.0, 1.0 / 19.0,
-                                 6.93147180369123816490e-01 /* ln2_hi, 32 significant bits */, 1.90821492927058770002e-10 /* ln2_lo */, 0.0};
+// coefficients of atanh(s)/s - 1 = s^2/3 + s^4/5 + ... travel as KERNEL PARAMETERS (LogCoef inside the argument
+// struct): bank-0 constants are legal DFMA operands, so the polynomial costs no loads or moves (a __constant__ array
+// costs one LDCU per use: profiles/r1_v2_summary.md).
+__host__ __device__ inline LogCoef make_log_coef() {
+    LogCoef k;
+    for (int i = 0; i < 9; ++i) k.c[i] = 1.0 / (double)(2 * i + 3);
+    k.c[9] = 6.93147180369123816490e-01;      // ln2_hi, 32 significant bits
+    k.c[10] = 1.90821492927058770002e-10;     // ln2_lo
+    return k;
+}
 
 __device__ __forceinline__ bool is_pos_normal(double p) {       // finite, normal, > 0 (one integer compare)
     return (unsigned)(__double2hiint(p) - 0x00100000) < 0x7fe00000u;
@@ -45,7 +52,7 @@ __device__ __forceinline__ double fast_rcp(double p) {          // p finite, nor
 
 // natural logarithm for finite normal p > 0: p = 2^e m, m in [sqrt(1/2), sqrt(2)),
 // log m = 2 atanh(s), s = (m-1)/(m+1), |s| <= 0.1716.
-__device__ __forceinline__ double fast_log_pos(double p) {
+__device__ __forceinline__ double fast_log_pos(double p, const LogCoef& kc) {
     int hi = __double2hiint(p);
     const int lo = __double2loint(p);
     int e = (hi >> 20) - 1023;
@@ -55,30 +62,31 @@ __device__ __forceinline__ double fast_log_pos(double p) {
     const double u = fast_rcp(m + 1.0);
     const double s = (m - 1.0) * u;
     const double s2 = s * s;
-    double q = kLogC[8];
-    q = fma(q, s2, kLogC[7]);
-    q = fma(q, s2, kLogC[6]);
-    q = fma(q, s2, kLogC[5]);
-    q = fma(q, s2, kLogC[4]);
-    q = fma(q, s2, kLogC[3]);
-    q = fma(q, s2, kLogC[2]);
-    q = fma(q, s2, kLogC[1]);
-    q = fma(q, s2, kLogC[0]);
+    double q = kc.c[8];
+    q = fma(q, s2, kc.c[7]);
+    q = fma(q, s2, kc.c[6]);
+    q = fma(q, s2, kc.c[5]);
+    q = fma(q, s2, kc.c[4]);
+    q = fma(q, s2, kc.c[3]);
+    q = fma(q, s2, kc.c[2]);
+    q = fma(q, s2, kc.c[1]);
+    q = fma(q, s2, kc.c[0]);
     const double ed = (double)e;
     const double two_s = s + s;
-    const double tail = fma(two_s * s2, q, ed * kLogC[10]);      // + e * ln2_lo
-    return fma(ed, kLogC[9], two_s + tail);                      // e * ln2_hi is exact
+    const double tail = fma(two_s * s2, q, ed * kc.c[10]);      // + e * ln2_lo
+    return fma(ed, kc.c[9], two_s + tail);                      // e * ln2_hi is exact
 }
 
-__device__ __forceinline__ double log_any(double p) {           // -inf at 0, nan below, slow path for odd inputs
-    if (is_pos_normal(p)) return fast_log_pos(p);
+__device__ __forceinline__ double log_any(double p, const LogCoef& kc) {   // -inf at 0, nan below, slow path for odd inputs
+    if (is_pos_normal(p)) return fast_log_pos(p, kc);
     return log(p);
 }
 
-__global__ void selftest_math_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ lg, double* __restrict__ rc) {
+__global__ void selftest_math_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ lg, double* __restrict__ rc,
+                                     const LogCoef kc) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    lg[i] = log_any(p[i]);
+    lg[i] = log_any(p[i], kc);
     rc[i] = is_pos_normal(p[i]) ? fast_rcp(p[i]) : 1.0 / p[i];
 }
 
@@ -183,7 +191,7 @@ __global__ void __launch_bounds__(kThreads2, 1) pass2_kernel(const PassArgs a) {
                 const double wd = (double)wv.v[j];
                 const bool on = wv.v[j] > 0;
                 double rcp, lg;
-                if (is_pos_normal(p[j])) { rcp = fast_rcp(p[j]); lg = fast_log_pos(p[j]); }
+                if (is_pos_normal(p[j])) { rcp = fast_rcp(p[j]); lg = fast_log_pos(p[j], a.logc); }
                 else { rcp = 1.0 / p[j]; lg = log(p[j]); }
                 rr[j] = on ? wd * rcp : 0.0;
                 ll[j] = on ? fma(wd, lg, ll[j]) : ll[j];
@@ -319,30 +327,37 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
     int* cs_s = reinterpret_cast<int*>(smem3 + L.cs);
     int* cid_s = reinterpret_cast<int*>(smem3 + L.cid);
 
-    // row-major entries + row pointers of chunk c -> buffer `buf`
-    auto stage_rows = [&](int c, int buf) {
-        const int r0 = a.chunk_row0[c], r1 = a.chunk_row0[c + 1];
-        const int e0 = a.row_ptr[r0], n = a.row_ptr[r1] - e0;
-        for (int i = threadIdx.x; i < n; i += NT) {
-            cp_async8(f1_s + (size_t)buf * cap + i, a.fval + e0 + i);
-            cp_async4(c1_s + (size_t)buf * cap + i, a.col32 + e0 + i);
+    // row-major entries + row pointers of a chunk -> buffer `buf`
+    auto stage_rows = [&](const ChunkDesc& d, int buf) {
+        for (int i = threadIdx.x; i < d.nent; i += NT) {
+            cp_async8(f1_s + (size_t)buf * cap + i, a.fval + d.e0 + i);
+            cp_async4(c1_s + (size_t)buf * cap + i, a.col32 + d.e0 + i);
         }
-        for (int i = threadIdx.x; i <= r1 - r0; i += NT) cp_async4(rp_s + buf * (RC + 1) + i, a.row_ptr + r0 + i);
+        for (int i = threadIdx.x; i <= d.nrows; i += NT) cp_async4(rp_s + buf * (RC + 1) + i, a.row_ptr + d.row0 + i);
     };
-    // column-major entries + column starts / ids of chunk c
-    auto stage_cols = [&](int c) {
-        const int c0 = a.ccol_ptr[c], c1 = a.ccol_ptr[c + 1];
-        const int e0 = a.ccol_start[c0], n = a.ccol_start[c1] - e0;
-        for (int i = threadIdx.x; i < n; i += NT) {
-            cp_async8(f2_s + i, a.cfval + e0 + i);
-            cp_async4(c2_s + i, a.crow32 + e0 + i);
+    // column-major entries + column starts / ids of a chunk
+    auto stage_cols = [&](const ChunkDesc& d) {
+        for (int i = threadIdx.x; i < d.ncent; i += NT) {
+            cp_async8(f2_s + i, a.cfval + d.ce0 + i);
+            cp_async4(c2_s + i, a.crow32 + d.ce0 + i);
         }
-        for (int i = threadIdx.x; i <= c1 - c0; i += NT) cp_async4(cs_s + i, a.ccol_start + c0 + i);
-        for (int i = threadIdx.x; i < c1 - c0; i += NT) cp_async4(cid_s + i, a.ccol_id + c0 + i);
+        for (int i = threadIdx.x; i <= d.ncol; i += NT) cp_async4(cs_s + i, a.ccol_start + d.c0 + i);
+        for (int i = threadIdx.x; i < d.ncol; i += NT) cp_async4(cid_s + i, a.ccol_id + d.c0 + i);
+    };
+    // chunk descriptors are fetched two chunks ahead: no dependent global loads inside the chunk loop
+    auto load_desc = [&](int c) {
+        ChunkDesc d;
+        if (c < a.n_chunks) {
+            const int4 lo = __ldg(reinterpret_cast<const int4*>(a.desc + c));
+            const int4 hi = __ldg(reinterpret_cast<const int4*>(a.desc + c) + 1);
+            d.row0 = lo.x; d.nrows = lo.y; d.e0 = lo.z; d.nent = lo.w; d.c0 = hi.x; d.ncol = hi.y; d.ce0 = hi.z; d.ncent = hi.w;
+        } else d = ChunkDesc{0, 0, 0, 0, 0, 0, 0, 0};
+        return d;
     };
 
     int c = split, buf = 0;
-    if (c < a.n_chunks) stage_rows(c, 0);
+    ChunkDesc cur = load_desc(c), nxt = load_desc(c + S);
+    stage_rows(cur, 0);
     cp_async_commit();
 
     for (int i = threadIdx.x; i < V * LT; i += NT) {
@@ -358,11 +373,12 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
     for (int j = 0; j < K; ++j) ll[j] = 0.0;
 
     for (; c < a.n_chunks; c += S, buf ^= 1) {
-        const int row0 = a.chunk_row0[c], row1 = a.chunk_row0[c + 1];
+        const ChunkDesc nx2 = load_desc(c + 2 * S);        // consumed two trips from now
+        const int row0 = cur.row0, row1 = cur.row0 + cur.nrows;
         cp_async_wait_all();
         __syncthreads();                                   // entries of chunk c (and x_s on the first trip) visible
-        if (BACKWARD) stage_cols(c);
-        if (c + S < a.n_chunks) stage_rows(c + S, buf ^ 1);
+        if (BACKWARD) stage_cols(cur);
+        if (c + S < a.n_chunks) stage_rows(nxt, buf ^ 1);
         cp_async_commit();
         // ---------------- phase 1: p = A x over the rows of the chunk
         const double* f1 = f1_s + (size_t)buf * cap;
@@ -403,7 +419,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
                     const double wd = (double)wv.v[j];
                     const bool on = wv.v[j] > 0;
                     rr[j] = on ? wd * fast_rcp(p[j]) : 0.0;
-                    ll[j] = on ? fma(wd, fast_log_pos(p[j]), ll[j]) : ll[j];
+                    ll[j] = on ? fma(wd, fast_log_pos(p[j], a.logc), ll[j]) : ll[j];
                 }
             } else {
 #pragma unroll
@@ -420,7 +436,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
             cp_async_wait_all();
             __syncthreads();                               // rr_s complete, column-major entries landed
             // ------------ phase 2: t += A^T rr over the non-empty columns of the chunk
-            const int ncol = a.ccol_ptr[c + 1] - a.ccol_ptr[c];
+            const int ncol = cur.ncol;
             const int ce0 = cs_s[0];
             for (int ci = wi; ci < ncol; ci += NW) {
                 const int v = cid_s[ci];
@@ -438,6 +454,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
                 sts_lanes<K>(t_s + v * LT, t, acc);
             }
         }
+        cur = nxt; nxt = nx2;
     }
     cp_async_wait_all();
     __syncthreads();
