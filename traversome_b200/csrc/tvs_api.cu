@@ -2,6 +2,7 @@
 // Host side: CSR validation and chunking, launch geometry, the batched L-BFGS driver loop.
 #include "tvs_kernels.cuh"
 #include "tvs_pass2.cuh"
+#include "tvs_newton.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -48,6 +49,7 @@ static void free_csr(Csr& c) {
     dev_free(c.ccol_start); dev_free(c.cent); dev_free(c.invL); dev_free(c.Ld);
     dev_free(c.col32); dev_free(c.fval); dev_free(c.crow32); dev_free(c.cfval);
     if (c.desc) { cudaFree(c.desc); c.desc = nullptr; }
+    dev_free(c.slab_ptr); dev_free(c.h_row); dev_free(c.h_val); dev_free(c.h_slot);
 }
 static void free_lanes(Lanes& l) {
     dev_free(l.w); dev_free(l.mask); dev_free(l.C); dev_free(l.N);
@@ -56,6 +58,8 @@ static void free_lanes(Lanes& l) {
 static void free_fit(FitState& f) {
     for (void* p : f.owned) cudaFree(p);
     if (f.h_nactive) cudaFreeHost(f.h_nactive);
+    if (f.Hpart) cudaFree(f.Hpart);
+    if (f.cr) cudaFree(f.cr);
     f = FitState();
 }
 
@@ -266,6 +270,7 @@ static int ensure_fit_state(tvs_problem* h, int m) {
     f.llpart_cap = f.tpart_cap / (size_t)V;
     A_(f.tpart, f.tpart_cap) A_(f.llpart, f.llpart_cap) A_(f.t_red, vb) A_(f.ll_red, B)
     A_(f.idx, B + 4) A_(f.nactive, 32)
+    A_(f.gha, vb) A_(f.lam, B) A_(f.need, B)
     A_(f.theta_io, vb) A_(f.ll_out, B) A_(f.kkt_out, 2 * (size_t)B) A_(f.iters_out, B) A_(f.status_out, B)
 #undef A_
     if (cudaMallocHost((void**)&f.h_nactive, 32 * sizeof(int32_t)) != cudaSuccess) { free_fit(f); set_error("cudaMallocHost failed"); return TVS_ENOMEM; }
@@ -410,6 +415,53 @@ int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, c
     UP_(ent, ent, uint32_t) UP_(cent, cent, uint32_t) UP_(chunk_row0, chunk_row0, int32_t) UP_(ccol_ptr, ccol_ptr, int32_t)
     if (ccol_id.empty()) ccol_id.push_back(0);
     UP_(ccol_id, ccol_id, int32_t) UP_(ccol_start, ccol_start, int32_t) UP_(invL, invL, double) UP_(Ld, Ld, double)
+    // Hessian slabs of the Newton phase (tvs_newton.cuh)
+    if (V <= kNewtonMaxV && env_int("TVS_NEWTON_LANES", 128) > 0) {
+        int64_t np = 0;
+        bool exact = true;
+        for (int64_t r = 0; r < R; ++r) { const int64_t n = row_ptr[r + 1] - row_ptr[r]; np += n * (n + 1) / 2; }
+        for (int64_t k = 0; k < nnz && exact; ++k) exact = val[k] < 4096;          // products stay below 2^24: exact in float
+        if (exact && np <= (int64_t)48 << 20) {
+            const int HB = std::max(32, std::min(env_int("TVS_HESS_ROWS", 1024), 16384));
+            const int NPk = (int)(V * (V + 1) / 2), NG = (NPk + 31) / 32;
+            const int nblk = (int)((R + HB - 1) / HB);
+            std::vector<int64_t> sp((size_t)nblk * (NG + 1));
+            std::vector<uint16_t> hrow, hslot((size_t)nblk * NG * 32, (uint16_t)0xFFFF);
+            std::vector<float> hval;
+            std::vector<std::vector<std::pair<uint16_t, float>>> lists((size_t)NPk);
+            std::vector<int> order((size_t)NPk);
+            int64_t steps = 0;
+            for (int b = 0; b < nblk; ++b) {
+                const int64_t rb0 = (int64_t)b * HB, rb1 = std::min<int64_t>(R, rb0 + HB);
+                for (auto& l : lists) l.clear();
+                for (int64_t r = rb0; r < rb1; ++r)
+                    for (int64_t i = row_ptr[r]; i < row_ptr[r + 1]; ++i)
+                        for (int64_t j = row_ptr[r]; j <= i; ++j)           // col[i] >= col[j]
+                            lists[(size_t)(col[i] * (col[i] + 1) / 2 + col[j])].push_back({(uint16_t)(r - rb0), (float)val[i] * (float)val[j]});
+                for (int i = 0; i < NPk; ++i) order[i] = i;
+                std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return lists[x].size() > lists[y].size(); });
+                for (int e = 0; e < NG; ++e) {
+                    sp[(size_t)b * (NG + 1) + e] = steps;
+                    const size_t len = (e * 32 < NPk) ? lists[order[e * 32]].size() : 0;
+                    for (size_t k = 0; k < len; ++k)
+                        for (int t = 0; t < 32; ++t) {
+                            const int pos = e * 32 + t;
+                            if (pos < NPk && k < lists[order[pos]].size()) { hrow.push_back(lists[order[pos]][k].first); hval.push_back(lists[order[pos]][k].second); }
+                            else { hrow.push_back((uint16_t)HB); hval.push_back(0.f); }
+                        }
+                    for (int t = 0; t < 32; ++t) {
+                        const int pos = e * 32 + t;
+                        if (pos < NPk && !lists[order[pos]].empty()) hslot[((size_t)b * NG + e) * 32 + t] = (uint16_t)order[pos];
+                    }
+                    steps += (int64_t)len;
+                }
+                sp[(size_t)b * (NG + 1) + NG] = steps;
+            }
+            if (hrow.empty()) { hrow.push_back(0); hval.push_back(0.f); }
+            c.h_HB = HB; c.h_nblk = nblk; c.h_NG = NG; c.h_steps = steps;
+            UP_(slab_ptr, sp, int64_t) UP_(h_row, hrow, uint16_t) UP_(h_val, hval, float) UP_(h_slot, hslot, uint16_t)
+        }
+    }
 #undef UP_
     *out = h;
     return TVS_OK;
@@ -626,6 +678,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
 
     std::vector<cudaEvent_t> pev, uev; // per-pass / per-update events when timing is requested
     std::vector<int64_t> pass_width;   // width of every pass (TVS_DUMP_PASSES)
+    std::vector<cudaEvent_t> nev;      // Newton phase: (before hess, after hess, after solve) per iteration
     int64_t passes = 0, launches = 3, lane_passes = 0, n_polls = 0, compactions = 0;
     const int64_t max_passes = (int64_t)opt.max_iter * 2 + 64;
     cudaError_t cerr = cudaSuccess;
@@ -641,6 +694,100 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         fa.V = (int)V; fa.B = s.width; fa.B0 = B0; fa.only_done = only_done;
         finalize_fit_kernel<<<(unsigned)((s.width + 127) / 128), 128, 0, st>>>(fa);
         ++launches;
+    };
+
+    // ---- damped Newton phase (tvs_newton.cuh): runs the lanes of a small set to convergence
+    const int newton_lanes = (h->csr.slab_ptr != nullptr && V <= kNewtonMaxV) ? env_int("TVS_NEWTON_LANES", 128) : 0;
+    int64_t newton_iters = 0;
+    bool newton_off = false;                                    // set when the shape has no staged pass kernel
+    auto newton_phase = [&](LaneSet& s, bool* ran) -> int {
+        *ran = false;
+        const int64_t W = s.width;
+        const int NP = (int)(V * (V + 1) / 2);
+        const Csr& c = h->csr;
+        // one warp per (lane, range of row blocks); all warps resident at once (<= 13 per SM by shared memory)
+        const size_t hess_smem = ((size_t)NP + c.h_HB + 1 + c.h_NG + 1) * 8 + (size_t)c.h_NG * 32 * 2;
+        const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(220 * 1024) / (hess_smem + 1024)));
+        int S_h = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * ctas_per_sm / W, c.h_nblk));
+        const int blocks_per_split = (c.h_nblk + S_h - 1) / S_h;
+        S_h = (c.h_nblk + blocks_per_split - 1) / blocks_per_split;
+        const size_t need_cap = (size_t)S_h * (size_t)W * (size_t)NP;
+        if (f.Hpart_cap < need_cap) {
+            if (f.Hpart) cudaFree(f.Hpart);
+    if (f.cr) cudaFree(f.cr);
+            f.Hpart = nullptr; f.Hpart_cap = 0;
+            TVS_CUDA(cudaMalloc((void**)&f.Hpart, need_cap * sizeof(double)));
+            f.Hpart_cap = need_cap;
+        }
+        if (f.cr_cap < (size_t)R * (size_t)W) {
+            if (f.cr) cudaFree(f.cr);
+            f.cr = nullptr; f.cr_cap = 0;
+            TVS_CUDA(cudaMalloc((void**)&f.cr, (size_t)R * (size_t)W * sizeof(double)));
+            f.cr_cap = (size_t)R * (size_t)W;
+        }
+        TVS_CUDA(cudaFuncSetAttribute(hess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hess_smem));
+        const size_t solve_smem = ((size_t)2 * V * (V + 1) + 2 * V) * 8;
+        TVS_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+        PassPlan pl;
+        int prc = make_plan<true>(h, W, &pl);
+        if (prc != TVS_OK) return prc;
+        if (pl.v3_warps == 0) { newton_off = true; return TVS_OK; }   // no staged pass kernel for this shape: stay with L-BFGS
+        *ran = true;
+        while (pl.splits > 1 && (size_t)pl.splits * (size_t)W * (size_t)V > f.tpart_cap) --pl.splits;
+        const bool pre_reduce = pl.splits > env_int("TVS_FUSE_SPLITS", 24);
+        newton_init_kernel<<<(unsigned)((W + 127) / 128), 128, 0, st>>>(s.z, s.g, s.mask, h->csr.invL, (int)V, W, f.gha, s.x, f.lam, f.need, s.ls);
+        ++launches;
+        PassArgs pa = base_args(h);
+        pa.w = s.w; pa.B = W; pa.x = s.x; pa.done = s.done; pa.tpart = f.tpart; pa.llpart = f.llpart; pa.cr = f.cr;
+        {   // refresh pass at the accepted point: c_r = w_r / p_r^2 for the first Hessian
+            int lrc = launch_pass<true>(h, pl, pa);
+            if (lrc != TVS_OK) return lrc;
+            ++launches;
+        }
+        HessArgs ha{};
+        ha.slab_ptr = c.slab_ptr; ha.h_row = c.h_row; ha.h_val = c.h_val; ha.h_slot = c.h_slot; ha.cr = f.cr;
+        ha.done = s.done; ha.need = f.need; ha.Hpart = f.Hpart;
+        ha.W = W; ha.R = R; ha.V = (int)V; ha.HB = c.h_HB; ha.nblk = c.h_nblk; ha.NG = c.h_NG; ha.blocks_per_split = blocks_per_split;
+        SolveArgs sa{};
+        sa.Hpart = f.Hpart; sa.S = S_h; sa.z = s.z; sa.g = s.g; sa.gha = f.gha; sa.invL = h->csr.invL; sa.N = s.N; sa.mask = s.mask;
+        sa.done = s.done; sa.lam = f.lam; sa.d = s.d; sa.zt = s.zt; sa.x = s.x; sa.dg = s.dg; sa.alpha = s.alpha; sa.W = W; sa.V = (int)V;
+        NewtonUpdArgs na{};
+        na.invL = h->csr.invL; na.N = s.N; na.mask = s.mask; na.z = s.z; na.zt = s.zt; na.g = s.g; na.gt = f.gt; na.gh = f.gh;
+        na.gha = f.gha; na.d = s.d; na.F = s.F; na.dg = s.dg; na.alpha = s.alpha; na.llsum = s.llsum; na.kkt = s.kkt;
+        na.sumphi = s.sumphi; na.lam = f.lam; na.ls = s.ls; na.iters = s.iters; na.status = s.status; na.done = s.done;
+        na.need = f.need; na.V = (int)V; na.B = W; na.max_iter = opt.max_iter; na.tol = opt.tol;
+        na.tol_dual = (double)env_int("TVS_DUAL_MULT", 100) * opt.tol;
+        const int max_newton = env_int("TVS_NEWTON_MAXIT", 300);
+        for (int it = 0; it < max_newton && passes < max_passes; ++it) {
+            const int slot = (int)(n_polls % 16);
+            cudaEvent_t eh0 = nullptr, eh1 = nullptr, eh2 = nullptr;
+            if (time_passes) { cudaEventCreate(&eh0); cudaEventCreate(&eh1); cudaEventCreate(&eh2); cudaEventRecord(eh0, st); }
+            hess_kernel<<<dim3((unsigned)W, (unsigned)S_h), 32 * kHessWarps, hess_smem, st>>>(ha);
+            if (time_passes) cudaEventRecord(eh1, st);
+            solve_kernel<<<(unsigned)W, kSolveThreads, solve_smem, st>>>(sa);
+            if (time_passes) { cudaEventRecord(eh2, st); nev.push_back(eh0); nev.push_back(eh1); nev.push_back(eh2); }
+            if (time_passes) { cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); pev.push_back(e0); pev.push_back(e1); cudaEventRecord(e0, st); }
+            int lrc = launch_pass<true>(h, pl, pa);
+            if (lrc != TVS_OK) return lrc;
+            if (time_passes) cudaEventRecord(pev.back(), st);
+            if (pre_reduce) {
+                reduce_partials_kernel<<<(unsigned)(((int64_t)(V + 1) * W + 255) / 256), 256, 0, st>>>(f.tpart, f.llpart, pl.splits, (int)V, W,
+                                                                                                      f.t_red, f.ll_red);
+                na.tpart = f.t_red; na.llpart = f.ll_red; na.S = 1;
+                ++launches;
+            } else { na.tpart = f.tpart; na.llpart = f.llpart; na.S = pl.splits; }
+            na.nactive = f.nactive + slot;
+            cudaMemsetAsync(f.nactive + slot, 0, 4, st);
+            newton_update_kernel<<<(unsigned)((W + kU2Lanes - 1) / kU2Lanes), kU2Threads, 0, st>>>(na);
+            if (time_passes) { cudaEvent_t e2; cudaEventCreate(&e2); uev.push_back(pev.back()); uev.push_back(e2); cudaEventRecord(e2, st); pass_width.push_back(-W); }
+            ++passes; launches += 5; lane_passes += W; ++newton_iters;
+            cudaMemcpyAsync(f.h_nactive + slot, f.nactive + slot, 4, cudaMemcpyDeviceToHost, st);
+            cerr = cudaStreamSynchronize(st);
+            if (cerr != cudaSuccess) return TVS_OK;       // reported by the caller through cerr
+            ++n_polls;
+            if (f.h_nactive[slot] == 0) { all_done = true; break; }
+        }
+        return TVS_OK;
     };
 
     while (!all_done && passes < max_passes && rc == TVS_OK) {
@@ -710,7 +857,8 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         const int64_t active = f.h_nactive[slot];
         if (active == 0) { all_done = true; break; }
         // ---- compaction: keep only the lanes that are still iterating
-        if (!no_compact && active * 2 <= W && W > 32 && active + 3 <= f.half) {
+        const bool to_newton = newton_lanes > 0 && !newton_off && active <= newton_lanes;
+        if (!no_compact && (active * 2 <= W || (to_newton && W > newton_lanes)) && W > 32 && active + 3 <= f.half) {
             finalize(s, 1);                                      // results of the finished lanes, at their original ids
             LaneSet& n = f.set[cur ^ 1];
             build_index_kernel<<<1, 1024, 0, st>>>(s.done, W, f.idx, f.nactive + 30);
@@ -753,6 +901,11 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
             ++compactions;
             cur ^= 1;
         }
+        if (to_newton && !newton_off && f.set[cur].width <= std::max(newton_lanes, 32)) {
+            bool ran = false;
+            rc = newton_phase(f.set[cur], &ran);
+            if (ran || rc != TVS_OK) break;                     // the phase runs its lanes to completion (or to the pass budget)
+        }
     }
     if (rc == TVS_OK && cerr == cudaSuccess) {
         finalize(f.set[cur], 0);
@@ -786,10 +939,17 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
                 cudaEventElapsedTime(&u, uev[i], uev[i + 1]);
                 fprintf(stderr, "pass %zu width %lld pass_us %.1f update_us %.1f\n", i / 2, (long long)pass_width[i / 2], q * 1e3, u * 1e3);
             }
+            for (size_t i = 0; i + 2 < nev.size(); i += 3) {
+                float q = 0.f, u = 0.f;
+                cudaEventElapsedTime(&q, nev[i], nev[i + 1]);
+                cudaEventElapsedTime(&u, nev[i + 1], nev[i + 2]);
+                fprintf(stderr, "newton %zu hess_us %.1f solve_us %.1f\n", i / 3, q * 1e3, u * 1e3);
+            }
         }
     }
     for (size_t i = 1; i < uev.size(); i += 2) cudaEventDestroy(uev[i]);
     for (auto e : pev) cudaEventDestroy(e);
+    for (auto e : nev) cudaEventDestroy(e);
     if (rc != TVS_OK) return rc;
     if (cerr != cudaSuccess) return cuda_fail(cerr, "tvs_fit", __FILE__, __LINE__);
     return TVS_OK;

@@ -42,6 +42,13 @@ struct Csr {
     double*   cfval = nullptr;       // [nnz]  count as double, column-major within chunk
     int       max_chunk_nnz = 0;     // largest number of entries in one chunk
     void*     desc = nullptr;        // [n_chunks] ChunkDesc (tvs_kernels.cuh)
+    // Newton phase (V <= 64): products A_ru A_rv (u >= v) grouped by H entry inside blocks of h_HB rows (tvs_newton.cuh)
+    int64_t*  slab_ptr = nullptr;    // [h_nblk * (h_NG + 1)] step offsets
+    uint16_t* h_row = nullptr;       // [h_steps * 32] block-local row (h_HB = padding)
+    float*    h_val = nullptr;       // [h_steps * 32] product (exact: < 2^24 checked)
+    uint16_t* h_slot = nullptr;      // [h_nblk * h_NG * 32] packed H index u(u+1)/2+v, 0xFFFF = none
+    int       h_HB = 0, h_nblk = 0, h_NG = 0;
+    int64_t   h_steps = 0;
     double*   invL = nullptr;        // [V] 1/L_v
     double*   Ld = nullptr;          // [V] L_v as double
     int64_t   n_ccol = 0;
@@ -84,6 +91,8 @@ struct FitState {               // all device, sized for (V, B, history)
     double *tpart = nullptr, *llpart = nullptr; size_t tpart_cap = 0, llpart_cap = 0;
     double *t_red = nullptr, *ll_red = nullptr;     // partials summed over the row splits
     int32_t *idx = nullptr;                          // compaction gather list
+    // Newton phase scratch
+    double *gha = nullptr, *lam = nullptr, *Hpart = nullptr, *cr = nullptr; int32_t* need = nullptr; size_t Hpart_cap = 0, cr_cap = 0;
     int32_t *nactive = nullptr;   // device counters (ring)
     int32_t *h_nactive = nullptr; // pinned host mirror
     // output staging at the ORIGINAL width

@@ -35,6 +35,7 @@ struct PassArgs {
     const int32_t* col32; const double* fval; const int32_t* crow32; const double* cfval; int stage_cap;
     const ChunkDesc* desc;
     LogCoef logc;
+    double* cr;          // optional [R*B]: w / p^2 per (row, lane) for the Newton phase's Hessian (pass3_kernel only)
 };
 
 template <int LPT, bool XS, bool BACKWARD>

@@ -1,0 +1,373 @@
+// Damped Newton phase of tvs_fit for small lane sets (sm_100a).  Included by tvs_api.cu.
+//
+// replaces: the last ~2/3 of the iterations of scipy's SLSQP multistart (ModelFitMaxLike.py:19-58) on the
+// few lanes that batched L-BFGS leaves behind (profiles/r1_v3_summary.md: ~130 iterations at <= 48 lanes,
+// ~55 us each whatever the width), and the whole fit of small batches (model-selection chunks, cfg1).
+//
+// Same objective as the L-BFGS phase, F(z) = -(1/N) sum_r w_r log (M z^2)_r + sum_v z_v^2, whose Hessian is
+//     Hz = 2 diag(1 - g) + 4 (z z^T) o H ,   H_uv = (1/N) sum_r w_r M_ru M_rv / p_r^2 ,  M_rv = A_rv / L_v .
+// One Newton iteration of a lane set =
+//   hess_kernel     H of every lane that moved, as per-split partial sums (one warp = one (lane, row range);
+//                   the warp owns a private packed-triangular H in shared memory and walks its rows in order,
+//                   so the summation order is fixed: bitwise reproducible, no atomics);
+//   solve_kernel    one CTA per lane: sums the partials, forms Hz + lambda I, Cholesky (lambda grows until
+//                   the factorisation succeeds: Levenberg-Marquardt damping, the z-parametrisation is not
+//                   convex), solves for the step, writes the trial point;
+//   pass kernel     the ordinary fused likelihood pass at the trial point;
+//   newton_update_kernel   Armijo accept / reject (reject -> lambda x 10 and re-solve with the same H),
+//                   KKT residuals, convergence flags.
+// Available when V <= 64 (H is 2,080 doubles per lane) and the pair lists fit (tvs_create builds them).
+#pragma once
+#include "tvs_kernels.cuh"
+#include "tvs_pass2.cuh"
+
+namespace tvs {
+
+constexpr int kNewtonMaxV = 64;
+
+// Hessian accumulation.  tvs_create cuts the rows into blocks of HB rows and, per block, stores the products
+// A_ru A_rv (u >= v) of every row GROUPED BY H ENTRY: entries sorted by their number of contributing rows, 32
+// entries to a slab, slab e = len_e steps of 32 (local row, product) pairs (thread t of the warp owns entry
+// t of the slab; shorter lists padded with (row HB, 0), cs[HB] = 0).  A warp = one (lane, range of blocks):
+// it loads c_r = w_r / p_r^2 of the block's rows (written by the likelihood pass at the accepted point) into
+// shared memory, then streams the block's steps -- coalesced loads, private accumulators, no atomics, a fixed
+// summation order -- and adds each slab's sums into its packed-triangular H in shared memory.
+struct HessArgs {
+    const int64_t* slab_ptr;      // [nblk * (NG + 1)] step offsets
+    const uint16_t* h_row;        // [steps * 32]
+    const float* h_val;           // [steps * 32]
+    const uint16_t* h_slot;       // [nblk * NG * 32] packed H index of (block, slab, thread); 0xFFFF = none
+    const double* cr;             // [R * W] w / p^2 at the accepted point (lane-minor)
+    const int32_t* done; const int32_t* need;
+    double* Hpart;                // [S][W][NP]
+    int64_t W, R; int V; int HB; int nblk; int NG; int blocks_per_split;
+};
+
+constexpr int kHessBatch = 16;    // steps whose loads are issued together
+constexpr int kHessWarps = 4;     // warps of one CTA = one (lane, range of blocks); they split each block's slabs
+
+struct HessBuf { int rw[kHessBatch]; float vl[kHessBatch]; };
+
+__device__ __forceinline__ void hess_load(HessBuf& b, const HessArgs& a, int64_t base, int64_t send, int t) {
+#pragma unroll
+    for (int i = 0; i < kHessBatch; ++i) {
+        const int64_t q = (base + i < send) ? base + i : send - 1;      // clamp: a valid address, weight 0 below
+        b.rw[i] = __ldg(a.h_row + q * 32 + t);
+        b.vl[i] = (base + i < send) ? __ldg(a.h_val + q * 32 + t) : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(32 * kHessWarps) hess_kernel(const HessArgs a) {
+    extern __shared__ double hs[];                 // Hs[NP] | cs[HB + 1] | sp[NG + 1] (int64) | slot[NG * 32] (uint16)
+    const int V = a.V, NP = V * (V + 1) / 2, HB = a.HB, NG = a.NG;
+    double* Hs = hs;
+    double* cs = hs + NP;
+    int64_t* sp = reinterpret_cast<int64_t*>(cs + HB + 1);
+    uint16_t* slots = reinterpret_cast<uint16_t*>(sp + NG + 1);
+    const int tid = threadIdx.x, t = tid & 31, wi = tid >> 5;
+    const int64_t lane = blockIdx.x;
+    const int split = blockIdx.y;
+    if (a.done[lane] != 0 || a.need[lane] == 0) return;
+    for (int i = tid; i < NP; i += 32 * kHessWarps) Hs[i] = 0.0;
+    const int b0 = split * a.blocks_per_split, b1 = min(a.nblk, b0 + a.blocks_per_split);
+    for (int blk = b0; blk < b1; ++blk) {
+        __syncthreads();
+        const int64_t r0 = (int64_t)blk * HB;
+        const int nrows = (int)min((int64_t)HB, a.R - r0);
+        for (int i = tid; i <= HB; i += 32 * kHessWarps) cs[i] = (i < nrows) ? __ldg(a.cr + (r0 + i) * a.W + lane) : 0.0;
+        for (int e = tid; e <= NG; e += 32 * kHessWarps) sp[e] = __ldg(a.slab_ptr + (int64_t)blk * (NG + 1) + e);
+        for (int i = tid; i < NG * 32; i += 32 * kHessWarps) slots[i] = __ldg(a.h_slot + (int64_t)blk * NG * 32 + i);
+        __syncthreads();
+        // this warp's slabs: a contiguous range holding ~1/kHessWarps of the block's steps (cut at slab boundaries)
+        const int64_t tot0 = sp[0], tot = sp[NG] - tot0;
+        int e_lo = 0, e_hi = NG;
+        {
+            const int64_t lo_target = tot0 + tot * wi / kHessWarps, hi_target = tot0 + tot * (wi + 1) / kHessWarps;
+            while (e_lo < NG && sp[e_lo] < lo_target) ++e_lo;
+            e_hi = e_lo;
+            while (e_hi < NG && sp[e_hi] < hi_target) ++e_hi;
+            if (wi == kHessWarps - 1) e_hi = NG;
+        }
+        if (e_lo < e_hi) {
+            int64_t s = sp[e_lo];
+            const int64_t send = sp[e_hi];
+            int e = e_lo;
+            int64_t nb = sp[e + 1];
+            double acc = 0.0;
+            auto flush = [&]() {
+                const int slot = slots[e * 32 + t];
+                if (slot != 0xFFFF) Hs[slot] += acc;          // slabs are owned by exactly one warp: no race
+                acc = 0.0;
+            };
+            auto compute = [&](const HessBuf& b) {
+#pragma unroll
+                for (int i = 0; i < kHessBatch; ++i) {
+                    if (s < send) {
+                        while (s == nb) { flush(); ++e; nb = sp[e + 1]; }
+                        acc = fma(cs[b.rw[i]], (double)b.vl[i], acc);
+                        ++s;
+                    }
+                }
+            };
+            HessBuf A, Bf;
+            if (s < send) hess_load(A, a, s, send, t);
+            while (s < send) {
+                if (s + kHessBatch < send) hess_load(Bf, a, s + kHessBatch, send, t);
+                compute(A);
+                if (!(s < send)) break;
+                if (s + kHessBatch < send) hess_load(A, a, s + kHessBatch, send, t);
+                compute(Bf);
+            }
+            flush();
+        }
+    }
+    __syncthreads();
+    double* out = a.Hpart + ((int64_t)split * a.W + lane) * NP;
+    for (int i = tid; i < NP; i += 32 * kHessWarps) out[i] = Hs[i];
+}
+
+struct SolveArgs {
+    const double* Hpart; int S;
+    const double* z; const double* g; const double* gha; const double* invL; const double* N; const uint8_t* mask;
+    const int32_t* done;
+    double* lam; double* d; double* zt; double* x; double* dg; double* alpha;
+    int64_t W; int V;
+};
+
+constexpr int kSolveThreads = 256;
+
+// one CTA per lane.  shared: A[V][V+1] (Hz + lam I, factorised in place) | H0[V][V+1] (Hz, kept for retries) | rhs[V]
+__global__ void __launch_bounds__(kSolveThreads) solve_kernel(const SolveArgs a) {
+    extern __shared__ double ss[];
+    const int V = a.V, LD = V + 1, NP = V * (V + 1) / 2;
+    double* A = ss;
+    double* H0 = ss + (size_t)V * LD;
+    double* rhs = H0 + (size_t)V * LD;
+    double* zv = rhs + V;
+    __shared__ double red[kSolveThreads / 32];
+    const int tid = threadIdx.x;
+    const int64_t lane = blockIdx.x;
+    if (a.done[lane] != 0) return;
+    const double invN = 1.0 / a.N[lane];
+    for (int v = tid; v < V; v += kSolveThreads) zv[v] = a.z[(int64_t)v * a.W + lane];
+    __syncthreads();
+    // ---- Hz from the per-split partial sums, added in fixed split order
+    for (int i = tid; i < NP; i += kSolveThreads) {
+        int u = (int)((sqrt(8.0 * i + 1.0) - 1.0) * 0.5);
+        while ((u + 1) * (u + 2) / 2 <= i) ++u;
+        while (u * (u + 1) / 2 > i) --u;
+        const int v = i - u * (u + 1) / 2;                     // u >= v
+        const double s = sum_splits(a.Hpart + (int64_t)lane * NP + i, a.S, (int64_t)a.W * NP);
+        double h = 4.0 * zv[u] * zv[v] * a.invL[u] * a.invL[v] * s * invN;
+        if (u == v) {
+            const bool mk = a.mask ? a.mask[(int64_t)u * a.W + lane] != 0 : true;
+            h = mk ? h + 2.0 * (1.0 - a.gha[(int64_t)u * a.W + lane]) : 1.0;
+            rhs[u] = mk ? -a.g[(int64_t)u * a.W + lane] : 0.0;
+        }
+        H0[u * LD + v] = h;
+        H0[v * LD + u] = h;
+    }
+    __syncthreads();
+    double lam = a.lam[lane];
+    double* invD = zv;                                         // zv is no longer needed: reuse as 1 / D_k
+    // ---- LDL^T of Hz + lam I with the matrix in REGISTERS: thread tid owns the packed lower-triangle entries
+    //      tid, tid + 256, ... (<= 9 for V <= 64) and, for tid < V, rhs[tid].  Step k: the owners of column k publish
+    //      it (and rhs_k) to one of two shared buffers, one barrier, everyone updates its own entries.  The forward
+    //      substitution rides along.  lam is raised until every pivot is positive (Levenberg-Marquardt damping).
+    constexpr int EPT = (kNewtonMaxV * (kNewtonMaxV + 1) / 2 + kSolveThreads - 1) / kSolveThreads;
+    int ei[EPT], ej[EPT];
+    double av[EPT];
+#pragma unroll
+    for (int m = 0; m < EPT; ++m) {
+        const int e = tid + kSolveThreads * m;
+        if (e < NP) {
+            int u = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+            while ((u + 1) * (u + 2) / 2 <= e) ++u;
+            while (u * (u + 1) / 2 > e) --u;
+            ei[m] = u; ej[m] = e - u * (u + 1) / 2;
+        } else { ei[m] = -1; ej[m] = -1; }
+    }
+    double* colbuf = A;                                        // A is only written back after the factorisation
+    double rv = 0.0;
+    for (int attempt = 0; attempt < 60; ++attempt) {
+#pragma unroll
+        for (int m = 0; m < EPT; ++m) av[m] = (ei[m] >= 0) ? H0[ei[m] * LD + ej[m]] + (ei[m] == ej[m] ? lam : 0.0) : 0.0;
+        rv = (tid < V) ? rhs[tid] : 0.0;
+        bool bad = false;
+        for (int k = 0; k < V; ++k) {
+            double* col = colbuf + (k & 1) * (V + 2);
+#pragma unroll
+            for (int m = 0; m < EPT; ++m)
+                if (ej[m] == k) col[ei[m]] = av[m];
+            if (tid == k) col[V] = rv;
+            __syncthreads();
+            const double piv = col[k];
+            if (!(piv > 1e-12 * fabs(H0[k * LD + k] + lam) && piv > 0.0 && piv < INFINITY)) { bad = true; break; }
+            const double rp = fast_rcp(piv);
+            if (tid == 0) invD[k] = rp;
+            const double bk = col[V];
+#pragma unroll
+            for (int m = 0; m < EPT; ++m)
+                if (ej[m] > k) av[m] = fma(-col[ei[m]] * rp, col[ej[m]], av[m]);
+            if (tid > k && tid < V) rv = fma(-col[tid] * rp, bk, rv);
+        }
+        __syncthreads();
+        if (!bad) break;
+        lam = fmax(10.0 * lam, 1e-6);
+    }
+    // unscaled columns of L and y back to shared memory for the backward substitution
+#pragma unroll
+    for (int m = 0; m < EPT; ++m)
+        if (ei[m] >= 0) A[ei[m] * LD + ej[m]] = av[m];
+    if (tid < V) rhs[tid] = rv;
+    __syncthreads();
+    // ---- D^-1, then L^T d = y with L_ki = A_ki / D_i (one warp; V <= 64)
+    if (tid < 32) {
+        for (int k = tid; k < V; k += 32) rhs[k] *= invD[k];
+        __syncwarp();
+        for (int k = V - 1; k >= 0; --k) {
+            const double xk = rhs[k];
+            __syncwarp();
+            for (int i = tid; i < k; i += 32) rhs[i] = fma(-A[k * LD + i] * invD[i], xk, rhs[i]);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // ---- step: d = rhs ; trial point ; directional derivative
+    double part = 0.0;
+    for (int v = tid; v < V; v += kSolveThreads) {
+        const int64_t i = (int64_t)v * a.W + lane;
+        const double dv = rhs[v];
+        const double zo = a.z[i];
+        a.d[i] = dv;
+        const double zn = zo + dv;
+        a.zt[i] = zn;
+        a.x[i] = zn * zn * a.invL[v];
+        part = fma(dv, a.g[i], part);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((tid & 31) == 0) red[tid >> 5] = part;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int q = 0; q < kSolveThreads / 32; ++q) s += red[q];
+        a.dg[lane] = s;
+        a.alpha[lane] = 1.0;
+        a.lam[lane] = lam;
+    }
+}
+
+// Entry into the Newton phase: g-hat at the ACCEPTED point recovered from the stored z-space gradient
+// g_z = 2 z (1 - g-hat); damping and flags reset.
+__global__ void newton_init_kernel(const double* __restrict__ z, const double* __restrict__ g, const uint8_t* __restrict__ mask,
+                                   const double* __restrict__ invL, int V, int64_t B, double* __restrict__ gha, double* __restrict__ x,
+                                   double* __restrict__ lam, int32_t* __restrict__ need, int32_t* __restrict__ ls) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    for (int v = 0; v < V; ++v) {
+        const int64_t i = (int64_t)v * B + b;
+        const bool mk = mask ? mask[i] != 0 : true;
+        const double zz = z[i];
+        gha[i] = (mk && zz != 0.0) ? 1.0 - g[i] / (2.0 * zz) : 1.0;
+        x[i] = zz * zz * invL[v];                   // the refresh pass evaluates c_r = w_r / p_r^2 at the ACCEPTED point
+    }
+    lam[b] = 0.0; need[b] = 1; ls[b] = 0;
+}
+
+// Accept / reject of the Newton trial point: phases A, B (residuals only), C of lbfgs_update_vl2_kernel.
+struct NewtonUpdArgs {
+    const double* tpart; const double* llpart; int S;
+    const double* invL; const double* N; const uint8_t* mask;
+    double *z, *zt, *g, *gt, *gh, *gha, *d;
+    double *F, *dg, *alpha, *llsum, *kkt, *sumphi, *lam;
+    int32_t *ls, *iters, *status, *done, *need, *nactive;
+    int V; int64_t B; int max_iter; double tol, tol_dual;
+};
+
+__global__ void __launch_bounds__(kU2Threads) newton_update_kernel(const NewtonUpdArgs a) {
+    __shared__ double part[kU2Warps * 4 * kU2Lanes];
+    __shared__ double accs[4][kU2Lanes];
+    double (*acc)[kU2Lanes] = accs;
+    const int tid = threadIdx.x, t = tid & 31, w = tid >> 5;
+    const int l = tid & (kU2Lanes - 1), vs = tid >> 3;
+    const int64_t B = a.B;
+    const int64_t b = (int64_t)blockIdx.x * kU2Lanes + l;
+    const bool valid = b < B;
+    const int64_t bb = valid ? b : B - 1;
+    const int V = a.V;
+    const bool active = valid && a.done[bb] == 0;
+    if (!__syncthreads_or(active)) return;
+
+    const double N = a.N[bb];
+    const double llsum = sum_splits(a.llpart + bb, a.S, B);
+    double r2[2] = {0.0, 0.0};
+    for (int v = vs; v < V; v += kU2Slots) {
+        const int64_t i = (int64_t)v * B + bb;
+        const double tv = sum_splits(a.tpart + i, a.S, (int64_t)V * B);
+        const double gh = tv * a.invL[v] / N;
+        const double ztv = a.zt[i];
+        const bool mk = a.mask ? a.mask[i] != 0 : true;
+        const double gtv = mk ? 2.0 * ztv * (1.0 - gh) : 0.0;
+        if (active) { a.gt[i] = gtv; a.gh[i] = gh; }
+        r2[0] = fma(ztv, ztv, r2[0]);
+        r2[1] = fma(a.d[i], gtv, r2[1]);
+    }
+    cta_reduce<2>(r2, 2, part, acc, w, t, l);
+    const double sumphi = acc[0][l], dgt = acc[1][l];
+    double Ft = -llsum / N + sumphi;
+    const bool fin = isfinite(llsum) && isfinite(sumphi) && sumphi > 0.0;
+    if (!fin) Ft = INFINITY;
+    const double F = a.F[bb], dg = a.dg[bb], alpha = a.alpha[bb];
+    bool accept = fin && (Ft <= F + 1e-4 * alpha * dg ||
+                          (fabs(Ft - F) <= 1e-14 * fabs(F) && fabs(dgt) <= 0.9 * fabs(dg)));
+    accept = accept && active;
+    __syncthreads();
+    double r3[2] = {0.0, -INFINITY};                            // comp, dual
+    if (accept) {
+        for (int v = vs; v < V; v += kU2Slots) {
+            const int64_t i = (int64_t)v * B + bb;
+            const bool mk = a.mask ? a.mask[i] != 0 : true;
+            if (mk) {
+                const double ztv = a.zt[i];
+                const double ghn = a.gh[i] * sumphi;
+                r3[0] = fmax(r3[0], ztv * ztv / sumphi * fabs(ghn - 1.0));
+                r3[1] = fmax(r3[1], ghn - 1.0);
+            }
+            a.z[i] = a.zt[i]; a.g[i] = a.gt[i]; a.gha[i] = a.gh[i];
+        }
+    }
+    cta_reduce<2>(r3, 0, part, acc, w, t, l);
+    const double comp = acc[0][l], dual = acc[1][l];
+    bool finished = false;
+    int status = TVS_CONVERGED;
+    if (vs == 0 && active) {
+        if (accept) {
+            const int iters = a.iters[bb] + 1;
+            if (comp <= a.tol && dual <= a.tol_dual) finished = true;
+            else if (iters >= a.max_iter) { finished = true; status = TVS_MAXITER; }
+            const double lam = a.lam[bb];
+            a.lam[bb] = (lam > 1e-12) ? 0.1 * lam : 0.0;
+            a.F[bb] = Ft; a.llsum[bb] = llsum; a.sumphi[bb] = sumphi;
+            a.kkt[bb] = comp; a.kkt[B + bb] = dual; a.iters[bb] = iters; a.ls[bb] = 0;
+            a.need[bb] = 1;
+        } else {
+            const int ls = a.ls[bb] + 1;
+            a.ls[bb] = ls;
+            a.lam[bb] = fmax(10.0 * a.lam[bb], 1e-6);
+            a.need[bb] = 0;
+            if (ls > 40) {
+                const double c0 = a.kkt[bb], d0 = a.kkt[B + bb];
+                finished = true;
+                status = (c0 <= 1e2 * a.tol && d0 <= 1e2 * a.tol_dual) ? TVS_CONVERGED : TVS_STALLED;
+            }
+        }
+        if (finished) { a.status[bb] = status; a.done[bb] = 1; }
+    }
+    if (w == 0) {
+        const unsigned still = __ballot_sync(0xffffffffu, t < kU2Lanes && active && !finished);
+        if (t == 0 && still) atomicAdd(a.nactive, __popc(still));
+    }
+}
+
+}  // namespace tvs

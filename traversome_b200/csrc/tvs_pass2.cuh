@@ -413,12 +413,15 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
 #pragma unroll
             for (int j = 0; j < K; ++j) fast = fast && is_pos_normal(p[j]);
             double rr[K];
+            double c2[K];                                  // w / p^2 (Newton phase only)
             if (fast) {
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
                     const double wd = (double)wv.v[j];
                     const bool on = wv.v[j] > 0;
-                    rr[j] = on ? wd * fast_rcp(p[j]) : 0.0;
+                    const double rcp = fast_rcp(p[j]);
+                    rr[j] = on ? wd * rcp : 0.0;
+                    c2[j] = rr[j] * rcp;
                     ll[j] = on ? fma(wd, fast_log_pos(p[j], a.logc), ll[j]) : ll[j];
                 }
             } else {
@@ -427,10 +430,20 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
                     const double wd = (double)wv.v[j];
                     const bool on = wv.v[j] > 0;
                     rr[j] = on ? wd / p[j] : 0.0;
+                    c2[j] = on ? rr[j] / p[j] : 0.0;
                     ll[j] = on ? fma(wd, log(p[j]), ll[j]) : ll[j];
                 }
             }
             if (BACKWARD) sts_lanes<K>(rr_s + (r - row0) * LT, t, rr);
+            if (a.cr != nullptr && lv) {
+                double* dst = a.cr + (int64_t)r * B + mylane;
+                if (K == 1) dst[0] = c2[0];
+                else if (K == 2) *reinterpret_cast<double2*>(dst) = make_double2(c2[0], c2[1]);
+                else {
+                    reinterpret_cast<double2*>(dst)[0] = make_double2(c2[0], c2[1]);
+                    reinterpret_cast<double2*>(dst)[1] = make_double2(c2[2], c2[3]);
+                }
+            }
         }
         if (BACKWARD) {
             cp_async_wait_all();
