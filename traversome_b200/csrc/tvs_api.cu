@@ -50,6 +50,7 @@ static void free_csr(Csr& c) {
     dev_free(c.col32); dev_free(c.fval); dev_free(c.crow32); dev_free(c.cfval);
     if (c.desc) { cudaFree(c.desc); c.desc = nullptr; }
     dev_free(c.slab_ptr); dev_free(c.h_row); dev_free(c.h_val); dev_free(c.h_slot);
+    dev_free(c.wide_ptr); if (c.wide_rec) { cudaFree(c.wide_rec); c.wide_rec = nullptr; }
 }
 static void free_lanes(Lanes& l) {
     dev_free(l.w); dev_free(l.mask); dev_free(l.C); dev_free(l.N);
@@ -60,6 +61,7 @@ static void free_fit(FitState& f) {
     if (f.h_nactive) cudaFreeHost(f.h_nactive);
     if (f.Hpart) cudaFree(f.Hpart);
     if (f.cr) cudaFree(f.cr);
+    if (f.crf) cudaFree(f.crf);
     f = FitState();
 }
 
@@ -460,6 +462,42 @@ int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, c
             if (hrow.empty()) { hrow.push_back(0); hval.push_back(0.f); }
             c.h_HB = HB; c.h_nblk = nblk; c.h_NG = NG; c.h_steps = steps;
             UP_(slab_ptr, sp, int64_t) UP_(h_row, hrow, uint16_t) UP_(h_val, hval, float) UP_(h_slot, hslot, uint16_t)
+            // entry-major lists inside blocks of WB rows for hess_wide_kernel
+            const int WB = std::max(32, std::min(env_int("TVS_HESS_WIDE_ROWS", 256), 512));
+            const int wnblk = (int)((R + WB - 1) / WB);
+            std::vector<int32_t> wp((size_t)wnblk * (NPk + 1));
+            std::vector<uint2> wrec((size_t)std::max<int64_t>(np, 1));
+            int64_t q = 0;
+            int wcap = 1;
+            for (int b = 0; b < wnblk; ++b) {
+                const int64_t rb0 = (int64_t)b * WB, rb1 = std::min<int64_t>(R, rb0 + WB);
+                for (auto& l : lists) l.clear();
+                for (int64_t r = rb0; r < rb1; ++r)
+                    for (int64_t i = row_ptr[r]; i < row_ptr[r + 1]; ++i)
+                        for (int64_t j = row_ptr[r]; j <= i; ++j)
+                            lists[(size_t)(col[i] * (col[i] + 1) / 2 + col[j])].push_back({(uint16_t)(r - rb0), (float)val[i] * (float)val[j]});
+                for (int e = 0; e < NPk; ++e) {
+                    wp[(size_t)b * (NPk + 1) + e] = (int32_t)q;
+                    for (auto& pr : lists[e]) {
+                        uint32_t bits;
+                        memcpy(&bits, &pr.second, 4);
+                        wrec[q] = make_uint2((uint32_t)pr.first * 128u, bits);
+                        ++q;
+                    }
+                }
+                wp[(size_t)b * (NPk + 1) + NPk] = (int32_t)q;
+                for (int e0 = 0; e0 < NPk; e0 += kWideSet)
+                    wcap = std::max(wcap, (int)(wp[(size_t)b * (NPk + 1) + std::min(NPk, e0 + kWideSet)] - wp[(size_t)b * (NPk + 1) + e0]));
+            }
+            c.w_HB = WB; c.w_nblk = wnblk; c.w_cap = wcap;
+            UP_(wide_ptr, wp, int32_t)
+            {
+                uint2* dd = nullptr;
+                if ((rc = dev_alloc(&dd, wrec.size())) != TVS_OK) return fail(rc);
+                c.wide_rec = dd;
+                if (cudaMemcpy(dd, wrec.data(), wrec.size() * sizeof(uint2), cudaMemcpyHostToDevice) != cudaSuccess)
+                    return fail(cuda_fail(cudaGetLastError(), "upload wide_rec", __FILE__, __LINE__));
+            }
         }
     }
 #undef UP_
@@ -700,33 +738,43 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
     const int newton_lanes = (h->csr.slab_ptr != nullptr && V <= kNewtonMaxV) ? env_int("TVS_NEWTON_LANES", 128) : 0;
     int64_t newton_iters = 0;
     bool newton_off = false;                                    // set when the shape has no staged pass kernel
-    auto newton_phase = [&](LaneSet& s, bool* ran) -> int {
+    // One SEGMENT of the Newton phase on lane set `s`: iterates until every lane has finished (all_done) or so many
+    // have that a compaction pays (`*active_out` <= width / 2); the caller compacts and calls again.
+    auto newton_phase = [&](LaneSet& s, bool* ran, int64_t* active_out) -> int {
         *ran = false;
         const int64_t W = s.width;
         const int NP = (int)(V * (V + 1) / 2);
         const Csr& c = h->csr;
-        // one warp per (lane, range of row blocks); all warps resident at once (<= 13 per SM by shared memory)
+        const bool wide = c.wide_ptr != nullptr && W >= env_int("TVS_HESS_WIDE_MIN", 256) && W % 4 == 0;
+        // slab kernel: one CTA per (lane, range of row blocks), all CTAs resident at once
         const size_t hess_smem = ((size_t)NP + c.h_HB + 1 + c.h_NG + 1) * 8 + (size_t)c.h_NG * 32 * 2;
         const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(220 * 1024) / (hess_smem + 1024)));
         int S_h = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * ctas_per_sm / W, c.h_nblk));
         const int blocks_per_split = (c.h_nblk + S_h - 1) / S_h;
         S_h = (c.h_nblk + blocks_per_split - 1) / blocks_per_split;
-        const size_t need_cap = (size_t)S_h * (size_t)W * (size_t)NP;
+        const size_t wide_smem = (size_t)2 * c.w_HB * 32 * sizeof(float) + (size_t)2 * c.w_cap * 8 + (size_t)2 * (kWideSet + 1) * 4;
+        const size_t need_cap = wide ? (size_t)W * (size_t)NP : (size_t)S_h * (size_t)W * (size_t)NP;
         if (f.Hpart_cap < need_cap) {
             if (f.Hpart) cudaFree(f.Hpart);
-    if (f.cr) cudaFree(f.cr);
             f.Hpart = nullptr; f.Hpart_cap = 0;
             TVS_CUDA(cudaMalloc((void**)&f.Hpart, need_cap * sizeof(double)));
             f.Hpart_cap = need_cap;
         }
-        if (f.cr_cap < (size_t)R * (size_t)W) {
+        if (!wide && f.cr_cap < (size_t)R * (size_t)W) {
             if (f.cr) cudaFree(f.cr);
             f.cr = nullptr; f.cr_cap = 0;
             TVS_CUDA(cudaMalloc((void**)&f.cr, (size_t)R * (size_t)W * sizeof(double)));
             f.cr_cap = (size_t)R * (size_t)W;
         }
+        if (wide && f.crf_cap < (size_t)R * (size_t)W) {
+            if (f.crf) cudaFree(f.crf);
+            f.crf = nullptr; f.crf_cap = 0;
+            TVS_CUDA(cudaMalloc((void**)&f.crf, (size_t)R * (size_t)W * sizeof(float)));
+            f.crf_cap = (size_t)R * (size_t)W;
+        }
         TVS_CUDA(cudaFuncSetAttribute(hess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hess_smem));
-        const size_t solve_smem = ((size_t)2 * V * (V + 1) + 2 * V) * 8;
+        TVS_CUDA(cudaFuncSetAttribute(hess_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem));
+        const size_t solve_smem = ((size_t)V * (V + 1) + 2 * (V + 2) + 2 * V) * 8;
         TVS_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
         PassPlan pl;
         int prc = make_plan<true>(h, W, &pl);
@@ -738,7 +786,8 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         newton_init_kernel<<<(unsigned)((W + 127) / 128), 128, 0, st>>>(s.z, s.g, s.mask, h->csr.invL, (int)V, W, f.gha, s.x, f.lam, f.need, s.ls);
         ++launches;
         PassArgs pa = base_args(h);
-        pa.w = s.w; pa.B = W; pa.x = s.x; pa.done = s.done; pa.tpart = f.tpart; pa.llpart = f.llpart; pa.cr = f.cr;
+        pa.w = s.w; pa.B = W; pa.x = s.x; pa.done = s.done; pa.tpart = f.tpart; pa.llpart = f.llpart;
+        pa.cr = wide ? nullptr : f.cr; pa.crf = wide ? f.crf : nullptr;
         {   // refresh pass at the accepted point: c_r = w_r / p_r^2 for the first Hessian
             int lrc = launch_pass<true>(h, pl, pa);
             if (lrc != TVS_OK) return lrc;
@@ -748,8 +797,14 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         ha.slab_ptr = c.slab_ptr; ha.h_row = c.h_row; ha.h_val = c.h_val; ha.h_slot = c.h_slot; ha.cr = f.cr;
         ha.done = s.done; ha.need = f.need; ha.Hpart = f.Hpart;
         ha.W = W; ha.R = R; ha.V = (int)V; ha.HB = c.h_HB; ha.nblk = c.h_nblk; ha.NG = c.h_NG; ha.blocks_per_split = blocks_per_split;
+        HessWideArgs hw{};
+        hw.wide_ptr = c.wide_ptr; hw.wide_rec = (const uint2*)c.wide_rec; hw.crf = f.crf; hw.H = f.Hpart;
+        hw.W = W; hw.R = R; hw.V = (int)V; hw.HB = c.w_HB; hw.nblk = c.w_nblk; hw.cap = c.w_cap;
+        const dim3 wide_grid((unsigned)((W + 31) / 32), (unsigned)((NP + kWideWarps * kWideEnt - 1) / (kWideWarps * kWideEnt)));
         SolveArgs sa{};
-        sa.Hpart = f.Hpart; sa.S = S_h; sa.z = s.z; sa.g = s.g; sa.gha = f.gha; sa.invL = h->csr.invL; sa.N = s.N; sa.mask = s.mask;
+        sa.Hpart = f.Hpart; sa.S = wide ? 1 : S_h;
+        sa.h_entry = wide ? W : 1; sa.h_lane = wide ? 1 : NP; sa.h_split = wide ? 0 : (int64_t)W * NP;
+        sa.z = s.z; sa.g = s.g; sa.gha = f.gha; sa.invL = h->csr.invL; sa.N = s.N; sa.mask = s.mask;
         sa.done = s.done; sa.lam = f.lam; sa.d = s.d; sa.zt = s.zt; sa.x = s.x; sa.dg = s.dg; sa.alpha = s.alpha; sa.W = W; sa.V = (int)V;
         NewtonUpdArgs na{};
         na.invL = h->csr.invL; na.N = s.N; na.mask = s.mask; na.z = s.z; na.zt = s.zt; na.g = s.g; na.gt = f.gt; na.gh = f.gh;
@@ -762,7 +817,8 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
             const int slot = (int)(n_polls % 16);
             cudaEvent_t eh0 = nullptr, eh1 = nullptr, eh2 = nullptr;
             if (time_passes) { cudaEventCreate(&eh0); cudaEventCreate(&eh1); cudaEventCreate(&eh2); cudaEventRecord(eh0, st); }
-            hess_kernel<<<dim3((unsigned)W, (unsigned)S_h), 32 * kHessWarps, hess_smem, st>>>(ha);
+            if (wide) hess_wide_kernel<<<wide_grid, 32 * kWideWarps, wide_smem, st>>>(hw);
+            else hess_kernel<<<dim3((unsigned)W, (unsigned)S_h), 32 * kHessWarps, hess_smem, st>>>(ha);
             if (time_passes) cudaEventRecord(eh1, st);
             solve_kernel<<<(unsigned)W, kSolveThreads, solve_smem, st>>>(sa);
             if (time_passes) { cudaEventRecord(eh2, st); nev.push_back(eh0); nev.push_back(eh1); nev.push_back(eh2); }
@@ -785,79 +841,86 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
             cerr = cudaStreamSynchronize(st);
             if (cerr != cudaSuccess) return TVS_OK;       // reported by the caller through cerr
             ++n_polls;
-            if (f.h_nactive[slot] == 0) { all_done = true; break; }
+            *active_out = f.h_nactive[slot];
+            if (*active_out == 0) { all_done = true; break; }
+            if (!no_compact && *active_out * 2 <= W && W > 32 && *active_out + 3 <= f.half) break;   // the caller compacts
         }
         return TVS_OK;
     };
 
+    bool in_newton = false;
+    int64_t newton_active = 0;
     while (!all_done && passes < max_passes && rc == TVS_OK) {
         LaneSet& s = f.set[cur];
         const int64_t W = s.width;
-        // ---- launch geometry for the current width
-        PassPlan pl;
-        {
-            rc = make_plan<true>(h, W, &pl);
-            if (rc != TVS_OK) break;
-            while (pl.splits > 1 && (size_t)pl.splits * (size_t)W * (size_t)V > f.tpart_cap) --pl.splits;
-            if ((size_t)pl.splits * (size_t)W * (size_t)V > f.tpart_cap) { set_error("partial buffer too small"); rc = TVS_ENOMEM; break; }
-        }
-        PassArgs pa = base_args(h);
-        pa.w = s.w; pa.B = W; pa.x = s.x; pa.done = s.done; pa.tpart = f.tpart; pa.llpart = f.llpart;
-        UpdArgs ua{};
-        ua.invL = h->csr.invL; ua.N = s.N; ua.mask = s.mask;
-        ua.z = s.z; ua.zt = s.zt; ua.g = s.g; ua.gt = f.gt; ua.gh = f.gh; ua.d = s.d; ua.x = s.x; ua.Sh = s.S; ua.Yh = s.Y;
-        ua.rho = s.rho; ua.gamma = s.gamma; ua.F = s.F; ua.dg = s.dg; ua.alpha = s.alpha; ua.llsum = s.llsum; ua.kkt = s.kkt;
-        ua.sumphi = s.sumphi; ua.ls = s.ls; ua.iters = s.iters; ua.status = s.status; ua.head = s.head; ua.cnt = s.cnt;
-        ua.done = s.done; ua.V = (int)V; ua.B = W; ua.m = m; ua.max_iter = opt.max_iter; ua.tol = opt.tol;
-        ua.tol_dual = (double)env_int("TVS_DUAL_MULT", 100) * opt.tol;
-        const unsigned ub = (unsigned)((W + 31) / 32);
+        int64_t active = newton_active;                        // Newton mode: the count of the last segment
+        if (!in_newton) {
+            // ---- launch geometry for the current width
+            PassPlan pl;
+            {
+                rc = make_plan<true>(h, W, &pl);
+                if (rc != TVS_OK) break;
+                while (pl.splits > 1 && (size_t)pl.splits * (size_t)W * (size_t)V > f.tpart_cap) --pl.splits;
+                if ((size_t)pl.splits * (size_t)W * (size_t)V > f.tpart_cap) { set_error("partial buffer too small"); rc = TVS_ENOMEM; break; }
+            }
+            PassArgs pa = base_args(h);
+            pa.w = s.w; pa.B = W; pa.x = s.x; pa.done = s.done; pa.tpart = f.tpart; pa.llpart = f.llpart;
+            UpdArgs ua{};
+            ua.invL = h->csr.invL; ua.N = s.N; ua.mask = s.mask;
+            ua.z = s.z; ua.zt = s.zt; ua.g = s.g; ua.gt = f.gt; ua.gh = f.gh; ua.d = s.d; ua.x = s.x; ua.Sh = s.S; ua.Yh = s.Y;
+            ua.rho = s.rho; ua.gamma = s.gamma; ua.F = s.F; ua.dg = s.dg; ua.alpha = s.alpha; ua.llsum = s.llsum; ua.kkt = s.kkt;
+            ua.sumphi = s.sumphi; ua.ls = s.ls; ua.iters = s.iters; ua.status = s.status; ua.head = s.head; ua.cnt = s.cnt;
+            ua.done = s.done; ua.V = (int)V; ua.B = W; ua.m = m; ua.max_iter = opt.max_iter; ua.tol = opt.tol;
+            ua.tol_dual = (double)env_int("TVS_DUAL_MULT", 100) * opt.tol;
+            const unsigned ub = (unsigned)((W + 31) / 32);
 
-        // ---- a batch of passes, then one synchronous poll of the device-side "still iterating" counter
-        const int slot = (int)(n_polls % 16);
-        for (int k = 0; k < opt.check_every && passes < max_passes; ++k) {
-            if (!pl.xs) { cudaMemsetAsync(f.tpart, 0, (size_t)V * W * pl.splits * 8, st); ++launches; }
-            if (time_passes) { cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); pev.push_back(e0); pev.push_back(e1); cudaEventRecord(e0, st); }
-            rc = launch_pass<true>(h, pl, pa);
+            // ---- a batch of passes, then one synchronous poll of the device-side "still iterating" counter
+            const int slot = (int)(n_polls % 16);
+            for (int k = 0; k < opt.check_every && passes < max_passes; ++k) {
+                if (!pl.xs) { cudaMemsetAsync(f.tpart, 0, (size_t)V * W * pl.splits * 8, st); ++launches; }
+                if (time_passes) { cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); pev.push_back(e0); pev.push_back(e1); cudaEventRecord(e0, st); }
+                rc = launch_pass<true>(h, pl, pa);
+                if (rc != TVS_OK) break;
+                if (time_passes) cudaEventRecord(pev.back(), st);
+                const bool last = (k == opt.check_every - 1) || (passes + 1 == max_passes);
+                const bool legacy_upd = upd_v1 || upd_v2;
+                const bool pre_reduce = legacy_upd || pl.splits > env_int("TVS_FUSE_SPLITS", 24);   // many splits: sum them with full parallelism first
+                if (pre_reduce) {
+                    reduce_partials_kernel<<<(unsigned)(((int64_t)(V + 1) * W + 255) / 256), 256, 0, st>>>(f.tpart, f.llpart, pl.splits, (int)V, W,
+                                                                                                          f.t_red, f.ll_red);
+                    ua.tpart = f.t_red; ua.llpart = f.ll_red; ua.S = 1;
+                    ++launches;
+                } else {
+                    ua.tpart = f.tpart; ua.llpart = f.llpart; ua.S = pl.splits;
+                }
+                if (legacy_upd) {           // the older update kernels need a memset of the poll counter
+                    ua.nactive = last ? f.nactive + slot : f.nactive + 31;   // word 31 = scratch between polls
+                    if (last) { cudaMemsetAsync(f.nactive + slot, 0, 4, st); ++launches; }
+                } else {                    // vl2: counters are reset one launch ahead
+                    ua.nactive = last ? f.nactive + slot : f.nactive + 31;
+                    ua.nreset = (k == 0 && !last) ? f.nactive + slot : nullptr;
+                    if (k == 0 && last) { cudaMemsetAsync(f.nactive + slot, 0, 4, st); ++launches; }
+                }
+                const unsigned ub2 = (unsigned)((W + kU2Lanes - 1) / kU2Lanes);
+                if (upd_v1) lbfgs_update_kernel<<<ub, kUpdWarps * 32, 0, st>>>(ua);
+                else if (!upd_v2 && m == 4) lbfgs_update_vl2_kernel<4><<<ub2, kU2Threads, Vl2Layout<4>::doubles * 8, st>>>(ua, s.gram);
+                else if (!upd_v2) lbfgs_update_vl2_kernel<8><<<ub2, kU2Threads, Vl2Layout<8>::doubles * 8, st>>>(ua, s.gram);
+                else if (m == 4) lbfgs_update_vl_kernel<4><<<ub, kUpdWarps * 32, VlLayout<4>::doubles * 8, st>>>(ua, s.gram);
+                else lbfgs_update_vl_kernel<8><<<ub, kUpdWarps * 32, VlLayout<8>::doubles * 8, st>>>(ua, s.gram);
+                if (time_passes) { cudaEvent_t e2; cudaEventCreate(&e2); uev.push_back(pev.back()); uev.push_back(e2); cudaEventRecord(e2, st); }
+                ++passes; launches += 2; lane_passes += W;
+                if (time_passes) pass_width.push_back(W);
+            }
             if (rc != TVS_OK) break;
-            if (time_passes) cudaEventRecord(pev.back(), st);
-            const bool last = (k == opt.check_every - 1) || (passes + 1 == max_passes);
-            const bool legacy_upd = upd_v1 || upd_v2;
-            const bool pre_reduce = legacy_upd || pl.splits > env_int("TVS_FUSE_SPLITS", 24);   // many splits: sum them with full parallelism first
-            if (pre_reduce) {
-                reduce_partials_kernel<<<(unsigned)(((int64_t)(V + 1) * W + 255) / 256), 256, 0, st>>>(f.tpart, f.llpart, pl.splits, (int)V, W,
-                                                                                                      f.t_red, f.ll_red);
-                ua.tpart = f.t_red; ua.llpart = f.ll_red; ua.S = 1;
-                ++launches;
-            } else {
-                ua.tpart = f.tpart; ua.llpart = f.llpart; ua.S = pl.splits;
-            }
-            if (legacy_upd) {           // the older update kernels need a memset of the poll counter
-                ua.nactive = last ? f.nactive + slot : f.nactive + 31;   // word 31 = scratch between polls
-                if (last) { cudaMemsetAsync(f.nactive + slot, 0, 4, st); ++launches; }
-            } else {                    // vl2: counters are reset one launch ahead
-                ua.nactive = last ? f.nactive + slot : f.nactive + 31;
-                ua.nreset = (k == 0 && !last) ? f.nactive + slot : nullptr;
-                if (k == 0 && last) { cudaMemsetAsync(f.nactive + slot, 0, 4, st); ++launches; }
-            }
-            const unsigned ub2 = (unsigned)((W + kU2Lanes - 1) / kU2Lanes);
-            if (upd_v1) lbfgs_update_kernel<<<ub, kUpdWarps * 32, 0, st>>>(ua);
-            else if (!upd_v2 && m == 4) lbfgs_update_vl2_kernel<4><<<ub2, kU2Threads, Vl2Layout<4>::doubles * 8, st>>>(ua, s.gram);
-            else if (!upd_v2) lbfgs_update_vl2_kernel<8><<<ub2, kU2Threads, Vl2Layout<8>::doubles * 8, st>>>(ua, s.gram);
-            else if (m == 4) lbfgs_update_vl_kernel<4><<<ub, kUpdWarps * 32, VlLayout<4>::doubles * 8, st>>>(ua, s.gram);
-            else lbfgs_update_vl_kernel<8><<<ub, kUpdWarps * 32, VlLayout<8>::doubles * 8, st>>>(ua, s.gram);
-            if (time_passes) { cudaEvent_t e2; cudaEventCreate(&e2); uev.push_back(pev.back()); uev.push_back(e2); cudaEventRecord(e2, st); }
-            ++passes; launches += 2; lane_passes += W;
-            if (time_passes) pass_width.push_back(W);
+            cudaMemcpyAsync(f.h_nactive + slot, f.nactive + slot, 4, cudaMemcpyDeviceToHost, st);
+            cerr = cudaStreamSynchronize(st);
+            if (cerr != cudaSuccess) break;
+            ++n_polls;
+            active = f.h_nactive[slot];
+            if (active == 0) { all_done = true; break; }
         }
-        if (rc != TVS_OK) break;
-        cudaMemcpyAsync(f.h_nactive + slot, f.nactive + slot, 4, cudaMemcpyDeviceToHost, st);
-        cerr = cudaStreamSynchronize(st);
-        if (cerr != cudaSuccess) break;
-        ++n_polls;
-        const int64_t active = f.h_nactive[slot];
-        if (active == 0) { all_done = true; break; }
         // ---- compaction: keep only the lanes that are still iterating
-        const bool to_newton = newton_lanes > 0 && !newton_off && active <= newton_lanes;
+        const bool to_newton = in_newton || (newton_lanes > 0 && !newton_off && active <= newton_lanes);
         if (!no_compact && (active * 2 <= W || (to_newton && W > newton_lanes)) && W > 32 && active + 3 <= f.half) {
             finalize(s, 1);                                      // results of the finished lanes, at their original ids
             LaneSet& n = f.set[cur ^ 1];
@@ -901,10 +964,12 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
             ++compactions;
             cur ^= 1;
         }
-        if (to_newton && !newton_off && f.set[cur].width <= std::max(newton_lanes, 32)) {
+        if (to_newton && !newton_off && (in_newton || f.set[cur].width <= std::max(newton_lanes, 32))) {
             bool ran = false;
-            rc = newton_phase(f.set[cur], &ran);
-            if (ran || rc != TVS_OK) break;                     // the phase runs its lanes to completion (or to the pass budget)
+            rc = newton_phase(f.set[cur], &ran, &newton_active);
+            if (rc != TVS_OK || cerr != cudaSuccess) break;
+            in_newton = ran;                                    // next trip: compact the survivors, then another segment
+            if (ran && !all_done && newton_active * 2 > f.set[cur].width) break;   // pass / iteration budget exhausted
         }
     }
     if (rc == TVS_OK && cerr == cudaSuccess) {

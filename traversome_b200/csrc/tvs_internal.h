@@ -48,6 +48,9 @@ struct Csr {
     float*    h_val = nullptr;       // [h_steps * 32] product (exact: < 2^24 checked)
     uint16_t* h_slot = nullptr;      // [h_nblk * h_NG * 32] packed H index u(u+1)/2+v, 0xFFFF = none
     int       h_HB = 0, h_nblk = 0, h_NG = 0;
+    int32_t*  wide_ptr = nullptr;    // [w_nblk * (NP + 1)] entry-major lists inside blocks of w_HB rows (hess_wide_kernel)
+    void*     wide_rec = nullptr;    // uint2 {row * 128, fp32 bits of the product}
+    int       w_HB = 0, w_nblk = 0, w_cap = 0;
     int64_t   h_steps = 0;
     double*   invL = nullptr;        // [V] 1/L_v
     double*   Ld = nullptr;          // [V] L_v as double
@@ -92,7 +95,7 @@ struct FitState {               // all device, sized for (V, B, history)
     double *t_red = nullptr, *ll_red = nullptr;     // partials summed over the row splits
     int32_t *idx = nullptr;                          // compaction gather list
     // Newton phase scratch
-    double *gha = nullptr, *lam = nullptr, *Hpart = nullptr, *cr = nullptr; int32_t* need = nullptr; size_t Hpart_cap = 0, cr_cap = 0;
+    double *gha = nullptr, *lam = nullptr, *Hpart = nullptr, *cr = nullptr; float* crf = nullptr; int32_t* need = nullptr; size_t Hpart_cap = 0, cr_cap = 0, crf_cap = 0;
     int32_t *nactive = nullptr;   // device counters (ring)
     int32_t *h_nactive = nullptr; // pinned host mirror
     // output staging at the ORIGINAL width

@@ -36,6 +36,7 @@ struct PassArgs {
     const ChunkDesc* desc;
     LogCoef logc;
     double* cr;          // optional [R*B]: w / p^2 per (row, lane) for the Newton phase's Hessian (pass3_kernel only)
+    float* crf;          // the same in fp32 (wide lane sets: hess_wide_kernel)
 };
 
 template <int LPT, bool XS, bool BACKWARD>

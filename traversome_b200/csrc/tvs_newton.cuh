@@ -126,8 +126,116 @@ __global__ void __launch_bounds__(32 * kHessWarps) hess_kernel(const HessArgs a)
     for (int i = tid; i < NP; i += 32 * kHessWarps) out[i] = Hs[i];
 }
 
+
+// Hessian accumulation for WIDE lane sets: the same sum as hess_kernel organised like the transposed product of the
+// likelihood pass -- a warp = 32 lanes (lane-minor, coalesced), a CTA = 8 warps x 32 H entries each, the entries'
+// accumulators live in registers, c_r = w_r / p_r^2 of a block of rows sits in shared memory as fp32 (the Hessian
+// of a Newton method tolerates 1e-7 relative error: it only steers the step, the KKT test certifies the answer),
+// per-block partial sums are fp32, the sum over blocks fp64, per-entry row lists are staged with the tile.
+// Every lane's H comes out complete (no partial sums): H[entry][lane], lane-minor.
+struct HessWideArgs {
+    const int32_t* wide_ptr;      // [nblk * (NP + 1)] record offsets, entry-major inside each block of HB rows
+    const uint2* wide_rec;        // {byte offset of the block-local row inside the staged tile (row * 128), fp32 bits of A_ru A_rv}
+    const float* crf;             // [R * W] w / p^2 (lane-minor)
+    double* H;                    // [NP][W]
+    int64_t W, R; int V; int HB; int nblk; int cap;    // cap = most records of one (block, entry set)
+};
+constexpr int kWideWarps = 8;
+constexpr int kWideEnt = 32;      // H entries per warp
+constexpr int kWideSet = kWideWarps * kWideEnt;
+
+// shared: Cs[2][HB*32] float | rec[2][cap] uint2 | ptr[2][kWideSet + 1] int
+__global__ void __launch_bounds__(32 * kWideWarps, 2) hess_wide_kernel(const HessWideArgs a) {
+    extern __shared__ __align__(16) unsigned char smw[];
+    const int V = a.V, NP = V * (V + 1) / 2, HB = a.HB, cap = a.cap;
+    float* Cs = reinterpret_cast<float*>(smw);
+    uint2* recs = reinterpret_cast<uint2*>(smw + (size_t)2 * HB * 32 * sizeof(float));
+    int* ptrs = reinterpret_cast<int*>(recs + (size_t)2 * cap);
+    const int tid = threadIdx.x, t = tid & 31, wi = tid >> 5;
+    const int64_t tile0 = (int64_t)blockIdx.x * 32;
+    const int64_t lane = tile0 + t;
+    const int set0 = blockIdx.y * kWideSet;                     // first entry of this CTA
+    const int nset = min(kWideSet, NP - set0);
+    const bool full_tile = tile0 + 32 <= a.W;
+
+    auto stage = [&](int blk, int buf) {
+        const int64_t r0 = (int64_t)blk * HB;
+        const int nrows = (int)min((int64_t)HB, a.R - r0);
+        float* dstC = Cs + (size_t)buf * HB * 32;
+        if (full_tile) {                                        // 16-byte copies: W % 4 == 0 is required by the caller
+            for (int i = tid; i < nrows * 8; i += 32 * kWideWarps) {
+                const int row = i >> 3, c4 = (i & 7) * 4;
+                const unsigned d = (unsigned)__cvta_generic_to_shared(dstC + row * 32 + c4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(a.crf + (r0 + row) * a.W + tile0 + c4));
+            }
+        } else {
+            for (int i = tid; i < nrows * 32; i += 32 * kWideWarps) {
+                const int row = i >> 5, l = i & 31;
+                dstC[i] = (tile0 + l < a.W) ? __ldg(a.crf + (r0 + row) * a.W + tile0 + l) : 0.f;
+            }
+        }
+        const int32_t* pp = a.wide_ptr + (int64_t)blk * (NP + 1) + set0;
+        const int qb = __ldg(pp), qe = __ldg(pp + nset);
+        for (int i = tid; i < qe - qb; i += 32 * kWideWarps) cp_async8(recs + (size_t)buf * cap + i, a.wide_rec + qb + i);
+        for (int i = tid; i <= nset; i += 32 * kWideWarps) cp_async4(ptrs + buf * (kWideSet + 1) + i, pp + i);
+    };
+
+    double acc[kWideEnt];
+#pragma unroll
+    for (int j = 0; j < kWideEnt; ++j) acc[j] = 0.0;
+    stage(0, 0);
+    cp_async_commit();
+    for (int blk = 0; blk < a.nblk; ++blk) {
+        const int buf = blk & 1;
+        cp_async_wait_all();
+        __syncthreads();                                        // block `blk` landed; buffer buf^1 is free again
+        if (blk + 1 < a.nblk) stage(blk + 1, buf ^ 1);
+        cp_async_commit();
+        const int* pt = ptrs + buf * (kWideSet + 1);
+        const int base = pt[0];
+        const uint2* rc = recs + (size_t)buf * cap;
+        const unsigned char* cbase = reinterpret_cast<const unsigned char*>(Cs + (size_t)buf * HB * 32 + t);
+#pragma unroll
+        for (int j = 0; j < kWideEnt; ++j) {
+            const int e = wi * kWideEnt + j;
+            if (e < nset) {
+                // fp32 partial sum over the (few) rows of this block; F2F.F64.F32 runs on the XU pipe at ~4 lanes/clk/SM
+                // and saturated it (profiles/r1_v4_summary.md), so the one widening per (entry, block) is done with
+                // integer ops (valid for normal positive floats, which these partial sums are).
+                const int q0 = pt[e] - base, n = pt[e + 1] - base - q0;
+                if (n > 0) {
+                    float part = 0.f;
+                    int q = q0;
+                    for (; q + 4 <= q0 + n; q += 4) {
+                        const uint2 r0 = rc[q], r1 = rc[q + 1], r2 = rc[q + 2], r3 = rc[q + 3];
+                        const float c0 = *reinterpret_cast<const float*>(cbase + r0.x), c1 = *reinterpret_cast<const float*>(cbase + r1.x);
+                        const float c2 = *reinterpret_cast<const float*>(cbase + r2.x), c3 = *reinterpret_cast<const float*>(cbase + r3.x);
+                        part = fmaf(__uint_as_float(r0.y), c0, part); part = fmaf(__uint_as_float(r1.y), c1, part);
+                        part = fmaf(__uint_as_float(r2.y), c2, part); part = fmaf(__uint_as_float(r3.y), c3, part);
+                    }
+                    const int rem = q0 + n - q;                 // 0..3 records left: predicated, no loop
+                    if (rem > 0) { const uint2 r = rc[q]; part = fmaf(__uint_as_float(r.y), *reinterpret_cast<const float*>(cbase + r.x), part); }
+                    if (rem > 1) { const uint2 r = rc[q + 1]; part = fmaf(__uint_as_float(r.y), *reinterpret_cast<const float*>(cbase + r.x), part); }
+                    if (rem > 2) { const uint2 r = rc[q + 2]; part = fmaf(__uint_as_float(r.y), *reinterpret_cast<const float*>(cbase + r.x), part); }
+                    const unsigned pb = __float_as_uint(part);
+                    const double wide = __hiloint2double((int)(((pb >> 3) & 0x0fffffffu) + 0x38000000u), (int)(pb << 29));
+                    acc[j] += (pb >= 0x00800000u && pb < 0x7f800000u) ? wide : (double)part;   // slow path: zero / denormal / inf / nan
+                }
+            }
+        }
+    }
+    if (lane < a.W) {
+#pragma unroll
+        for (int j = 0; j < kWideEnt; ++j) {
+            const int e = set0 + wi * kWideEnt + j;
+            if (e < NP) a.H[(int64_t)e * a.W + lane] = acc[j];
+        }
+    }
+}
+
 struct SolveArgs {
     const double* Hpart; int S;
+    int64_t h_entry, h_lane, h_split;     // element (split, lane, entry) of Hpart at split*h_split + lane*h_lane + entry*h_entry
     const double* z; const double* g; const double* gha; const double* invL; const double* N; const uint8_t* mask;
     const int32_t* done;
     double* lam; double* d; double* zt; double* x; double* dg; double* alpha;
@@ -136,13 +244,13 @@ struct SolveArgs {
 
 constexpr int kSolveThreads = 256;
 
-// one CTA per lane.  shared: A[V][V+1] (Hz + lam I, factorised in place) | H0[V][V+1] (Hz, kept for retries) | rhs[V]
+// one CTA per lane.  shared: H0[V][V+1] (Hz, kept for retries) | 2 column buffers | rhs[V] | zv[V]
 __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const SolveArgs a) {
     extern __shared__ double ss[];
     const int V = a.V, LD = V + 1, NP = V * (V + 1) / 2;
-    double* A = ss;
-    double* H0 = ss + (size_t)V * LD;
-    double* rhs = H0 + (size_t)V * LD;
+    double* H0 = ss;                                           // Hz; overwritten by the unscaled columns of L at the end
+    double* colbuf = ss + (size_t)V * LD;                      // two column buffers of V + 2
+    double* rhs = colbuf + 2 * (V + 2);
     double* zv = rhs + V;
     __shared__ double red[kSolveThreads / 32];
     const int tid = threadIdx.x;
@@ -157,7 +265,7 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const SolveArgs a)
         while ((u + 1) * (u + 2) / 2 <= i) ++u;
         while (u * (u + 1) / 2 > i) --u;
         const int v = i - u * (u + 1) / 2;                     // u >= v
-        const double s = sum_splits(a.Hpart + (int64_t)lane * NP + i, a.S, (int64_t)a.W * NP);
+        const double s = sum_splits(a.Hpart + lane * a.h_lane + (int64_t)i * a.h_entry, a.S, a.h_split);
         double h = 4.0 * zv[u] * zv[v] * a.invL[u] * a.invL[v] * s * invN;
         if (u == v) {
             const bool mk = a.mask ? a.mask[(int64_t)u * a.W + lane] != 0 : true;
@@ -187,7 +295,6 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const SolveArgs a)
             ei[m] = u; ej[m] = e - u * (u + 1) / 2;
         } else { ei[m] = -1; ej[m] = -1; }
     }
-    double* colbuf = A;                                        // A is only written back after the factorisation
     double rv = 0.0;
     for (int attempt = 0; attempt < 60; ++attempt) {
 #pragma unroll
@@ -216,6 +323,7 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const SolveArgs a)
         lam = fmax(10.0 * lam, 1e-6);
     }
     // unscaled columns of L and y back to shared memory for the backward substitution
+    double* A = H0;
 #pragma unroll
     for (int m = 0; m < EPT; ++m)
         if (ei[m] >= 0) A[ei[m] * LD + ej[m]] = av[m];

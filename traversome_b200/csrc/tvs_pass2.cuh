@@ -444,6 +444,12 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
                     reinterpret_cast<double2*>(dst)[1] = make_double2(c2[2], c2[3]);
                 }
             }
+            if (a.crf != nullptr && lv) {
+                float* dst = a.crf + (int64_t)r * B + mylane;
+                if (K == 1) dst[0] = (float)c2[0];
+                else if (K == 2) *reinterpret_cast<float2*>(dst) = make_float2((float)c2[0], (float)c2[1]);
+                else *reinterpret_cast<float4*>(dst) = make_float4((float)c2[0], (float)c2[1], (float)c2[2], (float)c2[3]);
+            }
         }
         if (BACKWARD) {
             cp_async_wait_all();
