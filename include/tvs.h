@@ -137,6 +137,8 @@ int tvs_measure_fp64_peak(int device, double* tflops_out);
 /* self-test of the device reciprocal / logarithm used inside the likelihood pass (they replace the
  * IEEE division and libdevice log there): log_out[i] = log(p[i]), rcp_out[i] = 1/p[i], host arrays. */
 int tvs_selftest_math(int device, int64_t n, const double* p, double* log_out, double* rcp_out);
+/* the table-driven logarithm of the staged likelihood pass (uses the handle's table): log_out[i] = log(p[i]). */
+int tvs_selftest_table_log(tvs_handle h, int64_t n, const double* p, double* log_out);
 
 #ifdef __cplusplus
 }

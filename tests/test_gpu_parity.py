@@ -103,6 +103,18 @@ def test_fit_matches_exact_optimum(gpu, V, R, density, B, n_true):
     assert np.all(out["status"] == _cabi.CONVERGED)
 
 
+@pytest.mark.parametrize("V,R,density,B", [(96, 3000, 0.08, 40), (200, 2500, 0.05, 24)])
+def test_fit_beyond_the_newton_phase_limit(gpu, V, R, density, B):
+    """V > 64: no Newton phase (tvs_newton.cuh), the batched L-BFGS runs every lane to the KKT certificate."""
+    wl = synthetic.make_workload(V, R, density, seed=300 + V)
+    w = synthetic.bootstrap_weights(wl.n_obs, B, seed=4)
+    with engine_for(wl) as eng:
+        eng.set_lanes(w)
+        out = eng.fit()
+    assert np.all(out["status"] == _cabi.CONVERGED)
+    check_fit_against_exact(wl, w, None, out, [0, 1, B - 1])
+
+
 def test_fit_with_subset_masks_and_infeasible_lane(gpu):
     V, B = 12, 20
     wl = synthetic.make_workload(V, 800, 0.35, seed=77)
@@ -210,6 +222,12 @@ def test_device_log_and_reciprocal_are_within_2_ulp(gpu):
     ulp_r = np.abs(rc - ref_r) / np.spacing(np.abs(ref_r))
     fin = np.isfinite(ref_r) & (np.abs(ref_r) > 1e-300)
     assert ulp_r[fin].max() <= 2
+    wl = synthetic.make_workload(4, 50, 0.5, seed=1)
+    with engine_for(wl) as eng:
+        lt = eng.selftest_table_log(p)
+    ulp_t = np.abs(lt - ref_l) / np.maximum(np.spacing(np.abs(ref_l)), 5e-324)
+    bad_t = (ulp_t > 2) & (np.abs(lt - ref_l) > 3.4e-16)
+    assert not bad_t.any(), (p[bad_t][:5], lt[bad_t][:5], ref_l[bad_t][:5])
     z = _cabi.selftest_math(np.array([0.0, -1.0, np.inf]))
     assert z[0][0] == -np.inf and np.isnan(z[0][1]) and z[0][2] == np.inf and z[1][0] == np.inf
 

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libtvs.so")
 SYMBOLS = (
     "tvs_version", "tvs_last_error", "tvs_device_count", "tvs_create", "tvs_destroy", "tvs_set_lanes",
     "tvs_set_lanes_indexed", "tvs_resample", "tvs_get_weights", "tvs_loglik", "tvs_fit", "tvs_last_fit_stats", "tvs_dims",
-    "tvs_measure_fp64_peak", "tvs_selftest_math",
+    "tvs_measure_fp64_peak", "tvs_selftest_math", "tvs_selftest_table_log",
 )
 
 TVS_OK, TVS_EINVAL, TVS_ECUDA, TVS_ENOMEM, TVS_ELIMIT, TVS_ESTATE = 0, -1, -2, -3, -4, -5
@@ -68,6 +68,7 @@ def load():
     lib.tvs_dims.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]
     lib.tvs_measure_fp64_peak.argtypes = [c_int, POINTER(c_double)]
     lib.tvs_selftest_math.argtypes = [c_int, c_int64, c_void_p, c_void_p, c_void_p]
+    lib.tvs_selftest_table_log.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("tvs_last_error",):
@@ -203,6 +204,13 @@ class Engine(object):
         _check(self._lib.tvs_fit(self._h, _ptr(theta0), ctypes.byref(opt), _ptr(theta), _ptr(ll), _ptr(kkt),
                                  _ptr(iters), _ptr(status)))
         return {"theta": theta, "loglike": ll, "kkt": kkt, "iters": iters, "status": status}
+
+    def selftest_table_log(self, p):
+        """log(p) by the table-driven routine of the staged likelihood pass."""
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        lg = np.empty_like(p)
+        _check(self._lib.tvs_selftest_table_log(self._h, p.size, _ptr(p), _ptr(lg)))
+        return lg
 
     def last_fit_stats(self):
         st = FitStats()

@@ -5,6 +5,7 @@
 #include "tvs_newton.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -49,6 +50,7 @@ static void free_csr(Csr& c) {
     dev_free(c.ccol_start); dev_free(c.cent); dev_free(c.invL); dev_free(c.Ld);
     dev_free(c.col32); dev_free(c.fval); dev_free(c.crow32); dev_free(c.cfval);
     if (c.desc) { cudaFree(c.desc); c.desc = nullptr; }
+    if (c.logtab) { cudaFree(c.logtab); c.logtab = nullptr; }
     dev_free(c.slab_ptr); dev_free(c.h_row); dev_free(c.h_val); dev_free(c.h_slot);
     dev_free(c.wide_ptr); if (c.wide_rec) { cudaFree(c.wide_rec); c.wide_rec = nullptr; }
 }
@@ -235,6 +237,7 @@ static PassArgs base_args(const tvs_problem* h) {
     a.n_chunks = c.n_chunks; a.rows_per_chunk = c.rows_per_chunk;
     a.col32 = c.col32; a.fval = c.fval; a.crow32 = c.crow32; a.cfval = c.cfval; a.stage_cap = std::max(c.max_chunk_nnz, 1);
     a.desc = (const ChunkDesc*)c.desc; a.logc = make_log_coef();
+    a.logtab = env_int("TVS_LOG_TABLE", 1) ? (const double2*)c.logtab : nullptr;
     return a;
 }
 
@@ -398,6 +401,20 @@ int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, c
     if ((rc = dev_alloc(&c.row_ptr, (size_t)R + 1)) != TVS_OK) return fail(rc);
     if (cudaMemcpy(c.row_ptr, row_ptr, ((size_t)R + 1) * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess)
         return fail(cuda_fail(cudaGetLastError(), "upload row_ptr", __FILE__, __LINE__));
+    {   // log table: c_i = 1/m_i rounded to 24 bits (so that m c_i - 1 has few bits), l_i = -log(c_i)
+        std::vector<double> tab(256);
+        for (int i = 0; i < 128; ++i) {
+            const double mi = 1.0 + (i + 0.5) / 128.0;
+            const double ci = (double)(float)(1.0 / mi);
+            tab[2 * i] = ci;
+            tab[2 * i + 1] = (double)(-logl((long double)ci));
+        }
+        double* dt = nullptr;
+        if ((rc = dev_alloc(&dt, tab.size())) != TVS_OK) return fail(rc);
+        c.logtab = dt;
+        if (cudaMemcpy(dt, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+            return fail(cuda_fail(cudaGetLastError(), "upload logtab", __FILE__, __LINE__));
+    }
     std::vector<ChunkDesc> descv((size_t)c.n_chunks);
     for (int ch = 0; ch < c.n_chunks; ++ch) {
         ChunkDesc& d = descv[ch];
@@ -552,7 +569,17 @@ static int finish_lanes(tvs_problem* h, const uint8_t* mask, const double* C) {
     const int64_t V = h->csr.V, B = l.B;
     if (mask) TVS_CUDA(cudaMemcpyAsync(l.mask, mask, (size_t)(V * B), cudaMemcpyDefault, h->stream));
     if (C) TVS_CUDA(cudaMemcpyAsync(l.C, C, (size_t)B * sizeof(double), cudaMemcpyDefault, h->stream));
-    lane_sum_kernel<<<(unsigned)((B + 127) / 128), 128, 0, h->stream>>>(l.w, h->csr.R, B, l.N);
+    {   // N_b = sum_r w[r,b] (exact integer sums; the solver state is not allocated yet, so use a scratch buffer)
+        unsigned long long* acc = nullptr;
+        TVS_CUDA(cudaMalloc((void**)&acc, (size_t)B * sizeof(unsigned long long)));
+        cudaMemsetAsync(acc, 0, (size_t)B * sizeof(unsigned long long), h->stream);
+        const unsigned tiles = (unsigned)((B + 31) / 32);
+        const unsigned slices = (unsigned)std::max<int64_t>(1, std::min<int64_t>(h->csr.R / 64 + 1, (int64_t)(4 * h->sm_count) / tiles + 1));
+        lane_sum_kernel<<<dim3(tiles, slices), 256, 0, h->stream>>>(l.w, h->csr.R, B, acc);
+        lane_sum_finish_kernel<<<(unsigned)((B + 255) / 256), 256, 0, h->stream>>>(acc, B, l.N);
+        cudaStreamSynchronize(h->stream);
+        cudaFree(acc);
+    }
     TVS_CUDA(cudaGetLastError());
     TVS_CUDA(cudaStreamSynchronize(h->stream));
     h->lanes_set = true;
@@ -928,46 +955,47 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
             const int bi = (int)(compactions & 1);
             // new width: survivors + up to 3 padding lanes (index -1 -> zeros, flagged done, no original id)
             const int64_t A = (active + 3) & ~(int64_t)3;
-            gather_rows(st, s.w, f.wbuf[bi], R, W, A, f.idx);
-            gather_rows(st, s.mask, f.mbuf[bi], V, W, A, f.idx);
-            gather_rows(st, s.N, f.nbuf[bi], 1, W, A, f.idx);
-            gather_rows(st, s.C, f.cbuf[bi], 1, W, A, f.idx);
             n.w = f.wbuf[bi]; n.mask = s.mask ? f.mbuf[bi] : nullptr; n.N = f.nbuf[bi]; n.C = s.C ? f.cbuf[bi] : nullptr;
-            gather_rows(st, (const int32_t*)s.orig, n.orig, 1, W, A, f.idx);
-            gather_rows(st, (const double*)s.z, n.z, V, W, A, f.idx);
-            gather_rows(st, (const double*)s.zt, n.zt, V, W, A, f.idx);
-            gather_rows(st, (const double*)s.g, n.g, V, W, A, f.idx);
-            gather_rows(st, (const double*)s.d, n.d, V, W, A, f.idx);
-            gather_rows(st, (const double*)s.x, n.x, V, W, A, f.idx);
-            gather_rows(st, (const double*)s.S, n.S, (int64_t)m * V, W, A, f.idx);
-            gather_rows(st, (const double*)s.Y, n.Y, (int64_t)m * V, W, A, f.idx);
-            gather_rows(st, (const double*)s.rho, n.rho, m, W, A, f.idx);
-            gather_rows(st, (const double*)s.gamma, n.gamma, 1, W, A, f.idx);
-            gather_rows(st, (const double*)s.F, n.F, 1, W, A, f.idx);
-            gather_rows(st, (const double*)s.dg, n.dg, 1, W, A, f.idx);
-            gather_rows(st, (const double*)s.alpha, n.alpha, 1, W, A, f.idx);
-            gather_rows(st, (const double*)s.llsum, n.llsum, 1, W, A, f.idx);
-            gather_rows(st, (const double*)s.sumphi, n.sumphi, 1, W, A, f.idx);
-            gather_rows(st, (const double*)s.kkt, n.kkt, 2, W, A, f.idx);
-            gather_rows(st, (const double*)s.gram, n.gram, (int64_t)((2 * m + 1) * (2 * m + 2) / 2), W, A, f.idx);
-            gather_rows(st, (const int32_t*)s.ls, n.ls, 1, W, A, f.idx);
-            gather_rows(st, (const int32_t*)s.iters, n.iters, 1, W, A, f.idx);
-            gather_rows(st, (const int32_t*)s.head, n.head, 1, W, A, f.idx);
-            gather_rows(st, (const int32_t*)s.cnt, n.cnt, 1, W, A, f.idx);
+            {   // one launch gathers every per-lane matrix (the L-BFGS history only while that phase is still running)
+                GatherArgs ga{};
+                int64_t row0 = 0;
+                auto add = [&](const void* src, void* dst, int64_t rows, int elem) {
+                    if (!src || !dst || rows <= 0) return;
+                    ga.t[ga.n].src = src; ga.t[ga.n].dst = dst; ga.t[ga.n].rows = rows; ga.t[ga.n].elem = elem; ga.t[ga.n].row0 = (int32_t)row0;
+                    row0 += rows; ++ga.n;
+                };
+                const int64_t ng = (int64_t)((2 * m + 1) * (2 * m + 2) / 2);
+                add(s.w, f.wbuf[bi], R, 4); add(s.mask, f.mbuf[bi], V, 1); add(s.N, f.nbuf[bi], 1, 8); add(s.C, f.cbuf[bi], 1, 8);
+                add(s.orig, n.orig, 1, 4); add(s.z, n.z, V, 8); add(s.zt, n.zt, V, 8); add(s.g, n.g, V, 8); add(s.d, n.d, V, 8); add(s.x, n.x, V, 8);
+                if (!in_newton && !to_newton) {
+                    add(s.S, n.S, (int64_t)m * V, 8); add(s.Y, n.Y, (int64_t)m * V, 8); add(s.rho, n.rho, m, 8); add(s.gamma, n.gamma, 1, 8);
+                    add(s.gram, n.gram, ng, 8); add(s.head, n.head, 1, 4); add(s.cnt, n.cnt, 1, 4);
+                }
+                add(s.F, n.F, 1, 8); add(s.dg, n.dg, 1, 8); add(s.alpha, n.alpha, 1, 8); add(s.llsum, n.llsum, 1, 8); add(s.sumphi, n.sumphi, 1, 8);
+                add(s.kkt, n.kkt, 2, 8); add(s.ls, n.ls, 1, 4); add(s.iters, n.iters, 1, 4);
+                ga.total_rows = row0; ga.Bs = W; ga.Bd = A; ga.idx = f.idx;
+                dim3 grid((unsigned)((A + 127) / 128), (unsigned)std::min<int64_t>(row0, 8192));
+                gather_all_kernel<<<grid, 128, 0, st>>>(ga);
+            }
             cudaMemsetAsync(n.done, 0, A * 4, st); cudaMemsetAsync(n.status, 0, A * 4, st);
             if (A > active) {
                 cudaMemsetAsync(n.done + active, 1, (A - active) * 4, st);
                 cudaMemsetAsync(n.orig + active, 0xFF, (A - active) * 4, st);
             }
             n.width = A;
-            launches += 28;
+            launches += 3;
             ++compactions;
             cur ^= 1;
         }
-        if (to_newton && !newton_off && (in_newton || f.set[cur].width <= std::max(newton_lanes, 32))) {
+        if (to_newton && !newton_off && (in_newton || f.set[cur].width <= std::max(newton_lanes, 32) + 3)) {
             bool ran = false;
             rc = newton_phase(f.set[cur], &ran, &newton_active);
             if (rc != TVS_OK || cerr != cudaSuccess) break;
+            if (!ran) {   // Newton is not available for this shape after all: L-BFGS goes on, from an empty history
+                LaneSet& q = f.set[cur];                       // (a compaction on the way here did not carry the history over)
+                cudaMemsetAsync(q.cnt, 0, q.width * 4, st); cudaMemsetAsync(q.head, 0, q.width * 4, st);
+                cudaMemsetAsync(q.gram, 0, (size_t)q.width * ((2 * m + 1) * (2 * m + 2) / 2) * 8, st);
+            }
             in_newton = ran;                                    // next trip: compact the survivors, then another segment
             if (ran && !all_done && newton_active * 2 > f.set[cur].width) break;   // pass / iteration budget exhausted
         }
@@ -1040,6 +1068,21 @@ int tvs_selftest_math(int device, int64_t n, const double* p, double* log_out, d
     if (e == cudaSuccess) { cudaMemcpy(log_out, d_l, (size_t)n * 8, cudaMemcpyDefault); cudaMemcpy(rcp_out, d_r, (size_t)n * 8, cudaMemcpyDefault); }
     cudaFree(d_p); cudaFree(d_l); cudaFree(d_r);
     if (e != cudaSuccess) return cuda_fail(e, "selftest_math_kernel", __FILE__, __LINE__);
+    return TVS_OK;
+}
+
+int tvs_selftest_table_log(tvs_handle h, int64_t n, const double* p, double* log_out) {
+    if (!h || n <= 0 || !p || !log_out) { set_error("tvs_selftest_table_log: bad argument"); return TVS_EINVAL; }
+    TVS_CUDA(cudaSetDevice(h->device));
+    double *d_p = nullptr, *d_l = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&d_p, (size_t)n)) != TVS_OK || (rc = dev_alloc(&d_l, (size_t)n)) != TVS_OK) { cudaFree(d_p); cudaFree(d_l); return rc; }
+    cudaMemcpy(d_p, p, (size_t)n * 8, cudaMemcpyDefault);
+    selftest_table_log_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_p, n, d_l, (const double2*)h->csr.logtab, make_log_coef());
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) cudaMemcpy(log_out, d_l, (size_t)n * 8, cudaMemcpyDefault);
+    cudaFree(d_p); cudaFree(d_l);
+    if (e != cudaSuccess) return cuda_fail(e, "selftest_table_log_kernel", __FILE__, __LINE__);
     return TVS_OK;
 }
 

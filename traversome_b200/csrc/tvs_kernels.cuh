@@ -37,6 +37,7 @@ struct PassArgs {
     LogCoef logc;
     double* cr;          // optional [R*B]: w / p^2 per (row, lane) for the Newton phase's Hessian (pass3_kernel only)
     float* crf;          // the same in fp32 (wide lane sets: hess_wide_kernel)
+    const double2* logtab;   // [128] {c_i, -log c_i} for table_log_pos, or null (atanh series)
 };
 
 template <int LPT, bool XS, bool BACKWARD>
@@ -190,12 +191,29 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
 // ------------------------------------------------------------------------------------------------
 // small per-lane kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void lane_sum_kernel(const int32_t* __restrict__ w, int64_t R, int64_t B, double* __restrict__ N) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+// N_b = sum_r w[r,b]: grid.x = lane tiles of 32, grid.y = row slices; exact integer partial sums, one atomicAdd
+// (64-bit integer: order-independent) per (slice, lane).  lane_sum_finish_kernel converts to double.
+__global__ void __launch_bounds__(256) lane_sum_kernel(const int32_t* __restrict__ w, int64_t R, int64_t B, unsigned long long* __restrict__ acc) {
+    __shared__ long long red[8][32];
+    const int t = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * 32 + t;
+    const int64_t rows = (R + gridDim.y - 1) / gridDim.y;
+    const int64_t r0 = (int64_t)blockIdx.y * rows, r1 = min(R, r0 + rows);
     long long s = 0;
-    for (int64_t r = 0; r < R; ++r) s += w[r * B + b];
-    N[b] = (double)s;
+    if (b < B)
+        for (int64_t r = r0 + wi; r < r1; r += 8) s += w[r * B + b];
+    red[wi][t] = s;
+    __syncthreads();
+    if (wi == 0 && b < B) {
+        long long tot = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) tot += red[q][t];
+        atomicAdd(acc + b, (unsigned long long)tot);
+    }
+}
+__global__ void lane_sum_finish_kernel(const unsigned long long* __restrict__ acc, int64_t B, double* __restrict__ N) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) N[b] = (double)(long long)acc[b];
 }
 
 // z0 from theta0 (or uniform over the mask): phi_v ~ theta_v * L_v, z = sqrt(phi)
@@ -1147,6 +1165,33 @@ __global__ void gather_rows_kernel(const T* __restrict__ src, T* __restrict__ ds
     if (j >= Bd) return;
     const int64_t sj = idx[j];                              // -1: padding lane -> zeros
     for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) dst[r * Bd + j] = (sj >= 0) ? src[r * Bs + sj] : T(0);
+}
+
+// All per-lane matrices of a lane set in ONE launch: task k copies columns idx[j] of src (rows x Bs, 4- or 8-byte
+// elements) into dst (rows x Bd); idx[j] < 0 -> zeros.  grid.y walks (task, row) pairs.
+struct GatherTask { const void* src; void* dst; int64_t rows; int32_t elem; int32_t row0; };   // row0 = first global row index of the task
+constexpr int kMaxGatherTasks = 32;
+struct GatherArgs { GatherTask t[kMaxGatherTasks]; int n; int64_t total_rows; int64_t Bs, Bd; const int32_t* idx; };
+
+__global__ void __launch_bounds__(128) gather_all_kernel(const GatherArgs a) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.Bd) return;
+    const int64_t sj = a.idx[j];
+    for (int64_t gr = blockIdx.y; gr < a.total_rows; gr += gridDim.y) {
+        int k = 0;
+        while (k + 1 < a.n && gr >= a.t[k + 1].row0) ++k;         // tasks are few: linear search, uniform across the CTA
+        const int64_t r = gr - a.t[k].row0;
+        if (a.t[k].elem == 8) {
+            const double v = (sj >= 0) ? static_cast<const double*>(a.t[k].src)[r * a.Bs + sj] : 0.0;
+            static_cast<double*>(a.t[k].dst)[r * a.Bd + j] = v;
+        } else if (a.t[k].elem == 4) {
+            const int32_t v = (sj >= 0) ? static_cast<const int32_t*>(a.t[k].src)[r * a.Bs + sj] : 0;
+            static_cast<int32_t*>(a.t[k].dst)[r * a.Bd + j] = v;
+        } else {
+            const uint8_t v = (sj >= 0) ? static_cast<const uint8_t*>(a.t[k].src)[r * a.Bs + sj] : (uint8_t)0;
+            static_cast<uint8_t*>(a.t[k].dst)[r * a.Bd + j] = v;
+        }
+    }
 }
 
 __global__ void iota_kernel(int32_t* p, int64_t n) {

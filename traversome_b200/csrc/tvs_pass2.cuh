@@ -77,6 +77,25 @@ __device__ __forceinline__ double fast_log_pos(double p, const LogCoef& kc) {
     return fma(ed, kc.c[9], two_s + tail);                      // e * ln2_hi is exact
 }
 
+// Table variant (pass3_kernel): p = 2^e m, m in [1,2); i = top 7 mantissa bits; tab[i] = {c_i ~ 1/m_i, -log c_i};
+// r = m c_i - 1 (exact in one FMA, |r| <= 2^-8); log m = -log c_i + log1p(r), log1p by a degree-7 Taylor polynomial
+// (truncation < 2^-67).  12 fp64 instructions instead of ~30; costs one 16-byte shared-memory read per call.
+__device__ __forceinline__ double table_log_pos(double p, const double2* __restrict__ tab, const LogCoef& kc) {
+    const int hi = __double2hiint(p);
+    const int e = (hi >> 20) - 1023;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(p));
+    const double2 cl = tab[(hi >> 13) & 127];
+    const double r = fma(m, cl.x, -1.0);
+    double q = fma(r, 1.0 / 7.0, -1.0 / 6.0);
+    q = fma(q, r, 0.2);
+    q = fma(q, r, -0.25);
+    q = fma(q, r, kc.c[0]);                                      // 1/3
+    q = fma(q, r, -0.5);
+    const double ed = (double)e;
+    const double tail = fma(r * r, q, fma(ed, kc.c[10], r));     // r + r^2 q + e ln2_lo
+    return fma(ed, kc.c[9], cl.y) + tail;                        // e ln2_hi (exact) - log c_i
+}
+
 __device__ __forceinline__ double log_any(double p, const LogCoef& kc) {   // -inf at 0, nan below, slow path for odd inputs
     if (is_pos_normal(p)) return fast_log_pos(p, kc);
     return log(p);
@@ -88,6 +107,16 @@ __global__ void selftest_math_kernel(const double* __restrict__ p, int64_t n, do
     if (i >= n) return;
     lg[i] = log_any(p[i], kc);
     rc[i] = is_pos_normal(p[i]) ? fast_rcp(p[i]) : 1.0 / p[i];
+}
+
+__global__ void selftest_table_log_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ lg, const double2* __restrict__ tab,
+                                          const LogCoef kc) {
+    __shared__ double2 tab_s[128];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) tab_s[i] = tab[i];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    lg[i] = is_pos_normal(p[i]) ? table_log_pos(p[i], tab_s, kc) : log(p[i]);
 }
 
 template <int K>
@@ -274,7 +303,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 struct Pass3Smem {            // byte offsets from the start of dynamic shared memory
-    size_t x, t, rr, f1, f2, c1, c2, rp, cs, cid, total;
+    size_t x, t, rr, f1, f2, c1, c2, rp, cs, cid, tab, total;
 };
 __host__ __device__ inline Pass3Smem pass3_layout(int V, int LT, int RC, int cap, bool backward, int nw) {
     Pass3Smem L;
@@ -289,6 +318,8 @@ __host__ __device__ inline Pass3Smem pass3_layout(int V, int LT, int RC, int cap
     L.rp = o; o += (size_t)2 * (RC + 1) * 4;
     L.cs = o; o += backward ? (size_t)(V + 1) * 4 : 0;
     L.cid = o; o += backward ? (size_t)V * 4 : 0;
+    o = (o + 15) & ~(size_t)15;
+    L.tab = o; o += 128 * 16;                          // log table (table_log_pos)
     L.total = (o + 15) & ~(size_t)15;
     return L;
 }
@@ -326,6 +357,10 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
     int* rp_s = reinterpret_cast<int*>(smem3 + L.rp);
     int* cs_s = reinterpret_cast<int*>(smem3 + L.cs);
     int* cid_s = reinterpret_cast<int*>(smem3 + L.cid);
+    double2* tab_s = reinterpret_cast<double2*>(smem3 + L.tab);
+    const bool use_tab = a.logtab != nullptr;
+    if (use_tab)
+        for (int i = threadIdx.x; i < 128; i += NT) tab_s[i] = a.logtab[i];
 
     // row-major entries + row pointers of a chunk -> buffer `buf`
     auto stage_rows = [&](const ChunkDesc& d, int buf) {
@@ -422,7 +457,8 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
                     const double rcp = fast_rcp(p[j]);
                     rr[j] = on ? wd * rcp : 0.0;
                     c2[j] = rr[j] * rcp;
-                    ll[j] = on ? fma(wd, fast_log_pos(p[j], a.logc), ll[j]) : ll[j];
+                    const double lg = use_tab ? table_log_pos(p[j], tab_s, a.logc) : fast_log_pos(p[j], a.logc);
+                    ll[j] = on ? fma(wd, lg, ll[j]) : ll[j];
                 }
             } else {
 #pragma unroll
