@@ -480,31 +480,33 @@ int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, c
             c.h_HB = HB; c.h_nblk = nblk; c.h_NG = NG; c.h_steps = steps;
             UP_(slab_ptr, sp, int64_t) UP_(h_row, hrow, uint16_t) UP_(h_val, hval, float) UP_(h_slot, hslot, uint16_t)
             // entry-major lists inside blocks of WB rows for hess_wide_kernel
-            const int WB = std::max(32, std::min(env_int("TVS_HESS_WIDE_ROWS", 256), 512));
+            const int WB = std::max(32, std::min(env_int("TVS_HESS_WIDE_ROWS", 128), 512));
             const int wnblk = (int)((R + WB - 1) / WB);
-            std::vector<int32_t> wp((size_t)wnblk * (NPk + 1));
+            const int NS = (NPk + kWideEnt - 1) / kWideEnt;
+            std::vector<int32_t> wp((size_t)wnblk * (NS + 1));
             std::vector<uint2> wrec((size_t)std::max<int64_t>(np, 1));
+            std::vector<std::vector<uint2>> sub((size_t)NS);
             int64_t q = 0;
             int wcap = 1;
             for (int b = 0; b < wnblk; ++b) {
                 const int64_t rb0 = (int64_t)b * WB, rb1 = std::min<int64_t>(R, rb0 + WB);
-                for (auto& l : lists) l.clear();
-                for (int64_t r = rb0; r < rb1; ++r)
+                for (auto& l : sub) l.clear();
+                for (int64_t r = rb0; r < rb1; ++r)                          // row-major inside every subset
                     for (int64_t i = row_ptr[r]; i < row_ptr[r + 1]; ++i)
-                        for (int64_t j = row_ptr[r]; j <= i; ++j)
-                            lists[(size_t)(col[i] * (col[i] + 1) / 2 + col[j])].push_back({(uint16_t)(r - rb0), (float)val[i] * (float)val[j]});
-                for (int e = 0; e < NPk; ++e) {
-                    wp[(size_t)b * (NPk + 1) + e] = (int32_t)q;
-                    for (auto& pr : lists[e]) {
-                        uint32_t bits;
-                        memcpy(&bits, &pr.second, 4);
-                        wrec[q] = make_uint2((uint32_t)pr.first * 128u, bits);
-                        ++q;
-                    }
+                        for (int64_t j = row_ptr[r]; j <= i; ++j) {
+                            const int e = col[i] * (col[i] + 1) / 2 + col[j];
+                            const float pv = (float)val[i] * (float)val[j];
+                            uint32_t bits;
+                            memcpy(&bits, &pv, 4);
+                            sub[(size_t)(e / kWideEnt)].push_back(make_uint2((uint32_t)(r - rb0) | ((uint32_t)(e % kWideEnt) << 16), bits));
+                        }
+                for (int sidx = 0; sidx < NS; ++sidx) {
+                    wp[(size_t)b * (NS + 1) + sidx] = (int32_t)q;
+                    for (auto& rec : sub[sidx]) wrec[q++] = rec;
                 }
-                wp[(size_t)b * (NPk + 1) + NPk] = (int32_t)q;
-                for (int e0 = 0; e0 < NPk; e0 += kWideSet)
-                    wcap = std::max(wcap, (int)(wp[(size_t)b * (NPk + 1) + std::min(NPk, e0 + kWideSet)] - wp[(size_t)b * (NPk + 1) + e0]));
+                wp[(size_t)b * (NS + 1) + NS] = (int32_t)q;
+                for (int s0 = 0; s0 < NS; s0 += kWideWarps)
+                    wcap = std::max(wcap, (int)(wp[(size_t)b * (NS + 1) + std::min(NS, s0 + kWideWarps)] - wp[(size_t)b * (NS + 1) + s0]));
             }
             c.w_HB = WB; c.w_nblk = wnblk; c.w_cap = wcap;
             UP_(wide_ptr, wp, int32_t)
@@ -779,7 +781,8 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         int S_h = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)h->sm_count * ctas_per_sm / W, c.h_nblk));
         const int blocks_per_split = (c.h_nblk + S_h - 1) / S_h;
         S_h = (c.h_nblk + blocks_per_split - 1) / blocks_per_split;
-        const size_t wide_smem = (size_t)2 * c.w_HB * 32 * sizeof(float) + (size_t)2 * c.w_cap * 8 + (size_t)2 * (kWideSet + 1) * 4;
+        const size_t wide_smem = (size_t)2 * c.w_HB * 32 * sizeof(float) + (size_t)2 * c.w_cap * 8 + (size_t)(2 * (kWideWarps + 1) + 2) * 4 +
+                                 (size_t)kWideWarps * kWideEnt * 32 * sizeof(float);
         const size_t need_cap = wide ? (size_t)W * (size_t)NP : (size_t)S_h * (size_t)W * (size_t)NP;
         if (f.Hpart_cap < need_cap) {
             if (f.Hpart) cudaFree(f.Hpart);
@@ -827,7 +830,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         HessWideArgs hw{};
         hw.wide_ptr = c.wide_ptr; hw.wide_rec = (const uint2*)c.wide_rec; hw.crf = f.crf; hw.H = f.Hpart;
         hw.W = W; hw.R = R; hw.V = (int)V; hw.HB = c.w_HB; hw.nblk = c.w_nblk; hw.cap = c.w_cap;
-        const dim3 wide_grid((unsigned)((W + 31) / 32), (unsigned)((NP + kWideWarps * kWideEnt - 1) / (kWideWarps * kWideEnt)));
+        const dim3 wide_grid((unsigned)((W + 31) / 32), (unsigned)((NP + kWideSet - 1) / kWideSet));
         SolveArgs sa{};
         sa.Hpart = f.Hpart; sa.S = wide ? 1 : S_h;
         sa.h_entry = wide ? W : 1; sa.h_lane = wide ? 1 : NP; sa.h_split = wide ? 0 : (int64_t)W * NP;

@@ -128,35 +128,48 @@ __global__ void __launch_bounds__(32 * kHessWarps) hess_kernel(const HessArgs a)
 
 
 // Hessian accumulation for WIDE lane sets: the same sum as hess_kernel organised like the transposed product of the
-// likelihood pass -- a warp = 32 lanes (lane-minor, coalesced), a CTA = 8 warps x 32 H entries each, the entries'
-// accumulators live in registers, c_r = w_r / p_r^2 of a block of rows sits in shared memory as fp32 (the Hessian
-// of a Newton method tolerates 1e-7 relative error: it only steers the step, the KKT test certifies the answer),
-// per-block partial sums are fp32, the sum over blocks fp64, per-entry row lists are staged with the tile.
-// Every lane's H comes out complete (no partial sums): H[entry][lane], lane-minor.
+// likelihood pass.  A warp = 32 lanes (lane-minor, coalesced) x 32 H entries; a CTA = 8 warps = 256 entries of one
+// lane tile.  Rows are walked in blocks of HB: c_r = w_r / p_r^2 of the block (fp32) and the block's records
+// {row, entry, A_ru A_rv} of the CTA's entries -- stored ROW-MAJOR per (block, warp subset), so the inner loop is one
+// flat loop with no per-entry control flow -- are staged by cp.async (double-buffered).  Each record is one
+// read-modify-write of the warp's private fp32 accumulators in shared memory (conflict-free: lane-minor); every
+// `kWideFlush` blocks the fp32 sums are widened with integer ops (F2F.F64.F32 runs on the XU pipe at ~4 lanes/clk/SM:
+// profiles/r1_v4_summary.md) and added to fp64 registers.  The Hessian of a damped Newton method tolerates the 1e-7
+// relative error of fp32 partial sums: it only steers the step, the KKT test certifies the answer.
 struct HessWideArgs {
-    const int32_t* wide_ptr;      // [nblk * (NP + 1)] record offsets, entry-major inside each block of HB rows
-    const uint2* wide_rec;        // {byte offset of the block-local row inside the staged tile (row * 128), fp32 bits of A_ru A_rv}
+    const int32_t* wide_ptr;      // [nblk * (NS + 1)] record offsets per (block, warp subset); NS = ceil(NP / 32)
+    const uint2* wide_rec;        // x = row | entry_in_subset << 16 ; y = fp32 bits of A_ru A_rv
     const float* crf;             // [R * W] w / p^2 (lane-minor)
     double* H;                    // [NP][W]
-    int64_t W, R; int V; int HB; int nblk; int cap;    // cap = most records of one (block, entry set)
+    int64_t W, R; int V; int HB; int nblk; int cap;    // cap = most records of one (block, 8 consecutive subsets)
 };
 constexpr int kWideWarps = 8;
 constexpr int kWideEnt = 32;      // H entries per warp
 constexpr int kWideSet = kWideWarps * kWideEnt;
+constexpr int kWideFlush = 8;     // blocks between two widenings of the fp32 accumulators
 
-// shared: Cs[2][HB*32] float | rec[2][cap] uint2 | ptr[2][kWideSet + 1] int
-__global__ void __launch_bounds__(32 * kWideWarps, 2) hess_wide_kernel(const HessWideArgs a) {
+__device__ __forceinline__ double widen_pos(float x) {          // exact float -> double for x = 0 or normal positive
+    const unsigned b = __float_as_uint(x);
+    const double w = __hiloint2double((int)(((b >> 3) & 0x0fffffffu) + 0x38000000u), (int)(b << 29));
+    return (b >= 0x00800000u && b < 0x7f800000u) ? w : (double)x;
+}
+
+// shared: Cs[2][HB*32] float | rec[2][cap] uint2 | ptr[2][kWideWarps + 1] int | acc[kWideWarps][32][32] float
+__global__ void __launch_bounds__(32 * kWideWarps) hess_wide_kernel(const HessWideArgs a) {
     extern __shared__ __align__(16) unsigned char smw[];
     const int V = a.V, NP = V * (V + 1) / 2, HB = a.HB, cap = a.cap;
+    const int NS = (NP + kWideEnt - 1) / kWideEnt;
     float* Cs = reinterpret_cast<float*>(smw);
     uint2* recs = reinterpret_cast<uint2*>(smw + (size_t)2 * HB * 32 * sizeof(float));
     int* ptrs = reinterpret_cast<int*>(recs + (size_t)2 * cap);
+    float* accs = reinterpret_cast<float*>(ptrs + 2 * (kWideWarps + 1) + 2);
     const int tid = threadIdx.x, t = tid & 31, wi = tid >> 5;
     const int64_t tile0 = (int64_t)blockIdx.x * 32;
     const int64_t lane = tile0 + t;
-    const int set0 = blockIdx.y * kWideSet;                     // first entry of this CTA
-    const int nset = min(kWideSet, NP - set0);
+    const int sub0 = blockIdx.y * kWideWarps;                   // first warp subset of this CTA
+    const int nsub = min(kWideWarps, NS - sub0);
     const bool full_tile = tile0 + 32 <= a.W;
+    float* my = accs + (size_t)wi * kWideEnt * 32 + t;          // my[e * 32] = accumulator of entry e, this lane
 
     auto stage = [&](int blk, int buf) {
         const int64_t r0 = (int64_t)blk * HB;
@@ -174,15 +187,15 @@ __global__ void __launch_bounds__(32 * kWideWarps, 2) hess_wide_kernel(const Hes
                 dstC[i] = (tile0 + l < a.W) ? __ldg(a.crf + (r0 + row) * a.W + tile0 + l) : 0.f;
             }
         }
-        const int32_t* pp = a.wide_ptr + (int64_t)blk * (NP + 1) + set0;
-        const int qb = __ldg(pp), qe = __ldg(pp + nset);
+        const int32_t* pp = a.wide_ptr + (int64_t)blk * (NS + 1) + sub0;
+        const int qb = __ldg(pp), qe = __ldg(pp + nsub);
         for (int i = tid; i < qe - qb; i += 32 * kWideWarps) cp_async8(recs + (size_t)buf * cap + i, a.wide_rec + qb + i);
-        for (int i = tid; i <= nset; i += 32 * kWideWarps) cp_async4(ptrs + buf * (kWideSet + 1) + i, pp + i);
+        for (int i = tid; i <= nsub; i += 32 * kWideWarps) cp_async4(ptrs + buf * (kWideWarps + 1) + i, pp + i);
     };
 
     double acc[kWideEnt];
 #pragma unroll
-    for (int j = 0; j < kWideEnt; ++j) acc[j] = 0.0;
+    for (int j = 0; j < kWideEnt; ++j) { acc[j] = 0.0; my[j * 32] = 0.f; }
     stage(0, 0);
     cp_async_commit();
     for (int blk = 0; blk < a.nblk; ++blk) {
@@ -191,43 +204,28 @@ __global__ void __launch_bounds__(32 * kWideWarps, 2) hess_wide_kernel(const Hes
         __syncthreads();                                        // block `blk` landed; buffer buf^1 is free again
         if (blk + 1 < a.nblk) stage(blk + 1, buf ^ 1);
         cp_async_commit();
-        const int* pt = ptrs + buf * (kWideSet + 1);
-        const int base = pt[0];
-        const uint2* rc = recs + (size_t)buf * cap;
-        const unsigned char* cbase = reinterpret_cast<const unsigned char*>(Cs + (size_t)buf * HB * 32 + t);
-#pragma unroll
-        for (int j = 0; j < kWideEnt; ++j) {
-            const int e = wi * kWideEnt + j;
-            if (e < nset) {
-                // fp32 partial sum over the (few) rows of this block; F2F.F64.F32 runs on the XU pipe at ~4 lanes/clk/SM
-                // and saturated it (profiles/r1_v4_summary.md), so the one widening per (entry, block) is done with
-                // integer ops (valid for normal positive floats, which these partial sums are).
-                const int q0 = pt[e] - base, n = pt[e + 1] - base - q0;
-                if (n > 0) {
-                    float part = 0.f;
-                    int q = q0;
-                    for (; q + 4 <= q0 + n; q += 4) {
-                        const uint2 r0 = rc[q], r1 = rc[q + 1], r2 = rc[q + 2], r3 = rc[q + 3];
-                        const float c0 = *reinterpret_cast<const float*>(cbase + r0.x), c1 = *reinterpret_cast<const float*>(cbase + r1.x);
-                        const float c2 = *reinterpret_cast<const float*>(cbase + r2.x), c3 = *reinterpret_cast<const float*>(cbase + r3.x);
-                        part = fmaf(__uint_as_float(r0.y), c0, part); part = fmaf(__uint_as_float(r1.y), c1, part);
-                        part = fmaf(__uint_as_float(r2.y), c2, part); part = fmaf(__uint_as_float(r3.y), c3, part);
-                    }
-                    const int rem = q0 + n - q;                 // 0..3 records left: predicated, no loop
-                    if (rem > 0) { const uint2 r = rc[q]; part = fmaf(__uint_as_float(r.y), *reinterpret_cast<const float*>(cbase + r.x), part); }
-                    if (rem > 1) { const uint2 r = rc[q + 1]; part = fmaf(__uint_as_float(r.y), *reinterpret_cast<const float*>(cbase + r.x), part); }
-                    if (rem > 2) { const uint2 r = rc[q + 2]; part = fmaf(__uint_as_float(r.y), *reinterpret_cast<const float*>(cbase + r.x), part); }
-                    const unsigned pb = __float_as_uint(part);
-                    const double wide = __hiloint2double((int)(((pb >> 3) & 0x0fffffffu) + 0x38000000u), (int)(pb << 29));
-                    acc[j] += (pb >= 0x00800000u && pb < 0x7f800000u) ? wide : (double)part;   // slow path: zero / denormal / inf / nan
-                }
+        if (wi < nsub) {
+            const int* pt = ptrs + buf * (kWideWarps + 1);
+            const int base = pt[0];
+            const uint2* rc = recs + (size_t)buf * cap;
+            const float* cb = Cs + (size_t)buf * HB * 32 + t;
+            const int q1 = pt[wi + 1] - base;
+#pragma unroll 4
+            for (int q = pt[wi] - base; q < q1; ++q) {
+                const uint2 r = rc[q];
+                float* slot = my + (r.x >> 16) * 32;
+                *slot = fmaf(__uint_as_float(r.y), cb[(r.x & 0xffffu) * 32], *slot);
             }
         }
+        if ((blk + 1) % kWideFlush == 0 || blk + 1 == a.nblk) {
+#pragma unroll
+            for (int j = 0; j < kWideEnt; ++j) { acc[j] += widen_pos(my[j * 32]); my[j * 32] = 0.f; }
+        }
     }
-    if (lane < a.W) {
+    if (lane < a.W && wi < nsub) {
 #pragma unroll
         for (int j = 0; j < kWideEnt; ++j) {
-            const int e = set0 + wi * kWideEnt + j;
+            const int e = (sub0 + wi) * kWideEnt + j;
             if (e < NP) a.H[(int64_t)e * a.W + lane] = acc[j];
         }
     }
