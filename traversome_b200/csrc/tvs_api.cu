@@ -704,8 +704,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
     if (opt.max_iter <= 0) opt.max_iter = 1000;
     if (opt.history <= 0) opt.history = 8;
     opt.history = std::min(opt.history, kMaxHistory);
-    const bool upd_v1 = env_int("TVS_UPD_V1", 0) != 0;       // the plain two-loop update kernel (any history)
-    if (!upd_v1) opt.history = (opt.history <= 4) ? 4 : 8;    // the vector-free kernel is instantiated for 4 and 8
+    opt.history = (opt.history <= 4) ? 4 : 8;                 // the vector-free update kernel is instantiated for 4 and 8
     if (opt.check_every <= 0) opt.check_every = 4;
     const bool time_passes = (opt.reserved & 1) != 0 || env_int("TVS_TIME_PASSES", 0) != 0;
     const bool no_compact = (opt.reserved & 2) != 0 || env_int("TVS_NO_COMPACT", 0) != 0;
@@ -718,11 +717,8 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
     cudaStream_t st = h->stream;
     const size_t vb0 = (size_t)V * B0;
 
-    TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(VlLayout<4>::doubles * 8)));
-    TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(VlLayout<8>::doubles * 8)));
     TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Vl2Layout<4>::doubles * 8)));
     TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Vl2Layout<8>::doubles * 8)));
-    const bool upd_v2 = env_int("TVS_UPD_V2", 0) != 0;        // the 32-lane x 8-warp vector-free kernel
     TVS_CUDA(cudaEventRecord(h->ev0, st));
     int cur = 0;
     {   // ---- reset set 0 (full width, views the caller's lanes)
@@ -902,8 +898,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
             ua.sumphi = s.sumphi; ua.ls = s.ls; ua.iters = s.iters; ua.status = s.status; ua.head = s.head; ua.cnt = s.cnt;
             ua.done = s.done; ua.V = (int)V; ua.B = W; ua.m = m; ua.max_iter = opt.max_iter; ua.tol = opt.tol;
             ua.tol_dual = (double)env_int("TVS_DUAL_MULT", 100) * opt.tol;
-            const unsigned ub = (unsigned)((W + 31) / 32);
-
+    
             // ---- a batch of passes, then one synchronous poll of the device-side "still iterating" counter
             const int slot = (int)(n_polls % 16);
             for (int k = 0; k < opt.check_every && passes < max_passes; ++k) {
@@ -913,31 +908,23 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
                 if (rc != TVS_OK) break;
                 if (time_passes) cudaEventRecord(pev.back(), st);
                 const bool last = (k == opt.check_every - 1) || (passes + 1 == max_passes);
-                const bool legacy_upd = upd_v1 || upd_v2;
-                const bool pre_reduce = legacy_upd || pl.splits > env_int("TVS_FUSE_SPLITS", 24);   // many splits: sum them with full parallelism first
-                if (pre_reduce) {
-                    reduce_partials_kernel<<<(unsigned)(((int64_t)(V + 1) * W + 255) / 256), 256, 0, st>>>(f.tpart, f.llpart, pl.splits, (int)V, W,
-                                                                                                          f.t_red, f.ll_red);
-                    ua.tpart = f.t_red; ua.llpart = f.ll_red; ua.S = 1;
-                    ++launches;
-                } else {
-                    ua.tpart = f.tpart; ua.llpart = f.llpart; ua.S = pl.splits;
-                }
-                if (legacy_upd) {           // the older update kernels need a memset of the poll counter
-                    ua.nactive = last ? f.nactive + slot : f.nactive + 31;   // word 31 = scratch between polls
-                    if (last) { cudaMemsetAsync(f.nactive + slot, 0, 4, st); ++launches; }
-                } else {                    // vl2: counters are reset one launch ahead
-                    ua.nactive = last ? f.nactive + slot : f.nactive + 31;
-                    ua.nreset = (k == 0 && !last) ? f.nactive + slot : nullptr;
-                    if (k == 0 && last) { cudaMemsetAsync(f.nactive + slot, 0, 4, st); ++launches; }
-                }
-                const unsigned ub2 = (unsigned)((W + kU2Lanes - 1) / kU2Lanes);
-                if (upd_v1) lbfgs_update_kernel<<<ub, kUpdWarps * 32, 0, st>>>(ua);
-                else if (!upd_v2 && m == 4) lbfgs_update_vl2_kernel<4><<<ub2, kU2Threads, Vl2Layout<4>::doubles * 8, st>>>(ua, s.gram);
-                else if (!upd_v2) lbfgs_update_vl2_kernel<8><<<ub2, kU2Threads, Vl2Layout<8>::doubles * 8, st>>>(ua, s.gram);
-                else if (m == 4) lbfgs_update_vl_kernel<4><<<ub, kUpdWarps * 32, VlLayout<4>::doubles * 8, st>>>(ua, s.gram);
-                else lbfgs_update_vl_kernel<8><<<ub, kUpdWarps * 32, VlLayout<8>::doubles * 8, st>>>(ua, s.gram);
-                if (time_passes) { cudaEvent_t e2; cudaEventCreate(&e2); uev.push_back(pev.back()); uev.push_back(e2); cudaEventRecord(e2, st); }
+                const bool pre_reduce = pl.splits > env_int("TVS_FUSE_SPLITS", 24);   // many splits: sum them with full parallelism first
+            if (pre_reduce) {
+                reduce_partials_kernel<<<(unsigned)(((int64_t)(V + 1) * W + 255) / 256), 256, 0, st>>>(f.tpart, f.llpart, pl.splits, (int)V, W,
+                                                                                                      f.t_red, f.ll_red);
+                ua.tpart = f.t_red; ua.llpart = f.ll_red; ua.S = 1;
+                ++launches;
+            } else {
+                ua.tpart = f.tpart; ua.llpart = f.llpart; ua.S = pl.splits;
+            }
+            // the poll counter of a group is zeroed by the group's first update launch (or a memset when the group is one pass)
+            ua.nactive = last ? f.nactive + slot : f.nactive + 31;   // word 31 = scratch between polls
+            ua.nreset = (k == 0 && !last) ? f.nactive + slot : nullptr;
+            if (k == 0 && last) { cudaMemsetAsync(f.nactive + slot, 0, 4, st); ++launches; }
+            const unsigned ub2 = (unsigned)((W + kU2Lanes - 1) / kU2Lanes);
+            if (m == 4) lbfgs_update_vl2_kernel<4><<<ub2, kU2Threads, Vl2Layout<4>::doubles * 8, st>>>(ua, s.gram);
+            else lbfgs_update_vl2_kernel<8><<<ub2, kU2Threads, Vl2Layout<8>::doubles * 8, st>>>(ua, s.gram);
+            if (time_passes) { cudaEvent_t e2; cudaEventCreate(&e2); uev.push_back(pev.back()); uev.push_back(e2); cudaEventRecord(e2, st); }
                 ++passes; launches += 2; lane_passes += W;
                 if (time_passes) pass_width.push_back(W);
             }

@@ -11,7 +11,6 @@ namespace tvs {
 constexpr int kWarps = 8;            // warps per CTA of the pass kernel
 constexpr int kThreads = kWarps * 32;
 constexpr int kMaxHistory = 16;
-constexpr int kUpdWarps = 8;         // warps per CTA of the L-BFGS update kernel (split V)
 
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);

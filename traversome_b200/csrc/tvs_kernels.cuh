@@ -269,7 +269,7 @@ __global__ void finish_loglik_kernel(const double* __restrict__ llpart, int S, i
 }
 
 // ------------------------------------------------------------------------------------------------
-// Batched L-BFGS step in z = sqrt(phi) (one CTA = 32 lanes x kUpdWarps warps that split V).
+// Batched L-BFGS step in z = sqrt(phi).
 //
 // minimise  F(z) = -(1/N) sum_r w_r log( sum_v A_rv z_v^2 / L_v ) + sum_v z_v^2      (no constraints)
 // whose minimisers are exactly the KKT points of the reference's constrained problem
@@ -286,522 +286,16 @@ struct UpdArgs {
     int32_t* nreset;     // counter zeroed by this launch for a LATER launch of the same poll group (or null)
 };
 
-__device__ __forceinline__ double blk_sum(double v, double (*red)[32], int wi, int t) {
-    red[wi][t] = v;
-    __syncthreads();
-    double s = 0.0;
-#pragma unroll
-    for (int q = 0; q < kUpdWarps; ++q) s += red[q][t];
-    __syncthreads();
-    return s;
-}
-__device__ __forceinline__ double blk_max(double v, double (*red)[32], int wi, int t) {
-    red[wi][t] = v;
-    __syncthreads();
-    double s = red[0][t];
-#pragma unroll
-    for (int q = 1; q < kUpdWarps; ++q) s = fmax(s, red[q][t]);
-    __syncthreads();
-    return s;
-}
-
-__global__ void __launch_bounds__(kUpdWarps * 32) lbfgs_update_kernel(const UpdArgs a) {
-    __shared__ double red[kUpdWarps][32];
-    __shared__ double alph[kMaxHistory][32];
-    const int t = threadIdx.x & 31, wi = threadIdx.x >> 5;
-    const int64_t B = a.B;
-    const int64_t b = (int64_t)blockIdx.x * 32 + t;
-    const bool valid = b < B;
-    const int64_t bb = valid ? b : B - 1;          // clamp so that every thread can load safely
-    const int V = a.V, m = a.m;
-    bool active = valid && a.done[bb] == 0;
-    if (!__syncthreads_or(active)) return;
-
-    const double N = a.N[bb];
-    // ---- A: gather partials of the pass evaluated at zt
-    double llsum = 0.0;
-    for (int q = 0; q < a.S; ++q) llsum += a.llpart[(int64_t)q * B + bb];
-    double sp = 0.0, dgt = 0.0;
-    for (int v = wi; v < V; v += kUpdWarps) {
-        const int64_t i = (int64_t)v * B + bb;
-        double tv = 0.0;
-        for (int q = 0; q < a.S; ++q) tv += a.tpart[((int64_t)q * V + v) * B + bb];
-        const double gh = tv * a.invL[v] / N;
-        const double ztv = a.zt[i];
-        const bool mk = a.mask ? a.mask[i] != 0 : true;
-        const double gtv = mk ? 2.0 * ztv * (1.0 - gh) : 0.0;
-        if (active) { a.gt[i] = gtv; a.gh[i] = gh; }
-        sp = fma(ztv, ztv, sp);
-        dgt = fma(a.d[i], gtv, dgt);
-    }
-    const double sumphi = blk_sum(sp, red, wi, t);
-    dgt = blk_sum(dgt, red, wi, t);
-    double Ft = -llsum / N + sumphi;
-    const bool fin = isfinite(llsum) && isfinite(sumphi) && sumphi > 0.0;
-    if (!fin) Ft = INFINITY;
-
-    const int it = a.iters[bb];
-    const bool first = it < 0;
-    const double F = a.F[bb], dg = a.dg[bb], alpha = a.alpha[bb];
-    bool accept;
-    if (first) accept = fin;
-    else accept = fin && (Ft <= F + 1e-4 * alpha * dg ||
-                          (fabs(Ft - F) <= 1e-14 * fabs(F) && fabs(dgt) <= 0.9 * fabs(dg)));
-    accept = accept && active;
-    bool finished = false;
-    int status = TVS_CONVERGED;
-    if (active && first && !fin) { finished = true; status = TVS_INFEASIBLE; }
-
-    // ---- C: accepted lanes move to zt; curvature pair; KKT residuals
-    double ss = 0.0, yy = 0.0, sy = 0.0, comp = 0.0, dual = -INFINITY;
-    for (int v = wi; v < V; v += kUpdWarps) {
-        const int64_t i = (int64_t)v * B + bb;
-        const double ztv = a.zt[i], gtv = a.gt[i];
-        const double sv = ztv - a.z[i], yv = gtv - a.g[i];
-        ss = fma(sv, sv, ss); yy = fma(yv, yv, yy); sy = fma(sv, yv, sy);
-        const bool mk = a.mask ? a.mask[i] != 0 : true;
-        if (mk) {
-            const double ghn = a.gh[i] * sumphi;           // gradient ratio at the normalised point
-            comp = fmax(comp, ztv * ztv / sumphi * fabs(ghn - 1.0));
-            dual = fmax(dual, ghn - 1.0);
-        }
-    }
-    ss = blk_sum(ss, red, wi, t); yy = blk_sum(yy, red, wi, t); sy = blk_sum(sy, red, wi, t);
-    comp = blk_max(comp, red, wi, t); dual = blk_max(dual, red, wi, t);
-
-    int head = a.head[bb], cnt = a.cnt[bb];
-    const bool store = accept && !first && sy > 1e-10 * sqrt(ss * yy) && sy > 0.0;
-    for (int v = wi; v < V; v += kUpdWarps) {
-        const int64_t i = (int64_t)v * B + bb;
-        if (accept) {
-            const double ztv = a.zt[i], gtv = a.gt[i];
-            if (store) {
-                a.Sh[((int64_t)head * V + v) * B + bb] = ztv - a.z[i];
-                a.Yh[((int64_t)head * V + v) * B + bb] = gtv - a.g[i];
-            }
-            a.z[i] = ztv; a.g[i] = gtv;
-        }
-    }
-    int iters = it;
-    if (accept) {
-        iters = it + 1;
-        if (store) {
-            if (wi == 0) { a.rho[(int64_t)head * B + bb] = 1.0 / sy; a.gamma[bb] = sy / yy; }
-            head = (head + 1) % m; cnt = min(cnt + 1, m);
-        }
-        if (comp <= a.tol && dual <= a.tol_dual) { finished = true; status = TVS_CONVERGED; }
-        else if (iters >= a.max_iter) { finished = true; status = TVS_MAXITER; }
-        if (wi == 0) {
-            a.F[bb] = Ft; a.llsum[bb] = llsum; a.sumphi[bb] = sumphi;
-            a.kkt[bb] = comp; a.kkt[B + bb] = dual; a.iters[bb] = iters; a.ls[bb] = 0;
-        }
-    }
-    __syncthreads();   // z, g, history visible to the whole CTA
-
-    // ---- D: two-loop recursion -> new direction for accepted, unfinished lanes (computed for all, used by those)
-    const bool newdir = accept && !finished;
-    // q = g  (held in a.d)
-    if (__syncthreads_or(newdir)) {
-        for (int v = wi; v < V; v += kUpdWarps) {
-            const int64_t i = (int64_t)v * B + bb;
-            if (newdir) a.d[i] = a.g[i];
-        }
-        for (int j = 0; j < m; ++j) {                      // newest -> oldest
-            const bool use = newdir && j < cnt;
-            const int slot = ((head - 1 - j) % m + m) % m;
-            double part = 0.0;
-            if (use)
-                for (int v = wi; v < V; v += kUpdWarps)
-                    part = fma(a.Sh[((int64_t)slot * V + v) * B + bb], a.d[(int64_t)v * B + bb], part);
-            const double dot1 = blk_sum(part, red, wi, t);     // every thread reaches the barrier
-            const double aj = use ? a.rho[(int64_t)slot * B + bb] * dot1 : 0.0;
-            if (wi == 0) alph[j][t] = aj;
-            if (use)
-                for (int v = wi; v < V; v += kUpdWarps) {
-                    const int64_t i = (int64_t)v * B + bb;
-                    a.d[i] = fma(-aj, a.Yh[((int64_t)slot * V + v) * B + bb], a.d[i]);
-                }
-        }
-        __syncthreads();
-        const double gamma = (cnt > 0) ? a.gamma[bb] : 1.0;
-        if (newdir)
-            for (int v = wi; v < V; v += kUpdWarps) a.d[(int64_t)v * B + bb] *= gamma;
-        for (int j = m - 1; j >= 0; --j) {                 // oldest -> newest
-            const bool use = newdir && j < cnt;
-            const int slot = ((head - 1 - j) % m + m) % m;
-            double part = 0.0;
-            if (use)
-                for (int v = wi; v < V; v += kUpdWarps)
-                    part = fma(a.Yh[((int64_t)slot * V + v) * B + bb], a.d[(int64_t)v * B + bb], part);
-            const double dot2 = blk_sum(part, red, wi, t);
-            const double beta = use ? a.rho[(int64_t)slot * B + bb] * dot2 : 0.0;
-            if (use) {
-                const double coef = alph[j][t] - beta;
-                for (int v = wi; v < V; v += kUpdWarps) {
-                    const int64_t i = (int64_t)v * B + bb;
-                    a.d[i] = fma(coef, a.Sh[((int64_t)slot * V + v) * B + bb], a.d[i]);
-                }
-            }
-        }
-        // d = -r ; descent check
-        double dgn = 0.0, gg = 0.0;
-        for (int v = wi; v < V; v += kUpdWarps) {
-            const int64_t i = (int64_t)v * B + bb;
-            const double gv = a.g[i];
-            if (newdir) { const double dv = -a.d[i]; a.d[i] = dv; dgn = fma(dv, gv, dgn); }
-            gg = fma(gv, gv, gg);
-        }
-        dgn = blk_sum(dgn, red, wi, t); gg = blk_sum(gg, red, wi, t);
-        double anew = 1.0;
-        if (newdir) {
-            if (!(dgn < 0.0) || cnt == 0) {                // not a descent direction (or no history): steepest descent
-                for (int v = wi; v < V; v += kUpdWarps) { const int64_t i = (int64_t)v * B + bb; a.d[i] = -a.g[i]; }
-                if (!(dgn < 0.0)) cnt = 0;
-                dgn = -gg;
-                anew = fmin(1.0, 1.0 / sqrt(fmax(gg, 1e-300)));
-            }
-            if (gg == 0.0) { finished = true; status = TVS_CONVERGED; }
-            if (wi == 0) { a.dg[bb] = dgn; a.alpha[bb] = anew; }
-        }
-        for (int v = wi; v < V; v += kUpdWarps) {
-            const int64_t i = (int64_t)v * B + bb;
-            if (newdir && !finished) {
-                const double zn = fma(anew, a.d[i], a.z[i]);
-                a.zt[i] = zn; a.x[i] = zn * zn * a.invL[v];
-            }
-        }
-    }
-
-    // ---- E: rejected lanes backtrack along the same direction
-    const bool reject = active && !accept && !finished;
-    if (__syncthreads_or(reject)) {
-        int ls = a.ls[bb] + 1;
-        double anew = alpha;
-        bool stall = false;
-        if (reject) {
-            if (ls > 40) stall = true;
-            else {
-                // safeguarded quadratic interpolation
-                double aq = 0.5 * alpha;
-                if (isfinite(Ft)) {
-                    const double den = 2.0 * (Ft - F - dg * alpha);
-                    if (den > 0.0) aq = -dg * alpha * alpha / den;
-                    aq = fmin(fmax(aq, 0.1 * alpha), 0.5 * alpha);
-                } else aq = 0.1 * alpha;
-                anew = aq;
-            }
-        }
-        for (int v = wi; v < V; v += kUpdWarps) {
-            const int64_t i = (int64_t)v * B + bb;
-            if (reject && !stall) {
-                const double zn = fma(anew, a.d[i], a.z[i]);
-                a.zt[i] = zn; a.x[i] = zn * zn * a.invL[v];
-            }
-        }
-        if (reject && wi == 0) { a.alpha[bb] = anew; a.ls[bb] = ls; }
-        if (stall) {   // judge the last ACCEPTED point (its residuals were stored when it was accepted)
-            const double c0 = a.kkt[bb], d0 = a.kkt[B + bb];
-            finished = true;
-            status = (c0 <= 1e2 * a.tol && d0 <= 1e2 * a.tol_dual) ? TVS_CONVERGED : TVS_STALLED;
-        }
-    }
-
-    if (valid && wi == 0) {
-        a.head[bb] = head; a.cnt[bb] = cnt;
-        if (active && finished) { a.status[bb] = status; a.done[bb] = 1; }
-    }
-    if (wi == 0) {
-        const unsigned still = __ballot_sync(0xffffffffu, active && !finished);
-        if (t == 0 && still) atomicAdd(a.nactive, __popc(still));
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // Update kernel, "vector-free" form (Chen et al. 2014): the two-loop recursion runs on the
 // (2M+1)x(2M+1) Gram matrix of the basis {s_k, y_k, g} held per lane (packed symmetric, lane-minor),
 // so that one update needs only two sweeps over V (dot products of the new vectors with the basis,
-// then d = sum_k delta_k b_k) instead of 2M dependent sweeps.  Same mathematics as
-// lbfgs_update_kernel above; all dot products of the NEW vectors are computed directly (not
-// derived algebraically) to keep the Gram entries accurate to fp64 rounding.
+// then d = sum_k delta_k b_k) instead of the 2M dependent sweeps of the textbook two-loop recursion.
+// All dot products of the NEW vectors are computed directly (not derived algebraically) to keep the
+// Gram entries accurate to fp64 rounding.
 // ------------------------------------------------------------------------------------------------
-template <int M>
-struct VlLayout {
-    static constexpr int NB = 2 * M + 1;
-    static constexpr int NG = NB * (NB + 1) / 2;
-    static constexpr int NACC = 6 * M + 9;
-    // shared-memory doubles: G, delta, accumulators (per-warp partials + reduced)
-    static constexpr size_t doubles = (size_t)NG * 32 + (size_t)NB * 32 + (size_t)kUpdWarps * NACC * 32 + (size_t)NACC * 32 +
-                                      (size_t)kUpdWarps * 32;
-};
 __device__ __forceinline__ int tri_idx(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
-template <int M>
-__global__ void __launch_bounds__(kUpdWarps * 32) lbfgs_update_vl_kernel(const UpdArgs a, double* __restrict__ Gm) {
-    constexpr int NB = VlLayout<M>::NB, NG = VlLayout<M>::NG, NACC = VlLayout<M>::NACC;
-    constexpr int GI = 2 * M;
-    extern __shared__ double sm[];
-    double (*Gs)[32] = reinterpret_cast<double (*)[32]>(sm);                       // [NG][32]
-    double (*dl)[32] = reinterpret_cast<double (*)[32]>(sm + (size_t)NG * 32);      // [NB][32] delta
-    double* part = sm + (size_t)NG * 32 + (size_t)NB * 32;                         // [W][NACC][32]
-    double (*acc)[32] = reinterpret_cast<double (*)[32]>(part + (size_t)kUpdWarps * NACC * 32);   // [NACC][32]
-    double (*red)[32] = reinterpret_cast<double (*)[32]>(part + (size_t)kUpdWarps * NACC * 32 + (size_t)NACC * 32);  // [W][32]
-
-    const int t = threadIdx.x & 31, wi = threadIdx.x >> 5;
-    const int64_t B = a.B;
-    const int64_t b = (int64_t)blockIdx.x * 32 + t;
-    const bool valid = b < B;
-    const int64_t bb = valid ? b : B - 1;
-    const int V = a.V;
-    const bool active = valid && a.done[bb] == 0;
-    if (!__syncthreads_or(active)) return;
-
-#pragma unroll
-    for (int i = 0; i < (NG + kUpdWarps - 1) / kUpdWarps; ++i) {       // all loads in flight at once
-        const int q = wi + i * kUpdWarps;
-        if (q < NG) Gs[q][t] = Gm[(int64_t)q * B + bb];
-    }
-
-    const double N = a.N[bb];
-    // ---- A: gather the per-split partials of the pass evaluated at zt
-    double llsum = 0.0;
-    for (int q = 0; q < a.S; ++q) llsum += a.llpart[(int64_t)q * B + bb];
-    double sp = 0.0, dgt = 0.0;
-    for (int v = wi; v < V; v += kUpdWarps) {
-        const int64_t i = (int64_t)v * B + bb;
-        double tv = 0.0;
-        for (int q = 0; q < a.S; ++q) tv += a.tpart[((int64_t)q * V + v) * B + bb];
-        const double gh = tv * a.invL[v] / N;
-        const double ztv = a.zt[i];
-        const bool mk = a.mask ? a.mask[i] != 0 : true;
-        const double gtv = mk ? 2.0 * ztv * (1.0 - gh) : 0.0;
-        if (active) { a.gt[i] = gtv; a.gh[i] = gh; }
-        sp = fma(ztv, ztv, sp);
-        dgt = fma(a.d[i], gtv, dgt);
-    }
-    const double sumphi = blk_sum(sp, red, wi, t);
-    dgt = blk_sum(dgt, red, wi, t);
-    double Ft = -llsum / N + sumphi;
-    const bool fin = isfinite(llsum) && isfinite(sumphi) && sumphi > 0.0;
-    if (!fin) Ft = INFINITY;
-
-    const int it = a.iters[bb];
-    const bool first = it < 0;
-    const double F = a.F[bb], dg = a.dg[bb], alpha = a.alpha[bb];
-    bool accept;
-    if (first) accept = fin;
-    else accept = fin && (Ft <= F + 1e-4 * alpha * dg ||
-                          (fabs(Ft - F) <= 1e-14 * fabs(F) && fabs(dgt) <= 0.9 * fabs(dg)));
-    accept = accept && active;
-    bool finished = false;
-    int status = TVS_CONVERGED;
-    if (active && first && !fin) { finished = true; status = TVS_INFEASIBLE; }
-
-    // ---- B: one sweep: dot products of the new vectors (s, y, g_new) with the whole basis + KKT residuals
-    double comp = 0.0, dual = -INFINITY;
-    if (__syncthreads_or(accept)) {
-        double ac[NACC];
-#pragma unroll
-        for (int q = 0; q < NACC; ++q) ac[q] = 0.0;
-        for (int v = wi; v < V; v += kUpdWarps) {
-            const int64_t i = (int64_t)v * B + bb;
-            const double ztv = a.zt[i], gn = a.gt[i], go = a.g[i];
-            const double sv = ztv - a.z[i], yv = gn - go;
-#pragma unroll
-            for (int k = 0; k < M; ++k) {
-                const double Sk = a.Sh[((int64_t)k * V + v) * B + bb], Yk = a.Yh[((int64_t)k * V + v) * B + bb];
-                ac[k] = fma(sv, Sk, ac[k]);             ac[M + k] = fma(sv, Yk, ac[M + k]);
-                ac[2 * M + k] = fma(yv, Sk, ac[2 * M + k]); ac[3 * M + k] = fma(yv, Yk, ac[3 * M + k]);
-                ac[4 * M + k] = fma(gn, Sk, ac[4 * M + k]); ac[5 * M + k] = fma(gn, Yk, ac[5 * M + k]);
-            }
-            ac[6 * M + 0] = fma(sv, sv, ac[6 * M + 0]); ac[6 * M + 1] = fma(sv, yv, ac[6 * M + 1]);
-            ac[6 * M + 2] = fma(yv, yv, ac[6 * M + 2]); ac[6 * M + 3] = fma(gn, gn, ac[6 * M + 3]);
-            ac[6 * M + 4] = fma(sv, gn, ac[6 * M + 4]); ac[6 * M + 5] = fma(yv, gn, ac[6 * M + 5]);
-            ac[6 * M + 6] = fma(sv, go, ac[6 * M + 6]); ac[6 * M + 7] = fma(yv, go, ac[6 * M + 7]);
-            ac[6 * M + 8] = fma(gn, go, ac[6 * M + 8]);
-            const bool mk = a.mask ? a.mask[i] != 0 : true;
-            if (mk) {
-                const double ghn = a.gh[i] * sumphi;
-                comp = fmax(comp, ztv * ztv / sumphi * fabs(ghn - 1.0));
-                dual = fmax(dual, ghn - 1.0);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < NACC; ++q) part[((size_t)wi * NACC + q) * 32 + t] = ac[q];
-        __syncthreads();
-        for (int q = wi; q < NACC; q += kUpdWarps) {
-            double ssum = 0.0;
-#pragma unroll
-            for (int w2 = 0; w2 < kUpdWarps; ++w2) ssum += part[((size_t)w2 * NACC + q) * 32 + t];
-            acc[q][t] = ssum;
-        }
-        __syncthreads();
-        comp = blk_max(comp, red, wi, t);
-        dual = blk_max(dual, red, wi, t);
-    }
-    const double ss = acc[6 * M + 0][t], sy = acc[6 * M + 1][t], yy = acc[6 * M + 2][t], gg = acc[6 * M + 3][t];
-
-    int head = a.head[bb], cnt = a.cnt[bb];
-    const bool store = accept && !first && sy > 1e-10 * sqrt(ss * yy) && sy > 0.0;
-    // ---- C: move accepted lanes, write the new curvature pair into ring slot `head`
-    for (int v = wi; v < V; v += kUpdWarps) {
-        const int64_t i = (int64_t)v * B + bb;
-        if (accept) {
-            const double ztv = a.zt[i], gtv = a.gt[i];
-            if (store) {
-                a.Sh[((int64_t)head * V + v) * B + bb] = ztv - a.z[i];
-                a.Yh[((int64_t)head * V + v) * B + bb] = gtv - a.g[i];
-            }
-            a.z[i] = ztv; a.g[i] = gtv;
-        }
-    }
-    int iters = it;
-    if (accept) {
-        iters = it + 1;
-        if (comp <= a.tol && dual <= a.tol_dual) { finished = true; status = TVS_CONVERGED; }
-        else if (iters >= a.max_iter) { finished = true; status = TVS_MAXITER; }
-    }
-    const bool newdir = accept && !finished;
-    double anew = 1.0;
-
-    // ---- D: scalar phase, one thread per lane (warp 0): Gram update, two-loop on coefficients
-    if (wi == 0 && accept) {
-        // g row (against every slot, valid or not)
-#pragma unroll
-        for (int k = 0; k < M; ++k) { Gs[tri_idx(GI, k)][t] = acc[4 * M + k][t]; Gs[tri_idx(GI, M + k)][t] = acc[5 * M + k][t]; }
-        Gs[tri_idx(GI, GI)][t] = gg;
-        if (store) {
-            const int h = head;
-            for (int k = 0; k < M; ++k) {
-                Gs[tri_idx(h, k)][t] = acc[k][t];             Gs[tri_idx(h, M + k)][t] = acc[M + k][t];
-                Gs[tri_idx(M + h, k)][t] = acc[2 * M + k][t]; Gs[tri_idx(M + h, M + k)][t] = acc[3 * M + k][t];
-            }
-            Gs[tri_idx(h, h)][t] = ss; Gs[tri_idx(h, M + h)][t] = sy; Gs[tri_idx(M + h, M + h)][t] = yy;
-            Gs[tri_idx(GI, h)][t] = acc[6 * M + 4][t]; Gs[tri_idx(GI, M + h)][t] = acc[6 * M + 5][t];
-            head = (h + 1) % M; cnt = min(cnt + 1, M);
-        }
-        double dgn = -gg;
-        if (newdir) {
-            double u[NB];
-            double* al = part;                               // [M][32] scratch (the partials are consumed)
-#pragma unroll
-            for (int k = 0; k < NB; ++k) { dl[k][t] = 0.0; u[k] = -Gs[tri_idx(k, GI)][t]; }
-            dl[GI][t] = -1.0;
-            for (int j = 0; j < cnt; ++j) {                       // newest -> oldest
-                const int sl = ((head - 1 - j) % M + M) % M;
-                double us = 0.0;
-#pragma unroll
-                for (int k = 0; k < NB; ++k) us = (k == sl) ? u[k] : us;
-                const double aj = us / Gs[tri_idx(sl, M + sl)][t];
-                al[j * 32 + t] = aj;
-                dl[M + sl][t] -= aj;
-#pragma unroll
-                for (int k = 0; k < NB; ++k) u[k] = fma(-aj, Gs[tri_idx(k, M + sl)][t], u[k]);
-            }
-            if (cnt > 0) {
-                const int sl = ((head - 1) % M + M) % M;
-                const double gamma = Gs[tri_idx(sl, M + sl)][t] / Gs[tri_idx(M + sl, M + sl)][t];
-#pragma unroll
-                for (int k = 0; k < NB; ++k) { dl[k][t] *= gamma; u[k] *= gamma; }
-            }
-            for (int j = cnt - 1; j >= 0; --j) {                  // oldest -> newest
-                const int sl = ((head - 1 - j) % M + M) % M;
-                double uy = 0.0;
-#pragma unroll
-                for (int k = 0; k < NB; ++k) uy = (k == M + sl) ? u[k] : uy;
-                const double cf = al[j * 32 + t] - uy / Gs[tri_idx(sl, M + sl)][t];
-                dl[sl][t] += cf;
-#pragma unroll
-                for (int k = 0; k < NB; ++k) u[k] = fma(cf, Gs[tri_idx(k, sl)][t], u[k]);
-            }
-            dgn = u[GI];
-            if (!(dgn < 0.0) || cnt == 0) {                       // not a descent direction / no history
-#pragma unroll
-                for (int k = 0; k < NB; ++k) dl[k][t] = 0.0;
-                dl[GI][t] = -1.0;
-                if (!(dgn < 0.0)) cnt = 0;
-                dgn = -gg;
-                anew = fmin(1.0, 1.0 / sqrt(fmax(gg, 1e-300)));
-            }
-            if (gg == 0.0) { finished = true; status = TVS_CONVERGED; }
-        }
-        a.F[bb] = Ft; a.llsum[bb] = llsum; a.sumphi[bb] = sumphi;
-        a.kkt[bb] = comp; a.kkt[B + bb] = dual; a.iters[bb] = iters; a.ls[bb] = 0;
-        a.dg[bb] = dgn; a.alpha[bb] = anew;
-        red[0][t] = anew; red[1][t] = finished ? 1.0 : 0.0;
-    }
-    __syncthreads();
-    if (accept) { anew = red[0][t]; finished = red[1][t] != 0.0; }
-
-    // ---- E: d = sum_k delta_k b_k ; next trial point
-    if (__syncthreads_or(newdir)) {
-        for (int v = wi; v < V; v += kUpdWarps) {
-            const int64_t i = (int64_t)v * B + bb;
-            if (newdir && !finished) {
-                double dv = dl[GI][t] * a.g[i];
-#pragma unroll
-                for (int k = 0; k < M; ++k) {
-                    dv = fma(dl[k][t], a.Sh[((int64_t)k * V + v) * B + bb], dv);
-                    dv = fma(dl[M + k][t], a.Yh[((int64_t)k * V + v) * B + bb], dv);
-                }
-                a.d[i] = dv;
-                const double zn = fma(anew, dv, a.z[i]);
-                a.zt[i] = zn; a.x[i] = zn * zn * a.invL[v];
-            }
-        }
-    }
-    if (accept)
-        for (int q = wi; q < NG; q += kUpdWarps) Gm[(int64_t)q * B + bb] = Gs[q][t];
-
-    // ---- F: rejected lanes backtrack along the stored direction
-    const bool reject = active && !accept && !finished;
-    if (__syncthreads_or(reject)) {
-        const int ls = a.ls[bb] + 1;
-        double ar = alpha;
-        bool stall = false;
-        if (reject) {
-            if (ls > 40) stall = true;
-            else {
-                double aq = 0.5 * alpha;
-                if (isfinite(Ft)) {
-                    const double den = 2.0 * (Ft - F - dg * alpha);
-                    if (den > 0.0) aq = -dg * alpha * alpha / den;
-                    aq = fmin(fmax(aq, 0.1 * alpha), 0.5 * alpha);
-                } else aq = 0.1 * alpha;
-                ar = aq;
-            }
-        }
-        for (int v = wi; v < V; v += kUpdWarps) {
-            const int64_t i = (int64_t)v * B + bb;
-            if (reject && !stall) {
-                const double zn = fma(ar, a.d[i], a.z[i]);
-                a.zt[i] = zn; a.x[i] = zn * zn * a.invL[v];
-            }
-        }
-        if (reject && wi == 0) { a.alpha[bb] = ar; a.ls[bb] = ls; }
-        if (stall) {
-            const double c0 = a.kkt[bb], d0 = a.kkt[B + bb];
-            finished = true;
-            status = (c0 <= 1e2 * a.tol && d0 <= 1e2 * a.tol_dual) ? TVS_CONVERGED : TVS_STALLED;
-        }
-    }
-
-    if (valid && wi == 0) {
-        if (accept) { a.head[bb] = head; a.cnt[bb] = cnt; }
-        if (active && finished) { a.status[bb] = status; a.done[bb] = 1; }
-    }
-    if (wi == 0) {
-        const unsigned still = __ballot_sync(0xffffffffu, active && !finished);
-        if (t == 0 && still) atomicAdd(a.nactive, __popc(still));
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Same update, latency-oriented geometry (profiles/r1_v2_summary.md: the 32-lane x 8-warp kernel above
-// takes ~65 us at ANY width because each warp walks V/8 variants one dependent global round trip at a
-// time and only B/32 CTAs exist).  Here a CTA owns 8 lanes and 32 "variant slots": thread = (lane l,
-// slot vs), a warp = 4 slots x 8 lanes (each slot row is a 64-byte segment of the lane-minor arrays), so
-// with 32 slots a sweep over V = 64 is two round trips and B/8 CTAs are resident.
-// ------------------------------------------------------------------------------------------------
 // sum_q src[q*stride], q = 0..S-1, 8 independent loads in flight, added in order
 __device__ __forceinline__ double sum_splits(const double* __restrict__ src, int S, int64_t stride) {
     double s0 = 0.0;
