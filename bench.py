@@ -298,8 +298,8 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "pass3_kernel (fused p = A x, w/p, w log p, t = A^T(w/p))",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                         "traffic": 76.0e6,
-                         "traffic_note": "dram read+write of ONE full-width (1000-lane) launch, ncu --set full (profiles/r1_v3_summary.md); "
+                         "traffic": 77.9e6,
+                         "traffic_note": "dram read+write of ONE full-width (1000-lane) launch, ncu --set full (profiles/r1_final_summary.md); "
                                          "algorithmic bytes of that launch: 74.3e6",
                          "avg_launch_us": 1e3 * prof["pass_ms"] / max(prof["passes"], 1), "launches_profiled": prof["passes"],
                          "pass_share_of_step": prof["pass_ms"] / prof["total_ms"] if prof["total_ms"] > 0 else None,
@@ -318,7 +318,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = 1
-            n_sample = 24
+            n_sample = 120                     # ~14 s of single-core CPU work
             rate, wall_cpu, lls = cpu_reference_rate(wl, n_sample, cores, seed=5)
             line["cpu_baseline"] = {
                 "value": rate, "unit": UNIT, "cores": cores, "kind": "port",

@@ -41,6 +41,15 @@ __device__ __forceinline__ bool is_pos_normal(double p) {       // finite, norma
     return (unsigned)(__double2hiint(p) - 0x00100000) < 0x7fe00000u;
 }
 
+// int32 -> double without the XU pipe (I2F.F64 and F2F.F64 run there at a few lanes/clk/SM and the pipe saturates:
+// profiles/r1_v4_summary.md): place the integer in the mantissa of 2^52 and subtract.
+__device__ __forceinline__ double u31_to_double(int v) {        // 0 <= v < 2^31
+    return __hiloint2double(0x43300000, v) - 4503599627370496.0;
+}
+__device__ __forceinline__ double i32_to_double(int v) {        // any int32
+    return __hiloint2double(0x43300000, v ^ 0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
+}
+
 __device__ __forceinline__ double fast_rcp(double p) {          // p finite, normal, > 0
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));        // MUFU.RCP64H, ~2^-20
@@ -71,7 +80,7 @@ __device__ __forceinline__ double fast_log_pos(double p, const LogCoef& kc) {
     q = fma(q, s2, kc.c[2]);
     q = fma(q, s2, kc.c[1]);
     q = fma(q, s2, kc.c[0]);
-    const double ed = (double)e;
+    const double ed = i32_to_double(e);
     const double two_s = s + s;
     const double tail = fma(two_s * s2, q, ed * kc.c[10]);      // + e * ln2_lo
     return fma(ed, kc.c[9], two_s + tail);                      // e * ln2_hi is exact
@@ -91,7 +100,7 @@ __device__ __forceinline__ double table_log_pos(double p, const double2* __restr
     q = fma(q, r, -0.25);
     q = fma(q, r, kc.c[0]);                                      // 1/3
     q = fma(q, r, -0.5);
-    const double ed = (double)e;
+    const double ed = i32_to_double(e);
     const double tail = fma(r * r, q, fma(ed, kc.c[10], r));     // r + r^2 q + e ln2_lo
     return fma(ed, kc.c[9], cl.y) + tail;                        // e ln2_hi (exact) - log c_i
 }
@@ -452,8 +461,8 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
             if (fast) {
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
-                    const double wd = (double)wv.v[j];
                     const bool on = wv.v[j] > 0;
+                    const double wd = u31_to_double(on ? wv.v[j] : 0);
                     const double rcp = fast_rcp(p[j]);
                     rr[j] = on ? wd * rcp : 0.0;
                     c2[j] = rr[j] * rcp;
