@@ -146,3 +146,23 @@ class OracleEngine(object):
 
     def close(self):
         pass
+
+
+def model_from_workload(wl, n_bins=3):
+    """Reference-style model objects (Bins/BinInfo/SubPathInfo/PathMultinomialModel) from a synthetic Workload:
+    every read path gets one BinInfo (X = wl.X[r], n = wl.n_obs[r]) in one of `n_bins` length ranges."""
+    all_sub_paths = OrderedDict()
+    bins_list = [Bins(min_len=1000 * (i + 1), max_len=1000 * (i + 2) - 1, min_id=0, max_id=0) for i in range(n_bins)]
+    rec = 0
+    for r in range(wl.R):
+        fv = {int(c): int(v) for c, v in zip(wl.col[wl.row_ptr[r]:wl.row_ptr[r + 1]], wl.val[wl.row_ptr[r]:wl.row_ptr[r + 1]])}
+        spi = SubPathInfo()
+        spi.from_variants = fv
+        spi.inner_len, spi.full_len = 0, 10 ** 6
+        n = int(wl.n_obs[r])
+        spi.mapped_records = list(range(rec, rec + n))
+        rec += n
+        all_sub_paths[(("rp%d" % r, True),)] = spi
+        bins_list[r % n_bins].rp_bins.append(BinInfo(from_variants=fv, num_possible_X=float(wl.X[r]), num_matched=n))
+    return PathMultinomialModel(variant_sizes=[int(x) for x in wl.L], variant_topos=[True] * wl.V, bins_list=bins_list,
+                                all_sub_paths=all_sub_paths)

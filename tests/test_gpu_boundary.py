@@ -13,8 +13,8 @@ import numpy as np
 import pytest
 
 from oracle import exact, loglik
-from tests.helpers import fit_context, hexf, model_from_tables
-from traversome_b200 import _cabi, bootstrap
+from tests.helpers import OracleEngine, fit_context, hexf, model_from_tables, model_from_workload
+from traversome_b200 import _cabi, bootstrap, synthetic
 from traversome_b200.ModelFitMaxLike import ModelFitMaxLike
 from traversome_b200.lanes import LaneContext, LaneRequest
 
@@ -189,3 +189,33 @@ def test_lane_context_batches_mixed_replicates_and_subsets(gpu):
         assert abs(-fr.fun - (r["loglike_no_C"] + rq.C)) < 1e-9 * abs(fr.fun)
     assert n_ok >= 4
     ctx.close()
+
+
+@pytest.mark.parametrize("criterion", ["BIC", "AIC"])
+def test_backward_selection_decisions_equal_exact_replay(gpu, criterion):
+    """cfg3-shaped case at test size: 24 candidates of which 8 carry reads.  The backward selection driven by the CUDA
+    solver takes exactly the decisions of the same driver fed with exact CPU optima (oracle), with a pinned shuffle:
+    same dropped variants in the same order, same final model, criterion within 1e-9 relative."""
+    wl = synthetic.make_workload(24, 1200, 0.5, seed=77, n_true=8)
+
+    def run(engine_factory):
+        model = model_from_workload(wl)
+        kw = fit_context(model)
+        ctx = LaneContext(wl.V, wl.L)
+        if engine_factory is not None:
+            ctx.engine_factory = engine_factory
+        fitter = ModelFitMaxLike(context=ctx, **kw)
+        rng = np.random.default_rng(5)
+        fitter._shuffle = lambda x: rng.shuffle(x)
+        out = fitter.reverse_model_selection(n_proc=1, criterion=criterion)
+        n = ctx.n_lanes_fitted
+        ctx.close()
+        return out, n
+
+    (gp, gl, gc), n_gpu = run(None)
+    (cp, cl, cc), n_cpu = run(OracleEngine)
+    assert sorted(gp) == sorted(cp)
+    assert n_gpu == n_cpu                                   # same number of candidate fits: same decision path
+    assert all(abs(gp[k] - cp[k]) < 1e-6 for k in gp)
+    assert abs(gl - cl) < 1e-9 * abs(cl) and abs(gc - cc) < 1e-9 * abs(cc)
+    assert n_gpu >= 5 and len(gp) < wl.V                    # the selection did drop variants and tested candidates
