@@ -876,6 +876,9 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
 
     bool in_newton = false;
     int64_t newton_active = 0;
+    // compact when at most this fraction of the set's lanes is still iterating (one gather launch per compaction)
+    // (measured on cfg2: thresholds of 50..85 % all land within 2 % of each other, the buffers are sized for 50 %)
+    const double compact_frac = std::min(0.5, std::max(0.1, env_int("TVS_COMPACT_PCT", 50) / 100.0));
     while (!all_done && passes < max_passes && rc == TVS_OK) {
         LaneSet& s = f.set[cur];
         const int64_t W = s.width;
@@ -938,7 +941,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         }
         // ---- compaction: keep only the lanes that are still iterating
         const bool to_newton = in_newton || (newton_lanes > 0 && !newton_off && active <= newton_lanes);
-        if (!no_compact && (active * 2 <= W || (to_newton && W > newton_lanes)) && W > 32 && active + 3 <= f.half) {
+        if (!no_compact && ((double)active <= compact_frac * (double)W || (to_newton && W > newton_lanes)) && W > 32 && active + 3 <= f.half) {
             finalize(s, 1);                                      // results of the finished lanes, at their original ids
             LaneSet& n = f.set[cur ^ 1];
             build_index_kernel<<<1, 1024, 0, st>>>(s.done, W, f.idx, f.nactive + 30);

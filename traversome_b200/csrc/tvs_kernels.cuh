@@ -374,6 +374,22 @@ __global__ void __launch_bounds__(kU2Threads) lbfgs_update_vl2_kernel(const UpdA
     if (!__syncthreads_or(active)) return;
 
     for (int q = vs; q < NG; q += kU2Slots) Gs[q][l] = Gm[(int64_t)q * B + bb];
+    if (active) {
+        // the likelihood pass has just streamed the weight matrix through L2, so the solver state is in DRAM: start
+        // fetching everything the later sweeps of this thread will read (profiles/r1_final_summary.md: 12 warps per
+        // issue stalled on long_scoreboard, 21 MB of DRAM reads per launch)
+        for (int v = vs; v < V; v += kU2Slots) {
+            const int64_t i = (int64_t)v * B + bb;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.z + i));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.g + i));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.d + i));
+#pragma unroll
+            for (int k = 0; k < M; ++k) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Sh + ((int64_t)k * V + v) * B + bb));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.Yh + ((int64_t)k * V + v) * B + bb));
+            }
+        }
+    }
 
     const double N = a.N[bb];
     // ---- A: sum the per-split partials of the pass evaluated at zt in FIXED split order (bitwise reproducible)
