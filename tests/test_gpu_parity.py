@@ -104,8 +104,9 @@ def test_fit_matches_exact_optimum(gpu, V, R, density, B, n_true):
 
 
 @pytest.mark.parametrize("V,R,density,B", [(96, 3000, 0.08, 40), (200, 2500, 0.05, 24)])
-def test_fit_beyond_the_newton_phase_limit(gpu, V, R, density, B):
-    """V > 64: no Newton phase (tvs_newton.cuh), the batched L-BFGS runs every lane to the KKT certificate."""
+def test_fit_medium_and_large_variant_counts(gpu, V, R, density, B):
+    """V = 96: the Newton phase with the 128-variant solve kernel; V = 200: beyond its limit (tvs_newton.cuh), the
+    batched L-BFGS alone runs every lane to the KKT certificate."""
     wl = synthetic.make_workload(V, R, density, seed=300 + V)
     w = synthetic.bootstrap_weights(wl.n_obs, B, seed=4)
     with engine_for(wl) as eng:

@@ -801,7 +801,8 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         TVS_CUDA(cudaFuncSetAttribute(hess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hess_smem));
         TVS_CUDA(cudaFuncSetAttribute(hess_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem));
         const size_t solve_smem = ((size_t)V * (V + 1) + 2 * (V + 2) + 2 * V) * 8;
-        TVS_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+        TVS_CUDA(cudaFuncSetAttribute(solve_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+        TVS_CUDA(cudaFuncSetAttribute(solve_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
         PassPlan pl;
         int prc = make_plan<true>(h, W, &pl);
         if (prc != TVS_OK) return prc;
@@ -846,7 +847,8 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
             if (wide) hess_wide_kernel<<<wide_grid, 32 * kWideWarps, wide_smem, st>>>(hw);
             else hess_kernel<<<dim3((unsigned)W, (unsigned)S_h), 32 * kHessWarps, hess_smem, st>>>(ha);
             if (time_passes) cudaEventRecord(eh1, st);
-            solve_kernel<<<(unsigned)W, kSolveThreads, solve_smem, st>>>(sa);
+            if (V <= 64) solve_kernel<64><<<(unsigned)W, kSolveThreads, solve_smem, st>>>(sa);
+            else solve_kernel<128><<<(unsigned)W, kSolveThreads, solve_smem, st>>>(sa);
             if (time_passes) { cudaEventRecord(eh2, st); nev.push_back(eh0); nev.push_back(eh1); nev.push_back(eh2); }
             if (time_passes) { cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); pev.push_back(e0); pev.push_back(e1); cudaEventRecord(e0, st); }
             int lrc = launch_pass<true>(h, pl, pa);

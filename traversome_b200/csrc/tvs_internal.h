@@ -42,7 +42,7 @@ struct Csr {
     int       max_chunk_nnz = 0;     // largest number of entries in one chunk
     void*     desc = nullptr;        // [n_chunks] ChunkDesc (tvs_kernels.cuh)
     void*     logtab = nullptr;      // [128] double2 {c_i, -log c_i} (table_log_pos)
-    // Newton phase (V <= 64): products A_ru A_rv (u >= v) grouped by H entry inside blocks of h_HB rows (tvs_newton.cuh)
+    // Newton phase (V <= 128): products A_ru A_rv (u >= v) grouped by H entry inside blocks of h_HB rows (tvs_newton.cuh)
     int64_t*  slab_ptr = nullptr;    // [h_nblk * (h_NG + 1)] step offsets
     uint16_t* h_row = nullptr;       // [h_steps * 32] block-local row (h_HB = padding)
     float*    h_val = nullptr;       // [h_steps * 32] product (exact: < 2^24 checked)

@@ -16,14 +16,15 @@
 //   pass kernel     the ordinary fused likelihood pass at the trial point;
 //   newton_update_kernel   Armijo accept / reject (reject -> lambda x 10 and re-solve with the same H),
 //                   KKT residuals, convergence flags.
-// Available when V <= 64 (H is 2,080 doubles per lane) and the pair lists fit (tvs_create builds them).
+// Available when V <= 128 (H is 2,080 doubles per lane at V = 64, 8,256 at 128) and the row-product lists fit
+// (tvs_create builds them).
 #pragma once
 #include "tvs_kernels.cuh"
 #include "tvs_pass2.cuh"
 
 namespace tvs {
 
-constexpr int kNewtonMaxV = 64;
+constexpr int kNewtonMaxV = 128;   // solve_kernel keeps V(V+1)/2 / 256 matrix entries per thread in registers: instantiated for 64 and 128
 
 // Hessian accumulation.  tvs_create cuts the rows into blocks of HB rows and, per block, stores the products
 // A_ru A_rv (u >= v) of every row GROUPED BY H ENTRY: entries sorted by their number of contributing rows, 32
@@ -243,6 +244,7 @@ struct SolveArgs {
 constexpr int kSolveThreads = 256;
 
 // one CTA per lane.  shared: H0[V][V+1] (Hz, kept for retries) | 2 column buffers | rhs[V] | zv[V]
+template <int VMAX>
 __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const SolveArgs a) {
     extern __shared__ double ss[];
     const int V = a.V, LD = V + 1, NP = V * (V + 1) / 2;
@@ -277,10 +279,10 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const SolveArgs a)
     double lam = a.lam[lane];
     double* invD = zv;                                         // zv is no longer needed: reuse as 1 / D_k
     // ---- LDL^T of Hz + lam I with the matrix in REGISTERS: thread tid owns the packed lower-triangle entries
-    //      tid, tid + 256, ... (<= 9 for V <= 64) and, for tid < V, rhs[tid].  Step k: the owners of column k publish
+    //      tid, tid + 256, ... (<= 9 for V <= 64, <= 33 for V <= 128) and, for tid < V, rhs[tid].  Step k: the owners of column k publish
     //      it (and rhs_k) to one of two shared buffers, one barrier, everyone updates its own entries.  The forward
     //      substitution rides along.  lam is raised until every pivot is positive (Levenberg-Marquardt damping).
-    constexpr int EPT = (kNewtonMaxV * (kNewtonMaxV + 1) / 2 + kSolveThreads - 1) / kSolveThreads;
+    constexpr int EPT = (VMAX * (VMAX + 1) / 2 + kSolveThreads - 1) / kSolveThreads;
     int ei[EPT], ej[EPT];
     double av[EPT];
 #pragma unroll
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const SolveArgs a)
         if (ei[m] >= 0) A[ei[m] * LD + ej[m]] = av[m];
     if (tid < V) rhs[tid] = rv;
     __syncthreads();
-    // ---- D^-1, then L^T d = y with L_ki = A_ki / D_i (one warp; V <= 64)
+    // ---- D^-1, then L^T d = y with L_ki = A_ki / D_i (one warp)
     if (tid < 32) {
         for (int k = tid; k < V; k += 32) rhs[k] *= invD[k];
         __syncwarp();
