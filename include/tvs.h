@@ -62,7 +62,7 @@ enum {
 typedef struct tvs_fit_options {
     double tol;          /* KKT tolerance: max_v phi_v*|g_v-1| and max_{v: phi_v~0} (g_v-1); <=0 -> 1e-9    */
     int32_t max_iter;    /* maximum accepted L-BFGS iterations per lane; <=0 -> 1000                        */
-    int32_t history;     /* L-BFGS memory (1..16); <=0 -> 8                                                  */
+    int32_t history;     /* L-BFGS memory (4, 8 or 16); <=0 -> 16                                                */
     int32_t check_every; /* host polls the device-side "active lanes" counter every k passes; <=0 -> 4      */
     int32_t reserved;
 } tvs_fit_options;

@@ -60,7 +60,7 @@ class ModelFitMaxLike(object):
     # solver settings (class level so that callers of the reference signature need not know them)
     tol = 1e-9      # KKT tolerance; observed |theta error| <= ~20 x tol
     max_iter = 2000
-    history = 8
+    history = 16
 
     def __init__(self,
                  model,

@@ -89,7 +89,7 @@ class LaneContext(object):
     """The shared CSR (one `tvs_create`) + registered weight columns of every model that is fitted
     against it (the full data and each bootstrap replicate)."""
 
-    def __init__(self, n_variants, variant_sizes, device=0, sharder=None, tol=1e-9, max_iter=2000, history=8):
+    def __init__(self, n_variants, variant_sizes, device=0, sharder=None, tol=1e-9, max_iter=2000, history=16):
         self.V = int(n_variants)
         self.L = np.asarray(variant_sizes, dtype=np.int64)
         self.device = int(device)
