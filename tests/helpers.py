@@ -148,14 +148,21 @@ class OracleEngine(object):
         pass
 
 
-def model_from_workload(wl, n_bins=3):
+def model_from_workload(wl, n_bins=3, shared_from_variants=None):
     """Reference-style model objects (Bins/BinInfo/SubPathInfo/PathMultinomialModel) from a synthetic Workload:
-    every read path gets one BinInfo (X = wl.X[r], n = wl.n_obs[r]) in one of `n_bins` length ranges."""
+    every read path gets one BinInfo (X = wl.X[r], n = wl.n_obs[r]) in one of `n_bins` length ranges.
+    `shared_from_variants`: list that receives / supplies the per-read-path from_variants dicts, so that replicate models
+    share those objects with the whole-data model exactly like Traversome.sample_sub_paths does (traversome.py:1671)."""
     all_sub_paths = OrderedDict()
     bins_list = [Bins(min_len=1000 * (i + 1), max_len=1000 * (i + 2) - 1, min_id=0, max_id=0) for i in range(n_bins)]
     rec = 0
     for r in range(wl.R):
-        fv = {int(c): int(v) for c, v in zip(wl.col[wl.row_ptr[r]:wl.row_ptr[r + 1]], wl.val[wl.row_ptr[r]:wl.row_ptr[r + 1]])}
+        if shared_from_variants is not None and len(shared_from_variants) > r:
+            fv = shared_from_variants[r]
+        else:
+            fv = {int(c): int(v) for c, v in zip(wl.col[wl.row_ptr[r]:wl.row_ptr[r + 1]], wl.val[wl.row_ptr[r]:wl.row_ptr[r + 1]])}
+            if shared_from_variants is not None:
+                shared_from_variants.append(fv)
         spi = SubPathInfo()
         spi.from_variants = fv
         spi.inner_len, spi.full_len = 0, 10 ** 6

@@ -151,3 +151,28 @@ def test_shard_bounds_cover_all_lanes():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_vectorised_cover_rule_equals_reference_set_logic(synthetic_small, plastome):
+    """ModelFitMaxLike.cover_all_observed_subpaths (numpy tables) == the reference's set unions (ModelFitMaxLike.py:568-580)."""
+    rng = np.random.default_rng(2)
+    cases = [(c["variant_sizes"], c["bins_list"], c["be_unidentifiable_to"], c["repr_to_merged_variants"]) for c in synthetic_small["cases"]]
+    cases.append((plastome["variant_sizes"], plastome["models"][3]["bins_list"], plastome["be_unidentifiable_to"], plastome["repr_to_merged_variants"]))
+    for L, bins, unid, groups in cases:
+        model = model_from_tables(L, bins)
+        kw = fit_context(model, unid, groups)
+        # make some read paths unobserved and drop some from the id table, like a bootstrap replicate does
+        for k, spi in enumerate(model.all_sub_paths.values()):
+            if k % 7 == 3:
+                spi.mapped_records = []
+        fitter = ModelFitMaxLike(context=_ctx(L), **kw)
+        fitter.update_observed_sp_ids()
+        V = len(L)
+        for _ in range(60):
+            ids = set(int(v) for v in rng.choice(V, rng.integers(0, V + 1), replace=False))
+            model_sp = set()
+            for v in ids:
+                for sp_ in kw["variant_subpath_counters"][kw["variant_paths"][v]]:
+                    if sp_ in kw["sbp_to_sbp_id"]:
+                        model_sp.add(kw["sbp_to_sbp_id"][sp_])
+            assert fitter.cover_all_observed_subpaths(ids) == fitter.observed_sbp_id_set.issubset(model_sp)

@@ -101,6 +101,7 @@ class ModelFitMaxLike(object):
         self._lane = None            # (weight column id, C, N) of this model inside the context
         self._shuffle = np.random.shuffle   # ModelFitMaxLike.py:203; tests may pin the permutation
         self.n_gpu_fits = 0          # lanes fitted so far (diagnostics)
+        self._cover_cache = None
 
     # ------------------------------------------------------------------ context / lanes
     def _ensure_lane(self):
@@ -379,14 +380,61 @@ class ModelFitMaxLike(object):
                 self.observed_sbp_id_set.add(go_sp)
             else:
                 logger.trace("Drop subpath without observation: {}: {}".format(go_sp, this_sub_path))
+        self._cover_cache = None
+
+    def _cover_tables(self):
+        """Matrix form of the tables cover_all_observed_subpaths walks (ModelFitMaxLike.py:568-580):
+        contains[s, v] = sub-path id s occurs in variant v (through variant_subpath_counters and sbp_to_sbp_id),
+        observed[s] = s is in observed_sbp_id_set.  Same sets, evaluated with numpy instead of Python set unions
+        (the reference spends O(sub-paths) dict operations per variant per candidate)."""
+        cache = getattr(self, "_cover_cache", None)
+        if cache is not None and cache[0] == len(self.observed_sbp_id_set):
+            return cache[1], cache[2]
+        n_sbp = (max(self.sbp_to_sbp_id.values()) + 1) if self.sbp_to_sbp_id else 0
+        n_sbp = max(n_sbp, (max(self.observed_sbp_id_set) + 1) if self.observed_sbp_id_set else 0)
+        # variant -> sub-path membership is the same for every replicate of a run: built once per context in the key
+        # space of the sub paths, then re-indexed by this model's own sbp_to_sbp_id
+        gid, contains_g = self._global_cover_table()
+        contains = np.zeros((n_sbp, self.num_put_variants), dtype=bool)
+        if self.sbp_to_sbp_id:
+            keys = list(self.sbp_to_sbp_id.keys())
+            local = np.fromiter(self.sbp_to_sbp_id.values(), dtype=np.int64, count=len(keys))
+            glob = np.fromiter((gid.get(k, -1) for k in keys), dtype=np.int64, count=len(keys))
+            ok = glob >= 0
+            np.logical_or.at(contains, local[ok], contains_g[glob[ok]])
+        observed = np.zeros(n_sbp, dtype=bool)
+        observed[list(self.observed_sbp_id_set)] = True
+        self._cover_cache = (len(self.observed_sbp_id_set), contains, observed)
+        return contains, observed
+
+    def _global_cover_table(self):
+        """(sub-path key -> row, contains[row, v]) for this run's variants; cached on the LaneContext when there is one."""
+        holder = self._context if self._context is not None else self
+        key = (id(self.variant_subpath_counters), id(self.variant_paths))
+        cached = getattr(holder, "_cover_global", None)
+        if cached is not None and cached[0] == key:
+            return cached[1], cached[2]
+        gid = {}
+        rows, cols = [], []
+        for go_var in range(self.num_put_variants):
+            for sp in self.variant_subpath_counters[self.variant_paths[go_var]]:
+                r = gid.get(sp)
+                if r is None:
+                    r = gid[sp] = len(gid)
+                rows.append(r)
+                cols.append(go_var)
+        contains_g = np.zeros((len(gid), self.num_put_variants), dtype=bool)
+        contains_g[rows, cols] = True
+        holder._cover_global = (key, gid, contains_g)
+        return gid, contains_g
 
     def cover_all_observed_subpaths(self, variant_ids):
         """Every observed read path must occur in >=1 variant of the set (ModelFitMaxLike.py:568-580)."""
         if not self.observed_sbp_id_set:
             self.update_observed_sp_ids()
-        model_sp_ids = set()
-        for go_var in variant_ids:
-            for sub_path in self.variant_subpath_counters[self.variant_paths[go_var]]:
-                if sub_path in self.sbp_to_sbp_id:
-                    model_sp_ids.add(self.sbp_to_sbp_id[sub_path])
-        return self.observed_sbp_id_set.issubset(model_sp_ids)
+        contains, observed = self._cover_tables()
+        ids = [int(v) for v in variant_ids]
+        if not ids:
+            return not observed.any()
+        covered = contains[:, ids].any(axis=1)
+        return bool(np.all(covered[observed]))

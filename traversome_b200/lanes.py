@@ -96,7 +96,7 @@ class LaneContext(object):
         self.sharder = sharder
         self.tol, self.max_iter, self.history = tol, max_iter, history
         self.matrix = ReadPathMatrix(self.V)
-        self._cols = []               # list of {row: count}
+        self._cols = []               # list of (rows, counts): sparse weight columns
         self._engine = None
         self._engine_R = -1
         self.n_lanes_fitted = 0
@@ -110,14 +110,22 @@ class LaneContext(object):
         if self.matrix.R == 0 and getattr(model, "all_sub_paths", None):
             self.matrix.add_sub_paths(model.all_sub_paths)
         w_map, C, N = lane_from_bins(model.bins_list, self.matrix)
-        self._cols.append(w_map)
+        self._cols.append(self._sparse_column(w_map))
         return len(self._cols) - 1, float(C), int(N)
 
     def add_weights(self, w):
         """Register a dense weight column w[R] (synthetic workloads)."""
         w = np.asarray(w)
-        self._cols.append({int(r): int(w[r]) for r in np.nonzero(w)[0]})
+        rows = np.nonzero(w)[0]
+        self._cols.append((rows.astype(np.int64), w[rows].astype(np.int32)))
         return len(self._cols) - 1
+
+    @staticmethod
+    def _sparse_column(w_map):
+        """{row: count} -> (rows int64[], counts int32[]): columns are scattered with numpy, not Python loops."""
+        rows = np.fromiter(w_map.keys(), dtype=np.int64, count=len(w_map))
+        vals = np.fromiter(w_map.values(), dtype=np.int32, count=len(w_map))
+        return rows, vals
 
     def engine(self):
         if self._engine is None or self._engine_R != self.matrix.R:
@@ -138,8 +146,8 @@ class LaneContext(object):
     def dense_columns(self, cols):
         w = np.zeros((self.matrix.R, len(cols)), dtype=np.int32)
         for j, c in enumerate(cols):
-            for r, n in self._cols[c].items():
-                w[r, j] = n
+            rows, vals = self._cols[c]
+            w[rows, j] = vals
         return w
 
     # ---- the batched fit
