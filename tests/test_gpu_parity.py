@@ -186,6 +186,23 @@ def test_fit_is_deterministic_and_warm_start_agrees(gpu):
     assert warm["iters"][0] <= 30
 
 
+@pytest.mark.parametrize("V,B", [(8, 5), (40, 200), (150, 12)])
+def test_fit_escapes_the_zero_saddle(gpu, V, B):
+    """z_v = 0 is a stationary point of the z-parametrisation for every variant.  Started from a one-hot theta0 (all
+    other variants at the floor) the solver must still reach the optimum, where those variants are positive: the
+    multiplier test g_v <= 1 keeps such lanes alive and the saddle escape moves the components off zero.  Covers the
+    Newton phase (small B, V <= 128), the L-BFGS phase (B > 128) and V > 128."""
+    wl = synthetic.make_workload(V, 60 * V, 0.3, seed=900 + V)
+    w = synthetic.bootstrap_weights(wl.n_obs, B, seed=3)
+    theta0 = np.zeros((V, B))
+    theta0[0, :] = 1.0
+    with engine_for(wl) as eng:
+        eng.set_lanes(w)
+        out = eng.fit(theta0=theta0)
+    assert np.all(out["status"] == _cabi.CONVERGED), np.bincount(out["status"], minlength=4)
+    check_fit_against_exact(wl, w, None, out, [0, B // 2, B - 1])
+
+
 def test_edge_cases(gpu):
     # single variant, single row, zero-weight rows, lane count not a multiple of 32
     rp = np.array([0, 1], np.int32)

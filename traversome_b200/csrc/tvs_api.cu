@@ -76,7 +76,22 @@ struct PassPlan {
 
 static int splits_for(const tvs_problem* h, int slots, int tiles) {
     const Csr& c = h->csr;
-    int s = slots / std::max(tiles, 1);
+    int s;
+    if (tiles <= slots) {
+        s = slots / std::max(tiles, 1);                        // one wave: every resident slot gets a CTA
+    } else {
+        // more lane tiles than resident slots: pick the split count whose CTA total fills whole waves best
+        // (e.g. 79 tiles on 148 slots: 1 split = 53 % of one wave, 15 splits = 1185 CTAs = 8.0 waves)
+        const int s_max = std::max(1, std::min(c.n_chunks / 4, 32));
+        double best = -1.0;
+        s = 1;
+        for (int cand = 1; cand <= s_max; ++cand) {
+            const int64_t total = (int64_t)tiles * cand;
+            const int64_t waves = (total + slots - 1) / slots;
+            const double eff = (double)total / (double)(waves * slots);
+            if (eff > best + 0.02) { best = eff; s = cand; }    // prefer fewer splits unless clearly better
+        }
+    }
     s = std::max(1, std::min(s, c.n_chunks));
     s = std::min(s, env_int("TVS_MAX_SPLITS", 1024));
     const int forced = env_int("TVS_SPLITS", 0);
@@ -801,7 +816,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         }
         TVS_CUDA(cudaFuncSetAttribute(hess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hess_smem));
         TVS_CUDA(cudaFuncSetAttribute(hess_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem));
-        const size_t solve_smem = ((size_t)V * (V + 1) + 2 * (V + 2) + 2 * V) * 8;
+        const size_t solve_smem = ((size_t)V * (V + 1) + 2 * (V + 2) + 3 * V) * 8;
         TVS_CUDA(cudaFuncSetAttribute(solve_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
         TVS_CUDA(cudaFuncSetAttribute(solve_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
         PassPlan pl;
@@ -834,6 +849,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         sa.h_entry = wide ? W : 1; sa.h_lane = wide ? 1 : NP; sa.h_split = wide ? 0 : (int64_t)W * NP;
         sa.z = s.z; sa.g = s.g; sa.gha = f.gha; sa.invL = h->csr.invL; sa.N = s.N; sa.mask = s.mask;
         sa.done = s.done; sa.lam = f.lam; sa.d = s.d; sa.zt = s.zt; sa.x = s.x; sa.dg = s.dg; sa.alpha = s.alpha; sa.W = W; sa.V = (int)V;
+        sa.sumphi = s.sumphi; sa.tol_dual = (double)env_int("TVS_DUAL_MULT", 100) * opt.tol;
         NewtonUpdArgs na{};
         na.invL = h->csr.invL; na.N = s.N; na.mask = s.mask; na.z = s.z; na.zt = s.zt; na.g = s.g; na.gt = f.gt; na.gh = f.gh;
         na.gha = f.gha; na.d = s.d; na.F = s.F; na.dg = s.dg; na.alpha = s.alpha; na.llsum = s.llsum; na.kkt = s.kkt;

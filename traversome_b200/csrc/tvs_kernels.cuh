@@ -555,6 +555,11 @@ __global__ void __launch_bounds__(kU2Threads) lbfgs_update_vl2_kernel(const UpdA
 
     // ---- E: d = sum_k delta_k b_k ; next trial point
     if (newdir && !finished) {
+        // Saddle escape (see solve_kernel in tvs_newton.cuh): z_v = 0 with g_v > 1 has zero gradient and negative
+        // curvature, so the quasi-Newton direction never moves it.  Once the complementarity residual has converged and
+        // only the multiplier test fails, such components are placed at a small positive share; F decreases to second
+        // order and the line search judges the trial point as usual.
+        const bool kick = comp <= a.tol && dual > a.tol_dual;
         for (int v = vs; v < V; v += kU2Slots) {
             const int64_t i = (int64_t)v * B + bb;
             double dv = dl[GI][l] * a.g[i];
@@ -563,8 +568,16 @@ __global__ void __launch_bounds__(kU2Threads) lbfgs_update_vl2_kernel(const UpdA
                 dv = fma(dl[k][l], a.Sh[((int64_t)k * V + v) * B + bb], dv);
                 dv = fma(dl[M + k][l], a.Yh[((int64_t)k * V + v) * B + bb], dv);
             }
+            const double zo = a.z[i];
+            double zn = fma(anew, dv, zo);
+            if (kick) {
+                const bool mk = a.mask ? a.mask[i] != 0 : true;
+                if (mk && a.gh[i] * sumphi - 1.0 > a.tol_dual && zo * zo < 1e-11 * sumphi) {
+                    zn = sqrt(1e-8 * sumphi);
+                    dv = (zn - zo) / anew;
+                }
+            }
             a.d[i] = dv;
-            const double zn = fma(anew, dv, a.z[i]);
             a.zt[i] = zn; a.x[i] = zn * zn * a.invL[v];
         }
     }

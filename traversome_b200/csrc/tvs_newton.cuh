@@ -239,6 +239,7 @@ struct SolveArgs {
     const int32_t* done;
     double* lam; double* d; double* zt; double* x; double* dg; double* alpha;
     int64_t W; int V;
+    const double* sumphi; double tol_dual;     // saddle escape (see solve_kernel)
 };
 
 constexpr int kSolveThreads = 256;
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const SolveArgs a)
     double* colbuf = ss + (size_t)V * LD;                      // two column buffers of V + 2
     double* rhs = colbuf + 2 * (V + 2);
     double* zv = rhs + V;
+    double* kickv = zv + V;                                    // target z of a component that leaves a saddle, else 0
     __shared__ double red[kSolveThreads / 32];
     const int tid = threadIdx.x;
     const int64_t lane = blockIdx.x;
@@ -269,11 +271,35 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const SolveArgs a)
         double h = 4.0 * zv[u] * zv[v] * a.invL[u] * a.invL[v] * s * invN;
         if (u == v) {
             const bool mk = a.mask ? a.mask[(int64_t)u * a.W + lane] != 0 : true;
-            h = mk ? h + 2.0 * (1.0 - a.gha[(int64_t)u * a.W + lane]) : 1.0;
-            rhs[u] = mk ? -a.g[(int64_t)u * a.W + lane] : 0.0;
+            const double gh_u = a.gha[(int64_t)u * a.W + lane];
+            // Saddle escape: z_u = 0 is a stationary point of F for every u; where the multiplier test fails there
+            // (g_u > 1: the variant wants a positive share) the gradient is ~0 and the curvature 2(1 - g_u) negative, so
+            // neither Newton nor L-BFGS ever leaves.  Such a component is taken out of the linear system and moved to the
+            // one-dimensional Newton point of phi_u: phi_u = (g_u - 1) / H_uu  (seen once in 20,000 cfg2 replicates).
+            const double sp = a.sumphi[lane];
+            const double phi_u = zv[u] * zv[u];
+            kickv[u] = 0.0;
+            if (mk && gh_u * sp - 1.0 > a.tol_dual && phi_u < 1e-11 * sp) {
+                const double hphi = s * a.invL[u] * a.invL[u] * invN;                 // d2F / dphi_u^2
+                const double target = fmin(fmax(gh_u - 1.0, 0.0) / fmax(hphi, 1e-300), 1e-3 * sp);
+                kickv[u] = sqrt(fmax(target, 1e-16 * sp));
+            }
+            const bool fixed = !mk || kickv[u] > 0.0;
+            h = fixed ? 1.0 : h + 2.0 * (1.0 - gh_u);
+            rhs[u] = fixed ? 0.0 : -a.g[(int64_t)u * a.W + lane];
         }
         H0[u * LD + v] = h;
         H0[v * LD + u] = h;
+    }
+    __syncthreads();
+    // rows / columns of fixed components (masked or kicked) carry no coupling
+    for (int i = tid; i < V * V; i += kSolveThreads) {
+        const int u = i / V, v = i - u * V;
+        if (u != v) {
+            const bool mu = a.mask ? a.mask[(int64_t)u * a.W + lane] != 0 : true;
+            const bool mv = a.mask ? a.mask[(int64_t)v * a.W + lane] != 0 : true;
+            if (!mu || !mv || kickv[u] > 0.0 || kickv[v] > 0.0) H0[u * LD + v] = 0.0;
+        }
     }
     __syncthreads();
     double lam = a.lam[lane];
@@ -345,8 +371,8 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const SolveArgs a)
     double part = 0.0;
     for (int v = tid; v < V; v += kSolveThreads) {
         const int64_t i = (int64_t)v * a.W + lane;
-        const double dv = rhs[v];
         const double zo = a.z[i];
+        const double dv = (kickv[v] > 0.0) ? kickv[v] - zo : rhs[v];
         a.d[i] = dv;
         const double zn = zo + dv;
         a.zt[i] = zn;
