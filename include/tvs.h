@@ -119,7 +119,8 @@ int tvs_get_weights(tvs_handle h, int32_t* w_out);
 int tvs_loglik(tvs_handle h, const double* theta, double* ll_out);
 
 /* maximum-likelihood fit of every lane (replaces minimize_neg_likelihood, ModelFitMaxLike.py:19-58).
- * theta0[V*B] or NULL (= uniform over the lane's mask).  Outputs (any may be NULL):
+ * theta0[V*B] or NULL (= uniform over the lane's mask).  A lane without any record (all weights zero) has a constant
+ * likelihood: it is reported TVS_CONVERGED at its starting point with ll = C.  Outputs (any may be NULL):
  * theta_out[V*B] (sums to 1 over the mask, 0 outside), ll_out[B] (includes C), kkt_out[2*B]
  * (complementarity, dual residual), iters_out[B], status_out[B]. */
 int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt,
