@@ -176,3 +176,33 @@ def test_vectorised_cover_rule_equals_reference_set_logic(synthetic_small, plast
                     if sp_ in kw["sbp_to_sbp_id"]:
                         model_sp.add(kw["sbp_to_sbp_id"][sp_])
             assert fitter.cover_all_observed_subpaths(ids) == fitter.observed_sbp_id_set.issubset(model_sp)
+
+
+def test_do_subsampling_from_records_reproduces_the_reference_run(plastome):
+    """cfg1 from the record pool in array form: replayed draws (random.Random(12345)), bit-exact bins, lock-step
+    selection -> the reference's support table and, per replicate, its proportions (engine = oracle stand-in)."""
+    import random
+    from traversome_b200.resample import RecordPool
+    L = plastome["variant_sizes"]
+    model0 = model_from_tables(L, plastome["models"][0]["bins_list"])
+    pool = RecordPool.from_golden(plastome)
+    pattern = np.zeros((pool.n_rows, len(L)), dtype=bool)
+    ctx = _ctx(L)
+    for r, rp in enumerate(plastome["read_paths"]):
+        fv = {int(v): int(c) for v, c in rp["from_variants"]}
+        assert ctx.matrix.row_index_distinct(fv) == r
+        pattern[r, list(fv)] = True
+    kw0 = fit_context(model0, plastome["be_unidentifiable_to"], plastome["repr_to_merged_variants"])
+    w0, C0, N0, obs0 = pool.lane_of(np.arange(pool.n_records))
+    full = ModelFitMaxLike.from_lane(ctx, (ctx.add_weights(w0), C0, N0), pattern, np.nonzero(obs0)[0],
+                                     kw0["repr_to_merged_variants"], kw0["be_unidentifiable_to"])
+    raw = full.reverse_model_selection(n_proc=1)
+    assert abs(raw[0][0] - 23 / 35.) < 1e-7
+    assert abs(raw[1] - plastome["final"]["res_loglike"]) < 1e-9 * abs(raw[1])
+    s = bootstrap.do_subsampling_from_records(pool, pattern, ctx, full, raw, random.Random(12345), n_replicate=100)
+    assert s.bs_eligible and s.n_replicates_run == 100
+    got = [[list(k), s.vp_unique_results[k]["support"]] for k in s.vp_unique_results_sorted]
+    assert got == plastome["final"]["support"]
+    for v_prop, fit in zip(s.variant_proportions_reps, plastome["fits"][1:]):
+        for cid, p in fit["prop"]:
+            assert abs(v_prop[cid] - p) < 5e-4

@@ -219,3 +219,39 @@ def test_backward_selection_decisions_equal_exact_replay(gpu, criterion):
     assert all(abs(gp[k] - cp[k]) < 1e-6 for k in gp)
     assert abs(gl - cl) < 1e-9 * abs(cl) and abs(gc - cc) < 1e-9 * abs(cc)
     assert n_gpu >= 5 and len(gp) < wl.V                    # the selection did drop variants and tested candidates
+
+
+def test_cfg1_bootstrap_from_record_pool_on_gpu(gpu, plastome):
+    """cfg1 without any per-replicate object graph: records -> replayed draws -> bit-exact bins -> weight columns ->
+    lock-step backward selection on the CUDA solver.  Same support table as the reference run; every replicate's
+    proportions within the reference's own SLSQP spread and within 1e-6 of the exact optimum of ITS replicate."""
+    import random
+    from traversome_b200.resample import RecordPool
+    L = plastome["variant_sizes"]
+    pool = RecordPool.from_golden(plastome)
+    pattern = np.zeros((pool.n_rows, len(L)), dtype=bool)
+    ctx = LaneContext(len(L), L)
+    for r, rp in enumerate(plastome["read_paths"]):
+        fv = {int(v): int(c) for v, c in rp["from_variants"]}
+        assert ctx.matrix.row_index_distinct(fv) == r
+        pattern[r, list(fv)] = True
+    groups = {int(k): [int(x) for x in v] for k, v in plastome["repr_to_merged_variants"]}
+    unid = {int(k): int(v) for k, v in plastome["be_unidentifiable_to"]}
+    w0, C0, N0, obs0 = pool.lane_of(np.arange(pool.n_records))
+    full = ModelFitMaxLike.from_lane(ctx, (ctx.add_weights(w0), C0, N0), pattern, np.nonzero(obs0)[0], groups, unid)
+    raw = full.reverse_model_selection(n_proc=1)
+    assert abs(raw[0][0] - 23 / 35.) < 1e-7 and abs(raw[1] - plastome["final"]["res_loglike"]) < 1e-9 * abs(raw[1])
+    s = bootstrap.do_subsampling_from_records(pool, pattern, ctx, full, raw, random.Random(12345), n_replicate=100)
+    assert s.bs_eligible and s.n_replicates_run == 100
+    got = [[list(k), s.vp_unique_results[k]["support"]] for k in s.vp_unique_results_sorted]
+    assert got == plastome["final"]["support"]
+    A = ctx.matrix.dense()
+    for k, (v_prop, fit) in enumerate(zip(s.variant_proportions_reps, plastome["fits"][1:])):
+        for cid, p in fit["prop"]:
+            assert abs(v_prop[cid] - p) < 5e-4
+        if k < 10:
+            w = ctx.dense_columns([k + 1])[:, 0]
+            r = exact.exact_fit(A, L, w)
+            assert abs(v_prop[0] - r["theta"][0]) < 1e-6 and abs(v_prop[1] - r["theta"][1]) < 1e-6
+    assert ctx.n_batches <= 6
+    ctx.close()

@@ -103,6 +103,41 @@ class ModelFitMaxLike(object):
         self.n_gpu_fits = 0          # lanes fitted so far (diagnostics)
         self._cover_cache = None
 
+    @classmethod
+    def from_lane(cls, context, lane, pattern, observed_rows, repr_to_merged_variants, be_unidentifiable_to,
+                  loglevel="INFO", bootstrap_mode=False):
+        """A fitter for one replicate given in ARRAY form (traversome_b200.resample.RecordPool.lane_of) instead of
+        model objects: `lane` = (weight column id in `context`, C, N); `pattern` [rows, V] bool = read path r occurs
+        in variant v (the non-zero pattern of from_variants); `observed_rows` = the replicate's read paths.  Same
+        decision logic, logging and results as a fitter built from a PathMultinomialModel."""
+        self = cls.__new__(cls)
+        self.model = None
+        self.variant_paths = [None] * int(pattern.shape[1])
+        self.num_put_variants = int(pattern.shape[1])
+        self.all_sub_paths = None
+        self.variant_subpath_counters = None
+        self.sbp_to_sbp_id = None
+        self.repr_to_merged_variants = repr_to_merged_variants
+        self.be_unidentifiable_to = be_unidentifiable_to
+        self.loglevel = loglevel
+        self.bootstrap_mode = bootstrap_mode
+        self.device = context.device
+        self.variant_percents = None
+        self.observed_sbp_id_set = set(int(r) for r in observed_rows)
+        self.pe_neg_loglike_obj = None
+        self.pe_best_proportions = None
+        self._ModelFitMaxLike__warning_sent = False
+        self._context = context
+        self._own_context = False
+        self._lane = (int(lane[0]), float(lane[1]), int(lane[2]))
+        self._shuffle = np.random.shuffle
+        self.n_gpu_fits = 0
+        observed = np.zeros(pattern.shape[0], dtype=bool)
+        observed[list(self.observed_sbp_id_set)] = True
+        self._cover_cache = (len(self.observed_sbp_id_set), np.asarray(pattern, dtype=bool), observed)
+        self._array_form = True
+        return self
+
     # ------------------------------------------------------------------ context / lanes
     def _ensure_lane(self):
         if self._lane is None:
@@ -374,6 +409,8 @@ class ModelFitMaxLike(object):
         return LogLikeFuncInfo(loglike_func=neg_loglike, variable_size=variable_size, sample_size=N)
 
     def update_observed_sp_ids(self):
+        if getattr(self, "_array_form", False):
+            return                                          # fixed at construction (from_lane)
         self.observed_sbp_id_set = set()
         for go_sp, (this_sub_path, this_sub_path_info) in enumerate(self.all_sub_paths.items()):
             if this_sub_path_info.mapped_records:

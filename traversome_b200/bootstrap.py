@@ -9,8 +9,10 @@ solver on a shared ``LaneContext`` (sharded over the GPUs of the box when the co
 ``LaneSharder``).  The decision logic inside each replicate is the reference's, untouched, so the
 selected models and the support table are those of the serial loop.
 
-The replicate models themselves (resampling of records and the per-replicate bin statistics,
-traversome.py:1636-1699 and :1305-1384) are inputs here: SURVEY.md section 8(f) item 1.
+Two entry points: ``do_subsampling`` takes the replicate models the reference's own code built
+(traversome.py:515-539); ``do_subsampling_from_records`` builds the replicates itself from the record pool in
+array form (``traversome_b200.resample``: the reference's draws replayed, its bins reproduced bit for bit), which
+removes the per-replicate Python object graph.
 """
 from collections import OrderedDict
 
@@ -150,6 +152,56 @@ def summarize_replicates(variant_proportions_reps, raw_variant_proportions, raw_
         if go_s == 0 and tuple_v_chosen != raw_res and chosen_dict["support"] > 0.05:
             out.variant_proportions_best = raw_prop
     return out
+
+
+def do_subsampling_from_records(pool, pattern, context, full_fit, raw_result, rng, n_replicate, criterion=Criterion.BIC,
+                                threshold=0.95, jackknife=0, n_proc=1, user_fixed_ids=None, masked_rows=(), batch=None,
+                                loglevel="INFO"):
+    """``Traversome.do_subsampling`` from the record pool in array form (traversome_b200.resample.RecordPool): the
+    replicates are drawn with the reference's own draws (`rng` = the reference's ``self.random``, e.g.
+    ``random.Random(12345)``), binned bit-exactly, registered as weight columns of `context` and selected in lock
+    step -- no per-replicate object graph.  `pattern` [rows, V] bool is the non-zero pattern of from_variants in
+    ``all_sub_paths`` order (the rows of `pool`); `context.matrix` must hold exactly those rows in that order."""
+    n_digit = len(str(n_replicate))
+    count_unique = {}
+    reps = []
+    bs_eligible = True
+    batch = n_replicate if not batch else int(batch)
+    go_bs = 0
+    while go_bs < n_replicate and bs_eligible:
+        fitters = []
+        for k in range(min(batch, n_replicate - go_bs)):
+            if jackknife:
+                sample = pool.sample_jackknife(rng, int(pool.n_records / float(n_replicate)))
+            else:
+                sample = pool.sample_bootstrap(rng, pool.n_records)
+            w, C, N, observed = pool.lane_of(sample, masked_rows)
+            col = context.add_weights(w)
+            f = ModelFitMaxLike.from_lane(context, (col, C, N), pattern, np.nonzero(observed)[0], full_fit.repr_to_merged_variants,
+                                          full_fit.be_unidentifiable_to, loglevel=loglevel,
+                                          bootstrap_mode=f"BS{go_bs + k + 1: 0{n_digit}d}")
+            f._shuffle = full_fit._shuffle
+            fitters.append(f)
+        results = run_selections(fitters, criterion=criterion, n_proc=n_proc, user_fixed_ids=user_fixed_ids)
+        for res in results:
+            if isinstance(res, Exception):
+                raise res
+            v_prop = res[0]
+            reps.append(v_prop)
+            if not check_bs_threshold(count_unique, v_prop, n_replicate, threshold):
+                if go_bs < n_replicate - 1:
+                    logger.info("Sampling terminates due to divergence in bootstraps (see '--bs-threshold'). "
+                                "No convincing support can be found given the dataset and parameters. ")
+                bs_eligible = False
+                break
+            go_bs += 1
+    logger.info("Summarizing the replicates ..")
+    raw_prop, raw_like, raw_crit = raw_result
+    summary = summarize_replicates(
+        reps, raw_prop, raw_like, raw_crit, bs_eligible=bs_eligible,
+        refit=lambda ids: full_fit.point_estimate(chosen_ids=ids, criterion=criterion))
+    summary.n_replicates_run = len(reps)
+    return summary
 
 
 def do_subsampling(replicate_models, fit_kwargs, full_fit, raw_result, criterion=Criterion.BIC, n_replicate=None,

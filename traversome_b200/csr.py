@@ -58,6 +58,18 @@ class ReadPathMatrix(object):
         self._by_id[key] = (row, from_variants)
         return row
 
+    def row_index_distinct(self, from_variants):
+        """Append a row for this read path even when another read path has the same from_variants content (array-form
+        replicates keep one row per read path of ``all_sub_paths``, in that order)."""
+        sig = _signature(from_variants)
+        if not sig:
+            raise ValueError("a read path without any variant cannot be modelled (empty from_variants)")
+        if sig[0][0] < 0 or sig[-1][0] >= self.V:
+            raise ValueError("variant id out of range in from_variants: %r" % (sig,))
+        self._sigs.append(sig)
+        self._row_of.setdefault(sig, len(self._sigs) - 1)
+        return len(self._sigs) - 1
+
     def add_sub_paths(self, all_sub_paths):
         """Register every read path of ``model.all_sub_paths`` (rows then follow that order)."""
         for info in all_sub_paths.values():
