@@ -266,8 +266,11 @@ static int fit_alloc(FitState& f, T** p, size_t n) {
 
 static int ensure_fit_state(tvs_problem* h, int m) {
     FitState& f = h->fs;
-    const int64_t V = h->csr.V, B = h->lanes.B, R = h->csr.R;
-    if (f.V == V && f.B == B && f.m == m && f.R == R) return TVS_OK;
+    const int64_t V = h->csr.V, R = h->csr.R;
+    // every array below is [rows x lanes] with the CURRENT lane count as stride, so a state allocated for more lanes
+    // serves any smaller batch: successive batches of a model selection (1, 20, 19, ... lanes) reuse one allocation
+    if (f.V == V && h->lanes.B <= f.B && f.m == m && f.R == R) return TVS_OK;
+    const int64_t B = (h->lanes.B + 31) / 32 * 32;              // capacity
     free_fit(f);
     const size_t vb = (size_t)V * B;
     int rc;
