@@ -95,6 +95,10 @@ int tvs_destroy(tvs_handle h);
  * C[B] or NULL (= 0).  Computes N_b = sum_r w[r,b] on the device. */
 int tvs_set_lanes(tvs_handle h, int64_t B, const int32_t* w, const uint8_t* mask, const double* C);
 
+/* same with 16-bit weights (counts <= 65535, e.g. bootstrap replicates): halves the host->device traffic of a batch;
+ * widened to the int32 lane-minor matrix on the device. */
+int tvs_set_lanes_u16(tvs_handle h, int64_t B, const uint16_t* w, const uint8_t* mask, const double* C);
+
 /* same, for batches in which many lanes share one weight column (all candidate subsets of one
  * replicate in a backward-selection step, ModelFitMaxLike.py:206-262): w_cols[R*n_cols] int32
  * (element (r, c) at [r*n_cols + c]) holds the DISTINCT weight columns and lane b uses column

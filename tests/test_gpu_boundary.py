@@ -157,6 +157,11 @@ def test_indexed_lanes_equal_expanded_lanes(gpu):
         b = eng.fit()
     assert np.array_equal(a["theta"], b["theta"], equal_nan=True) and np.array_equal(a["loglike"], b["loglike"])
     assert np.array_equal(a["status"], b["status"]) and (a["status"] == _cabi.CONVERGED).sum() >= 5
+    with _cabi.Engine(wl.row_ptr, wl.col, wl.val, wl.L) as eng:       # 16-bit upload == 32-bit upload
+        eng.set_lanes(cols[:, idx].astype(np.uint16), mask=mask)
+        assert np.array_equal(eng.get_weights(), cols[:, idx])
+        c = eng.fit()
+    assert np.array_equal(a["theta"], c["theta"], equal_nan=True) and np.array_equal(a["loglike"], c["loglike"])
     with pytest.raises(_cabi.TvsError):
         with _cabi.Engine(wl.row_ptr, wl.col, wl.val, wl.L) as eng:
             eng.set_lanes_indexed(cols, np.array([0, 3], np.int32))

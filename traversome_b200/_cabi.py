@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libtvs.so")
 # every symbol include/tvs.h declares (tests check that the library exports all of them)
 SYMBOLS = (
     "tvs_version", "tvs_last_error", "tvs_device_count", "tvs_create", "tvs_destroy", "tvs_set_lanes",
-    "tvs_set_lanes_indexed", "tvs_resample", "tvs_get_weights", "tvs_loglik", "tvs_fit", "tvs_last_fit_stats", "tvs_dims",
+    "tvs_set_lanes_u16", "tvs_set_lanes_indexed", "tvs_resample", "tvs_get_weights", "tvs_loglik", "tvs_fit", "tvs_last_fit_stats", "tvs_dims",
     "tvs_measure_fp64_peak", "tvs_selftest_math", "tvs_selftest_table_log",
 )
 
@@ -59,6 +59,7 @@ def load():
     lib.tvs_create.argtypes = [POINTER(c_void_p), c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.tvs_destroy.argtypes = [c_void_p]
     lib.tvs_set_lanes.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
+    lib.tvs_set_lanes_u16.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     lib.tvs_set_lanes_indexed.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.tvs_resample.argtypes = [c_void_p, c_int64, c_void_p, c_uint64, c_int, c_void_p, c_void_p]
     lib.tvs_get_weights.argtypes = [c_void_p, c_void_p]
@@ -149,7 +150,19 @@ class Engine(object):
 
     # ---- lanes
     def set_lanes(self, w, mask=None, C=None, B=None):
-        """w [R,B] int32 lane-minor; mask [V,B] uint8 or None; C [B] float64 or None."""
+        """w [R,B] lane-minor, int32 -- or uint16 (numpy array / torch tensor), which halves the upload;
+        mask [V,B] uint8 or None; C [B] float64 or None."""
+        is_u16 = (isinstance(w, np.ndarray) and w.dtype == np.uint16) or str(getattr(w, "dtype", "")) == "torch.uint16"
+        if is_u16:
+            w = np.ascontiguousarray(w) if isinstance(w, np.ndarray) else w
+            if B is None:
+                B = int(w.shape[1]) if len(w.shape) == 2 else int(w.numel() // self.R)
+            mask = _as(mask, np.uint8)
+            C = _as(C, np.float64)
+            self._keep = (w, mask, C)
+            _check(self._lib.tvs_set_lanes_u16(self._h, int(B), _ptr(w), _ptr(mask), _ptr(C)))
+            self.B = int(B)
+            return
         w = _as(w, np.int32)
         if B is None:
             B = int(w.shape[1]) if w.ndim == 2 else int(w.size // self.R)

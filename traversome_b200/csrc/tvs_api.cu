@@ -55,7 +55,8 @@ static void free_csr(Csr& c) {
     dev_free(c.wide_ptr); if (c.wide_rec) { cudaFree(c.wide_rec); c.wide_rec = nullptr; }
 }
 static void free_lanes(Lanes& l) {
-    dev_free(l.w); dev_free(l.mask); dev_free(l.C); dev_free(l.N);
+    dev_free(l.w); dev_free(l.mask); dev_free(l.C); dev_free(l.N); dev_free(l.w16);
+    if (l.acc) cudaFree(l.acc);
     l = Lanes();
 }
 static void free_fit(FitState& f) {
@@ -590,15 +591,18 @@ static int finish_lanes(tvs_problem* h, const uint8_t* mask, const double* C) {
     if (mask) TVS_CUDA(cudaMemcpyAsync(l.mask, mask, (size_t)(V * B), cudaMemcpyDefault, h->stream));
     if (C) TVS_CUDA(cudaMemcpyAsync(l.C, C, (size_t)B * sizeof(double), cudaMemcpyDefault, h->stream));
     {   // N_b = sum_r w[r,b] (exact integer sums; the solver state is not allocated yet, so use a scratch buffer)
-        unsigned long long* acc = nullptr;
-        TVS_CUDA(cudaMalloc((void**)&acc, (size_t)B * sizeof(unsigned long long)));
+        if (l.cap_acc < B) {
+            if (l.acc) cudaFree(l.acc);
+            l.acc = nullptr; l.cap_acc = 0;
+            TVS_CUDA(cudaMalloc((void**)&l.acc, (size_t)B * sizeof(unsigned long long)));
+            l.cap_acc = B;
+        }
+        unsigned long long* acc = l.acc;
         cudaMemsetAsync(acc, 0, (size_t)B * sizeof(unsigned long long), h->stream);
         const unsigned tiles = (unsigned)((B + 31) / 32);
         const unsigned slices = (unsigned)std::max<int64_t>(1, std::min<int64_t>(h->csr.R / 64 + 1, (int64_t)(4 * h->sm_count) / tiles + 1));
         lane_sum_kernel<<<dim3(tiles, slices), 256, 0, h->stream>>>(l.w, h->csr.R, B, acc);
         lane_sum_finish_kernel<<<(unsigned)((B + 255) / 256), 256, 0, h->stream>>>(acc, B, l.N);
-        cudaStreamSynchronize(h->stream);
-        cudaFree(acc);
     }
     TVS_CUDA(cudaGetLastError());
     TVS_CUDA(cudaStreamSynchronize(h->stream));
@@ -614,6 +618,21 @@ int tvs_set_lanes(tvs_handle h, int64_t B, const int32_t* w, const uint8_t* mask
     if (rc != TVS_OK) return rc;
     TVS_CUDA(cudaMemcpyAsync(h->lanes.w, w, (size_t)(h->csr.R * B) * sizeof(int32_t), cudaMemcpyDefault, h->stream));
     return finish_lanes(h, mask, C);
+}
+
+int tvs_set_lanes_u16(tvs_handle h, int64_t B, const uint16_t* w, const uint8_t* mask, const double* C) {
+    if (!h || B <= 0 || !w) { set_error("tvs_set_lanes_u16: null handle/weights or B<=0"); return TVS_EINVAL; }
+    TVS_CUDA(cudaSetDevice(h->device));
+    h->lanes_set = false;
+    int rc = reserve_lanes(h, B, mask != nullptr, C != nullptr);
+    if (rc != TVS_OK) return rc;
+    const int64_t n = h->csr.R * B;
+    Lanes& l = h->lanes;
+    if (l.cap_w16 < n) { dev_free(l.w16); if ((rc = dev_alloc(&l.w16, (size_t)n)) != TVS_OK) return rc; l.cap_w16 = n; }
+    TVS_CUDA(cudaMemcpyAsync(l.w16, w, (size_t)n * sizeof(uint16_t), cudaMemcpyDefault, h->stream));
+    widen_u16_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, h->stream>>>(l.w16, l.w, n);
+    cudaError_t e = cudaGetLastError();
+    return (e == cudaSuccess) ? finish_lanes(h, mask, C) : cuda_fail(e, "widen_u16_kernel", __FILE__, __LINE__);
 }
 
 int tvs_set_lanes_indexed(tvs_handle h, int64_t B, int64_t n_cols, const int32_t* w_cols, const int32_t* col_of_lane,

@@ -64,6 +64,10 @@ struct Lanes {
     double*  C = nullptr;      // [B]
     double*  N = nullptr;      // [B]
     int64_t  cap_w = 0, cap_mask = 0, cap_b = 0;
+    uint16_t* w16 = nullptr;   // staging of tvs_set_lanes_u16
+    int64_t  cap_w16 = 0;
+    unsigned long long* acc = nullptr;   // integer lane sums (finish_lanes)
+    int64_t  cap_acc = 0;
 };
 
 // One set of per-lane arrays at some width.  tvs_fit keeps two of them and "compacts" the lanes

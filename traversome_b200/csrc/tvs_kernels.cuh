@@ -717,6 +717,16 @@ __global__ void __launch_bounds__(128) gather_all_kernel(const GatherArgs a) {
     }
 }
 
+__global__ void widen_u16_kernel(const uint16_t* __restrict__ src, int32_t* __restrict__ dst, int64_t n) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 4 <= n) {
+        const ushort4 v = *reinterpret_cast<const ushort4*>(src + i);
+        *reinterpret_cast<int4*>(dst + i) = make_int4(v.x, v.y, v.z, v.w);
+    } else {
+        for (int64_t k = i; k < n; ++k) dst[k] = src[k];
+    }
+}
+
 __global__ void iota_kernel(int32_t* p, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = (int32_t)i;
