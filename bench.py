@@ -297,6 +297,7 @@ def main():
             "data": "synthetic", "config": workload_config(args, wl),
             "e2e": {"value": total_lanes / (e2e_step_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(wl.R) * B * 2,
+                    "step_ms_p50": float(np.median(e2e_ms)), "step_ms_max": float(np.max(e2e_ms)),
                     "d2h_bytes_per_step": int(wl.V) * B * 8 + B * (8 + 16 + 4 + 4)},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -8,7 +8,7 @@ which, B = sys.argv[1], int(sys.argv[2])
 wl = synthetic.make_config(which)
 eng = _cabi.Engine(wl.row_ptr, wl.col, wl.val, wl.L)
 eng.resample(B, wl.n_obs, seed=2024, keep_lane0=True)
-for m in (8, 16):
+for m in (8, 12, 16):
     eng.fit(history=m, max_iter=3000)
     out = eng.fit(history=m, max_iter=3000, time_passes=True)
     st = eng.last_fit_stats()

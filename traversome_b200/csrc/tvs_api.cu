@@ -741,7 +741,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
     if (opt.max_iter <= 0) opt.max_iter = 1000;
     if (opt.history <= 0) opt.history = 16;
     opt.history = std::min(opt.history, kMaxHistory);
-    opt.history = (opt.history <= 4) ? 4 : (opt.history <= 8) ? 8 : 16;   // the vector-free update kernel is instantiated for 4, 8 and 16
+    opt.history = (opt.history <= 4) ? 4 : (opt.history <= 8) ? 8 : (opt.history <= 12) ? 12 : 16;   // instantiations of the update kernel
     if (opt.check_every <= 0) opt.check_every = 4;
     const bool time_passes = (opt.reserved & 1) != 0 || env_int("TVS_TIME_PASSES", 0) != 0;
     const bool no_compact = (opt.reserved & 2) != 0 || env_int("TVS_NO_COMPACT", 0) != 0;
@@ -757,6 +757,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
     TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Vl2Layout<4>::doubles * 8)));
     TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Vl2Layout<8>::doubles * 8)));
     TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Vl2Layout<16>::doubles * 8)));
+    TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl2_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Vl2Layout<12>::doubles * 8)));
     TVS_CUDA(cudaEventRecord(h->ev0, st));
     int cur = 0;
     {   // ---- reset set 0 (full width, views the caller's lanes)
@@ -968,6 +969,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
             const unsigned ub2 = (unsigned)((W + kU2Lanes - 1) / kU2Lanes);
             if (m == 4) lbfgs_update_vl2_kernel<4><<<ub2, kU2Threads, Vl2Layout<4>::doubles * 8, st>>>(ua, s.gram);
             else if (m == 8) lbfgs_update_vl2_kernel<8><<<ub2, kU2Threads, Vl2Layout<8>::doubles * 8, st>>>(ua, s.gram);
+            else if (m == 12) lbfgs_update_vl2_kernel<12><<<ub2, kU2Threads, Vl2Layout<12>::doubles * 8, st>>>(ua, s.gram);
             else lbfgs_update_vl2_kernel<16><<<ub2, kU2Threads, Vl2Layout<16>::doubles * 8, st>>>(ua, s.gram);
             if (time_passes) { cudaEvent_t e2; cudaEventCreate(&e2); uev.push_back(pev.back()); uev.push_back(e2); cudaEventRecord(e2, st); }
                 ++passes; launches += 2; lane_passes += W;
