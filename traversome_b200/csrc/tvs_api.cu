@@ -946,13 +946,16 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
     
             // ---- a batch of passes, then one synchronous poll of the device-side "still iterating" counter
             const int slot = (int)(n_polls % 16);
-            for (int k = 0; k < opt.check_every && passes < max_passes; ++k) {
+            // the first poll comes later: no lane of a cold start converges within a dozen L-BFGS iterations, and a poll
+            // costs a stream synchronisation plus the relaunch gap (kernels of finished lane sets exit at once anyway)
+            const int group = (passes == 0 && !theta0) ? std::max(opt.check_every, env_int("TVS_FIRST_GROUP", 12)) : opt.check_every;
+            for (int k = 0; k < group && passes < max_passes; ++k) {
                 if (!pl.xs) { cudaMemsetAsync(f.tpart, 0, (size_t)V * W * pl.splits * 8, st); ++launches; }
                 if (time_passes) { cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); pev.push_back(e0); pev.push_back(e1); cudaEventRecord(e0, st); }
                 rc = launch_pass<true>(h, pl, pa);
                 if (rc != TVS_OK) break;
                 if (time_passes) cudaEventRecord(pev.back(), st);
-                const bool last = (k == opt.check_every - 1) || (passes + 1 == max_passes);
+                const bool last = (k == group - 1) || (passes + 1 == max_passes);
                 const bool pre_reduce = pl.splits > env_int("TVS_FUSE_SPLITS", 24);   // many splits: sum them with full parallelism first
             if (pre_reduce) {
                 reduce_partials_kernel<<<(unsigned)(((int64_t)(V + 1) * W + 255) / 256), 256, 0, st>>>(f.tpart, f.llpart, pl.splits, (int)V, W,
