@@ -322,7 +322,7 @@ struct Vl2Layout {
     static constexpr int NG = NB * (NB + 1) / 2;
     static constexpr int NACC = 6 * M + 9;
     // Gs[NG][8] dl[NB][8] acc[NACC+4][8] part[W][NACC+4][8]
-    static constexpr size_t doubles = (size_t)(NG + NB + (NACC + 4) + (size_t)kU2Warps * (NACC + 4)) * kU2Lanes + 4 * kU2Lanes;
+    static constexpr size_t doubles = (size_t)(NG + NB + (NACC + 4) + (size_t)kU2Warps * (NACC + 4)) * kU2Lanes + 8 * kU2Lanes;
 };
 
 // sums (or maxima for q >= first_max) of vals[0..n) over the 64 slots of each lane -> acc[q][l]
@@ -484,74 +484,97 @@ __global__ void __launch_bounds__(kU2Threads) lbfgs_update_vl2_kernel(const UpdA
     const bool newdir = accept && !finished;
     double anew = 1.0;
 
-    // ---- D: scalar phase, one thread per lane: Gram update, two-loop on coefficients
-    if (vs == 0 && accept) {
-#pragma unroll
-        for (int k = 0; k < M; ++k) { Gs[tri_idx(GI, k)][l] = acc[4 * M + k][l]; Gs[tri_idx(GI, M + k)][l] = acc[5 * M + k][l]; }
-        Gs[tri_idx(GI, GI)][l] = gg;
-        if (store) {
-            const int h = head;
-            for (int k = 0; k < M; ++k) {
+    // ---- D: Gram update and two-loop recursion on the coefficients.  The recursion is a sequence of 2*cnt rank-one
+    //      updates of the NB-vector u; thread (lane l, slot vs) owns u[vs] (and u[vs + 32] when NB > 32), the pivot
+    //      element of each step travels through shared memory (double-buffered, one barrier per step).  One thread
+    //      per lane did all of it before: ~10k dependent instructions at M = 16, a third of the kernel's time.
+    //      Every element sees the same operations in the same order, so the results are bitwise unchanged.
+    {
+        double (*bc)[kU2Lanes] = misc + 2;                       // [2] pivot broadcast, [1] scalar broadcast
+        double* al = part;                                       // [M][8] scratch (the partials are consumed)
+        const bool own0 = vs < NB, own1 = vs + 32 < NB;
+        if (accept && vs < M) {
+            const int k = vs;
+            Gs[tri_idx(GI, k)][l] = acc[4 * M + k][l]; Gs[tri_idx(GI, M + k)][l] = acc[5 * M + k][l];
+            if (store) {
+                const int h = head;
                 Gs[tri_idx(h, k)][l] = acc[k][l];             Gs[tri_idx(h, M + k)][l] = acc[M + k][l];
                 Gs[tri_idx(M + h, k)][l] = acc[2 * M + k][l]; Gs[tri_idx(M + h, M + k)][l] = acc[3 * M + k][l];
             }
-            Gs[tri_idx(h, h)][l] = ss; Gs[tri_idx(h, M + h)][l] = sy; Gs[tri_idx(M + h, M + h)][l] = yy;
-            Gs[tri_idx(GI, h)][l] = acc[6 * M + 4][l]; Gs[tri_idx(GI, M + h)][l] = acc[6 * M + 5][l];
-            head = (h + 1) % M; cnt = min(cnt + 1, M);
         }
+        __syncthreads();
+        if (accept && vs == 0) {                                 // entries the loop above wrote provisionally
+            Gs[tri_idx(GI, GI)][l] = gg;
+            if (store) {
+                const int h = head;
+                Gs[tri_idx(h, h)][l] = ss; Gs[tri_idx(h, M + h)][l] = sy; Gs[tri_idx(M + h, M + h)][l] = yy;
+                Gs[tri_idx(GI, h)][l] = acc[6 * M + 4][l]; Gs[tri_idx(GI, M + h)][l] = acc[6 * M + 5][l];
+            }
+        }
+        if (store) { head = (head + 1) % M; cnt = min(cnt + 1, M); }
+        __syncthreads();
         double dgn = -gg;
+        double u0 = 0.0, u1 = 0.0;
         if (newdir) {
-            double u[NB];
-            double* al = part;                                   // [M][8] scratch (the partials are consumed)
-#pragma unroll
-            for (int k = 0; k < NB; ++k) { dl[k][l] = 0.0; u[k] = -Gs[tri_idx(k, GI)][l]; }
-            dl[GI][l] = -1.0;
-            for (int j = 0; j < cnt; ++j) {                       // newest -> oldest
-                const int sl = ((head - 1 - j) % M + M) % M;
-                double us = 0.0;
-#pragma unroll
-                for (int k = 0; k < NB; ++k) us = (k == sl) ? u[k] : us;
-                const double aj = us / Gs[tri_idx(sl, M + sl)][l];
-                al[j * kU2Lanes + l] = aj;
-                dl[M + sl][l] -= aj;
-#pragma unroll
-                for (int k = 0; k < NB; ++k) u[k] = fma(-aj, Gs[tri_idx(k, M + sl)][l], u[k]);
+            if (own0) { dl[vs][l] = 0.0; u0 = -Gs[tri_idx(vs, GI)][l]; }
+            if (own1) { dl[vs + 32][l] = 0.0; u1 = -Gs[tri_idx(vs + 32, GI)][l]; }
+        }
+        __syncthreads();
+        if (newdir && vs == 0) dl[GI][l] = -1.0;
+        for (int j = 0; j < M; ++j) {                             // newest -> oldest
+            const bool on = newdir && j < cnt;
+            const int sl = ((head - 1 - j) % M + M) % M;          // sl < M <= 16: owned in slot 0 of thread vs == sl
+            if (on && vs == sl) bc[j & 1][l] = u0;
+            __syncthreads();
+            if (on) {
+                const double aj = bc[j & 1][l] / Gs[tri_idx(sl, M + sl)][l];
+                if (vs == 0) { al[j * kU2Lanes + l] = aj; dl[M + sl][l] -= aj; }
+                if (own0) u0 = fma(-aj, Gs[tri_idx(vs, M + sl)][l], u0);
+                if (own1) u1 = fma(-aj, Gs[tri_idx(vs + 32, M + sl)][l], u1);
             }
-            if (cnt > 0) {
-                const int sl = ((head - 1) % M + M) % M;
-                const double gamma = Gs[tri_idx(sl, M + sl)][l] / Gs[tri_idx(M + sl, M + sl)][l];
-#pragma unroll
-                for (int k = 0; k < NB; ++k) { dl[k][l] *= gamma; u[k] *= gamma; }
+        }
+        __syncthreads();
+        if (newdir && cnt > 0) {
+            const int sl = ((head - 1) % M + M) % M;
+            const double gamma = Gs[tri_idx(sl, M + sl)][l] / Gs[tri_idx(M + sl, M + sl)][l];
+            if (own0) { dl[vs][l] *= gamma; u0 *= gamma; }
+            if (own1) { dl[vs + 32][l] *= gamma; u1 *= gamma; }
+        }
+        __syncthreads();
+        for (int jj = 0; jj < M; ++jj) {                          // oldest -> newest
+            const int j = M - 1 - jj;
+            const bool on = newdir && j < cnt;
+            const int sl = ((head - 1 - j) % M + M) % M;          // M + sl < 2M <= 32: slot 0 of thread vs == M + sl
+            if (on && vs == M + sl) bc[jj & 1][l] = u0;
+            __syncthreads();
+            if (on) {
+                const double cf = al[j * kU2Lanes + l] - bc[jj & 1][l] / Gs[tri_idx(sl, M + sl)][l];
+                if (vs == 0) dl[sl][l] += cf;
+                if (own0) u0 = fma(cf, Gs[tri_idx(vs, sl)][l], u0);
+                if (own1) u1 = fma(cf, Gs[tri_idx(vs + 32, sl)][l], u1);
             }
-            for (int j = cnt - 1; j >= 0; --j) {                  // oldest -> newest
-                const int sl = ((head - 1 - j) % M + M) % M;
-                double uy = 0.0;
-#pragma unroll
-                for (int k = 0; k < NB; ++k) uy = (k == M + sl) ? u[k] : uy;
-                const double cf = al[j * kU2Lanes + l] - uy / Gs[tri_idx(sl, M + sl)][l];
-                dl[sl][l] += cf;
-#pragma unroll
-                for (int k = 0; k < NB; ++k) u[k] = fma(cf, Gs[tri_idx(k, sl)][l], u[k]);
-            }
-            dgn = u[GI];
+        }
+        if (newdir && ((GI < 32 && vs == GI) || (GI >= 32 && vs == GI - 32))) misc[4][l] = (GI < 32) ? u0 : u1;
+        __syncthreads();
+        if (newdir) {
+            dgn = misc[4][l];
             if (!(dgn < 0.0) || cnt == 0) {                       // not a descent direction / no history
-#pragma unroll
-                for (int k = 0; k < NB; ++k) dl[k][l] = 0.0;
-                dl[GI][l] = -1.0;
+                if (own0) dl[vs][l] = (vs == GI) ? -1.0 : 0.0;
+                if (own1) dl[vs + 32][l] = (vs + 32 == GI) ? -1.0 : 0.0;
                 if (!(dgn < 0.0)) cnt = 0;
                 dgn = -gg;
                 anew = fmin(1.0, 1.0 / sqrt(fmax(gg, 1e-300)));
             }
             if (gg == 0.0) { finished = true; status = TVS_CONVERGED; }
         }
-        a.F[bb] = Ft; a.llsum[bb] = llsum; a.sumphi[bb] = sumphi;
-        a.kkt[bb] = comp; a.kkt[B + bb] = dual; a.iters[bb] = iters; a.ls[bb] = 0;
-        a.dg[bb] = dgn; a.alpha[bb] = anew;
-        a.head[bb] = head; a.cnt[bb] = cnt;
-        misc[0][l] = anew; misc[1][l] = finished ? 1.0 : 0.0;
+        if (vs == 0 && accept) {
+            a.F[bb] = Ft; a.llsum[bb] = llsum; a.sumphi[bb] = sumphi;
+            a.kkt[bb] = comp; a.kkt[B + bb] = dual; a.iters[bb] = iters; a.ls[bb] = 0;
+            a.dg[bb] = dgn; a.alpha[bb] = anew;
+            a.head[bb] = head; a.cnt[bb] = cnt;
+        }
     }
     __syncthreads();
-    if (accept) { anew = misc[0][l]; finished = misc[1][l] != 0.0; }
 
     // ---- E: d = sum_k delta_k b_k ; next trial point
     if (newdir && !finished) {
