@@ -206,3 +206,40 @@ def test_do_subsampling_from_records_reproduces_the_reference_run(plastome):
     for v_prop, fit in zip(s.variant_proportions_reps, plastome["fits"][1:]):
         for cid, p in fit["prop"]:
             assert abs(v_prop[cid] - p) < 5e-4
+
+
+def test_jackknife_from_records_equals_serial_fits(plastome):
+    """Jackknife replicates (random.sample replay), AIC, a user-fixed variant: the lock-step batch gives, replicate by
+    replicate, what one fitter at a time gives on the same lanes."""
+    import random
+    from traversome_b200.resample import RecordPool
+    from traversome_b200.lanes import LaneRequest
+    L = plastome["variant_sizes"]
+    pool = RecordPool.from_golden(plastome)
+    pattern = np.zeros((pool.n_rows, len(L)), dtype=bool)
+    ctx = _ctx(L)
+    for r, rp in enumerate(plastome["read_paths"]):
+        fv = {int(v): int(c) for v, c in rp["from_variants"]}
+        ctx.matrix.row_index_distinct(fv)
+        pattern[r, list(fv)] = True
+    groups = {int(k): [int(x) for x in v] for k, v in plastome["repr_to_merged_variants"]}
+    unid = {int(k): int(v) for k, v in plastome["be_unidentifiable_to"]}
+    w0, C0, N0, obs0 = pool.lane_of(np.arange(pool.n_records))
+    full = ModelFitMaxLike.from_lane(ctx, (ctx.add_weights(w0), C0, N0), pattern, np.nonzero(obs0)[0], groups, unid)
+    raw = full.reverse_model_selection(n_proc=1, criterion="AIC", user_fixed_ids=[1])
+    s = bootstrap.do_subsampling_from_records(pool, pattern, ctx, full, raw, random.Random(99), n_replicate=10, criterion="AIC",
+                                              jackknife=10, user_fixed_ids=[1], threshold=0.5)
+    assert s.n_replicates_run == 10
+    rng = random.Random(99)
+    for k in range(10):
+        sample = pool.sample_jackknife(rng, int(pool.n_records / 10.0))
+        assert len(sample) == pool.n_records - pool.n_records // 10
+        w, C, N, observed = pool.lane_of(sample)
+        ctx1 = _ctx(L)
+        for rp in plastome["read_paths"]:
+            ctx1.matrix.row_index_distinct({int(v): int(c) for v, c in rp["from_variants"]})
+        f = ModelFitMaxLike.from_lane(ctx1, (ctx1.add_weights(w), C, N), pattern, np.nonzero(observed)[0], groups, unid)
+        prop, like, crit = f.reverse_model_selection(n_proc=1, criterion="AIC", user_fixed_ids=[1])
+        got = s.variant_proportions_reps[k]
+        assert list(got) == list(prop) and all(abs(got[c] - prop[c]) < 1e-12 for c in prop)
+        assert 1 in prop
