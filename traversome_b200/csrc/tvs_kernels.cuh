@@ -296,18 +296,17 @@ struct UpdArgs {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int tri_idx(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
-// sum_q src[q*stride], q = 0..S-1, 8 independent loads in flight, added in order
+// sum_q src[q*stride], q = 0..S-1, added in order.  Loads are issued 8 at a time with the out-of-range ones
+// predicated off (adding +0.0 leaves the sum unchanged): no serial tail loop.
 __device__ __forceinline__ double sum_splits(const double* __restrict__ src, int S, int64_t stride) {
     double s0 = 0.0;
-    int q = 0;
-    for (; q + 8 <= S; q += 8) {
+    for (int q = 0; q < S; q += 8) {
         double v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = src[(int64_t)(q + i) * stride];
+        for (int i = 0; i < 8; ++i) v[i] = (q + i < S) ? src[(int64_t)(q + i) * stride] : 0.0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) s0 += v[i];
     }
-    for (; q < S; ++q) s0 += src[(int64_t)q * stride];
     return s0;
 }
 
@@ -373,7 +372,13 @@ __global__ void __launch_bounds__(kU2Threads) lbfgs_update_vl2_kernel(const UpdA
     if (a.nreset != nullptr && blockIdx.x == 0 && tid == 0) *a.nreset = 0;
     if (!__syncthreads_or(active)) return;
 
-    for (int q = vs; q < NG; q += kU2Slots) Gs[q][l] = Gm[(int64_t)q * B + bb];
+    // the Gram matrix is first needed in phase D: fetch it asynchronously so that the loads of phases A and B are not
+    // queued behind it (a plain load + shared store stalls the warp until the data arrives)
+    for (int q = vs; q < NG; q += kU2Slots) {
+        const unsigned dsts = (unsigned)__cvta_generic_to_shared(&Gs[q][l]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dsts), "l"(Gm + (int64_t)q * B + bb));
+    }
+    asm volatile("cp.async.commit_group;");
     if (active) {
         // the likelihood pass has just streamed the weight matrix through L2, so the solver state is in DRAM: start
         // fetching everything the later sweeps of this thread will read (profiles/r1_final_summary.md: 12 warps per
@@ -489,6 +494,8 @@ __global__ void __launch_bounds__(kU2Threads) lbfgs_update_vl2_kernel(const UpdA
     //      element of each step travels through shared memory (double-buffered, one barrier per step).  One thread
     //      per lane did all of it before: ~10k dependent instructions at M = 16, a third of the kernel's time.
     //      Every element sees the same operations in the same order, so the results are bitwise unchanged.
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                             // Gram matrix landed
     {
         double (*bc)[kU2Lanes] = misc + 2;                       // [2] pivot broadcast, [1] scalar broadcast
         double* al = part;                                       // [M][8] scratch (the partials are consumed)
