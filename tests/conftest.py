@@ -31,6 +31,11 @@ def synthetic_small():
 
 
 @pytest.fixture(scope="session")
+def subpaths_golden():
+    return _load("subpaths.json.gz")
+
+
+@pytest.fixture(scope="session")
 def lib_built():
     """libtvs.so must exist for both CPU (symbol checks) and GPU tests; build it if absent."""
     from traversome_b200 import _cabi

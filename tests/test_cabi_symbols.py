@@ -1,4 +1,4 @@
-"""CPU: the C-ABI library loads, exports every symbol include/tvs.h declares, and fails LOUDLY without a GPU."""
+"""CPU: the C-ABI library loads, exports every symbol include/*.h declares, and fails LOUDLY without a GPU."""
 import ctypes
 import os
 import re
@@ -12,9 +12,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def header_symbols():
-    src = open(os.path.join(ROOT, "include", "tvs.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(tvs_[a-z0-9_]+)\s*\(", src)))
+    names = set()
+    for header in ("tvs.h", "tvs_subpaths.h"):
+        src = open(os.path.join(ROOT, "include", header)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(tvs_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_header_and_binding_agree():

@@ -18,6 +18,8 @@ SYMBOLS = (
     "tvs_version", "tvs_last_error", "tvs_device_count", "tvs_create", "tvs_destroy", "tvs_set_lanes",
     "tvs_set_lanes_u16", "tvs_set_lanes_indexed", "tvs_resample", "tvs_get_weights", "tvs_loglik", "tvs_fit", "tvs_last_fit_stats", "tvs_dims",
     "tvs_measure_fp64_peak", "tvs_selftest_math", "tvs_selftest_table_log",
+    # include/tvs_subpaths.h
+    "tvs_subpaths_count", "tvs_subpaths_fetch", "tvs_subpaths_destroy",
 )
 
 TVS_OK, TVS_EINVAL, TVS_ECUDA, TVS_ENOMEM, TVS_ELIMIT, TVS_ESTATE = 0, -1, -2, -3, -4, -5
@@ -70,6 +72,11 @@ def load():
     lib.tvs_measure_fp64_peak.argtypes = [c_int, POINTER(c_double)]
     lib.tvs_selftest_math.argtypes = [c_int, c_int64, c_void_p, c_void_p, c_void_p]
     lib.tvs_selftest_table_log.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
+    lib.tvs_subpaths_count.argtypes = [POINTER(c_void_p), c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                       POINTER(c_int64), POINTER(c_int64), POINTER(c_double)]
+    lib.tvs_subpaths_fetch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.tvs_subpaths_destroy.argtypes = [c_void_p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("tvs_last_error",):
@@ -246,3 +253,43 @@ def selftest_math(p, device=0):
     rc = np.empty_like(p)
     _check(load().tvs_selftest_math(int(device), p.size, _ptr(p), _ptr(lg), _ptr(rc)))
     return lg, rc
+
+
+def count_subpaths(var_ptr, var_tok, var_step, var_circular, n_rows, key_ptr, key_tok, key_row_circular,
+                   key_row_linear, max_internal_len, device=0):
+    """tvs_subpaths_count + tvs_subpaths_fetch: CSR (by read path) of the read-path x variant occurrence counts.
+
+    Returns (row_ptr int64[n_rows+1], col int32[nnz], val int32[nnz], first int64[nnz], stats dict)."""
+    lib = load()
+    var_ptr = np.ascontiguousarray(var_ptr, dtype=np.int64)
+    var_tok = np.ascontiguousarray(var_tok, dtype=np.int32)
+    var_step = np.ascontiguousarray(var_step, dtype=np.int32)
+    var_circular = np.ascontiguousarray(var_circular, dtype=np.uint8)
+    key_ptr = np.ascontiguousarray(key_ptr, dtype=np.int64)
+    key_tok = np.ascontiguousarray(key_tok, dtype=np.int32)
+    key_row_circular = np.ascontiguousarray(key_row_circular, dtype=np.int32)
+    key_row_linear = np.ascontiguousarray(key_row_linear, dtype=np.int32)
+    n_variants, n_keys = var_ptr.size - 1, key_ptr.size - 1
+    if var_tok.size != var_ptr[-1] or var_step.size != var_ptr[-1] or var_circular.size != n_variants:
+        raise ValueError("variant arrays do not match var_ptr")
+    if key_tok.size != key_ptr[-1] or key_row_circular.size != n_keys or key_row_linear.size != n_keys:
+        raise ValueError("key arrays do not match key_ptr")
+    for rows in (key_row_circular, key_row_linear):
+        if n_keys and (rows.min() < -1 or rows.max() >= n_rows):
+            raise ValueError("key rows out of range")
+    h = c_void_p()
+    nnz, n_windows, ms = c_int64(), c_int64(), c_double()
+    _check(lib.tvs_subpaths_count(ctypes.byref(h), int(device), n_variants, var_ptr.ctypes.data, var_tok.ctypes.data,
+                                  var_step.ctypes.data, var_circular.ctypes.data, int(n_rows), n_keys,
+                                  key_ptr.ctypes.data, key_tok.ctypes.data, key_row_circular.ctypes.data,
+                                  key_row_linear.ctypes.data,
+                                  int(max_internal_len), ctypes.byref(nnz), ctypes.byref(n_windows), ctypes.byref(ms)))
+    try:
+        row_ptr = np.empty(int(n_rows) + 1, dtype=np.int64)
+        col = np.empty(nnz.value, dtype=np.int32)
+        val = np.empty(nnz.value, dtype=np.int32)
+        first = np.empty(nnz.value, dtype=np.int64)
+        _check(lib.tvs_subpaths_fetch(h, row_ptr.ctypes.data, col.ctypes.data, val.ctypes.data, first.ctypes.data))
+    finally:
+        lib.tvs_subpaths_destroy(h)
+    return row_ptr, col, val, first, {"n_windows": n_windows.value, "kernel_ms": ms.value, "nnz": nnz.value}
