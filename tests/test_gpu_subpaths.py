@@ -7,7 +7,7 @@ from oracle import subpaths as osp
 from traversome_b200 import _cabi
 from traversome_b200 import subpaths as sp
 from tests.subpath_helpers import emulate_count, random_graph_case
-from tests.test_subpaths_oracle import check_against_golden
+from tests.test_subpaths_oracle import check_against_golden, check_plastome
 
 pytestmark = pytest.mark.gpu
 
@@ -16,6 +16,12 @@ def test_golden_cases_through_the_device(subpaths_golden, lib_built):
     for case in subpaths_golden["cases"]:
         counts = check_against_golden(case, sp.VariantSubPathsGenerator)
         assert counts.stats["n_windows"] > 0 and counts.stats["kernel_ms"] > 0
+
+
+def test_plastome_tables_through_the_device(plastome, lib_built):
+    """BASELINE configs[0]: from the graph, the two isomers and the observed read paths to the reference's
+    all_sub_paths table (order, lengths, from_variants)."""
+    check_plastome(plastome, sp.VariantSubPathsGenerator)
 
 
 @pytest.mark.parametrize("seed,circular,n_contigs,n_variants,var_len", [
@@ -88,7 +94,7 @@ def test_counts_feed_the_fitter(lib_built):
     w = np.round(50000 * p / p.sum()).astype(np.int32).reshape(R, 1)
     eng.set_lanes(w, np.ones((2, 1), dtype=np.uint8), np.zeros(1))
     res = eng.fit()
-    assert res["status"][0] == _cabi.CONVERGED and res["kkt"][0] <= 1e-9
+    assert res["status"][0] == _cabi.CONVERGED and res["kkt"][0, 0] <= 1e-9
     best = res["loglike"][0]
     t0 = res["theta"][0, 0]
     assert 0.0 < t0 < 1.0

@@ -123,3 +123,67 @@ def test_emulation_equals_oracle_on_random_graphs():
         got = gen.count(variants).counters()
         want = [osp.count_read_paths_in_variant(graph, v, set(read_paths), mal) for v in variants]
         assert [list(c.items()) for c in got] == [list(c.items()) for c in want]
+
+
+def test_array_key_encoder_equals_the_general_one(subpaths_golden):
+    def as_set(k):
+        return {(tuple(k[1][k[0][i]:k[0][i + 1]].tolist()), int(k[2][i]), int(k[3][i])) for i in range(len(k[2]))}
+
+    n_closed = 0
+    for case in subpaths_golden["cases"]:
+        graph, _, read_paths = load_case(case)
+        tables = sp.GraphTables(graph)
+        if tables.palindromic:
+            continue
+        n_closed += sum(len(r) > 1 and tables.is_circular(r) for r in read_paths)
+        assert as_set(sp.encode_read_paths(tables, read_paths)) == as_set(sp._encode_read_paths_general(tables, read_paths))
+    assert n_closed > 0                                   # the closed-walk branch was exercised
+    graph, _, read_paths, _ = random_graph_case(9, 50, 20, (10, 60), True, 40, 6, 700)
+    tables = sp.GraphTables(graph)
+    # non-standard and duplicated-by-reversal read paths are handled alike
+    extra = [p for p in (tables.reverse(r) for r in read_paths[:40]) if p not in set(read_paths)]
+    assert extra
+    assert as_set(sp.encode_read_paths(tables, read_paths + extra)) == \
+        as_set(sp._encode_read_paths_general(tables, read_paths + extra))
+
+
+def plastome_inputs(plastome):
+    """BASELINE configs[0]: the processed plastome graph (contig lengths as the fixture's full_len values imply,
+    overlaps trimmed to 0 by the reference's graph processing), the two isomer variants, the observed read paths."""
+    lens = {}
+    for rp in plastome["read_paths"]:
+        if len(rp["path"]) == 1:
+            lens[rp["path"][0][0]] = rp["full_len"]
+    links = []
+    for a, ae, b, be in (("LSC", True, "IR", True), ("LSC", False, "IR", True), ("IR", True, "SSC", True),
+                         ("IR", True, "SSC", False)):
+        links.append([a, ae, b, not be, 0])
+        links.append([b, not be, a, ae, 0])
+    graph = osp.PlainGraph([[n, lens[n]] for n in ("LSC", "IR", "SSC")], links)
+    variants = [tuple((tok[:-1], tok[-1] == "+") for tok in line.replace("(circular)", "").split(","))
+                for line in ("LSC+,IR+,SSC+,IR-", "LSC+,IR+,SSC-,IR-")]
+    # the reference standardises user variants first (Assembly.get_standardized_variant, Assembly.py:1229-1260:
+    # smallest rotation over both strands)
+    variants = [osp.canonical(graph, v, rotations=True) for v in variants]
+    read_paths = [osp.as_path(rp["path"]) for rp in plastome["read_paths"]]
+    return graph, variants, read_paths[::-1], max(plastome["records"]["align_len"])
+
+
+def check_plastome(plastome, generator_cls):
+    graph, variants, read_paths, mal = plastome_inputs(plastome)
+    gen = generator_cls(graph, min(plastome["records"]["align_len"]), mal, read_paths)
+    _, be, merged, table, counts = sp.gen_all_informative_sub_paths(gen, variants, plastome["variant_sizes"])
+    want = plastome["read_paths"]
+    assert list(table) == [osp.as_path(rp["path"]) for rp in want]             # the reference's all_sub_paths order
+    for info, rp in zip(table.values(), want):
+        assert (info.inner_len, info.full_len) == (rp["inner_len"], rp["full_len"])
+        assert [[v, c] for v, c in info.from_variants.items()] == rp["from_variants"]
+    assert [[k, v] for k, v in be.items()] == [[0, 0], [1, 1]]
+    return counts
+
+
+def test_plastome_tables_from_graph_and_variants(plastome):
+    graph, variants, read_paths, mal = plastome_inputs(plastome)
+    _, _, _, table = osp.informative_sub_paths(graph, variants, plastome["variant_sizes"], read_paths, mal)
+    assert list(table) == [osp.as_path(rp["path"]) for rp in plastome["read_paths"]]
+    check_plastome(plastome, EmulatedGenerator)

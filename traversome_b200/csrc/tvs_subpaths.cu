@@ -192,17 +192,26 @@ __global__ void sp_row_nnz_kernel(const int32_t* __restrict__ cnt, int64_t V, in
     row_nnz[r] = n;
 }
 
-// exclusive scan of row_nnz into row_ptr[R+1] by ONE CTA of 1024 threads (R is at most a few 10^5..10^6)
+// exclusive scan of row_nnz into row_ptr[R+1] by ONE CTA of 1024 threads, 8 consecutive items per thread and round
+// (R is at most a few 10^5..10^6: a few dozen rounds)
+constexpr int kScanItems = 8;
 __global__ void sp_scan_kernel(const int64_t* __restrict__ row_nnz, int64_t R, int64_t* __restrict__ row_ptr) {
     __shared__ int64_t s_warp[32];
     __shared__ int64_t s_carry;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     if (t == 0) s_carry = 0;
     __syncthreads();
-    for (int64_t r0 = 0; r0 < R; r0 += blockDim.x) {
-        const int64_t r = r0 + t;
-        const int64_t x = r < R ? row_nnz[r] : 0;
-        int64_t incl = x;
+    const int64_t tile = (int64_t)blockDim.x * kScanItems;
+    for (int64_t r0 = 0; r0 < R; r0 += tile) {
+        const int64_t base = r0 + (int64_t)t * kScanItems;
+        int64_t x[kScanItems];
+        int64_t sum = 0;
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+            x[i] = base + i < R ? row_nnz[base + i] : 0;
+            sum += x[i];
+        }
+        int64_t incl = sum;
         for (int o = 1; o < 32; o <<= 1) {
             int64_t y = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += y;
@@ -218,28 +227,42 @@ __global__ void sp_scan_kernel(const int64_t* __restrict__ row_nnz, int64_t R, i
             s_warp[lane] = w;                       // inclusive over warps
         }
         __syncthreads();
-        const int64_t before = s_carry + (wid ? s_warp[wid - 1] : 0) + incl - x;
-        if (r < R) row_ptr[r] = before;
+        int64_t run = s_carry + (wid ? s_warp[wid - 1] : 0) + incl - sum;
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+            if (base + i < R) row_ptr[base + i] = run;
+            run += x[i];
+        }
         __syncthreads();
-        if (t == blockDim.x - 1) s_carry = before + x;
+        if (t == blockDim.x - 1) s_carry = run;
         __syncthreads();
     }
     if (t == 0) row_ptr[R] = s_carry;
 }
 
+// dense -> CSR entries; thread per read path, loads batched 8 variants at a time so that the sweep is bandwidth-bound
 __global__ void sp_fill_kernel(const int32_t* __restrict__ cnt, const uint32_t* __restrict__ first, int64_t V, int64_t R,
                                const int64_t* __restrict__ row_ptr, int32_t* __restrict__ col, int32_t* __restrict__ val,
                                int64_t* __restrict__ rank) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     int64_t k = row_ptr[r];
-    for (int64_t v = 0; v < V; ++v) {
-        const int32_t c = cnt[v * R + r];
-        if (c != 0) {
-            col[k] = (int32_t)v;
-            val[k] = c;
-            rank[k] = (int64_t)first[v * R + r];
-            ++k;
+    if (row_ptr[r + 1] == k) return;                    // read path no variant contains
+    for (int64_t v0 = 0; v0 < V; v0 += 8) {
+        int32_t c[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[i] = v0 + i < V ? cnt[(v0 + i) * R + r] : 0;
+        uint32_t f[8];                                    // predicated loads, issued together (not one miss per hit)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = c[i] != 0 ? first[(v0 + i) * R + r] : 0u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (c[i] != 0) {
+                col[k] = (int32_t)(v0 + i);
+                val[k] = c[i];
+                rank[k] = (int64_t)f[i];
+                ++k;
+            }
         }
     }
 }

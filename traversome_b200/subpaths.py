@@ -169,8 +169,9 @@ def encode_variants(tables, variant_paths):
     return ptr, tables.corrected(raw), step.astype(np.int32), circular.astype(np.uint8)
 
 
-def encode_read_paths(tables, read_paths):
-    """Keys of the read paths: (key_ptr, key_tok, key_row_circular, key_row_linear), see include/tvs_subpaths.h.
+def _encode_read_paths_general(tables, read_paths, rows=None):
+    """Keys of the read paths (`rows` = their row numbers, default 0..n-1), one path at a time with the standardisers
+    themselves: (key_ptr, key_tok, key_row_circular, key_row_linear), see include/tvs_subpaths.h.
 
     Windows of circular variants are standardised by get_standardized_path (utils.py:461): a window W stands for read
     path r iff r is min(W, rc W), i.e. W is r or rc(r) and r is standard.  Windows of linear variants go through
@@ -183,7 +184,7 @@ def encode_read_paths(tables, read_paths):
         if table.setdefault(seq, row) != row:
             raise ValueError("two read paths claim the same window: rows %d and %d" % (table[seq], row))
 
-    for row, r in enumerate(read_paths):
+    for row, r in (enumerate(read_paths) if rows is None else zip(rows, read_paths)):
         r = tuple(r)
         if not r or tables.correct(r) != r:
             continue                                        # a window is strand-corrected first: r can never be hit
@@ -204,6 +205,56 @@ def encode_read_paths(tables, read_paths):
     key_row_circ = np.fromiter((circ_row.get(s, -1) for s in seqs), dtype=np.int32, count=len(seqs))
     key_row_lin = np.fromiter((lin_row.get(s, -1) for s in seqs), dtype=np.int32, count=len(seqs))
     return key_ptr, raw, key_row_circ, key_row_lin
+
+
+def encode_read_paths(tables, read_paths):
+    """Keys of all read paths.  Without palindromic contigs a read path that is not itself a closed walk has the keys
+    {r, rc(r)} under both standardisers, provided r <= rc(r) in the reference's ordering of (name, strand) tuples; that
+    common case is done on the token arrays.  Closed walks (and everything on a graph with palindromic contigs) go
+    through `_encode_read_paths_general`."""
+    read_paths = [tuple(p) for p in read_paths]
+    if tables.palindromic or not read_paths:
+        return _encode_read_paths_general(tables, read_paths)
+    ptr, tok = tables.tokens(read_paths)
+    n = len(read_paths)
+    lens = np.diff(ptr)
+    if np.any(lens == 0):
+        raise ValueError("empty read path")
+    seg = np.repeat(np.arange(n, dtype=np.int64), lens)
+    idx = np.arange(tok.size, dtype=np.int64)
+    mirror = ptr[seg] + ptr[seg + 1] - 1 - idx
+    rev = tok[mirror] ^ 1
+    # order of (name, strand) tuples: by name as a string, then False < True
+    rank = np.empty(len(tables.names), dtype=np.int64)
+    rank[np.argsort(np.asarray(tables.names, dtype=object), kind="stable")] = np.arange(len(tables.names))
+    ord_fwd = 2 * rank[tok >> 1] + (tok & 1)
+    ord_rev = 2 * rank[rev >> 1] + (rev & 1)
+    differ = ord_fwd != ord_rev
+    first_diff = np.minimum.reduceat(np.where(differ, idx, tok.size), ptr[:-1])
+    self_rc = first_diff == tok.size
+    at = np.minimum(first_diff, tok.size - 1)
+    standard = self_rc | (ord_fwd[at] < ord_rev[at])
+    closes, _ = tables.edge_overlap(tok[ptr[1:] - 1], tok[ptr[:-1]])
+    slow = closes & (lens > 1)
+    fast_rows = np.flatnonzero(standard & ~slow)
+    both = fast_rows[~self_rc[fast_rows]]
+
+    def gather(rows_, source):
+        ln = lens[rows_]
+        out_ptr = np.zeros(rows_.size + 1, dtype=np.int64)
+        np.cumsum(ln, out=out_ptr[1:])
+        take = np.repeat(ptr[rows_] - out_ptr[:-1], ln) + np.arange(int(out_ptr[-1]), dtype=np.int64)
+        return out_ptr, source[take]
+
+    parts = [gather(fast_rows, tok) + (fast_rows, fast_rows), gather(both, rev) + (both, both)]
+    slow_rows = np.flatnonzero(slow)
+    if slow_rows.size:
+        parts.append(_encode_read_paths_general(tables, [read_paths[i] for i in slow_rows.tolist()], slow_rows.tolist()))
+    key_ptr = np.zeros(1, dtype=np.int64)
+    for part_ptr, _, _, _ in parts:
+        key_ptr = np.concatenate([key_ptr, part_ptr[1:] + key_ptr[-1]])
+    return (key_ptr, np.concatenate([p[1] for p in parts]).astype(np.int32),
+            np.concatenate([p[2] for p in parts]).astype(np.int32), np.concatenate([p[3] for p in parts]).astype(np.int32))
 
 
 # ---------------------------------------------------------------------------------------------- result
@@ -316,6 +367,8 @@ class VariantSubPathsGenerator(object):
     def _prepare(self):
         if self._keys is None:
             self._rows = [tuple(p) for p in self.read_paths_hashed]
+            if len(set(self._rows)) != len(self._rows):
+                raise ValueError("read_paths_hashed holds the same read path twice")
             self._keys = encode_read_paths(self.tables, self._rows)
         return self._rows, self._keys
 
