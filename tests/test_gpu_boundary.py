@@ -138,6 +138,22 @@ def test_cfg1_bootstrap_flow_on_gpu(gpu, plastome):
         A, w, C, N = loglik.rows_from_bins(L, m["bins_list"])
         r = exact.exact_fit(A, L, w)
         assert abs(v_prop[0] - r["theta"][0]) < 1e-6 and abs(v_prop[1] - r["theta"][1]) < 1e-6
+    # the result tables of this run against the files the reference wrote: same layout, fids and
+    # support; %.4f cells within the reference's SLSQP noise, log-likelihood and BIC within 1e-9 relative
+    from traversome_b200 import output
+    cid_to_fid = output.cid_to_fid_table(s.vp_unique_results_sorted, raw[0])
+    mine = output.final_result_tab(s, raw[0], raw[1], raw[2], cid_to_fid).strip().split("\n")
+    ref = plastome["output_tables"]["final.result.tab"].strip().split("\n")
+    assert mine[0] == ref[0] and len(mine) == len(ref) == 2
+    a, b = mine[1].split("\t"), ref[1].split("\t")
+    assert a[:2] == b[:2]                                                        # solution id, support
+    assert all(abs(float(x) - float(y)) <= 1e-9 * abs(float(y)) for x, y in zip(a[2:4], b[2:4]))
+    assert all(abs(float(x) - float(y)) <= 1.01e-4 for x, y in zip(a[4:6], b[4:6]))
+    assert all(abs(float(x) - float(y)) <= 2e-4 for x, y in zip(a[6].split(","), b[6].split(",")))
+    rep_mine = output.replicates_tab(s.variant_proportions_reps, cid_to_fid).split("\n")
+    rep_ref = plastome["output_tables"]["bootstraps.replicates.tab"].split("\n")
+    assert rep_mine[0] == rep_ref[0] and len(rep_mine) == len(rep_ref)
+    assert [ln.split("\t")[0] for ln in rep_mine] == [ln.split("\t")[0] for ln in rep_ref]
     full.close()
 
 
