@@ -45,14 +45,18 @@ class ClockSampler(object):
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.gpu_index = gpu_index
+    def __init__(self, gpu_indices):
+        """gpu_indices: the GPUs of this job.  ONE nvidia-smi process (on rank 0) watches all of them: a poller per
+        rank takes the driver's locks N times as often and shows up in the step time at N = 8."""
+        self.gpu_index = ",".join(str(i) for i in gpu_indices)
         self.proc = None
         self.lines = []
 
     def start(self):
+        if not self.gpu_index:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.gpu_index, "--query-gpu=" + self.FIELDS,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
@@ -65,6 +69,8 @@ class ClockSampler(object):
             self.lines.append(line.strip())
 
     def stop(self):
+        if not self.gpu_index:
+            return None
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -229,7 +235,7 @@ def main():
         flush.zero_()
         eng.fit(out=outs)
     # ---- timed: device-resident weights
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(range(world) if rank == 0 else ())     # single node: local ranks = GPU indices
     sampler.start()
     barrier()
     dev_ms, launches, passes, lane_passes = [], 0, 0, 0
@@ -272,8 +278,12 @@ def main():
 
     step_ms = float(np.sum(dev_ms)) / args.steps
     e2e_step_ms = float(np.sum(e2e_ms)) / args.steps
+    per_rank_ms = [step_ms]
     if world > 1:
         t = torch.tensor([step_ms, e2e_step_ms], dtype=torch.float64, device="cuda")
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        per_rank_ms = [float(x[0]) for x in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         step_ms, e2e_step_ms = float(t[0]), float(t[1])
         c = torch.tensor([converged, launches], dtype=torch.int64, device="cuda")
@@ -293,7 +303,7 @@ def main():
         sm_count, smem_bw = 148, 128.0 * 1.965e9          # 128 B/clk/SM at the 1965 MHz boost clock
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": step_ms, "ms_per_step_by_rank": [round(x, 3) for x in per_rank_ms], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, wl),
             "e2e": {"value": total_lanes / (e2e_step_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(wl.R) * B * 2,

@@ -801,6 +801,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
     // ---- damped Newton phase (tvs_newton.cuh): runs the lanes of a small set to convergence
     const int newton_lanes = (h->csr.slab_ptr != nullptr && V <= kNewtonMaxV) ? env_int("TVS_NEWTON_LANES", 128) : 0;
     int64_t newton_iters = 0;
+    const bool newton_trace = env_int("TVS_NEWTON_TRACE", 0) != 0;
     bool newton_off = false;                                    // set when the shape has no staged pass kernel
     // One SEGMENT of the Newton phase on lane set `s`: iterates until every lane has finished (all_done) or so many
     // have that a compaction pays (`*active_out` <= width / 2); the caller compacts and calls again.
@@ -872,7 +873,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         sa.h_entry = wide ? W : 1; sa.h_lane = wide ? 1 : NP; sa.h_split = wide ? 0 : (int64_t)W * NP;
         sa.z = s.z; sa.g = s.g; sa.gha = f.gha; sa.invL = h->csr.invL; sa.N = s.N; sa.mask = s.mask;
         sa.done = s.done; sa.lam = f.lam; sa.d = s.d; sa.zt = s.zt; sa.x = s.x; sa.dg = s.dg; sa.alpha = s.alpha; sa.W = W; sa.V = (int)V;
-        sa.sumphi = s.sumphi; sa.tol_dual = (double)env_int("TVS_DUAL_MULT", 100) * opt.tol;
+        sa.sumphi = s.sumphi; sa.tol_dual = (double)env_int("TVS_DUAL_MULT", 100) * opt.tol; sa.ls = s.ls;
         NewtonUpdArgs na{};
         na.invL = h->csr.invL; na.N = s.N; na.mask = s.mask; na.z = s.z; na.zt = s.zt; na.g = s.g; na.gt = f.gt; na.gh = f.gh;
         na.gha = f.gha; na.d = s.d; na.F = s.F; na.dg = s.dg; na.alpha = s.alpha; na.llsum = s.llsum; na.kkt = s.kkt;
@@ -910,6 +911,18 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
             if (cerr != cudaSuccess) return TVS_OK;       // reported by the caller through cerr
             ++n_polls;
             *active_out = f.h_nactive[slot];
+            if (newton_trace && W <= 8) {                         // developer trace: per-lane damping and residuals
+                double lam[8], kkt[16], F[8]; int32_t ls[8], dn[8];
+                cudaMemcpy(lam, f.lam, W * 8, cudaMemcpyDeviceToHost);
+                cudaMemcpy(kkt, s.kkt, W * 16, cudaMemcpyDeviceToHost);
+                cudaMemcpy(F, s.F, W * 8, cudaMemcpyDeviceToHost);
+                cudaMemcpy(ls, s.ls, W * 4, cudaMemcpyDeviceToHost);
+                cudaMemcpy(dn, s.done, W * 4, cudaMemcpyDeviceToHost);
+                for (int64_t b = 0; b < W; ++b)
+                    if (!dn[b] || it < 2)
+                        fprintf(stderr, "newton it %d lane %lld done %d ls %d lam %.3e comp %.3e dual %.3e F %.17g\n", it,
+                                (long long)b, dn[b], ls[b], lam[b], kkt[b], kkt[W + b], F[b]);
+            }
             if (*active_out == 0) { all_done = true; break; }
             if (!no_compact && *active_out * 2 <= W && W > 32 && *active_out + 3 <= f.half) break;   // the caller compacts
         }

@@ -240,6 +240,7 @@ struct SolveArgs {
     double* lam; double* d; double* zt; double* x; double* dg; double* alpha;
     int64_t W; int V;
     const double* sumphi; double tol_dual;     // saddle escape (see solve_kernel)
+    const int32_t* ls;                         // consecutive rejected trial points of the lane (shrinks the escape step)
 };
 
 constexpr int kSolveThreads = 256;
@@ -276,13 +277,19 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const SolveArgs a)
             // (g_u > 1: the variant wants a positive share) the gradient is ~0 and the curvature 2(1 - g_u) negative, so
             // neither Newton nor L-BFGS ever leaves.  Such a component is taken out of the linear system and moved to the
             // one-dimensional Newton point of phi_u: phi_u = (g_u - 1) / H_uu  (seen once in 20,000 cfg2 replicates).
+            // The same holds NEAR the saddle: with phi_u two orders of magnitude below that point the z-space step only
+            // grows z_u by ~15 % per iteration (26 iterations on one lane of the 8-GPU bench workload), so such a
+            // component is moved the same way.  A rejected trial point shrinks the move (x 1/4 per rejection).
             const double sp = a.sumphi[lane];
             const double phi_u = zv[u] * zv[u];
             kickv[u] = 0.0;
-            if (mk && gh_u * sp - 1.0 > a.tol_dual && phi_u < 1e-11 * sp) {
+            if (mk && gh_u * sp - 1.0 > a.tol_dual) {
                 const double hphi = s * a.invL[u] * a.invL[u] * invN;                 // d2F / dphi_u^2
-                const double target = fmin(fmax(gh_u - 1.0, 0.0) / fmax(hphi, 1e-300), 1e-3 * sp);
-                kickv[u] = sqrt(fmax(target, 1e-16 * sp));
+                const double full = fmin(fmax(gh_u - 1.0, 0.0) / fmax(hphi, 1e-300), 1e-3 * sp);
+                if (phi_u < 1e-11 * sp || phi_u < 1e-2 * full) {
+                    const double target = phi_u + full * exp2(-2.0 * (double)min(a.ls[lane], 20));
+                    kickv[u] = sqrt(fmax(target, 1e-16 * sp));
+                }
             }
             const bool fixed = !mk || kickv[u] > 0.0;
             h = fixed ? 1.0 : h + 2.0 * (1.0 - gh_u);
