@@ -177,6 +177,25 @@ def test_vectorised_cover_rule_equals_reference_set_logic(synthetic_small, plast
                         model_sp.add(kw["sbp_to_sbp_id"][sp_])
             assert fitter.cover_all_observed_subpaths(ids) == fitter.observed_sbp_id_set.issubset(model_sp)
 
+        # with the cover counts of a base set cached (what a selection round does), leave-one-out subsets, the base set
+        # itself and unrelated sets all answer like the set logic
+        def by_sets(ids):
+            model_sp = set()
+            for v in ids:
+                for sp_ in kw["variant_subpath_counters"][kw["variant_paths"][v]]:
+                    if sp_ in kw["sbp_to_sbp_id"]:
+                        model_sp.add(kw["sbp_to_sbp_id"][sp_])
+            return fitter.observed_sbp_id_set.issubset(model_sp)
+
+        for _ in range(12):
+            base = set(int(v) for v in rng.choice(V, rng.integers(1, V + 1), replace=False))
+            fitter._set_cover_base(base)
+            assert fitter.cover_all_observed_subpaths(base) == by_sets(base)
+            for v in base:
+                assert fitter.cover_all_observed_subpaths(base - {v}) == by_sets(base - {v})
+            other = set(int(v) for v in rng.choice(V, rng.integers(1, V + 1), replace=False))
+            assert fitter.cover_all_observed_subpaths(other) == by_sets(other)
+
 
 def test_do_subsampling_from_records_reproduces_the_reference_run(plastome):
     """cfg1 from the record pool in array form: replayed draws (random.Random(12345)), bit-exact bins, lock-step

@@ -13,6 +13,7 @@ Same constructor, methods, attributes, log lines and exceptions as the reference
 There is no CPU fallback: constructing the engine raises when ``libtvs.so`` or a CUDA device is
 missing.
 """
+import os
 from collections import OrderedDict
 from typing import OrderedDict as typingODict
 from typing import Set, Union
@@ -102,6 +103,11 @@ class ModelFitMaxLike(object):
         self._shuffle = np.random.shuffle   # ModelFitMaxLike.py:203; tests may pin the permutation
         self.n_gpu_fits = 0          # lanes fitted so far (diagnostics)
         self._cover_cache = None
+        self._cover_base = None
+        # backward selection starts each candidate subset from the accepted model's optimum (see _start_point)
+        self.warm_start = os.environ.get("TVS_WARM_START", "1") != "0"
+        self._warm = None            # {representative id: proportion} of the accepted model, inside a selection only
+        self._batch_x = None
 
     @classmethod
     def from_lane(cls, context, lane, pattern, observed_rows, repr_to_merged_variants, be_unidentifiable_to,
@@ -134,7 +140,16 @@ class ModelFitMaxLike(object):
         self.n_gpu_fits = 0
         observed = np.zeros(pattern.shape[0], dtype=bool)
         observed[list(self.observed_sbp_id_set)] = True
-        self._cover_cache = (len(self.observed_sbp_id_set), np.asarray(pattern, dtype=bool), observed)
+        pattern = np.asarray(pattern, dtype=bool)
+        # the variant-major copy of the pattern is shared by all replicates of the context
+        shared = getattr(context, "_pattern_by_variant", None)
+        if shared is None or shared[0] is not pattern:
+            shared = context._pattern_by_variant = (pattern, np.ascontiguousarray(pattern.T))
+        self._cover_cache = (len(self.observed_sbp_id_set), pattern, observed, shared[1])
+        self._cover_base = None
+        self.warm_start = os.environ.get("TVS_WARM_START", "1") != "0"
+        self._warm = None
+        self._batch_x = None
         self._array_form = True
         return self
 
@@ -156,7 +171,21 @@ class ModelFitMaxLike(object):
         """Lane descriptions of ML fits restricted to subsets[b] (sets of representative ids)."""
         self._ensure_lane()
         col, C, _N = self._lane
-        return [LaneRequest(col, C, ids) for ids in subsets]
+        return [LaneRequest(col, C, ids, self._start_point(ids)) for ids in subsets]
+
+    def _start_point(self, ids):
+        """Starting proportions of a candidate subset during backward selection: the accepted model's optimum restricted
+        to the subset (a leave-one-out optimum is close to it), floored so that no component starts at the stationary
+        point z = 0 of the solver's parametrisation.  None (uniform start) outside a selection."""
+        warm = self._warm
+        if not warm or not self.warm_start:
+            return None
+        x = np.array([warm.get(v, 0.0) for v in sorted(ids)], dtype=np.float64)
+        total = x.sum()
+        if not np.isfinite(total) or total <= 0.0:
+            return None
+        x = np.maximum(x / total, 1e-3 / len(x))
+        return x / x.sum()
 
     def _fit_subsets(self, subsets):
         """One GPU call: lane b = ML fit restricted to subsets[b].  Returns a list of FitResult
@@ -240,13 +269,16 @@ class ModelFitMaxLike(object):
             indispensable_ids = {}
 
         first_sets = [set(chosen_ids)]
+        self._warm = None
         previous_prop, previous_echo, previous_like, previous_criteria = \
             self.__summarize_batch(first_sets, (yield first_sets), criterion)[0]
+        self._warm = self._batch_x[0]
         self.__drop_zero_variants(chosen_ids, previous_prop, previous_echo, diff_tolerance, indispensable_ids)
 
         while len(chosen_ids) > 1:
             logger.debug("Trying dropping {} variant(s) ..".format(self.num_put_variants - len(chosen_ids) + 1))
             chosen_ids_sorted = sorted(chosen_ids)
+            self._set_cover_base(chosen_ids)
             chosen_rd_list = list(range(len(chosen_ids_sorted)))
             self._shuffle(chosen_rd_list)
             changed = False
@@ -272,12 +304,14 @@ class ModelFitMaxLike(object):
                         logger.debug("Test variants [{}] - {}: skipped for necessary subpath(s) (case **)"
                                      .format(label, self.__str_rep_id(var_id)))
                 # -- one batch of lanes for the whole chunk
+                batch_x = {}
                 if to_fit:
                     id_sets = [ids for _, ids in to_fit]
                     batch = self.__summarize_batch(id_sets, (yield id_sets), criterion)
-                    for (var_id, _), res_list in zip(to_fit, batch):
+                    for (var_id, _), res_list, x in zip(to_fit, batch, self._batch_x):
                         test_id_res[var_id] = {"prop": res_list[0], "echo": res_list[1], "loglike": res_list[2],
                                                criterion: res_list[3]}
+                        batch_x[var_id] = x
                 if test_id_res:
                     best_drop_id, best_val = sorted([[_go_var_, test_id_res[_go_var_][criterion]]
                                                      for _go_var_ in test_id_res],
@@ -288,6 +322,7 @@ class ModelFitMaxLike(object):
                         previous_prop = test_id_res[best_drop_id]["prop"]
                         previous_echo = test_id_res[best_drop_id]["echo"]
                         chosen_ids.remove(best_drop_id)
+                        self._warm = batch_x.get(best_drop_id) or self._warm
                         log = logger.debug if self.bootstrap_mode else logger.info
                         log("Drop {}".format(self.__str_rep_id(best_drop_id)))
                         log("Proportions: " + ", ".join(["%s:%.4f" % (_id, _p) for _id, _p, in previous_echo.items()]))
@@ -297,8 +332,10 @@ class ModelFitMaxLike(object):
                         changed = True
                         break
             if not changed:
+                self._warm = None
                 self.__echo_res(previous_echo, previous_like)
                 return previous_prop, previous_like, previous_criteria
+        self._warm = None
         self.__echo_res(previous_echo, previous_like)
         return previous_prop, previous_like, previous_criteria
 
@@ -337,6 +374,8 @@ class ModelFitMaxLike(object):
                 logger.info("Maximizing the likelihood function for {} variants".format(len(ids)))
         _col, _C, sample_size = self._lane
         out = []
+        self._batch_x = [dict(zip(sorted(ids), (float(v) for v in res.x))) if res.success else None
+                         for ids, res in zip(id_sets, results)]
         for ids, res in zip(id_sets, results):
             info = LogLikeFuncInfo(loglike_func=None, variable_size=self.__variable_size(ids), sample_size=sample_size)
             out.append(self.__summarize_like_and_criteria(res if res.success else False, ids, criteria, info))
@@ -441,7 +480,9 @@ class ModelFitMaxLike(object):
             np.logical_or.at(contains, local[ok], contains_g[glob[ok]])
         observed = np.zeros(n_sbp, dtype=bool)
         observed[list(self.observed_sbp_id_set)] = True
-        self._cover_cache = (len(self.observed_sbp_id_set), contains, observed)
+        # variant-major copy: a candidate set is a gather of contiguous rows
+        self._cover_cache = (len(self.observed_sbp_id_set), contains, observed, np.ascontiguousarray(contains.T))
+        self._cover_base = None
         return contains, observed
 
     def _global_cover_table(self):
@@ -470,8 +511,28 @@ class ModelFitMaxLike(object):
         if not self.observed_sbp_id_set:
             self.update_observed_sp_ids()
         contains, observed = self._cover_tables()
-        ids = [int(v) for v in variant_ids]
+        by_variant = self._cover_cache[3]                       # [V, sub paths]
+        ids = frozenset(int(v) for v in variant_ids)
         if not ids:
             return not observed.any()
-        covered = contains[:, ids].any(axis=1)
-        return bool(np.all(covered[observed]))
+        base = getattr(self, "_cover_base", None)
+        if base is not None and ids <= base[0] and len(base[0]) - len(ids) <= 1:
+            # leave-one-out of the set whose per-sub-path cover counts are cached (the candidates of one selection
+            # round): uncovered iff some observed sub path is held by the dropped variant alone
+            if base[1]:
+                return False
+            dropped = base[0] - ids
+            if not dropped:
+                return True
+            return not bool(np.any(by_variant[next(iter(dropped))] & base[2]))
+        return bool(by_variant[sorted(ids)].any(axis=0)[observed].all())
+
+    def _set_cover_base(self, variant_ids):
+        """Cache the cover counts of `variant_ids` so that its leave-one-out subsets are tested in O(sub paths)."""
+        if not self.observed_sbp_id_set:
+            self.update_observed_sp_ids()
+        self._cover_tables()
+        ids = frozenset(int(v) for v in variant_ids)
+        observed = self._cover_cache[2]
+        counts = self._cover_cache[3][sorted(ids)].sum(axis=0, dtype=np.int32)
+        self._cover_base = (ids, bool(np.any((counts == 0) & observed)), (counts == 1) & observed)

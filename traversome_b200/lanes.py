@@ -23,11 +23,13 @@ class FitResult(object):
 
 
 class LaneRequest(object):
-    """One lane: weight column `col` of the context, the theta-free constant C, candidate ids."""
-    __slots__ = ("col", "C", "ids")
+    """One lane: weight column `col` of the context, the theta-free constant C, candidate ids, and optionally a
+    starting point `theta0` (proportions of `ids` in increasing id order; None = uniform)."""
+    __slots__ = ("col", "C", "ids", "theta0")
 
-    def __init__(self, col, C, ids):
+    def __init__(self, col, C, ids, theta0=None):
         self.col, self.C, self.ids = int(col), float(C), sorted(int(v) for v in ids)
+        self.theta0 = None if theta0 is None else np.asarray(theta0, dtype=np.float64)
 
 
 class LaneSharder(object):
@@ -169,7 +171,12 @@ class LaneContext(object):
                 mask[rq.ids, b] = 1
             eng = self.engine()
             eng.set_lanes_indexed(w_cols, col_of_lane, mask=mask, C=np.array([rq.C for rq in mine]))
-            local = eng.fit(tol=self.tol, max_iter=self.max_iter, history=self.history)
+            theta0 = None
+            if any(rq.theta0 is not None for rq in mine):
+                theta0 = np.zeros((self.V, hi - lo), dtype=np.float64)
+                for b, rq in enumerate(mine):
+                    theta0[rq.ids, b] = rq.theta0 if rq.theta0 is not None else 1.0 / len(rq.ids)
+            local = eng.fit(theta0=theta0, tol=self.tol, max_iter=self.max_iter, history=self.history)
         out = local if self.sharder is None else self.sharder.gather(local, B, self.V)
         self.n_lanes_fitted += B
         self.n_batches += 1
