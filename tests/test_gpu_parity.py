@@ -116,6 +116,48 @@ def test_fit_medium_and_large_variant_counts(gpu, V, R, density, B):
     check_fit_against_exact(wl, w, None, out, [0, 1, B - 1])
 
 
+def test_dense_contraction_pass_equals_sparse_pass_and_exact_optimum(gpu, monkeypatch):
+    """Dense shapes (V > 400, >= 12 % of A non-zero: BASELINE configs[4]) run the likelihood pass as two fp64 GEMMs on a
+    dense copy of A (tvs_api.cu: launch_dense).  Same log-likelihoods as the sparse kernels to fp64 round-off, the
+    same optimum, subset masks and finished lanes honoured; TVS_DENSE=0 keeps the sparse path."""
+    V, B = 448, 24
+    wl = synthetic.make_workload(V, 1800, 0.3, seed=812)
+    w = synthetic.bootstrap_weights(wl.n_obs, B, seed=3)
+    mask = np.ones((V, B), np.uint8)
+    mask[5:40, 3] = 0
+    mask[::2, 7] = 0
+    theta = np.random.default_rng(4).dirichlet(np.ones(V), size=B).T * mask
+    theta /= theta.sum(axis=0)
+    res = {}
+    for mode in ("0", "auto"):
+        if mode == "0":
+            monkeypatch.setenv("TVS_DENSE", "0")
+        else:
+            monkeypatch.delenv("TVS_DENSE")
+        with engine_for(wl) as eng:
+            eng.set_lanes(w, mask=mask)
+            ll = eng.loglik(theta)
+            out = eng.fit()
+            res[mode] = (ll, out, eng.last_fit_stats()["kernel_launches"])
+    (ll_s, out_s, _), (ll_d, out_d, _) = res["0"], res["auto"]
+    assert np.all(np.abs(ll_s - ll_d) <= 1e-13 * np.abs(ll_s))
+    assert np.all(out_s["status"] == _cabi.CONVERGED) and np.all(out_d["status"] == _cabi.CONVERGED)
+    assert np.all(np.abs(out_s["loglike"] - out_d["loglike"]) <= 1e-11 * np.abs(out_s["loglike"]))
+    assert np.abs(out_s["theta"] - out_d["theta"]).max() < 1e-6
+    assert np.all(out_d["theta"][mask == 0] == 0.0)
+    check_fit_against_exact(wl, w, mask, out_d, [0, 3, 7, B - 1])
+    # a sparse matrix of the same width does not take the dense path (density below the threshold): both settings agree bitwise
+    wl2 = synthetic.make_workload(V, 1500, 0.04, seed=813)
+    w2 = synthetic.bootstrap_weights(wl2.n_obs, 4, seed=3)
+    outs = []
+    for mode in ("0", "auto"):
+        monkeypatch.setenv("TVS_DENSE", "0") if mode == "0" else monkeypatch.delenv("TVS_DENSE")
+        with engine_for(wl2) as eng:
+            eng.set_lanes(w2)
+            outs.append(eng.fit(max_iter=30)["theta"])
+    assert np.array_equal(outs[0], outs[1])
+
+
 def test_fit_with_subset_masks_and_infeasible_lane(gpu):
     V, B = 12, 20
     wl = synthetic.make_workload(V, 800, 0.35, seed=77)

@@ -4,6 +4,8 @@
 #include "tvs_pass2.cuh"
 #include "tvs_newton.cuh"
 
+#include <cublas_v2.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -53,6 +55,7 @@ static void free_csr(Csr& c) {
     if (c.logtab) { cudaFree(c.logtab); c.logtab = nullptr; }
     dev_free(c.slab_ptr); dev_free(c.h_row); dev_free(c.h_val); dev_free(c.h_slot);
     dev_free(c.wide_ptr); if (c.wide_rec) { cudaFree(c.wide_rec); c.wide_rec = nullptr; }
+    dev_free(c.dense);
 }
 static void free_lanes(Lanes& l) {
     dev_free(l.w); dev_free(l.mask); dev_free(l.C); dev_free(l.N); dev_free(l.w16);
@@ -71,6 +74,7 @@ static void free_fit(FitState& f) {
 // ---------------------------------------------------------------------------------- launch geometry
 struct PassPlan {
     int lpt = 1; bool xs = false; int tiles = 0; int splits = 1; size_t smem = 0;
+    bool dense = false;   // two cuBLAS DGEMMs on the dense copy of A + dense_mid_kernel (dense shapes, see launch_dense)
     bool v2 = false;      // pass2_kernel<lpt, BW> (lpt = lanes per thread)
     int v3_warps = 0;     // > 0: pass3_kernel<lpt, v3_warps, BW> (entries staged in shared memory)
 };
@@ -193,6 +197,11 @@ static int plan_one(const tvs_problem* h, int64_t B, PassPlan* out) {
 
 template <bool BW>
 static int make_plan(const tvs_problem* h, int64_t B, PassPlan* out) {
+    if (h->csr.dense != nullptr && env_int("TVS_DENSE", 1) != 0) {
+        *out = PassPlan();
+        out->dense = true; out->tiles = 1; out->splits = 1;
+        return TVS_OK;
+    }
     if (env_int("TVS_PASS_V1", 0) == 0) {
         const int rc2 = make_plan_v2<BW>(h, B, out);
         if (rc2 == TVS_OK || rc2 == TVS_ECUDA) return rc2;       // otherwise: tiles too large for shared memory
@@ -212,8 +221,93 @@ static int make_plan(const tvs_problem* h, int64_t B, PassPlan* out) {
     return rc;
 }
 
+// ---- dense pass: for shapes whose compatibility matrix is dense enough that a full fp64 contraction beats the sparse
+// kernels (BASELINE configs[4]: 4,096 variants at 30 % density; the sparse pass there runs at ~12 % of the fp64 FMA
+// peak because every non-zero gathers its operand from L2, a DGEMM runs near the fp64 tensor peak and wastes 70 %).
+//   P^T [W x R] = X^T [W x V] * A^T [V x R]      (lane-minor arrays are column-major matrices with ld = W)
+//   rr = w / p, ll += w log p                     (dense_mid_kernel, fixed summation order)
+//   T^T [W x V] = RR^T [W x R] * A [R x V]
+__global__ void dense_mid_kernel(double* __restrict__ P, const int32_t* __restrict__ w, const int32_t* __restrict__ done,
+                                 int64_t W, int64_t R, int64_t rows_per_split, double* __restrict__ llpart, int backward) {
+    const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= W) return;
+    const bool live = done == nullptr || done[lane] == 0;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_split, r1 = min(R, r0 + rows_per_split);
+    double ll = 0.0;
+    for (int64_t r = r0; r < r1; ++r) {
+        const int64_t i = r * W + lane;
+        const int32_t wv = w[i];
+        double rr = 0.0;
+        if (live && wv != 0) {
+            const double p = P[i];
+            const double wd = (double)wv;
+            ll = fma(wd, log(p), ll);
+            rr = wd / p;
+        }
+        if (backward) P[i] = rr;
+    }
+    llpart[(int64_t)blockIdx.y * W + lane] = ll;
+}
+
+__global__ void dense_ll_reduce_kernel(const double* __restrict__ part, int S, int64_t W, double* __restrict__ out) {
+    const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= W) return;
+    double s = 0.0;
+    for (int q = 0; q < S; ++q) s += part[(int64_t)q * W + lane];
+    out[lane] = s;
+}
+
+static int launch_dense(tvs_problem* h, const PassArgs& a, bool backward) {
+    const Csr& c = h->csr;
+    const int64_t W = a.B, R = c.R, V = c.V;
+    if (h->cublas == nullptr) {
+        cublasHandle_t hd = nullptr;
+        if (cublasCreate(&hd) != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed"); return TVS_ECUDA; }
+        cublasSetStream(hd, h->stream);
+        cublasSetPointerMode(hd, CUBLAS_POINTER_MODE_HOST);
+        h->cublas = hd;
+    }
+    cublasHandle_t hd = (cublasHandle_t)h->cublas;
+    const int S = (int)std::max<int64_t>(1, std::min<int64_t>(R / 256 + 1, (int64_t)h->sm_count * 8 / ((W + 127) / 128)));
+    const int64_t rows_per_split = (R + S - 1) / S;
+    if (h->dense_p_cap < (size_t)R * (size_t)W) {
+        if (h->dense_p) cudaFree(h->dense_p);
+        h->dense_p = nullptr; h->dense_p_cap = 0;
+        TVS_CUDA(cudaMalloc((void**)&h->dense_p, (size_t)R * (size_t)W * sizeof(double)));
+        h->dense_p_cap = (size_t)R * (size_t)W;
+    }
+    if (h->dense_ll_cap < (size_t)S * (size_t)W) {
+        if (h->dense_ll) cudaFree(h->dense_ll);
+        h->dense_ll = nullptr; h->dense_ll_cap = 0;
+        TVS_CUDA(cudaMalloc((void**)&h->dense_ll, (size_t)S * (size_t)W * sizeof(double)));
+        h->dense_ll_cap = (size_t)S * (size_t)W;
+    }
+    const double one = 1.0, zero = 0.0;
+    cublasStatus_t cs = cublasDgemm(hd, CUBLAS_OP_N, CUBLAS_OP_N, (int)W, (int)R, (int)V, &one, a.x, (int)W, c.dense, (int)V, &zero,
+                                    h->dense_p, (int)W);
+    if (cs != CUBLAS_STATUS_SUCCESS) { set_error("cublasDgemm (p = A x) failed: %d", (int)cs); return TVS_ECUDA; }
+    dense_mid_kernel<<<dim3((unsigned)((W + 127) / 128), (unsigned)S), 128, 0, h->stream>>>(h->dense_p, a.w, a.done, W, R, rows_per_split,
+                                                                                          h->dense_ll, backward ? 1 : 0);
+    dense_ll_reduce_kernel<<<(unsigned)((W + 127) / 128), 128, 0, h->stream>>>(h->dense_ll, S, W, a.llpart);
+    TVS_CUDA(cudaGetLastError());
+    if (backward) {
+        cs = cublasDgemm(hd, CUBLAS_OP_N, CUBLAS_OP_T, (int)W, (int)V, (int)R, &one, h->dense_p, (int)W, c.dense, (int)V, &zero,
+                         a.tpart, (int)W);
+        if (cs != CUBLAS_STATUS_SUCCESS) { set_error("cublasDgemm (t = A^T rr) failed: %d", (int)cs); return TVS_ECUDA; }
+    }
+    return TVS_OK;
+}
+
+__global__ void densify_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double* __restrict__ val,
+                               int64_t R, int64_t V, double* __restrict__ dense) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    for (int32_t k = row_ptr[r]; k < row_ptr[r + 1]; ++k) dense[r * V + col[k]] = val[k];
+}
+
 template <bool BW>
 static int launch_pass(tvs_problem* h, const PassPlan& pl, const PassArgs& a) {
+    if (pl.dense) return launch_dense(h, a, BW);
     dim3 grid(pl.tiles, pl.splits), block(kThreads);
     if (pl.v3_warps == 16) {
         if (pl.lpt == 4) pass3_kernel<4, 16, BW><<<grid, 512, pl.smem, h->stream>>>(a);
@@ -539,6 +633,21 @@ int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, c
         }
     }
 #undef UP_
+    {   // dense copy of A for the DGEMM pass: only where the staged sparse kernels do not apply (their x / t tiles need
+        // V <= ~400) and the matrix is dense enough for a full contraction to win (TVS_DENSE=1 forces, 0 forbids)
+        const int want = env_int("TVS_DENSE", -1);
+        const double density = (double)nnz / ((double)R * (double)V);
+        const double min_density = env_int("TVS_DENSE_MIN_PCT", 12) / 100.0;   // measured crossover ~10 % (profiles/r1_dense_summary.md)
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const bool fits = (double)R * (double)V * 8.0 < 0.25 * (double)free_b;
+        if (want != 0 && fits && nnz > 0 && (want == 1 || (V > 400 && density >= min_density))) {
+            if ((rc = dev_alloc(&c.dense, (size_t)R * (size_t)V)) != TVS_OK) return fail(rc);
+            cudaMemset(c.dense, 0, (size_t)R * (size_t)V * sizeof(double));
+            densify_kernel<<<(unsigned)((R + 127) / 128), 128>>>(c.row_ptr, c.col32, c.fval, R, V, c.dense);
+            if (cudaDeviceSynchronize() != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "densify", __FILE__, __LINE__));
+        }
+    }
     *out = h;
     return TVS_OK;
 }
@@ -548,6 +657,9 @@ int tvs_destroy(tvs_handle h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_fit(h->fs); free_lanes(h->lanes); free_csr(h->csr);
+    if (h->cublas) cublasDestroy((cublasHandle_t)h->cublas);
+    if (h->dense_p) cudaFree(h->dense_p);
+    if (h->dense_ll) cudaFree(h->dense_ll);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evp0) cudaEventDestroy(h->evp0);

@@ -52,6 +52,7 @@ struct Csr {
     void*     wide_rec = nullptr;    // uint2 {row * 128, fp32 bits of the product}
     int       w_HB = 0, w_nblk = 0, w_cap = 0;
     int64_t   h_steps = 0;
+    double*   dense = nullptr;       // [R*V] row-major fp64 copy of A for the DGEMM pass (dense shapes only, see tvs_create)
     double*   invL = nullptr;        // [V] 1/L_v
     double*   Ld = nullptr;          // [V] L_v as double
     int64_t   n_ccol = 0;
@@ -119,4 +120,8 @@ struct tvs_problem {
     tvs::FitState fs;
     tvs_fit_stats stats{};
     bool lanes_set = false;
+    // dense (DGEMM) pass: cuBLAS handle bound to `stream`, p / w/p matrix [R x width], per-split log-likelihood partials
+    void* cublas = nullptr;
+    double* dense_p = nullptr; size_t dense_p_cap = 0;
+    double* dense_ll = nullptr; size_t dense_ll_cap = 0;
 };
