@@ -96,6 +96,57 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ------------------------------------------------------------------------------------------ model selection
+def selection_rate(device, n_rep=8):
+    """SURVEY.md 8d asks for replicates/s too (one replicate = one complete backward model selection): BASELINE
+    configs[2] -- 256 candidate variants (32 carry reads) x 50k read paths -- for `n_rep` bootstrap replicates advanced
+    in lock step through the public classes (array-form fitters, traversome_b200.bootstrap.run_selections)."""
+    from loguru import logger
+    from traversome_b200 import bootstrap, synthetic
+    from traversome_b200.ModelFitMaxLike import ModelFitMaxLike
+    from traversome_b200.lanes import LaneContext
+    logger.disable("traversome_b200")
+    wl = synthetic.make_config("cfg3")
+    W = synthetic.bootstrap_weights(wl.n_obs, n_rep, seed=3, keep_lane0=True)
+    ctx = LaneContext(wl.V, wl.L, device=device)
+    pattern = np.zeros((wl.R, wl.V), dtype=bool)
+    for r in range(wl.R):
+        lo, hi = int(wl.row_ptr[r]), int(wl.row_ptr[r + 1])
+        ctx.matrix.row_index_distinct(dict(zip(wl.col[lo:hi].tolist(), wl.val[lo:hi].tolist())))
+        pattern[r, wl.col[lo:hi]] = True
+    groups = {v: [v] for v in range(wl.V)}
+    ident = {v: v for v in range(wl.V)}
+    fitters = []
+    for b in range(n_rep):
+        col = ctx.add_weights(W[:, b])
+        f = ModelFitMaxLike.from_lane(ctx, (col, 0.0, int(W[:, b].sum())), pattern, np.nonzero(W[:, b])[0], groups, ident,
+                                      bootstrap_mode="BS%d" % (b + 1))
+        f._shuffle = lambda x: None
+        fitters.append(f)
+    ctx.engine()
+    solver = [0.0]
+    inner = ctx.fit
+
+    def timed(requests):
+        t = time.perf_counter()
+        out = inner(requests)
+        solver[0] += time.perf_counter() - t
+        return out
+    ctx.fit = timed
+    t0 = time.perf_counter()
+    res = bootstrap.run_selections(fitters, criterion="BIC")
+    wall = time.perf_counter() - t0
+    sizes = [len(r[0]) for r in res if not isinstance(r, Exception)]
+    out = {"workload": "cfg3: backward selection (BIC) from %d candidate variants x %d read paths, %d bootstrap replicates in "
+                       "lock step" % (wl.V, wl.R, n_rep),
+           "replicates_per_s": n_rep / wall, "lane_fits_per_s": ctx.n_lanes_fitted / wall, "lanes": ctx.n_lanes_fitted,
+           "batches": ctx.n_batches, "wall_s": wall, "solver_s": solver[0],
+           "selected_variants_median": float(np.median(sizes)) if sizes else None,
+           "failures": sum(isinstance(r, Exception) for r in res)}
+    ctx.close()
+    return out
+
+
 # ------------------------------------------------------------------------------------------ reference arm
 def _cpu_fit_one(args):
     """One lane through the restated reference driver (oracle/slsqp_port.py): returns (seconds, loglike)."""
@@ -183,6 +234,7 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-selection", action="store_true", help="skip the model-selection figure (replicates/s)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -341,6 +393,11 @@ def main():
                           "serial), %.1f s of CPU work" % (n_sample, B, wall_cpu),
                 "note": "restated reference driver (scipy SLSQP multistart) + numpy closure of the reference objective; "
                         "omits the reference's symengine build + LLVM JIT, i.e. faster than the true reference"}
+        if world == 1 and not args.no_selection:
+            try:
+                line["selection"] = selection_rate(local_rank)
+            except Exception as e:                       # a secondary figure must never cost the headline line
+                line["selection"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
