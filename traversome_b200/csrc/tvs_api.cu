@@ -50,7 +50,6 @@ static void dev_free(T*& p) {
 static void free_csr(Csr& c) {
     dev_free(c.row_ptr); dev_free(c.ent); dev_free(c.chunk_row0); dev_free(c.ccol_ptr); dev_free(c.ccol_id);
     dev_free(c.ccol_start); dev_free(c.cent); dev_free(c.invL); dev_free(c.Ld);
-    dev_free(c.col32); dev_free(c.fval); dev_free(c.crow32); dev_free(c.cfval);
     if (c.desc) { cudaFree(c.desc); c.desc = nullptr; }
     if (c.logtab) { cudaFree(c.logtab); c.logtab = nullptr; }
     dev_free(c.slab_ptr); dev_free(c.h_row); dev_free(c.h_val); dev_free(c.h_slot);
@@ -124,7 +123,7 @@ static int plan_v2(const tvs_problem* h, int64_t B, PassPlan* out) {
     return TVS_OK;
 }
 
-// pass3_kernel: pass2 + cp.async staging of each chunk's entries (needs max_chunk_nnz * 36 bytes more).
+// pass3_kernel: pass2 + cp.async staging of each chunk's entries (needs max_chunk_nnz * 12 bytes more).
 template <int K, int NW, bool BW>
 static int plan_v3(const tvs_problem* h, int64_t B, PassPlan* out) {
     const int LT = 32 * K;
@@ -298,11 +297,11 @@ static int launch_dense(tvs_problem* h, const PassArgs& a, bool backward) {
     return TVS_OK;
 }
 
-__global__ void densify_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const double* __restrict__ val,
-                               int64_t R, int64_t V, double* __restrict__ dense) {
+__global__ void densify_kernel(const int32_t* __restrict__ row_ptr, const uint32_t* __restrict__ ent, int64_t R, int64_t V,
+                               double* __restrict__ dense) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
-    for (int32_t k = row_ptr[r]; k < row_ptr[r + 1]; ++k) dense[r * V + col[k]] = val[k];
+    for (int32_t k = row_ptr[r]; k < row_ptr[r + 1]; ++k) dense[r * V + (ent[k] & 0xffffu)] = (double)(ent[k] >> 16);
 }
 
 template <bool BW>
@@ -345,7 +344,7 @@ static PassArgs base_args(const tvs_problem* h) {
     a.row_ptr = c.row_ptr; a.ent = c.ent; a.chunk_row0 = c.chunk_row0; a.ccol_ptr = c.ccol_ptr; a.ccol_id = c.ccol_id;
     a.ccol_start = c.ccol_start; a.cent = c.cent; a.w = h->lanes.w; a.B = h->lanes.B; a.V = (int)c.V;
     a.n_chunks = c.n_chunks; a.rows_per_chunk = c.rows_per_chunk;
-    a.col32 = c.col32; a.fval = c.fval; a.crow32 = c.crow32; a.cfval = c.cfval; a.stage_cap = std::max(c.max_chunk_nnz, 1);
+    a.stage_cap = std::max(c.max_chunk_nnz, 1);
     a.desc = (const ChunkDesc*)c.desc; a.logc = make_log_coef();
     a.logtab = env_int("TVS_LOG_TABLE", 1) ? (const double2*)c.logtab : nullptr;
     return a;
@@ -466,7 +465,16 @@ int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, c
 
     Csr& c = h->csr;
     c.R = R; c.V = V; c.nnz = nnz;
-    int rpc = env_int("TVS_RC", 64);
+    // rows per chunk: 80 when the widest staged kernel (4 lanes per thread, 16 warps) still fits shared memory with it
+    // (cfg2: 139.6 us per full-width pass against 143.7 us with 64; 96 no longer fits and falls back to 2 lanes per
+    // thread, 166 us), else 64
+    int rpc = env_int("TVS_RC", 0);
+    if (rpc <= 0) {
+        rpc = 64;
+        int64_t cap80 = 1;
+        for (int64_t r0 = 0; r0 < R; r0 += 80) cap80 = std::max<int64_t>(cap80, row_ptr[std::min<int64_t>(R, r0 + 80)] - row_ptr[r0]);
+        if (pass3_layout((int)V, 128, 80, (int)cap80, true, 16).total <= 225 * 1024) rpc = 80;
+    }
     rpc = std::max(kWarps2, std::min(rpc, 4096));
     c.rows_per_chunk = rpc;
     c.n_chunks = (int)((R + rpc - 1) / rpc);
@@ -491,12 +499,6 @@ int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, c
     }
     chunk_row0[c.n_chunks] = (int32_t)R;
     ccol_ptr[c.n_chunks] = (int32_t)ccol_id.size();
-    std::vector<int32_t> col32v((size_t)std::max<int64_t>(nnz, 1)), crow32v((size_t)std::max<int64_t>(nnz, 1));
-    std::vector<double> fvalv((size_t)std::max<int64_t>(nnz, 1)), cfvalv((size_t)std::max<int64_t>(nnz, 1));
-    for (int64_t k = 0; k < nnz; ++k) {
-        col32v[k] = col[k]; fvalv[k] = (double)val[k];
-        crow32v[k] = (int32_t)(cent[k] & 0xffffu); cfvalv[k] = (double)(cent[k] >> 16);
-    }
     c.max_chunk_nnz = 0;
     for (int ch = 0; ch < c.n_chunks; ++ch) {
         const int64_t r0 = (int64_t)ch * rpc, r1 = std::min<int64_t>(R, r0 + rpc);
@@ -543,7 +545,6 @@ int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, c
         if (cudaMemcpy(dd, descv.data(), descv.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice) != cudaSuccess)
             return fail(cuda_fail(cudaGetLastError(), "upload desc", __FILE__, __LINE__));
     }
-    UP_(col32, col32v, int32_t) UP_(fval, fvalv, double) UP_(crow32, crow32v, int32_t) UP_(cfval, cfvalv, double)
     UP_(ent, ent, uint32_t) UP_(cent, cent, uint32_t) UP_(chunk_row0, chunk_row0, int32_t) UP_(ccol_ptr, ccol_ptr, int32_t)
     if (ccol_id.empty()) ccol_id.push_back(0);
     UP_(ccol_id, ccol_id, int32_t) UP_(ccol_start, ccol_start, int32_t) UP_(invL, invL, double) UP_(Ld, Ld, double)
@@ -644,7 +645,7 @@ int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, c
         if (want != 0 && fits && nnz > 0 && (want == 1 || (V > 400 && density >= min_density))) {
             if ((rc = dev_alloc(&c.dense, (size_t)R * (size_t)V)) != TVS_OK) return fail(rc);
             cudaMemset(c.dense, 0, (size_t)R * (size_t)V * sizeof(double));
-            densify_kernel<<<(unsigned)((R + 127) / 128), 128>>>(c.row_ptr, c.col32, c.fval, R, V, c.dense);
+            densify_kernel<<<(unsigned)((R + 127) / 128), 128>>>(c.row_ptr, c.ent, R, V, c.dense);
             if (cudaDeviceSynchronize() != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "densify", __FILE__, __LINE__));
         }
     }

@@ -35,10 +35,6 @@ struct Csr {
     int32_t*  ccol_id = nullptr;     // [n_ccol] column id of each non-empty (chunk, column)
     int32_t*  ccol_start = nullptr;  // [n_ccol+1] -> index into cent
     uint32_t* cent = nullptr;        // [nnz]  local_row | val<<16, column-major within chunk
-    int32_t*  col32 = nullptr;       // [nnz]  column, row-major            (decoded copies for pass3_kernel)
-    double*   fval = nullptr;        // [nnz]  count as double, row-major
-    int32_t*  crow32 = nullptr;      // [nnz]  chunk-local row, column-major within chunk
-    double*   cfval = nullptr;       // [nnz]  count as double, column-major within chunk
     int       max_chunk_nnz = 0;     // largest number of entries in one chunk
     void*     desc = nullptr;        // [n_chunks] ChunkDesc (tvs_kernels.cuh)
     void*     logtab = nullptr;      // [128] double2 {c_i, -log c_i} (table_log_pos)

@@ -31,8 +31,7 @@ struct PassArgs {
     const int32_t* w; const double* x; const int32_t* done;
     double* tpart; double* llpart;
     int64_t B; int V; int n_chunks; int rows_per_chunk;
-    // decoded entries (pass3_kernel): column / chunk-local row as int32, count as double
-    const int32_t* col32; const double* fval; const int32_t* crow32; const double* cfval; int stage_cap;
+    int stage_cap;       // capacity (entries) of the shared-memory staging buffers of pass3_kernel
     const ChunkDesc* desc;
     LogCoef logc;
     double* cr;          // optional [R*B]: w / p^2 per (row, lane) for the Newton phase's Hessian (pass3_kernel only)

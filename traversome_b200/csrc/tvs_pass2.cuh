@@ -292,12 +292,13 @@ __global__ void __launch_bounds__(kThreads2, 1) pass2_kernel(const PassArgs a) {
 // ------------------------------------------------------------------------------------------------
 // pass3_kernel: pass2 + the CSR entries of each chunk staged in shared memory by cp.async
 // (profiles/r1_v2_summary.md: pass2 stalls on the dependent LDG(entry) -> LDS(x) -> DFMA chain).
-//   * entries are stored decoded in global memory (column / local row as int32, count as double), so
-//     the inner loops are  LDS.32 (broadcast) + LDS.64 (broadcast) + K/2 x LDS.128 + K x DFMA;
+//   * entries stay packed (column or chunk-local row | count << 16, one 32-bit word): the inner loops are
+//     LDS.32 (broadcast) + unpack (the count goes into the mantissa of 2^52, one DADD: no XU conversion) +
+//     K/2 x LDS.128 + K x DFMA.  One broadcast read per non-zero instead of two took 3 % off the pass;
 //   * the row-major entries of the NEXT chunk and the column-major entries of THIS chunk are in flight
 //     while phase 1 runs (double buffer / single buffer);
 //   * the weights of a warp's next row are loaded one row ahead (the only HBM stream of the pass).
-// shared: x_s[V][LT] t_s[V][LT] rr_s[RC][LT] | f1[2][cap] f2[cap] (double) | c1[2][cap] c2[cap] rp[2][RC+1]
+// shared: x_s[V][LT] t_s[V][LT] rr_s[RC][LT] | c1[2][cap] c2[cap] (packed entries) rp[2][RC+1]
 //         cs[V+1] cid[V] (int32)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
@@ -312,7 +313,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 struct Pass3Smem {            // byte offsets from the start of dynamic shared memory
-    size_t x, t, rr, f1, f2, c1, c2, rp, cs, cid, tab, total;
+    size_t x, t, rr, c1, c2, rp, cs, cid, tab, total;
 };
 __host__ __device__ inline Pass3Smem pass3_layout(int V, int LT, int RC, int cap, bool backward, int nw) {
     Pass3Smem L;
@@ -320,8 +321,6 @@ __host__ __device__ inline Pass3Smem pass3_layout(int V, int LT, int RC, int cap
     L.x = o; o += (size_t)V * LT * 8;
     L.t = o; o += backward ? (size_t)V * LT * 8 : 0;
     L.rr = o; o += (size_t)(RC > nw ? RC : nw) * LT * 8;
-    L.f1 = o; o += (size_t)2 * cap * 8;
-    L.f2 = o; o += backward ? (size_t)cap * 8 : 0;
     L.c1 = o; o += (size_t)2 * cap * 4;
     L.c2 = o; o += backward ? (size_t)cap * 4 : 0;
     L.rp = o; o += (size_t)2 * (RC + 1) * 4;
@@ -359,10 +358,8 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
     double* x_s = reinterpret_cast<double*>(smem3 + L.x);
     double* t_s = reinterpret_cast<double*>(smem3 + L.t);
     double* rr_s = reinterpret_cast<double*>(smem3 + L.rr);
-    double* f1_s = reinterpret_cast<double*>(smem3 + L.f1);
-    double* f2_s = reinterpret_cast<double*>(smem3 + L.f2);
-    int* c1_s = reinterpret_cast<int*>(smem3 + L.c1);
-    int* c2_s = reinterpret_cast<int*>(smem3 + L.c2);
+    uint32_t* c1_s = reinterpret_cast<uint32_t*>(smem3 + L.c1);
+    uint32_t* c2_s = reinterpret_cast<uint32_t*>(smem3 + L.c2);
     int* rp_s = reinterpret_cast<int*>(smem3 + L.rp);
     int* cs_s = reinterpret_cast<int*>(smem3 + L.cs);
     int* cid_s = reinterpret_cast<int*>(smem3 + L.cid);
@@ -374,16 +371,14 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
     // row-major entries + row pointers of a chunk -> buffer `buf`
     auto stage_rows = [&](const ChunkDesc& d, int buf) {
         for (int i = threadIdx.x; i < d.nent; i += NT) {
-            cp_async8(f1_s + (size_t)buf * cap + i, a.fval + d.e0 + i);
-            cp_async4(c1_s + (size_t)buf * cap + i, a.col32 + d.e0 + i);
+            cp_async4(c1_s + (size_t)buf * cap + i, a.ent + d.e0 + i);
         }
         for (int i = threadIdx.x; i <= d.nrows; i += NT) cp_async4(rp_s + buf * (RC + 1) + i, a.row_ptr + d.row0 + i);
     };
     // column-major entries + column starts / ids of a chunk
     auto stage_cols = [&](const ChunkDesc& d) {
         for (int i = threadIdx.x; i < d.ncent; i += NT) {
-            cp_async8(f2_s + i, a.cfval + d.ce0 + i);
-            cp_async4(c2_s + i, a.crow32 + d.ce0 + i);
+            cp_async4(c2_s + i, a.cent + d.ce0 + i);
         }
         for (int i = threadIdx.x; i <= d.ncol; i += NT) cp_async4(cs_s + i, a.ccol_start + d.c0 + i);
         for (int i = threadIdx.x; i < d.ncol; i += NT) cp_async4(cid_s + i, a.ccol_id + d.c0 + i);
@@ -425,8 +420,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
         if (c + S < a.n_chunks) stage_rows(nxt, buf ^ 1);
         cp_async_commit();
         // ---------------- phase 1: p = A x over the rows of the chunk
-        const double* f1 = f1_s + (size_t)buf * cap;
-        const int* c1 = c1_s + (size_t)buf * cap;
+        const uint32_t* c1 = c1_s + (size_t)buf * cap;
         const int* rp = rp_s + buf * (RC + 1);
         const int e0 = rp[0];
         WVec<K> wnext;
@@ -447,9 +441,11 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
             for (int j = 0; j < K; ++j) p[j] = 0.0;
 #pragma unroll 4
             for (int k = k0; k < k1; ++k) {
-                const double f = f1[k];
+                const unsigned e = c1[k];                            // column | count << 16
+                const double f = u31_to_double((int)(e >> 16));
+                const int cidx = (int)(e & 0xffffu);
                 double xv[K];
-                lds_lanes<K>(x_s + c1[k] * LT, t, xv);
+                lds_lanes<K>(x_s + cidx * LT, t, xv);
 #pragma unroll
                 for (int j = 0; j < K; ++j) p[j] = fma(f, xv[j], p[j]);
             }
@@ -509,9 +505,11 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
                 lds_lanes<K>(t_s + v * LT, t, acc);
 #pragma unroll 4
                 for (int k = k0; k < k1; ++k) {
-                    const double f = f2_s[k];
+                    const unsigned e = c2_s[k];                      // chunk-local row | count << 16
+                    const double f = u31_to_double((int)(e >> 16));
+                    const int ridx = (int)(e & 0xffffu);
                     double rv[K];
-                    lds_lanes<K>(rr_s + c2_s[k] * LT, t, rv);
+                    lds_lanes<K>(rr_s + ridx * LT, t, rv);
 #pragma unroll
                     for (int j = 0; j < K; ++j) acc[j] = fma(f, rv[j], acc[j]);
                 }
