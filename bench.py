@@ -282,10 +282,18 @@ def main():
             "iters": torch.empty(B, dtype=torch.int32, pin_memory=True).numpy(),
             "status": torch.empty(B, dtype=torch.int32, pin_memory=True).numpy()}
 
-    # ---- warm-up
+    # ---- warm-up: both timed paths (resident weights; weights uploaded from pinned host memory)
     for _ in range(args.warmup):
         flush.zero_()
         eng.fit(out=outs)
+    for _ in range(args.warmup):
+        flush.zero_()
+        eng.set_lanes(w_host, B=B)
+        eng.fit(out=outs)
+    eng.resample(B, wl.n_obs, seed=2024 + 7919 * rank, keep_lane0=(rank == 0))      # back to the device-resident lanes
+    import gc
+    gc.collect()
+    gc.disable()                                  # no collector pauses inside the timed regions
     # ---- timed: device-resident weights
     sampler = ClockSampler(range(world) if rank == 0 else ())     # single node: local ranks = GPU indices
     sampler.start()
