@@ -373,8 +373,8 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "pass3_kernel (fused p = A x, w/p, w log p, t = A^T(w/p))",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                         "traffic": 77.9e6,
-                         "traffic_note": "dram read+write of ONE full-width (1000-lane) launch, ncu --set full (profiles/r1_final_summary.md); "
+                         "traffic": 76.2e6,
+                         "traffic_note": "dram read+write of ONE full-width (1000-lane) launch, ncu --set full (profiles/r1_end_pass3_full.csv); "
                                          "algorithmic bytes of that launch: 74.3e6",
                          "avg_launch_us": 1e3 * prof["pass_ms"] / max(prof["passes"], 1), "launches_profiled": prof["passes"],
                          "pass_share_of_step": prof["pass_ms"] / prof["total_ms"] if prof["total_ms"] > 0 else None,
