@@ -28,6 +28,9 @@
  *   - a handle owns one CUDA stream on one device; calls on one handle are serialised by the
  *     caller; different handles are independent (re-entrant per handle).
  *   - there is NO CPU fallback: without a usable CUDA device tvs_create fails with TVS_ECUDA.
+ *   - shapes with more than ~400 variants of which at least 12 % of A is non-zero keep a dense fp64 copy of A
+ *     (R*V*8 bytes) and run the likelihood pass as two cuBLAS DGEMMs (the library links libcublas); TVS_DENSE=0
+ *     in the environment forbids that, TVS_DENSE=1 forces it.
  */
 #ifndef TVS_H_
 #define TVS_H_
