@@ -13,6 +13,7 @@ row order of ``all_sub_paths``).  Integer work: results are identical to the ref
 call ``graph.detect_palindromic_repeats()`` first on a reference graph, Assembly.py:613-641).
 """
 from collections import OrderedDict
+from itertools import chain
 
 import numpy as np
 
@@ -33,6 +34,10 @@ class GraphTables(object):
         self.palindromic = set(pal or ())
         self.names = list(graph.vertex_info)
         self.id_of = {n: i for i, n in enumerate(self.names)}
+        self._tok_of = {}
+        for i, n in enumerate(self.names):
+            self._tok_of[(n, True)] = 2 * i + 1
+            self._tok_of[(n, False)] = 2 * i
         n = len(self.names)
         self.length = np.fromiter((int(graph.vertex_info[v].len) for v in self.names), dtype=np.int64, count=n)
         self.is_pal = np.zeros(n, dtype=bool)
@@ -59,9 +64,8 @@ class GraphTables(object):
         """(ptr int64[n+1], raw tokens int32[total]) of a list of paths."""
         ptr = np.zeros(len(paths) + 1, dtype=np.int64)
         np.cumsum([len(p) for p in paths], out=ptr[1:])
-        id_of = self.id_of
-        tok = np.fromiter((2 * id_of[n] + (1 if e else 0) for p in paths for n, e in p), dtype=np.int32,
-                          count=int(ptr[-1]))
+        # one C-level pass: (name, strand) tuples are looked up whole, no per-token Python bytecode
+        tok = np.fromiter(map(self._tok_of.__getitem__, chain.from_iterable(paths)), dtype=np.int32, count=int(ptr[-1]))
         return ptr, tok
 
     def corrected(self, tok):
