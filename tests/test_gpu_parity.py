@@ -146,6 +146,23 @@ def test_dense_contraction_pass_equals_sparse_pass_and_exact_optimum(gpu, monkey
     assert np.abs(out_s["theta"] - out_d["theta"]).max() < 1e-6
     assert np.all(out_d["theta"][mask == 0] == 0.0)
     check_fit_against_exact(wl, w, mask, out_d, [0, 3, 7, B - 1])
+    # a single lane, and a lane whose subset leaves a read path uncovered, on the dense path
+    monkeypatch.delenv("TVS_DENSE", raising=False)
+    A = wl.dense()
+    keep = np.zeros(V, bool)
+    keep[:3] = True
+    uncovered = bool(np.any((A[:, keep].sum(1) == 0) & (w[:, 0] > 0)))
+    assert uncovered, "three variants should not cover every read path of this fixture"
+    m2 = np.ones((V, 2), np.uint8)
+    m2[:, 1] = keep
+    with engine_for(wl) as eng:
+        eng.set_lanes(w[:, :2], mask=m2)
+        o2 = eng.fit()
+        assert o2["status"][0] == _cabi.CONVERGED and o2["status"][1] == _cabi.INFEASIBLE and np.isinf(o2["loglike"][1])
+        eng.set_lanes(w[:, :1])
+        o1 = eng.fit()
+    assert o1["status"][0] == _cabi.CONVERGED
+    assert np.abs(o1["theta"][:, 0] - o2["theta"][:, 0]).max() < 1e-7
     # a sparse matrix of the same width does not take the dense path (density below the threshold): both settings agree bitwise
     wl2 = synthetic.make_workload(V, 1500, 0.04, seed=813)
     w2 = synthetic.bootstrap_weights(wl2.n_obs, 4, seed=3)
