@@ -3,6 +3,7 @@ flow of BASELINE configs[0]) with this package's classes swapped in exactly as I
 
     traversome.traversome.ModelFitMaxLike          <- traversome_b200.ModelFitMaxLike.ModelFitMaxLike
     traversome.traversome.VariantSubPathsGenerator <- traversome_b200.subpaths.VariantSubPathsGenerator
+    Traversome.generate_read_paths                 <- traversome_b200.readpaths.generate_read_paths
 
 There is no GPU here, so the two device calls are replaced by their test stand-ins (the oracle-backed engine of
 tests/helpers.py and the contract emulation of tests/subpath_helpers.py); everything above the C ABI -- constructor
@@ -55,6 +56,17 @@ def test_reference_thorough_flow_with_the_swapped_classes(plastome, tmp_path, mo
             created["generators"] += 1
             super().__init__(*a, **k)
 
+    from traversome_b200 import readpaths
+    created["read_path_calls"] = 0
+
+    def generate_read_paths(self, graph_alignment, filter_by_graph=True, min_alignment_counts=1):
+        created["read_path_calls"] += 1
+        assert not self.read_paths                                         # the reference starts from an empty table
+        table = readpaths.generate_read_paths(self.graph, graph_alignment.raw_records, filter_by_graph=filter_by_graph,
+                                              min_alignment_counts=min_alignment_counts)
+        readpaths.install_on(self, table)
+
+    monkeypatch.setattr(tvm.Traversome, "generate_read_paths", generate_read_paths)
     monkeypatch.setattr(lanes._cabi, "Engine", OracleEngine)               # no GPU in this container
     monkeypatch.setattr(tvm, "ModelFitMaxLike", CountingMirror)
     monkeypatch.setattr(tvm, "VariantSubPathsGenerator", CountingGenerator)
@@ -80,6 +92,7 @@ def test_reference_thorough_flow_with_the_swapped_classes(plastome, tmp_path, mo
         logger.remove()
 
     assert created["generators"] == 1 and created["fitters"] >= 101        # full data + 100 replicates
+    assert created["read_path_calls"] >= 1
     # what the reference's own objects hold afterwards
     assert [int(s) for s in trv.variant_sizes] == plastome["variant_sizes"]
     assert [[int(k), int(v)] for k, v in trv.be_unidentifiable_to.items()] == plastome["be_unidentifiable_to"]
