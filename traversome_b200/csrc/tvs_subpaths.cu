@@ -3,11 +3,16 @@
 // Replaces VariantSubPathsGenerator.gen_subpaths (traversome/utils.py:416-501): one thread per (variant, start
 // position) grows the window contig by contig, keeps a running 64-bit hash of the tokens, and looks every prefix up
 // in an open-addressing table of the read paths' key sequences (exact token comparison on a tag match, so hash
-// collisions cannot change a count).  Hits go to a dense variant-major [V x R] pair of arrays with integer atomics
-// (add for the count, min for the rank of the first hit): order-independent, hence deterministic.  Two coalesced
-// sweeps then turn the dense arrays into the CSR that tvs_create takes.
+// collisions cannot change a count).  Every hit becomes one record {(read path, variant), rank of the window in the
+// reference's enumeration order}: a first sweep counts the hits, a second writes them; the records are radix-sorted by
+// (read path, variant) (cub::DeviceRadixSort) and each run is reduced to (occurrences, smallest rank).  The result is
+// the CSR that tvs_create takes, independent of the order in which threads found the hits.  Memory is proportional to
+// the number of hits, not to variants x read paths (the first version kept a dense [V x R] scratch: 3.3 GB and 80 % of
+// the device time at 2,048 x 200k, and out of reach at 10^5 x 10^5).
 #include "tvs_internal.h"
 #include "../../include/tvs_subpaths.h"
+
+#include <cub/cub.cuh>
 
 #include <algorithm>
 #include <cstdio>
@@ -46,8 +51,9 @@ struct SubpathArgs {
     uint64_t* tags;                    // [cap]
     int32_t* slots;                    // [cap] key index
     uint64_t cap_mask;
-    int32_t* cnt;                      // [V x R]
-    uint32_t* first;                   // [V x R]
+    unsigned long long* n_hits;        // [1] number of hits (count sweep) / write cursor (emit sweep)
+    uint64_t* hit_key;                 // [hits] read path << 32 | variant   (null in the count sweep)
+    uint32_t* hit_rank;                // [hits] start * rank_stride + (rank_stride - 1 - length)
     unsigned long long* n_windows;     // [1]
     int* max_window;                   // [1]
     int* overflow;                     // [1]
@@ -79,9 +85,11 @@ __global__ void sp_insert_kernel(SubpathArgs a) {
 
 // One thread per (variant, start): grows the window (utils.py:441-457 circular / :471-486 linear) and looks every
 // prefix up (utils.py:459-470 / :488-498).
+template <bool EMIT>
 __global__ void sp_window_kernel(SubpathArgs a) {
     int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= a.n_starts) return;
+    unsigned long long my_hits = 0;
     const int64_t v = variant_of(a.var_ptr, a.n_variants, pos);
     const int64_t base = a.var_ptr[v];
     const int64_t n = a.var_ptr[v + 1] - base;
@@ -112,9 +120,11 @@ __global__ void sp_window_kernel(SubpathArgs a) {
                         if (++q == n) q = 0;
                     }
                     if (same) {
-                        const int64_t cell = v * a.n_rows + row;
-                        atomicAdd(&a.cnt[cell], 1);
-                        atomicMin(&a.first[cell], (uint32_t)(start * a.rank_stride + (a.rank_stride - 1 - len)));
+                        if (EMIT) {
+                            const unsigned long long at = atomicAdd(a.n_hits, 1ull);
+                            a.hit_key[at] = ((uint64_t)(uint32_t)row << 32) | (uint64_t)(uint32_t)v;
+                            a.hit_rank[at] = (uint32_t)(start * a.rank_stride + (a.rank_stride - 1 - len));
+                        } else ++my_hits;
                         break;
                     }
                 }
@@ -133,6 +143,7 @@ __global__ void sp_window_kernel(SubpathArgs a) {
         ++len;
         h = hash_step(h, a.var_tok[base + j]);
     }
+    if (!EMIT && my_hits) atomicAdd(a.n_hits, my_hits);
 }
 
 // Statistics pre-pass: longest window over all starts (sizes the 32-bit rank) and the number of windows.
@@ -183,88 +194,27 @@ __global__ void sp_stats_kernel(SubpathArgs a) {
     }
 }
 
-// dense [V x R] -> per-row non-zero counts; thread per read path, coalesced over r
-__global__ void sp_row_nnz_kernel(const int32_t* __restrict__ cnt, int64_t V, int64_t R, int64_t* __restrict__ row_nnz) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    int64_t n = 0;
-    for (int64_t v = 0; v < V; ++v) n += cnt[v * R + r] != 0;
-    row_nnz[r] = n;
+// sorted hit records -> run heads: head[i] = 1 where a new (read path, variant) pair starts
+__global__ void sp_heads_kernel(const uint64_t* __restrict__ key, int64_t n, int32_t* __restrict__ head) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) head[i] = (i == 0 || key[i] != key[i - 1]) ? 1 : 0;
 }
 
-// exclusive scan of row_nnz into row_ptr[R+1] by ONE CTA of 1024 threads, 8 consecutive items per thread and round
-// (R is at most a few 10^5..10^6: a few dozen rounds)
-constexpr int kScanItems = 8;
-__global__ void sp_scan_kernel(const int64_t* __restrict__ row_nnz, int64_t R, int64_t* __restrict__ row_ptr) {
-    __shared__ int64_t s_warp[32];
-    __shared__ int64_t s_carry;
-    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    if (t == 0) s_carry = 0;
-    __syncthreads();
-    const int64_t tile = (int64_t)blockDim.x * kScanItems;
-    for (int64_t r0 = 0; r0 < R; r0 += tile) {
-        const int64_t base = r0 + (int64_t)t * kScanItems;
-        int64_t x[kScanItems];
-        int64_t sum = 0;
-#pragma unroll
-        for (int i = 0; i < kScanItems; ++i) {
-            x[i] = base + i < R ? row_nnz[base + i] : 0;
-            sum += x[i];
-        }
-        int64_t incl = sum;
-        for (int o = 1; o < 32; o <<= 1) {
-            int64_t y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
-        }
-        if (lane == 31) s_warp[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            int64_t w = s_warp[lane];
-            for (int o = 1; o < 32; o <<= 1) {
-                int64_t y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += y;
-            }
-            s_warp[lane] = w;                       // inclusive over warps
-        }
-        __syncthreads();
-        int64_t run = s_carry + (wid ? s_warp[wid - 1] : 0) + incl - sum;
-#pragma unroll
-        for (int i = 0; i < kScanItems; ++i) {
-            if (base + i < R) row_ptr[base + i] = run;
-            run += x[i];
-        }
-        __syncthreads();
-        if (t == blockDim.x - 1) s_carry = run;
-        __syncthreads();
-    }
-    if (t == 0) row_ptr[R] = s_carry;
-}
-
-// dense -> CSR entries; thread per read path, loads batched 8 variants at a time so that the sweep is bandwidth-bound
-__global__ void sp_fill_kernel(const int32_t* __restrict__ cnt, const uint32_t* __restrict__ first, int64_t V, int64_t R,
-                               const int64_t* __restrict__ row_ptr, int32_t* __restrict__ col, int32_t* __restrict__ val,
-                               int64_t* __restrict__ rank) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    int64_t k = row_ptr[r];
-    if (row_ptr[r + 1] == k) return;                    // read path no variant contains
-    for (int64_t v0 = 0; v0 < V; v0 += 8) {
-        int32_t c[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) c[i] = v0 + i < V ? cnt[(v0 + i) * R + r] : 0;
-        uint32_t f[8];                                    // predicated loads, issued together (not one miss per hit)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = c[i] != 0 ? first[(v0 + i) * R + r] : 0u;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (c[i] != 0) {
-                col[k] = (int32_t)(v0 + i);
-                val[k] = c[i];
-                rank[k] = (int64_t)f[i];
-                ++k;
-            }
-        }
-    }
+// one thread per run head: occurrences = run length, first = smallest rank of the run; also the per-row entry counts
+__global__ void sp_runs_kernel(const uint64_t* __restrict__ key, const uint32_t* __restrict__ rank, const int32_t* __restrict__ head,
+                               const int32_t* __restrict__ pos, int64_t n, int32_t* __restrict__ col, int32_t* __restrict__ val,
+                               int64_t* __restrict__ first, unsigned long long* __restrict__ row_nnz) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || head[i] == 0) return;
+    const uint64_t k = key[i];
+    uint32_t best = rank[i];
+    int32_t c = 1;
+    for (int64_t j = i + 1; j < n && key[j] == k; ++j) { best = min(best, rank[j]); ++c; }
+    const int32_t o = pos[i];
+    col[o] = (int32_t)(uint32_t)(k & 0xffffffffull);
+    val[o] = c;
+    first[o] = (int64_t)best;
+    atomicAdd(&row_nnz[k >> 32], 1ull);
 }
 
 template <class T>
@@ -294,14 +244,17 @@ struct Scratch {
     int64_t* var_ptr = nullptr; int32_t* var_tok = nullptr; int32_t* var_step = nullptr; uint8_t* var_circ = nullptr;
     int64_t* key_ptr = nullptr; int32_t* key_tok = nullptr; int32_t* key_row_circ = nullptr; int32_t* key_row_lin = nullptr;
     uint64_t* tags = nullptr; int32_t* slots = nullptr;
-    int32_t* cnt = nullptr; uint32_t* first = nullptr;
+    unsigned long long* n_hits = nullptr;
+    uint64_t* key_a = nullptr; uint64_t* key_b = nullptr; uint32_t* rank_a = nullptr; uint32_t* rank_b = nullptr;
+    int32_t* head = nullptr; int32_t* pos = nullptr; void* cub_tmp = nullptr;
     unsigned long long* n_windows = nullptr; int* max_window = nullptr; int* overflow = nullptr;
-    int64_t* row_nnz = nullptr;
+    unsigned long long* row_nnz = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     ~Scratch() {
         cudaFree(var_ptr); cudaFree(var_tok); cudaFree(var_step); cudaFree(var_circ);
         cudaFree(key_ptr); cudaFree(key_tok); cudaFree(key_row_circ); cudaFree(key_row_lin);
-        cudaFree(tags); cudaFree(slots); cudaFree(cnt); cudaFree(first);
+        cudaFree(tags); cudaFree(slots); cudaFree(n_hits);
+        cudaFree(key_a); cudaFree(key_b); cudaFree(rank_a); cudaFree(rank_b); cudaFree(head); cudaFree(pos); cudaFree(cub_tmp);
         cudaFree(n_windows); cudaFree(max_window); cudaFree(overflow); cudaFree(row_nnz);
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
@@ -325,15 +278,13 @@ int count_impl(tvs_subpath_counts* res, int64_t n_variants, const int64_t* var_p
 
     uint64_t cap = 64;
     while (cap < (uint64_t)n_keys * 2 + 2) cap <<= 1;
-    const size_t cells = (size_t)n_variants * (size_t)n_rows;
     TVS_CUDA(cudaMalloc((void**)&s.tags, cap * sizeof(uint64_t)));
     TVS_CUDA(cudaMalloc((void**)&s.slots, cap * sizeof(int32_t)));
-    TVS_CUDA(cudaMalloc((void**)&s.cnt, (cells ? cells : 1) * sizeof(int32_t)));
-    TVS_CUDA(cudaMalloc((void**)&s.first, (cells ? cells : 1) * sizeof(uint32_t)));
+    TVS_CUDA(cudaMalloc((void**)&s.n_hits, sizeof(unsigned long long)));
     TVS_CUDA(cudaMalloc((void**)&s.n_windows, sizeof(unsigned long long)));
     TVS_CUDA(cudaMalloc((void**)&s.max_window, sizeof(int)));
     TVS_CUDA(cudaMalloc((void**)&s.overflow, sizeof(int)));
-    TVS_CUDA(cudaMalloc((void**)&s.row_nnz, ((size_t)n_rows + 1) * sizeof(int64_t)));
+    TVS_CUDA(cudaMalloc((void**)&s.row_nnz, ((size_t)n_rows + 1) * sizeof(unsigned long long)));
     TVS_CUDA(cudaEventCreate(&s.e0));
     TVS_CUDA(cudaEventCreate(&s.e1));
 
@@ -343,19 +294,20 @@ int count_impl(tvs_subpath_counts* res, int64_t n_variants, const int64_t* var_p
     a.key_ptr = s.key_ptr; a.key_tok = s.key_tok; a.key_row_circ = s.key_row_circ; a.key_row_lin = s.key_row_lin;
     a.max_internal_len = max_internal_len;
     a.tags = s.tags; a.slots = s.slots; a.cap_mask = cap - 1;
-    a.cnt = s.cnt; a.first = s.first;
+    a.n_hits = s.n_hits; a.hit_key = nullptr; a.hit_rank = nullptr;
     a.n_windows = s.n_windows; a.max_window = s.max_window; a.overflow = s.overflow;
 
     const int T = 256;
+    const unsigned grid_starts = (unsigned)((n_tok + T - 1) / T);
     TVS_CUDA(cudaEventRecord(s.e0));
     TVS_CUDA(cudaMemsetAsync(s.tags, 0, cap * sizeof(uint64_t)));
-    TVS_CUDA(cudaMemsetAsync(s.cnt, 0, (cells ? cells : 1) * sizeof(int32_t)));
-    TVS_CUDA(cudaMemsetAsync(s.first, 0xff, (cells ? cells : 1) * sizeof(uint32_t)));
+    TVS_CUDA(cudaMemsetAsync(s.n_hits, 0, sizeof(unsigned long long)));
     TVS_CUDA(cudaMemsetAsync(s.n_windows, 0, sizeof(unsigned long long)));
     TVS_CUDA(cudaMemsetAsync(s.max_window, 0, sizeof(int)));
     TVS_CUDA(cudaMemsetAsync(s.overflow, 0, sizeof(int)));
+    TVS_CUDA(cudaMemsetAsync(s.row_nnz, 0, ((size_t)n_rows + 1) * sizeof(unsigned long long)));
     if (n_keys) sp_insert_kernel<<<(unsigned)((n_keys + T - 1) / T), T>>>(a);
-    if (n_tok) sp_stats_kernel<<<(unsigned)((n_tok + T - 1) / T), T>>>(a);
+    if (n_tok) sp_stats_kernel<<<grid_starts, T>>>(a);
     TVS_CUDA(cudaGetLastError());
     int h_max = 0, h_over = 0;
     unsigned long long h_windows = 0;
@@ -374,24 +326,65 @@ int count_impl(tvs_subpath_counts* res, int64_t n_variants, const int64_t* var_p
         return TVS_ELIMIT;
     }
     a.rank_stride = h_max + 1;
-    if (n_tok && n_keys && cells) sp_window_kernel<<<(unsigned)((n_tok + T - 1) / T), T>>>(a);
-    TVS_CUDA(cudaGetLastError());
-
-    // dense -> CSR by read path
-    TVS_CUDA(cudaMalloc((void**)&res->row_ptr, ((size_t)n_rows + 1) * sizeof(int64_t)));
-    if (n_rows) sp_row_nnz_kernel<<<(unsigned)((n_rows + T - 1) / T), T>>>(s.cnt, n_variants, n_rows, s.row_nnz);
-    sp_scan_kernel<<<1, 1024>>>(s.row_nnz, n_rows, res->row_ptr);
-    TVS_CUDA(cudaGetLastError());
+    // ---- sweep 1: count the hits; sweep 2: write one record per hit
+    unsigned long long n_hits = 0;
+    if (n_tok && n_keys && n_rows) {
+        sp_window_kernel<false><<<grid_starts, T>>>(a);
+        TVS_CUDA(cudaGetLastError());
+        TVS_CUDA(cudaMemcpy(&n_hits, s.n_hits, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
+    if (n_hits > 2000000000ull) { set_error("tvs_subpaths_count: %llu hits exceed the 32-bit record index", n_hits); return TVS_ELIMIT; }
+    const int64_t H = (int64_t)n_hits;
     int64_t nnz = 0;
-    TVS_CUDA(cudaMemcpy(&nnz, res->row_ptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    TVS_CUDA(cudaMalloc((void**)&res->row_ptr, ((size_t)n_rows + 1) * sizeof(int64_t)));
+    if (H > 0) {
+        TVS_CUDA(cudaMalloc((void**)&s.key_a, (size_t)H * sizeof(uint64_t)));
+        TVS_CUDA(cudaMalloc((void**)&s.key_b, (size_t)H * sizeof(uint64_t)));
+        TVS_CUDA(cudaMalloc((void**)&s.rank_a, (size_t)H * sizeof(uint32_t)));
+        TVS_CUDA(cudaMalloc((void**)&s.rank_b, (size_t)H * sizeof(uint32_t)));
+        TVS_CUDA(cudaMalloc((void**)&s.head, (size_t)H * sizeof(int32_t)));
+        TVS_CUDA(cudaMalloc((void**)&s.pos, (size_t)H * sizeof(int32_t)));
+        TVS_CUDA(cudaMemsetAsync(s.n_hits, 0, sizeof(unsigned long long)));
+        a.hit_key = s.key_a; a.hit_rank = s.rank_a;
+        sp_window_kernel<true><<<grid_starts, T>>>(a);
+        TVS_CUDA(cudaGetLastError());
+        // ---- sort by (read path, variant); key bits actually in use: 32 for the variant + those of n_rows
+        int row_bits = 1;
+        while (((int64_t)1 << row_bits) < n_rows) ++row_bits;
+        size_t tmp_sort = 0, tmp_scan = 0;
+        cub::DoubleBuffer<uint64_t> dk(s.key_a, s.key_b);
+        cub::DoubleBuffer<uint32_t> dv(s.rank_a, s.rank_b);
+        TVS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, dk, dv, (int)H, 0, 32 + row_bits));
+        TVS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, s.head, s.pos, (int)H));
+        size_t tmp_rows = 0;
+        TVS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_rows, s.row_nnz, (unsigned long long*)res->row_ptr, (int)n_rows + 1));
+        const size_t tmp_bytes = std::max(tmp_sort, std::max(tmp_scan, tmp_rows));
+        TVS_CUDA(cudaMalloc(&s.cub_tmp, tmp_bytes ? tmp_bytes : 1));
+        size_t tb = tmp_bytes;
+        TVS_CUDA(cub::DeviceRadixSort::SortPairs(s.cub_tmp, tb, dk, dv, (int)H, 0, 32 + row_bits));
+        const uint64_t* keys = dk.Current();
+        const uint32_t* ranks = dv.Current();
+        sp_heads_kernel<<<(unsigned)((H + T - 1) / T), T>>>(keys, H, s.head);
+        tb = tmp_bytes;
+        TVS_CUDA(cub::DeviceScan::ExclusiveSum(s.cub_tmp, tb, s.head, s.pos, (int)H));
+        int32_t last_pos = 0, last_head = 0;
+        TVS_CUDA(cudaMemcpy(&last_pos, s.pos + (H - 1), sizeof(int32_t), cudaMemcpyDeviceToHost));
+        TVS_CUDA(cudaMemcpy(&last_head, s.head + (H - 1), sizeof(int32_t), cudaMemcpyDeviceToHost));
+        nnz = (int64_t)last_pos + last_head;
+        TVS_CUDA(cudaMalloc((void**)&res->col, (size_t)nnz * sizeof(int32_t)));
+        TVS_CUDA(cudaMalloc((void**)&res->val, (size_t)nnz * sizeof(int32_t)));
+        TVS_CUDA(cudaMalloc((void**)&res->rank, (size_t)nnz * sizeof(int64_t)));
+        sp_runs_kernel<<<(unsigned)((H + T - 1) / T), T>>>(keys, ranks, s.head, s.pos, H, res->col, res->val, res->rank, s.row_nnz);
+        TVS_CUDA(cudaGetLastError());
+        tb = tmp_bytes;
+        TVS_CUDA(cub::DeviceScan::ExclusiveSum(s.cub_tmp, tb, s.row_nnz, (unsigned long long*)res->row_ptr, (int)n_rows + 1));
+    } else {
+        TVS_CUDA(cudaMemsetAsync(res->row_ptr, 0, ((size_t)n_rows + 1) * sizeof(int64_t)));
+        TVS_CUDA(cudaMalloc((void**)&res->col, sizeof(int32_t)));
+        TVS_CUDA(cudaMalloc((void**)&res->val, sizeof(int32_t)));
+        TVS_CUDA(cudaMalloc((void**)&res->rank, sizeof(int64_t)));
+    }
     res->nnz = nnz;
-    TVS_CUDA(cudaMalloc((void**)&res->col, (size_t)(nnz ? nnz : 1) * sizeof(int32_t)));
-    TVS_CUDA(cudaMalloc((void**)&res->val, (size_t)(nnz ? nnz : 1) * sizeof(int32_t)));
-    TVS_CUDA(cudaMalloc((void**)&res->rank, (size_t)(nnz ? nnz : 1) * sizeof(int64_t)));
-    if (n_rows && nnz)
-        sp_fill_kernel<<<(unsigned)((n_rows + T - 1) / T), T>>>(s.cnt, s.first, n_variants, n_rows, res->row_ptr, res->col,
-                                                               res->val, res->rank);
-    TVS_CUDA(cudaGetLastError());
     TVS_CUDA(cudaEventRecord(s.e1));
     TVS_CUDA(cudaEventSynchronize(s.e1));
     float ms = 0.f;
@@ -441,13 +434,6 @@ int tvs_subpaths_count(tvs_subpaths_handle* out, int device, int64_t n_variants,
     }
     if (device < 0 || device >= ndev) { set_error("tvs_subpaths_count: device %d out of range", device); return TVS_EINVAL; }
     TVS_CUDA(cudaSetDevice(device));
-    size_t free_b = 0, total_b = 0;
-    TVS_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    if ((double)n_variants * (double)n_rows * 8.0 > 0.8 * (double)free_b) {
-        set_error("tvs_subpaths_count: %lld variants x %lld read paths needs %.1f GB of scratch, %.1f GB free",
-                  (long long)n_variants, (long long)n_rows, (double)n_variants * n_rows * 8e-9, free_b * 1e-9);
-        return TVS_ENOMEM;
-    }
     tvs_subpath_counts* res = new (std::nothrow) tvs_subpath_counts();
     if (!res) { set_error("out of host memory"); return TVS_ENOMEM; }
     res->device = device;
