@@ -102,3 +102,35 @@ def test_counts_feed_the_fitter(lib_built):
     for t in (t0 - 0.05, t0 - 1e-3, t0 + 1e-3, t0 + 0.05, 0.7):
         if 0.0 < t < 1.0:
             assert eng.loglik(np.array([[t], [1.0 - t]]))[0] <= best + 1e-9 * abs(best)
+
+
+def test_large_variant_by_read_path_product(lib_built):
+    """20,000 variants x 100,000 read paths: 16 GB as a dense scratch, a few MB as a hit list.  Raw C-ABI arrays,
+    compared with the plain-Python statement of the contract."""
+    rng = np.random.default_rng(11)
+    n_var, var_len, n_tok_kinds = 20000, 6, 4000
+    var_tok = rng.integers(0, n_tok_kinds, size=n_var * var_len).astype(np.int32)
+    var_ptr = np.arange(0, n_var * var_len + 1, var_len, dtype=np.int64)
+    var_step = rng.integers(50, 400, size=var_tok.size).astype(np.int32)
+    var_circ = (rng.random(n_var) < 0.5).astype(np.uint8)
+    keys = {}
+    while len(keys) < 100000:
+        ln = int(rng.integers(1, 4))
+        if rng.random() < 0.7:                              # most keys are real windows
+            v = int(rng.integers(0, n_var))
+            s = int(rng.integers(0, var_len - ln + 1))
+            seq = tuple(var_tok[v * var_len + s:v * var_len + s + ln].tolist())
+        else:
+            seq = tuple(rng.integers(0, n_tok_kinds, size=ln).tolist())
+        keys.setdefault(seq, len(keys))
+    seqs = list(keys)
+    key_ptr = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum([len(q) for q in seqs], out=key_ptr[1:])
+    key_tok = np.fromiter((t for q in seqs for t in q), dtype=np.int32, count=int(key_ptr[-1]))
+    key_row = np.arange(len(seqs), dtype=np.int32)
+    lin_row = np.where(rng.random(len(seqs)) < 0.9, key_row, -1).astype(np.int32)
+    got = _cabi.count_subpaths(var_ptr, var_tok, var_step, var_circ, len(seqs), key_ptr, key_tok, key_row, lin_row, 600)
+    want = emulate_count(var_ptr, var_tok, var_step, var_circ, len(seqs), key_ptr, key_tok, key_row, lin_row, 600)
+    for a, b in zip(got[:4], want[:4]):
+        assert np.array_equal(a, b)
+    assert got[4]["nnz"] == want[4]["nnz"] > 50000 and got[4]["n_windows"] == want[4]["n_windows"]
