@@ -326,15 +326,19 @@ int count_impl(tvs_subpath_counts* res, int64_t n_variants, const int64_t* var_p
         return TVS_ELIMIT;
     }
     a.rank_stride = h_max + 1;
-    // ---- sweep 1: count the hits; sweep 2: write one record per hit
+    // ---- hit records.  Every window yields at most one hit, so with few windows (< 64 M: < 2 GB of records and sort
+    //      buffers) the list is sized for all of them and written in ONE sweep; otherwise a first sweep counts the hits.
     unsigned long long n_hits = 0;
-    if (n_tok && n_keys && n_rows) {
+    const bool any = n_tok && n_keys && n_rows;
+    const bool one_sweep = any && h_windows <= (64ull << 20);
+    if (any && !one_sweep) {
         sp_window_kernel<false><<<grid_starts, T>>>(a);
         TVS_CUDA(cudaGetLastError());
         TVS_CUDA(cudaMemcpy(&n_hits, s.n_hits, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     }
-    if (n_hits > 2000000000ull) { set_error("tvs_subpaths_count: %llu hits exceed the 32-bit record index", n_hits); return TVS_ELIMIT; }
-    const int64_t H = (int64_t)n_hits;
+    const unsigned long long cap_hits = one_sweep ? h_windows : n_hits;
+    if (cap_hits > 2000000000ull) { set_error("tvs_subpaths_count: %llu hits exceed the 32-bit record index", cap_hits); return TVS_ELIMIT; }
+    int64_t H = (int64_t)cap_hits;
     int64_t nnz = 0;
     TVS_CUDA(cudaMalloc((void**)&res->row_ptr, ((size_t)n_rows + 1) * sizeof(int64_t)));
     if (H > 0) {
@@ -348,6 +352,12 @@ int count_impl(tvs_subpath_counts* res, int64_t n_variants, const int64_t* var_p
         a.hit_key = s.key_a; a.hit_rank = s.rank_a;
         sp_window_kernel<true><<<grid_starts, T>>>(a);
         TVS_CUDA(cudaGetLastError());
+        if (one_sweep) {
+            TVS_CUDA(cudaMemcpy(&n_hits, s.n_hits, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            H = (int64_t)n_hits;
+        }
+    }
+    if (H > 0) {
         // ---- sort by (read path, variant); key bits actually in use: 32 for the variant + those of n_rows
         int row_bits = 1;
         while (((int64_t)1 << row_bits) < n_rows) ++row_bits;
