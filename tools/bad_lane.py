@@ -1,3 +1,5 @@
+#!/usr/bin/env python
+"""Developer tool (GPU box): find the lanes of a 20,000-replicate cfg2 fit that do not converge and refit them alone."""
 import json, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
