@@ -262,3 +262,34 @@ def test_jackknife_from_records_equals_serial_fits(plastome):
         got = s.variant_proportions_reps[k]
         assert list(got) == list(prop) and all(abs(got[c] - prop[c]) < 1e-12 for c in prop)
         assert 1 in prop
+
+
+def test_large_batches_run_as_two_concurrent_halves(synthetic_small):
+    """LaneContext.fit cuts a batch of >= concurrent_min_lanes lanes in two halves on two handles (two threads); the
+    results come back in request order and equal those of the single-handle path."""
+    from traversome_b200.lanes import LaneRequest
+    case = synthetic_small["cases"][0]
+    L = case["variant_sizes"]
+    model = model_from_tables(L, case["bins_list"])
+    V = len(L)
+    rng = np.random.default_rng(5)
+    outs = []
+    for limit in (0, 4):
+        ctx = _ctx(L)
+        ctx.concurrent_min_lanes = limit
+        col, C, _N = ctx.add_model(model)
+        reqs = []
+        rng = np.random.default_rng(5)
+        for b in range(9):
+            ids = sorted(set(rng.choice(V, rng.integers(max(2, V - 2), V + 1), replace=False).tolist()))
+            reqs.append(LaneRequest(col, C, ids))
+        res = ctx.fit(reqs)
+        outs.append(res)
+        assert (ctx._engine2 is not None) == (limit == 4)
+        if limit == 4:
+            assert ctx._engine.calls == 1 and ctx._engine2.calls == 1
+        ctx.close()
+    for a, b in zip(*outs):
+        assert a.success == b.success and a.status == b.status
+        if a.success:
+            assert np.allclose(a.x, b.x, atol=1e-12) and abs(a.fun - b.fun) <= 1e-12 * abs(a.fun)

@@ -276,3 +276,26 @@ def test_cfg1_bootstrap_from_record_pool_on_gpu(gpu, plastome):
             assert abs(v_prop[0] - r["theta"][0]) < 1e-6 and abs(v_prop[1] - r["theta"][1]) < 1e-6
     assert ctx.n_batches <= 6
     ctx.close()
+
+
+def test_lane_context_concurrent_halves_on_gpu(gpu):
+    """A 3,200-lane batch through LaneContext: two concurrent handles give the same fits as one (each lane is an
+    independent problem; only the batch a lane shares its iterations with differs)."""
+    from traversome_b200 import synthetic
+    from traversome_b200.lanes import LaneContext, LaneRequest
+    wl = synthetic.make_workload(24, 3000, 0.25, seed=61)
+    W = synthetic.bootstrap_weights(wl.n_obs, 3200, seed=2)
+    res = []
+    for limit in (0, 3000):
+        ctx = LaneContext(wl.V, wl.L)
+        ctx.concurrent_min_lanes = limit
+        for r in range(wl.R):
+            lo, hi = int(wl.row_ptr[r]), int(wl.row_ptr[r + 1])
+            ctx.matrix.row_index_distinct(dict(zip(wl.col[lo:hi].tolist(), wl.val[lo:hi].tolist())))
+        reqs = [LaneRequest(ctx.add_weights(W[:, b]), 0.0, range(wl.V)) for b in range(W.shape[1])]
+        res.append(ctx.fit(reqs))
+        assert (ctx._engine2 is not None) == (limit > 0)
+        ctx.close()
+    assert all(r.success for r in res[0]) and all(r.success for r in res[1])
+    assert max(np.abs(a.x - b.x).max() for a, b in zip(*res)) < 1e-7
+    assert max(abs(a.fun - b.fun) / abs(a.fun) for a, b in zip(*res)) < 1e-12
