@@ -133,14 +133,19 @@ def selection_rate(device, n_rep=8):
         solver[0] += time.perf_counter() - t
         return out
     ctx.fit = timed
-    t0 = time.perf_counter()
-    res = bootstrap.run_selections(fitters, criterion="BIC")
-    wall = time.perf_counter() - t0
+    walls = []
+    for _ in range(3):                                   # one warm-up run, then the better of two (a 0.5 s figure on a shared host)
+        solver[0] = 0.0
+        lanes0, batches0 = ctx.n_lanes_fitted, ctx.n_batches
+        t0 = time.perf_counter()
+        res = bootstrap.run_selections(fitters, criterion="BIC")
+        walls.append((time.perf_counter() - t0, solver[0], ctx.n_lanes_fitted - lanes0, ctx.n_batches - batches0))
+    wall, solver[0], n_lanes, n_batches = min(walls[1:])
     sizes = [len(r[0]) for r in res if not isinstance(r, Exception)]
     out = {"workload": "cfg3: backward selection (BIC) from %d candidate variants x %d read paths, %d bootstrap replicates in "
                        "lock step" % (wl.V, wl.R, n_rep),
-           "replicates_per_s": n_rep / wall, "lane_fits_per_s": ctx.n_lanes_fitted / wall, "lanes": ctx.n_lanes_fitted,
-           "batches": ctx.n_batches, "wall_s": wall, "solver_s": solver[0],
+           "replicates_per_s": n_rep / wall, "lane_fits_per_s": n_lanes / wall, "lanes": n_lanes,
+           "batches": n_batches, "wall_s": wall, "solver_s": solver[0], "runs": "1 warm-up + 2 timed, better of the two",
            "selected_variants_median": float(np.median(sizes)) if sizes else None,
            "failures": sum(isinstance(r, Exception) for r in res)}
     ctx.close()
