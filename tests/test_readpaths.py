@@ -85,3 +85,26 @@ def test_array_form_equals_oracle_on_a_larger_random_record_set():
         table, lengths = orp.read_paths_from_records(graph, paths, lens, True, mac)
         out = rp.generate_read_paths(graph, [Rec(p, l) for p, l in zip(paths, lens)], min_alignment_counts=mac)
         assert list(out.read_paths.items()) == list(table.items()) and out.align_len_at_path_map == lengths
+
+
+def test_hash_collisions_fall_back_to_exact_comparison(monkeypatch):
+    """The hashes are lookup devices only: with a degenerate hash (every permutation of a path collides) the grouping and
+    the window support still equal the oracle's."""
+    import random
+    from tests.subpath_helpers import random_graph_case
+    monkeypatch.setattr(rp, "_HASH_MUL", 1)
+    graph, variants, _, _ = random_graph_case(78, 20, 8, (10, 30), True, 5, 6, 700)
+    rnd = random.Random(4)
+    paths, lens = [], []
+    for _ in range(1500):
+        v = variants[rnd.randrange(len(variants))]
+        s0, k = rnd.randrange(len(v)), rnd.randint(1, 5)
+        w = tuple(v[(s0 + i) % len(v)] for i in range(k))
+        if rnd.random() < 0.5:
+            w = tuple((n, not e) for n, e in reversed(w))
+        paths.append(w)
+        lens.append(rnd.randint(100, 900))
+    for mac in (1, 3):
+        table, lengths = orp.read_paths_from_records(graph, paths, lens, True, mac)
+        out = rp.generate_read_paths(graph, [Rec(p, l) for p, l in zip(paths, lens)], min_alignment_counts=mac)
+        assert list(out.read_paths.items()) == list(table.items()) and out.align_len_at_path_map == lengths

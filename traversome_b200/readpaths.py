@@ -74,7 +74,16 @@ def _window_support(flat_ptr, tok, lens, cand, is_pal):
             order = np.argsort(h_c, kind="stable")
             h_sorted = h_c[order]
             if np.any(h_sorted[1:] == h_sorted[:-1]):
-                raise NotImplementedError("two shallow read paths of one size share a 64-bit hash")
+                # two candidates of one size with the same 64-bit hash: count this size exactly, window by window
+                index = {tuple(tok[flat_ptr[c]:flat_ptr[c] + k].tolist()): int(np.searchsorted(cand, c)) for c in c_k.tolist()}
+                for s0 in start.tolist():
+                    f = tuple(tok[s0:s0 + k].tolist())
+                    r = tok[s0:s0 + k][::-1] ^ 1
+                    r = tuple(np.where(is_pal[r >> 1], r | 1, r).tolist())
+                    hit = index.get(f, index.get(r))
+                    if hit is not None:
+                        support[hit] += 1
+                continue
             for h_w, mask, reverse in ((h_fwd, None, False), (h_rev, ~self_rc, True)):
                 pos = np.minimum(np.searchsorted(h_sorted, h_w), h_sorted.size - 1)
                 hit = h_sorted[pos] == h_w
@@ -165,7 +174,7 @@ def generate_read_paths(graph, raw_records, filter_by_graph=True, min_alignment_
     std = np.where(np.repeat(use_rev, lens), rev, fwd)
     # ---- group equal paths (64-bit hash + length as the sort key, then verified token by token)
     with np.errstate(over="ignore"):
-        key = _hash_segments(std, ptr, 0x100000001B3) * np.uint64(31) + lens.astype(np.uint64)
+        key = _hash_segments(std, ptr, _HASH_MUL) * np.uint64(31) + lens.astype(np.uint64)
     _, first_rec, inverse = np.unique(key, return_index=True, return_inverse=True)
     rep = first_rec[inverse]                                   # first record of each record's group
     same = std == std[np.repeat(ptr[rep], lens) + (idx - np.repeat(ptr[:-1], lens))]
