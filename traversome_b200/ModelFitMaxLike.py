@@ -477,7 +477,10 @@ class ModelFitMaxLike(object):
             local = np.fromiter(self.sbp_to_sbp_id.values(), dtype=np.int64, count=len(keys))
             glob = np.fromiter((gid.get(k, -1) for k in keys), dtype=np.int64, count=len(keys))
             ok = glob >= 0
-            np.logical_or.at(contains, local[ok], contains_g[glob[ok]])
+            if np.unique(local[ok]).size == int(ok.sum()):            # ids are distinct: a plain row assignment
+                contains[local[ok]] = contains_g[glob[ok]]
+            else:
+                np.logical_or.at(contains, local[ok], contains_g[glob[ok]])
         observed = np.zeros(n_sbp, dtype=bool)
         observed[list(self.observed_sbp_id_set)] = True
         # variant-major copy: a candidate set is a gather of contiguous rows
