@@ -3,6 +3,7 @@
 #include "tvs_kernels.cuh"
 #include "tvs_pass2.cuh"
 #include "tvs_newton.cuh"
+#include "tvs_blk.cuh"
 
 #include <cublas_v2.h>
 
@@ -55,6 +56,11 @@ static void free_csr(Csr& c) {
     dev_free(c.slab_ptr); dev_free(c.h_row); dev_free(c.h_val); dev_free(c.h_slot);
     dev_free(c.wide_ptr); if (c.wide_rec) { cudaFree(c.wide_rec); c.wide_rec = nullptr; }
     dev_free(c.dense);
+    for (Csr::Blk* b : {&c.blk_f, &c.blk_b}) {
+        dev_free(b->seg_off);
+        if (b->blob) { cudaFree(b->blob); b->blob = nullptr; }
+    }
+    c.has_blk = false;
 }
 static void free_lanes(Lanes& l) {
     dev_free(l.w); dev_free(l.mask); dev_free(l.C); dev_free(l.N); dev_free(l.w16);
@@ -76,6 +82,9 @@ struct PassPlan {
     bool dense = false;   // two cuBLAS DGEMMs on the dense copy of A + dense_mid_kernel (dense shapes, see launch_dense)
     bool v2 = false;      // pass2_kernel<lpt, BW> (lpt = lanes per thread)
     int v3_warps = 0;     // > 0: pass3_kernel<lpt, v3_warps, BW> (entries staged in shared memory)
+    bool blk = false;     // blk_kernel<lpt, ., bulk>: forward (splits = row-chunk splits) + backward (bsplits row-panel splits)
+    bool bulk = false;
+    int bsplits = 1; size_t bsmem = 0;
 };
 
 static int splits_for(const tvs_problem* h, int slots, int tiles) {
@@ -194,6 +203,91 @@ static int plan_one(const tvs_problem* h, int64_t B, PassPlan* out) {
     return TVS_OK;
 }
 
+
+static int upload_blk(const BlkHost& hb, Csr::Blk* d) {
+    int rc;
+    if ((rc = dev_alloc(&d->seg_off, hb.seg_off.size())) != TVS_OK) return rc;
+    uint32_t* blob = nullptr;
+    if ((rc = dev_alloc(&blob, hb.blob.size())) != TVS_OK) return rc;
+    d->blob = blob;
+    TVS_CUDA(cudaMemcpy(d->seg_off, hb.seg_off.data(), hb.seg_off.size() * 4, cudaMemcpyHostToDevice));
+    TVS_CUDA(cudaMemcpy(blob, hb.blob.data(), hb.blob.size() * 4, cudaMemcpyHostToDevice));
+    d->n_chunks = hb.n_chunks; d->n_panels = hb.n_panels; d->max_seg_bytes = hb.max_seg_bytes;
+    return TVS_OK;
+}
+
+// blk_kernel geometry for a lane set of width W: 2 lanes per thread and bulk operand copies when W is even, else 1 lane
+// per thread with 8-byte cp.async rows.  Fails with TVS_ELIMIT when a segment does not fit the shared-memory ring.
+template <int K, int MODE, bool BULK>
+static int blk_prepare(const tvs_problem* h, size_t smem, int* occ) {
+    auto kern = blk_kernel<K, MODE, BULK>;
+    TVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TVS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, kBlkThreads, smem));
+    (void)h;
+    return TVS_OK;
+}
+
+template <bool BW>
+static int plan_blk(const tvs_problem* h, int64_t W, PassPlan* out) {
+    const Csr& c = h->csr;
+    if (!c.has_blk) return TVS_ELIMIT;
+    const size_t limit = 227 * 1024;
+    int K = (W % 2 == 0) ? 2 : 1;
+    const bool bulk = (W % 2 == 0);
+    const int forcedK = env_int("TVS_BLK_K", 0);
+    if (forcedK == 1) K = 1;
+    size_t sf = blk_layout(32 * K, c.blk_f.max_seg_bytes).total, sb = blk_layout(32 * K, c.blk_b.max_seg_bytes).total;
+    if (K == 2 && (sf > limit || (BW && sb > limit))) {
+        K = 1;
+        sf = blk_layout(32, c.blk_f.max_seg_bytes).total; sb = blk_layout(32, c.blk_b.max_seg_bytes).total;
+    }
+    if (sf > limit || (BW && sb > limit)) return TVS_ELIMIT;
+    int occ_f = 0, occ_b = 0, rc;
+    if (K == 2) {
+        if ((rc = blk_prepare<2, 0, true>(h, sf, &occ_f)) != TVS_OK) return rc;
+        if (BW && (rc = blk_prepare<2, 1, true>(h, sb, &occ_b)) != TVS_OK) return rc;
+    } else if (bulk) {
+        if ((rc = blk_prepare<1, 0, true>(h, sf, &occ_f)) != TVS_OK) return rc;
+        if (BW && (rc = blk_prepare<1, 1, true>(h, sb, &occ_b)) != TVS_OK) return rc;
+    } else {
+        if ((rc = blk_prepare<1, 0, false>(h, sf, &occ_f)) != TVS_OK) return rc;
+        if (BW && (rc = blk_prepare<1, 1, false>(h, sb, &occ_b)) != TVS_OK) return rc;
+    }
+    if (occ_f < 1 || (BW && occ_b < 1)) return TVS_ELIMIT;
+    *out = PassPlan();
+    out->blk = true; out->bulk = bulk; out->lpt = K; out->xs = true; out->smem = sf; out->bsmem = sb;
+    const int LT = 32 * K;
+    out->tiles = (int)((W + LT - 1) / LT);
+    const int slots = h->sm_count;                                 // one CTA per SM
+    // split count whose CTA total (units * s) fills whole waves of `slots` CTAs best; fewer splits unless clearly better
+    auto fill_waves = [&](int units, int s_max) {
+        int s = 1;
+        double best = -1.0;
+        for (int cand = 1; cand <= std::max(1, s_max); ++cand) {
+            const int64_t total = (int64_t)units * cand;
+            const int64_t waves = (total + slots - 1) / slots;
+            const double eff = (double)total / (double)(waves * slots);
+            if (eff > best + 0.02) { best = eff; s = cand; }
+        }
+        return s;
+    };
+    // forward: CTA (tile, split) walks the row chunks split, split + S, ...; every split writes one ll partial
+    {
+        int s = fill_waves(out->tiles, std::min(48, std::max(1, c.blk_f.n_chunks / 4)));
+        const int forced = env_int("TVS_SPLITS", 0);
+        if (forced > 0) s = forced;
+        out->splits = std::max(1, std::min(s, c.blk_f.n_chunks));
+    }
+    // backward: CTA (tile, variant chunk, split) walks the row panels split, split + S, ...; tpart[split][V][W]
+    if (BW) {
+        int s = fill_waves(out->tiles * c.blk_b.n_chunks, std::min(24, std::max(1, c.blk_b.n_panels / 4)));
+        const int forced = env_int("TVS_BSPLITS", 0);
+        if (forced > 0) s = forced;
+        out->bsplits = std::max(1, std::min(s, c.blk_b.n_panels));
+    }
+    return TVS_OK;
+}
+
 template <bool BW>
 static int make_plan(const tvs_problem* h, int64_t B, PassPlan* out) {
     if (h->csr.dense != nullptr && env_int("TVS_DENSE", 1) != 0) {
@@ -201,9 +295,18 @@ static int make_plan(const tvs_problem* h, int64_t B, PassPlan* out) {
         out->dense = true; out->tiles = 1; out->splits = 1;
         return TVS_OK;
     }
+    const int want_blk = env_int("TVS_BLK", -1);                  // 1: prefer blk_kernel whenever it is built, 0: never
+    if (want_blk == 1) {
+        const int rcb = plan_blk<BW>(h, B, out);
+        if (rcb == TVS_OK || rcb == TVS_ECUDA) return rcb;
+    }
     if (env_int("TVS_PASS_V1", 0) == 0) {
         const int rc2 = make_plan_v2<BW>(h, B, out);
         if (rc2 == TVS_OK || rc2 == TVS_ECUDA) return rc2;       // otherwise: tiles too large for shared memory
+    }
+    if (want_blk != 0) {
+        const int rcb = plan_blk<BW>(h, B, out);
+        if (rcb == TVS_OK || rcb == TVS_ECUDA) return rcb;       // otherwise: a segment too large for the ring
     }
     int lpt = (B > 32) ? 2 : 1;
     const int forced = env_int("TVS_LPT", 0);
@@ -304,9 +407,52 @@ __global__ void densify_kernel(const int32_t* __restrict__ row_ptr, const uint32
     for (int32_t k = row_ptr[r]; k < row_ptr[r + 1]; ++k) dense[r * V + (ent[k] & 0xffffu)] = (double)(ent[k] >> 16);
 }
 
+
+template <int K, bool BULK>
+static void blk_launch_one(const BlkArgs& a, int mode, dim3 grid, size_t smem, cudaStream_t st) {
+    if (mode == 0) blk_kernel<K, 0, BULK><<<grid, kBlkThreads, smem, st>>>(a);
+    else blk_kernel<K, 1, BULK><<<grid, kBlkThreads, smem, st>>>(a);
+}
+
+template <bool BW>
+static int launch_blk(tvs_problem* h, const PassPlan& pl, const PassArgs& a) {
+    const Csr& c = h->csr;
+    const int64_t W = a.B, R = c.R, V = c.V;
+    if (BW && h->blk_rr_cap < (size_t)R * (size_t)W) {
+        if (h->blk_rr) cudaFree(h->blk_rr);
+        h->blk_rr = nullptr; h->blk_rr_cap = 0;
+        TVS_CUDA(cudaMalloc((void**)&h->blk_rr, (size_t)R * (size_t)W * sizeof(double)));
+        h->blk_rr_cap = (size_t)R * (size_t)W;
+    }
+    BlkArgs f{};
+    f.m.seg_off = c.blk_f.seg_off; f.m.blob = (const uint4*)c.blk_f.blob; f.m.n_chunks = c.blk_f.n_chunks;
+    f.m.n_panels = c.blk_f.n_panels; f.m.max_seg_bytes = c.blk_f.max_seg_bytes;
+    f.src = a.x; f.n_minor = V; f.n_major = R; f.W = W; f.done = a.done; f.w32 = a.w; f.w16 = nullptr;
+    f.rr = BW ? h->blk_rr : nullptr; f.llpart = a.llpart; f.tpart = nullptr; f.splits = pl.splits;
+    f.logc = a.logc; f.logtab = a.logtab;
+    const dim3 gf((unsigned)pl.tiles, (unsigned)pl.splits);
+    if (pl.lpt == 2) blk_launch_one<2, true>(f, 0, gf, pl.smem, h->stream);
+    else if (pl.bulk) blk_launch_one<1, true>(f, 0, gf, pl.smem, h->stream);
+    else blk_launch_one<1, false>(f, 0, gf, pl.smem, h->stream);
+    TVS_CUDA(cudaGetLastError());
+    if (BW) {
+        BlkArgs b = f;
+        b.m.seg_off = c.blk_b.seg_off; b.m.blob = (const uint4*)c.blk_b.blob; b.m.n_chunks = c.blk_b.n_chunks;
+        b.m.n_panels = c.blk_b.n_panels; b.m.max_seg_bytes = c.blk_b.max_seg_bytes;
+        b.src = h->blk_rr; b.n_minor = R; b.n_major = V; b.rr = nullptr; b.llpart = nullptr; b.tpart = a.tpart; b.splits = pl.bsplits;
+        const dim3 gb((unsigned)pl.tiles, (unsigned)(c.blk_b.n_chunks * pl.bsplits));
+        if (pl.lpt == 2) blk_launch_one<2, true>(b, 1, gb, pl.bsmem, h->stream);
+        else if (pl.bulk) blk_launch_one<1, true>(b, 1, gb, pl.bsmem, h->stream);
+        else blk_launch_one<1, false>(b, 1, gb, pl.bsmem, h->stream);
+        TVS_CUDA(cudaGetLastError());
+    }
+    return TVS_OK;
+}
+
 template <bool BW>
 static int launch_pass(tvs_problem* h, const PassPlan& pl, const PassArgs& a) {
     if (pl.dense) return launch_dense(h, a, BW);
+    if (pl.blk) return launch_blk<BW>(h, pl, a);
     dim3 grid(pl.tiles, pl.splits), block(kThreads);
     if (pl.v3_warps == 16) {
         if (pl.lpt == 4) pass3_kernel<4, 16, BW><<<grid, 512, pl.smem, h->stream>>>(a);
@@ -649,6 +795,17 @@ int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, c
             if (cudaDeviceSynchronize() != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "densify", __FILE__, __LINE__));
         }
     }
+    {   // blocked copies of A and A^T for blk_kernel: candidate sets too wide for the staged kernel's shared-memory tiles
+        const int want = env_int("TVS_BLK", -1);
+        if (nnz > 0 && want != 0 && (want == 1 || V > env_int("TVS_BLK_MIN_V", 256)) && c.dense == nullptr) {
+            BlkHost hf, hb;
+            const bool ok = build_blk<int32_t>(R, V, row_ptr, col, val, &hf) && build_blk_transposed(R, V, nnz, row_ptr, col, val, &hb);
+            if (ok) {
+                if ((rc = upload_blk(hf, &c.blk_f)) != TVS_OK || (rc = upload_blk(hb, &c.blk_b)) != TVS_OK) return fail(rc);
+                c.has_blk = true;
+            }
+        }
+    }
     *out = h;
     return TVS_OK;
 }
@@ -661,6 +818,7 @@ int tvs_destroy(tvs_handle h) {
     if (h->cublas) cublasDestroy((cublasHandle_t)h->cublas);
     if (h->dense_p) cudaFree(h->dense_p);
     if (h->dense_ll) cudaFree(h->dense_ll);
+    if (h->blk_rr) cudaFree(h->blk_rr);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evp0) cudaEventDestroy(h->evp0);
@@ -1009,7 +1167,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
             if (lrc != TVS_OK) return lrc;
             if (time_passes) cudaEventRecord(pev.back(), st);
             if (pre_reduce) {
-                reduce_partials_kernel<<<(unsigned)(((int64_t)(V + 1) * W + 255) / 256), 256, 0, st>>>(f.tpart, f.llpart, pl.splits, (int)V, W,
+                reduce_partials_kernel<<<(unsigned)(((int64_t)(V + 1) * W + 255) / 256), 256, 0, st>>>(f.tpart, f.llpart, pl.splits, pl.splits, (int)V, W,
                                                                                                       f.t_red, f.ll_red);
                 na.tpart = f.t_red; na.llpart = f.ll_red; na.S = 1;
                 ++launches;
@@ -1057,8 +1215,10 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
             {
                 rc = make_plan<true>(h, W, &pl);
                 if (rc != TVS_OK) break;
-                while (pl.splits > 1 && (size_t)pl.splits * (size_t)W * (size_t)V > f.tpart_cap) --pl.splits;
-                if ((size_t)pl.splits * (size_t)W * (size_t)V > f.tpart_cap) { set_error("partial buffer too small"); rc = TVS_ENOMEM; break; }
+                int& tsplits = pl.blk ? pl.bsplits : pl.splits;          // splits of the t partials
+                while (tsplits > 1 && (size_t)tsplits * (size_t)W * (size_t)V > f.tpart_cap) --tsplits;
+                if ((size_t)tsplits * (size_t)W * (size_t)V > f.tpart_cap) { set_error("partial buffer too small"); rc = TVS_ENOMEM; break; }
+                while (pl.splits > 1 && (size_t)pl.splits * (size_t)W > f.llpart_cap) --pl.splits;
             }
             PassArgs pa = base_args(h);
             pa.w = s.w; pa.B = W; pa.x = s.x; pa.done = s.done; pa.tpart = f.tpart; pa.llpart = f.llpart;
@@ -1082,15 +1242,17 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
                 if (rc != TVS_OK) break;
                 if (time_passes) cudaEventRecord(pev.back(), st);
                 const bool last = (k == group - 1) || (passes + 1 == max_passes);
-                const bool pre_reduce = pl.splits > env_int("TVS_FUSE_SPLITS", 24);   // many splits: sum them with full parallelism first
+                const int t_splits = pl.blk ? pl.bsplits : pl.splits;               // blk: t and ll partials have their own split counts
+                const bool pre_reduce = std::max(t_splits, pl.splits) > env_int("TVS_FUSE_SPLITS", 24);   // many splits: sum them with full parallelism first
             if (pre_reduce) {
-                reduce_partials_kernel<<<(unsigned)(((int64_t)(V + 1) * W + 255) / 256), 256, 0, st>>>(f.tpart, f.llpart, pl.splits, (int)V, W,
+                reduce_partials_kernel<<<(unsigned)(((int64_t)(V + 1) * W + 255) / 256), 256, 0, st>>>(f.tpart, f.llpart, t_splits, pl.splits, (int)V, W,
                                                                                                       f.t_red, f.ll_red);
-                ua.tpart = f.t_red; ua.llpart = f.ll_red; ua.S = 1;
+                ua.tpart = f.t_red; ua.llpart = f.ll_red; ua.S = 1; ua.S_ll = 1;
                 ++launches;
             } else {
-                ua.tpart = f.tpart; ua.llpart = f.llpart; ua.S = pl.splits;
+                ua.tpart = f.tpart; ua.llpart = f.llpart; ua.S = t_splits; ua.S_ll = pl.splits;
             }
+                if (pl.blk) ++launches;                                              // forward + backward
             // the poll counter of a group is zeroed by the group's first update launch (or a memset when the group is one pass)
             ua.nactive = last ? f.nactive + slot : f.nactive + 31;   // word 31 = scratch between polls
             ua.nreset = (k == 0 && !last) ? f.nactive + slot : nullptr;

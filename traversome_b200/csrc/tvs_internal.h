@@ -49,6 +49,10 @@ struct Csr {
     int       w_HB = 0, w_nblk = 0, w_cap = 0;
     int64_t   h_steps = 0;
     double*   dense = nullptr;       // [R*V] row-major fp64 copy of A for the DGEMM pass (dense shapes only, see tvs_create)
+    // blocked copies of A (major = read path) and A^T (major = variant) for blk_kernel (wide candidate sets, tvs_blk.cuh)
+    struct Blk { uint32_t* seg_off = nullptr; void* blob = nullptr; int n_chunks = 0, n_panels = 0, max_seg_bytes = 0; };
+    Blk blk_f, blk_b;
+    bool has_blk = false;
     double*   invL = nullptr;        // [V] 1/L_v
     double*   Ld = nullptr;          // [V] L_v as double
     int64_t   n_ccol = 0;
@@ -120,4 +124,6 @@ struct tvs_problem {
     void* cublas = nullptr;
     double* dense_p = nullptr; size_t dense_p_cap = 0;
     double* dense_ll = nullptr; size_t dense_ll_cap = 0;
+    // blk pass: w/p of the forward product [R x width], read back by the backward product
+    double* blk_rr = nullptr; size_t blk_rr_cap = 0;
 };

@@ -167,11 +167,12 @@ __global__ void __launch_bounds__(kThreads) pass_kernel(const PassArgs a) {
 // t[v,b] = sum_q tpart[q,v,b] (rows 0..V-1) and ll[b] = sum_q llpart[q,b] (row V).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ tpart, const double* __restrict__ llpart,
-                                                              int S, int V, int64_t B, double* __restrict__ t_red,
+                                                              int S_t, int S_ll, int V, int64_t B, double* __restrict__ t_red,
                                                               double* __restrict__ ll_red) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (int64_t)(V + 1) * B) return;
     const bool is_ll = e >= (int64_t)V * B;
+    const int S = is_ll ? S_ll : S_t;
     const double* src = is_ll ? llpart + (e - (int64_t)V * B) : tpart + e;
     const int64_t stride = is_ll ? B : (int64_t)V * B;
     double s0 = 0.0;
@@ -276,7 +277,7 @@ __global__ void finish_loglik_kernel(const double* __restrict__ llpart, int S, i
 // replaces: scipy SLSQP multistart (ModelFitMaxLike.py:19-58).
 // ------------------------------------------------------------------------------------------------
 struct UpdArgs {
-    const double* tpart; const double* llpart; int S;
+    const double* tpart; const double* llpart; int S; int S_ll;   // split counts of the t / ll partials
     const double* invL; const double* N; const uint8_t* mask;
     double *z, *zt, *g, *gt, *gh, *d, *x, *Sh, *Yh, *rho, *gamma;
     double *F, *dg, *alpha, *llsum, *kkt, *sumphi;
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(kU2Threads) lbfgs_update_vl2_kernel(const UpdA
 
     const double N = a.N[bb];
     // ---- A: sum the per-split partials of the pass evaluated at zt in FIXED split order (bitwise reproducible)
-    const double llsum = sum_splits(a.llpart + bb, a.S, B);
+    const double llsum = sum_splits(a.llpart + bb, a.S_ll, B);
     double r2[2] = {0.0, 0.0};                                  // sum phi, d.gt
     for (int v = vs; v < V; v += kU2Slots) {
         const int64_t i = (int64_t)v * B + bb;
