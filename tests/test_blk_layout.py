@@ -62,8 +62,8 @@ def test_blocked_products_reproduce_the_csr(harness, R, V, density, big):
     p, t, info = products(harness, a, row_ptr, col, val, x, r)
     assert np.array_equal(p, (a @ x.astype(np.int64)).astype(np.float64))
     assert np.array_equal(t, (a.T @ r.astype(np.int64)).astype(np.float64))
-    assert info[0] == (R + 255) // 256 and info[1] == (V + 127) // 128
-    assert info[4] == (V + 255) // 256 and info[5] == (R + 127) // 128
+    assert info[0] == (R + 239) // 240 and info[1] == (V + 127) // 128     # chunks of 240 major x panels of 128 minor indices
+    assert info[4] == (V + 239) // 240 and info[5] == (R + 127) // 128
     assert info[2] % 16 == 0 and info[6] % 16 == 0
 
 

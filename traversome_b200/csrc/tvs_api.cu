@@ -84,7 +84,7 @@ struct PassPlan {
     int v3_warps = 0;     // > 0: pass3_kernel<lpt, v3_warps, BW> (entries staged in shared memory)
     bool blk = false;     // blk_kernel<lpt, ., bulk>: forward (splits = row-chunk splits) + backward (bsplits row-panel splits)
     bool bulk = false;
-    int bsplits = 1; size_t bsmem = 0;
+    int bsplits = 1; size_t bsmem = 0; int stages = 2, bstages = 2;
 };
 
 static int splits_for(const tvs_problem* h, int slots, int tiles) {
@@ -236,12 +236,19 @@ static int plan_blk(const tvs_problem* h, int64_t W, PassPlan* out) {
     const bool bulk = (W % 2 == 0);
     const int forcedK = env_int("TVS_BLK_K", 0);
     if (forcedK == 1) K = 1;
-    size_t sf = blk_layout(32 * K, c.blk_f.max_seg_bytes).total, sb = blk_layout(32 * K, c.blk_b.max_seg_bytes).total;
-    if (K == 2 && (sf > limit || (BW && sb > limit))) {
+    // deepest ring (2..kBlkMaxStages stages of operand tile + blob) that fits the shared memory of one CTA
+    auto stages_for = [&](int k, int seg_bytes) {
+        int n = std::min(kBlkMaxStages, std::max(2, env_int("TVS_BLK_STAGES", kBlkMaxStages)));
+        while (n >= 2 && blk_layout(32 * k, seg_bytes, n).total > limit) --n;
+        return n;
+    };
+    int nf = stages_for(K, c.blk_f.max_seg_bytes), nb = stages_for(K, c.blk_b.max_seg_bytes);
+    if (K == 2 && (nf < 2 || (BW && nb < 2))) {
         K = 1;
-        sf = blk_layout(32, c.blk_f.max_seg_bytes).total; sb = blk_layout(32, c.blk_b.max_seg_bytes).total;
+        nf = stages_for(1, c.blk_f.max_seg_bytes); nb = stages_for(1, c.blk_b.max_seg_bytes);
     }
-    if (sf > limit || (BW && sb > limit)) return TVS_ELIMIT;
+    if (nf < 2 || (BW && nb < 2)) return TVS_ELIMIT;
+    const size_t sf = blk_layout(32 * K, c.blk_f.max_seg_bytes, nf).total, sb = blk_layout(32 * K, c.blk_b.max_seg_bytes, nb).total;
     int occ_f = 0, occ_b = 0, rc;
     if (K == 2) {
         if ((rc = blk_prepare<2, 0, true>(h, sf, &occ_f)) != TVS_OK) return rc;
@@ -256,6 +263,7 @@ static int plan_blk(const tvs_problem* h, int64_t W, PassPlan* out) {
     if (occ_f < 1 || (BW && occ_b < 1)) return TVS_ELIMIT;
     *out = PassPlan();
     out->blk = true; out->bulk = bulk; out->lpt = K; out->xs = true; out->smem = sf; out->bsmem = sb;
+    out->stages = nf; out->bstages = nb;
     const int LT = 32 * K;
     out->tiles = (int)((W + LT - 1) / LT);
     const int slots = h->sm_count;                                 // one CTA per SM
@@ -273,7 +281,7 @@ static int plan_blk(const tvs_problem* h, int64_t W, PassPlan* out) {
     };
     // forward: CTA (tile, split) walks the row chunks split, split + S, ...; every split writes one ll partial
     {
-        int s = fill_waves(out->tiles, std::min(48, std::max(1, c.blk_f.n_chunks / 4)));
+        int s = fill_waves(out->tiles, std::min(2 * slots, std::max(1, c.blk_f.n_chunks / 2)));
         const int forced = env_int("TVS_SPLITS", 0);
         if (forced > 0) s = forced;
         out->splits = std::max(1, std::min(s, c.blk_f.n_chunks));
@@ -428,7 +436,7 @@ static int launch_blk(tvs_problem* h, const PassPlan& pl, const PassArgs& a) {
     f.m.seg_off = c.blk_f.seg_off; f.m.blob = (const uint4*)c.blk_f.blob; f.m.n_chunks = c.blk_f.n_chunks;
     f.m.n_panels = c.blk_f.n_panels; f.m.max_seg_bytes = c.blk_f.max_seg_bytes;
     f.src = a.x; f.n_minor = V; f.n_major = R; f.W = W; f.done = a.done; f.w32 = a.w; f.w16 = nullptr;
-    f.rr = BW ? h->blk_rr : nullptr; f.llpart = a.llpart; f.tpart = nullptr; f.splits = pl.splits;
+    f.rr = BW ? h->blk_rr : nullptr; f.llpart = a.llpart; f.tpart = nullptr; f.stages = pl.stages;
     f.logc = a.logc; f.logtab = a.logtab;
     const dim3 gf((unsigned)pl.tiles, (unsigned)pl.splits);
     if (pl.lpt == 2) blk_launch_one<2, true>(f, 0, gf, pl.smem, h->stream);
@@ -439,8 +447,8 @@ static int launch_blk(tvs_problem* h, const PassPlan& pl, const PassArgs& a) {
         BlkArgs b = f;
         b.m.seg_off = c.blk_b.seg_off; b.m.blob = (const uint4*)c.blk_b.blob; b.m.n_chunks = c.blk_b.n_chunks;
         b.m.n_panels = c.blk_b.n_panels; b.m.max_seg_bytes = c.blk_b.max_seg_bytes;
-        b.src = h->blk_rr; b.n_minor = R; b.n_major = V; b.rr = nullptr; b.llpart = nullptr; b.tpart = a.tpart; b.splits = pl.bsplits;
-        const dim3 gb((unsigned)pl.tiles, (unsigned)(c.blk_b.n_chunks * pl.bsplits));
+        b.src = h->blk_rr; b.n_minor = R; b.n_major = V; b.rr = nullptr; b.llpart = nullptr; b.tpart = a.tpart; b.stages = pl.bstages;
+        const dim3 gb((unsigned)c.blk_b.n_chunks, (unsigned)pl.tiles, (unsigned)pl.bsplits);   // the chunks of one (tile, split) are neighbours: they stream the same rr panels
         if (pl.lpt == 2) blk_launch_one<2, true>(b, 1, gb, pl.bsmem, h->stream);
         else if (pl.bulk) blk_launch_one<1, true>(b, 1, gb, pl.bsmem, h->stream);
         else blk_launch_one<1, false>(b, 1, gb, pl.bsmem, h->stream);

@@ -8,14 +8,15 @@
 
 namespace tvs {
 
-constexpr int kBlkCH = 256;                         // major indices per chunk
+constexpr int kBlkCH = 240;                         // major indices per chunk = 15 consumer warps x 16 accumulator rows
 constexpr int kBlkPN = 128;                         // minor indices per panel (rows of the operand tile)
 constexpr int kBlkPtrBytes = ((kBlkCH + 1) * 2 + 15) & ~15;
 
 // ---- blocked matrices for blk_kernel (tvs_blk.cuh).  `ptr/idx/val`: a major-sorted sparse matrix (CSR of A for the
 // forward product, CSR of A^T for the backward one).  Segment (chunk, panel) = u16 entry pointers of the chunk's 256
 // major indices + packed entries (minor_local * 512 | top 16 bits of the fp64 count).  A count that needs more than 5
-// significant bits is split into several entries of the same position (each exactly representable in 16 bits).
+// significant bits is split into several entries of the same position (each exactly representable in 16 bits).  The entry
+// list of every major index is padded to an even length with zero entries (count +0.0).
 struct BlkHost {
     std::vector<uint32_t> seg_off;     // 16-byte units
     std::vector<uint32_t> blob;        // 32-bit words
@@ -58,10 +59,11 @@ inline bool build_blk(int64_t n_major, int64_t n_minor, const PtrT* ptr, const i
         for (int64_t m = m0; m < m1; ++m)
             for (int64_t k = (int64_t)ptr[m]; k < (int64_t)ptr[m + 1]; ++k)
                 cnt[(size_t)(idx[k] / PN) * (CH + 1) + (m - m0) + 1] += blk_terms((uint32_t)val[k], terms);
-        // per panel: prefix sums over the major index, segment sizes
+        // per panel: prefix sums over the major index (every list padded to an even length: the kernel reads entries in
+        // 8-byte pairs; a padding entry is 0 = offset 0 with count +0.0), segment sizes
         for (int pn = 0; pn < n_panels; ++pn) {
             int32_t* cp = &cnt[(size_t)pn * (CH + 1)];
-            for (int i = 1; i <= CH; ++i) cp[i] += cp[i - 1];
+            for (int i = 1; i <= CH; ++i) cp[i] = cp[i - 1] + ((cp[i] + 1) & ~1);
             const int64_t n_ent = cp[CH];
             const size_t seg = (size_t)ch * n_panels + pn;
             out->seg_off[seg] = (uint32_t)(out->blob.size() / 4);
