@@ -39,6 +39,26 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """dram bytes (read + write) of ONE full-width launch of the dominant kernel from the committed `ncu --set full`
+    capture (profiles/): the latest r*_pass3_full.csv.  None when no capture is committed."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_pass3_full.csv")))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for path in reversed(files):
+        try:
+            found = {}
+            for r in csv.reader(open(path)):                 # rows: metric, unit, value
+                if len(r) >= 3 and r[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    found[r[0]] = float(r[2]) * scale[r[1]]
+            if len(found) == 2:
+                return sum(found.values()), os.path.relpath(path, ROOT) + " (ncu --set full, one full-width launch, dram read + write)"
+        except Exception:
+            continue
+    return None, "no committed capture"
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -97,7 +117,7 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------ model selection
-def selection_rate(device, n_rep=8):
+def selection_rate(device, n_rep=256, nit_cfg2=None):
     """SURVEY.md 8d asks for replicates/s too (one replicate = one complete backward model selection): BASELINE
     configs[2] -- 256 candidate variants (32 carry reads) x 50k read paths -- for `n_rep` bootstrap replicates advanced
     in lock step through the public classes (array-form fitters, traversome_b200.bootstrap.run_selections)."""
@@ -108,12 +128,9 @@ def selection_rate(device, n_rep=8):
     logger.disable("traversome_b200")
     wl = synthetic.make_config("cfg3")
     W = synthetic.bootstrap_weights(wl.n_obs, n_rep, seed=3, keep_lane0=True)
-    ctx = LaneContext(wl.V, wl.L, device=device)
+    ctx = LaneContext.from_csr(wl.V, wl.L, wl.row_ptr, wl.col, wl.val, device=device)
     pattern = np.zeros((wl.R, wl.V), dtype=bool)
-    for r in range(wl.R):
-        lo, hi = int(wl.row_ptr[r]), int(wl.row_ptr[r + 1])
-        ctx.matrix.row_index_distinct(dict(zip(wl.col[lo:hi].tolist(), wl.val[lo:hi].tolist())))
-        pattern[r, wl.col[lo:hi]] = True
+    pattern[np.repeat(np.arange(wl.R), np.diff(wl.row_ptr)), wl.col] = True
     groups = {v: [v] for v in range(wl.V)}
     ident = {v: v for v in range(wl.V)}
     fitters = []
@@ -149,6 +166,9 @@ def selection_rate(device, n_rep=8):
            "selected_variants_median": float(np.median(sizes)) if sizes else None,
            "failures": sum(isinstance(r, Exception) for r in res)}
     ctx.close()
+    if nit_cfg2 is not None:
+        out["cpu_baseline"] = cpu_eval_extrapolation(wl, nit_cfg2)
+        out["cpu_baseline"]["unit"] = "lane-fits/s (full candidate set; leave-one-out lanes are at most as wide)"
     return out
 
 
@@ -170,7 +190,7 @@ def _cpu_fit_one(args):
     dt = time.perf_counter() - t0
     if limiter is not None:
         limiter.restore_original_limits()
-    return dt, (-float(res.fun) if res is not False else float("nan"))
+    return dt, (-float(res.fun) if res is not False else float("nan")), (int(res.nit) if res is not False else 0)
 
 
 def cpu_reference_rate(wl, lanes, n_proc, seed=0):
@@ -187,7 +207,7 @@ def cpu_reference_rate(wl, lanes, n_proc, seed=0):
         with mp.get_context("fork").Pool(n_proc) as pool:
             res = pool.map(_cpu_fit_one, jobs, chunksize=1)
     wall = time.perf_counter() - t0
-    return lanes / wall, wall, [r[1] for r in res]
+    return lanes / wall, wall, [r[1] for r in res], [r[2] for r in res]
 
 
 def run_reference(args, wl):
@@ -202,7 +222,7 @@ def run_reference(args, wl):
         cpu_reference_rate(wl, max(cores, 2), cores, seed=99)
     times, lls = [], []
     for k in range(args.steps):
-        rate, wall, ll = cpu_reference_rate(wl, lanes_per_step, cores, seed=k)
+        rate, wall, ll, _nit = cpu_reference_rate(wl, lanes_per_step, cores, seed=k)
         times.append(wall)
         lls += ll
     total = float(np.sum(times))
@@ -229,6 +249,147 @@ def workload_config(args, wl):
             "parallelism": "lanes sharded over ranks, no data-path collective"}
 
 
+# ---------------------------------------------------------------------------------- other BASELINE configs
+def cpu_eval_extrapolation(wl, nit_mean, lanes=8, evals=3, seed=31):
+    """CPU baseline for the wide configs (a reference lane-fit takes minutes to hours there):
+    seconds per objective evaluation MEASURED on `lanes` bootstrap lanes (numpy closure of the reference objective,
+    oracle/slsqp_port.py) x the evaluations of one reference fit.  The reference's SLSQP has no analytic gradient
+    (ModelFitMaxLike.py:36-40, jac=False), so one iteration costs V+1 evaluations; 6 successful restarts per fit
+    (:31-53).  `nit_mean` = SLSQP iterations per restart measured on cfg2 in this run: a LOWER bound for wider candidate
+    sets, i.e. the extrapolated baseline is faster than the reference would be."""
+    from oracle import slsqp_port
+    from traversome_b200 import synthetic
+    A = wl.scipy_csr()
+    w = synthetic.bootstrap_weights(wl.n_obs, lanes, seed=seed, keep_lane0=False)
+    rng = np.random.default_rng(seed)
+    per_eval = []
+    for b in range(lanes):
+        fun, n = slsqp_port.neg_loglike_closure(A, wl.L, w[:, b], 0.0)
+        x0 = rng.random(n)
+        x0 /= x0.sum()
+        fun(x0)
+        t0 = time.perf_counter()
+        for _ in range(evals):
+            fun(x0)
+        per_eval.append((time.perf_counter() - t0) / evals)
+    sec_eval = float(np.median(per_eval))
+    evals_per_fit = 6.0 * max(nit_mean, 1.0) * (wl.V + 1)
+    return {"value": 1.0 / (sec_eval * evals_per_fit), "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "EXTRAPOLATED: %.4f s per objective evaluation measured on %d bootstrap lanes x (V+1 = %d evaluations per "
+                      "SLSQP iteration, finite-difference gradient) x %.1f iterations per restart (measured on cfg2 in this run; a "
+                      "lower bound for wider candidate sets) x 6 restarts" % (sec_eval, lanes, wl.V + 1, nit_mean),
+            "sec_per_eval": sec_eval, "evals_per_fit": evals_per_fit}
+
+
+def pass_roofline(wl, st, fp64_peak, hbm_peak):
+    """Roofline figures of the likelihood-pass launches of one profiled fit (SURVEY.md 8d algorithmic bytes / flops)."""
+    alg_bytes = (8.0 * wl.nnz + 4.0 * (wl.R + 1)) * st["passes"] + (4.0 * wl.R + 16.0 * wl.V) * st["lane_passes"]
+    flops = (4.0 * wl.nnz + 6.0 * wl.R) * st["lane_passes"]
+    sec = st["pass_ms"] * 1e-3
+    if sec <= 0:
+        return None
+    return {"bound": "fp64", "achieved": flops / sec / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": flops / sec / 1e12 / fp64_peak if fp64_peak > 0 else None,
+            "hbm": {"achieved": alg_bytes / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / sec / 1e9 / hbm_peak},
+            "pass_ms_total": st["pass_ms"], "passes": st["passes"], "lane_passes": st["lane_passes"],
+            "pass_share_of_fit": st["pass_ms"] / st["total_ms"] if st["total_ms"] > 0 else None}
+
+
+def run_cfg4(torch, dist, local_rank, rank, world, sharder, lanes_total, fp64_peak, hbm_peak, nit_cfg2):
+    """BASELINE configs[3]: 2,048 variants x 200k read paths, `lanes_total` bootstrap replicates STRONG-scaled over the
+    ranks through the product's multi-GPU path: LaneContext(sharder=LaneSharder()).fit_batch -- every rank draws and fits
+    its slice of the replicates, one NCCL all_gather of {theta, loglike, kkt, iters, status} inside the timed region."""
+    from traversome_b200 import synthetic
+    from traversome_b200.lanes import LaneBatch, LaneContext
+    t0 = time.perf_counter()
+    wl = synthetic.make_config("cfg4")
+    t_make = time.perf_counter() - t0
+    ctx = LaneContext.from_csr(wl.V, wl.L, wl.row_ptr, wl.col, wl.val, device=local_rank, sharder=sharder, max_iter=4000)
+    ctx.concurrent_min_lanes = 0
+    ctx.time_passes = True                      # events around 18 ms passes cost nothing measurable
+    cols = ctx.add_resampled(wl.n_obs, lanes_total, seed=4004)
+    batch = LaneBatch(cols)
+    lo, hi = (0, lanes_total) if sharder is None else sharder.my_slice(lanes_total)
+    t0 = time.perf_counter()
+    ctx.make_resident(cols[lo:hi])
+    t_setup = time.perf_counter() - t0
+    ctx.max_iter = 1                             # warm-up: allocates the solver state, loads the kernels (2 passes)
+    ctx.fit_batch(batch)
+    ctx.max_iter = 4000
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    g0 = sharder.bytes_gathered if sharder is not None else 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = ctx.fit_batch(batch)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    st = ctx.engine().last_fit_stats()
+    per_rank = [ms]
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        per_rank = [float(x[0]) for x in every]
+    ms_max = max(per_rank)
+    res = None
+    if rank == 0:
+        ok = ctx.lane_ok(out)
+        res = {"workload": "cfg4: %d variants x %d read paths (nnz %d), %d bootstrap replicates strong-scaled over %d GPU(s), "
+                           "full-candidate-set ML fit to KKT 1e-9" % (wl.V, wl.R, wl.nnz, lanes_total, world),
+               "value": lanes_total / (ms_max * 1e-3), "unit": UNIT, "scaling": "strong", "n_gpus": world, "lanes": lanes_total,
+               "ms_per_step": ms_max, "ms_per_step_by_rank": [round(x, 1) for x in per_rank],
+               "converged_lanes": int(ok.sum()), "mean_iters": float(out["iters"].mean()), "max_iters": int(out["iters"].max()),
+               "collective": {"op": "all_gather_into_tensor (NCCL)" if world > 1 else "none (single GPU)",
+                              "bytes_received_per_rank": int((sharder.bytes_gathered - g0) if sharder is not None else 0),
+                              "inside_timed_region": True},
+               "kernel": "blk_kernel (csrc/tvs_blk.cuh): register accumulators, operand tiles by cp.async.bulk (TMA), forward + backward launch per pass",
+               "roofline_rank0": pass_roofline(wl, st, fp64_peak, hbm_peak),
+               "setup_s": {"make_workload": round(t_make, 1), "draw_replicates_on_device": round(t_setup, 2)}}
+        if world == 1 and nit_cfg2 is not None:
+            res["cpu_baseline"] = cpu_eval_extrapolation(wl, nit_cfg2)
+    ctx.close()
+    return res
+
+
+def run_cfg5(torch, local_rank, fp64_peak, hbm_peak, nit_cfg2, lanes=256):
+    """BASELINE configs[4]: 4,096 variants at 30 % density x 100k read paths, 256 bootstrap lanes on one GPU (dense path)."""
+    from traversome_b200 import synthetic
+    from traversome_b200.lanes import LaneBatch, LaneContext
+    wl = synthetic.make_config("cfg5")
+    ctx = LaneContext.from_csr(wl.V, wl.L, wl.row_ptr, wl.col, wl.val, device=local_rank, max_iter=4000)
+    ctx.time_passes = True
+    cols = ctx.add_resampled(wl.n_obs, lanes, seed=5005)
+    batch = LaneBatch(cols)
+    ctx.make_resident(cols)
+    ctx.max_iter = 1
+    ctx.fit_batch(batch)
+    ctx.max_iter = 4000
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = ctx.fit_batch(batch)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    st = ctx.engine().last_fit_stats()
+    rf = pass_roofline(wl, st, fp64_peak, hbm_peak)
+    if rf is not None:      # the dense contraction executes 2*2*R*V flops per lane and pass, whatever the sparsity
+        dense_flops = 4.0 * wl.R * wl.V * st["lane_passes"]
+        rf["dense_contraction"] = {"executed_tflops": dense_flops / (st["pass_ms"] * 1e-3) / 1e12,
+                                   "frac_of_fp64_peak": dense_flops / (st["pass_ms"] * 1e-3) / 1e12 / fp64_peak if fp64_peak > 0 else None}
+    res = {"workload": "cfg5: %d variants x %d read paths (nnz %d, %.0f %% dense), %d bootstrap lanes on 1 GPU" % (
+               wl.V, wl.R, wl.nnz, 100.0 * wl.nnz / (wl.R * wl.V), lanes),
+           "value": lanes / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "converged_lanes": int(ctx.lane_ok(out).sum()),
+           "mean_iters": float(out["iters"].mean()), "roofline": rf}
+    if nit_cfg2 is not None:
+        res["cpu_baseline"] = cpu_eval_extrapolation(wl, nit_cfg2, lanes=8, evals=2)
+    ctx.close()
+    return res
+
+
 # ------------------------------------------------------------------------------------------------- ours
 def main():
     ap = argparse.ArgumentParser()
@@ -240,6 +401,8 @@ def main():
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-selection", action="store_true", help="skip the secondary figures (model selection, two streams)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (cfg4 strong scaling, cfg5)")
+    ap.add_argument("--cfg4-lanes", type=int, default=10000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -255,6 +418,7 @@ def main():
     import torch
     import torch.distributed as dist
     from traversome_b200 import _cabi
+    from traversome_b200.lanes import LaneBatch, LaneContext, LaneSharder
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -262,91 +426,104 @@ def main():
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    sharder = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        sharder = LaneSharder()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- the product path: one LaneContext per rank over the shared read-path x variant matrix; the lanes of every
+    #      batch (B replicates per rank: weak scaling) are split over the ranks by the LaneSharder, each rank fits its slice
+    #      and ONE NCCL all_gather returns {theta, loglike, kkt, iters, status} of all lanes to all ranks
     B = args.lanes
-    eng = _cabi.Engine(wl.row_ptr, wl.col, wl.val, wl.L, device=local_rank)
+    total = B * world
+    ctx = LaneContext.from_csr(wl.V, wl.L, wl.row_ptr, wl.col, wl.val, device=local_rank, sharder=sharder)
+    ctx.concurrent_min_lanes = 0                  # `value` times one batch on one stream (two_streams is reported apart)
+    cols = ctx.add_resampled(wl.n_obs, total, seed=2024)      # replicate j = Philox stream j: the same on any rank
+    batch = LaneBatch(cols)
+    lo, hi = (0, total) if sharder is None else sharder.my_slice(total)
+    ctx.make_resident(cols[lo:hi])                # drawn on this rank's device, resident in HBM from here on
+    eng = ctx.engine()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    # every rank: its own B bootstrap replicates, drawn on the device (lane 0 of rank 0 = the observed data)
-    eng.resample(B, wl.n_obs, seed=2024 + 7919 * rank, keep_lane0=(rank == 0))
-    # end-to-end input: the replicate weights in pinned host memory, 16 bits per count (bootstrap counts are small;
-    # tvs_set_lanes_u16 widens them on the device)
+    # end-to-end input: this rank's replicate weights in pinned HOST memory, 16 bits per count
+    eng.set_lanes_columns(ctx._slots(eng, np.asarray(cols[lo:hi])))
     w32 = eng.get_weights()
     assert int(w32.max()) <= 65535
     w_host = torch.empty((wl.R, B), dtype=torch.uint16, pin_memory=True)
     w_host.numpy()[:] = w32.astype(np.uint16)
-    outs = {"theta": torch.empty((wl.V, B), dtype=torch.float64, pin_memory=True).numpy(),
-            "loglike": torch.empty(B, dtype=torch.float64, pin_memory=True).numpy(),
-            "kkt": torch.empty((B, 2), dtype=torch.float64, pin_memory=True).numpy(),
-            "iters": torch.empty(B, dtype=torch.int32, pin_memory=True).numpy(),
-            "status": torch.empty(B, dtype=torch.int32, pin_memory=True).numpy()}
+    del w32
 
-    # ---- warm-up: both timed paths (resident weights; weights uploaded from pinned host memory)
+    # ---- warm-up: both timed paths
     for _ in range(args.warmup):
         flush.zero_()
-        eng.fit(out=outs)
+        ctx.fit_batch(batch)
     for _ in range(args.warmup):
         flush.zero_()
-        eng.set_lanes(w_host, B=B)
-        eng.fit(out=outs)
-    eng.resample(B, wl.n_obs, seed=2024 + 7919 * rank, keep_lane0=(rank == 0))      # back to the device-resident lanes
+        ctx.fit_weights(w_host, B=total)
     import gc
     gc.collect()
     gc.disable()                                  # no collector pauses inside the timed regions
-    # ---- timed: device-resident weights
+    # ---- timed: device-resident replicate weights (CUDA events around the whole step: column gather, fit, NCCL gather
+    #      of the results from the device buffers, device->host copy of the gathered block)
     sampler = ClockSampler(range(world) if rank == 0 else ())     # single node: local ranks = GPU indices
     sampler.start()
     barrier()
-    dev_ms, launches, passes, lane_passes = [], 0, 0, 0
+    dev_ms, fit_ms, launches, passes, lane_passes = [], [], 0, 0, 0
+    g0 = (sharder.bytes_gathered, sharder.n_gathers) if sharder is not None else (0, 0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         flush.zero_()
         torch.cuda.synchronize()
-        out = eng.fit(out=outs)
+        e0.record()
+        out = ctx.fit_batch(batch)
+        e1.record()
+        torch.cuda.synchronize()
+        dev_ms.append(e0.elapsed_time(e1))
         st = eng.last_fit_stats()
-        dev_ms.append(st["total_ms"])
-        launches += st["kernel_launches"]
+        fit_ms.append(st["total_ms"])
+        launches += st["kernel_launches"] + 4        # + column gather, 16-bit copy, lane sums (tvs_set_lanes_columns)
         passes += st["passes"]
         lane_passes += st["lane_passes"]
     barrier()
     wall = time.perf_counter() - t0
-    converged = int((out["status"] == _cabi.CONVERGED).sum())
+    g1 = (sharder.bytes_gathered, sharder.n_gathers) if sharder is not None else (0, 0)
+    ok = ctx.lane_ok(out)
+    converged = int(ok.sum())                     # all lanes of the job (gathered)
     iters_mean = float(out["iters"].mean())
-    # ---- timed: end to end through the public API, weights in pinned host memory
+    # ---- timed: end to end through the public API, weights in pinned host memory (H2D of this rank's weights, fit,
+    #      gather, D2H of all results) -- wall clock per step
     e2e_ms = []
     for _ in range(args.steps):
         flush.zero_()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        eng.set_lanes(w_host, B=B)            # H2D of this step's weights
-        eng.fit(out=outs)                     # D2H of theta / loglike / kkt / iters / status into pinned memory
+        ctx.fit_weights(w_host, B=total)
         e2e_ms.append(1e3 * (time.perf_counter() - t1))
     barrier()
     clocks = sampler.stop()
-    # ---- the same steps once more with CUDA events around every launch of the dominant kernel (the events
+    # ---- the same fits once more with CUDA events around every launch of the dominant kernel (the events
     #      cost ~1 ms per step, so they are kept out of the steps that produce `value`)
     prof = {"pass_ms": 0.0, "update_ms": 0.0, "total_ms": 0.0, "passes": 0, "lane_passes": 0}
+    eng.set_lanes_columns(ctx._slots(eng, np.asarray(cols[lo:hi])))
     for _ in range(args.steps):
         flush.zero_()
         torch.cuda.synchronize()
-        eng.fit(out=outs, time_passes=True)
+        eng.fit(time_passes=True)
         stp = eng.last_fit_stats()
         for k in prof:
             prof[k] += stp[k]
     fp64_peak = _cabi.measure_fp64_peak(local_rank)
+    smem_peak = _cabi.measure_smem_peak(local_rank)
     # ---- informational: the same batches through two handles (two CUDA streams, two host threads), i.e. consecutive
     #      batches of a long bootstrap overlapped -- the narrow tail of one hides under the wide phase of the next.
-    #      Not the headline: `value` times one batch at a time.
     two_streams = None
     if world == 1 and not args.no_selection:
         try:
-            import threading
             eng2 = _cabi.Engine(wl.row_ptr, wl.col, wl.val, wl.L, device=local_rank)
             eng2.resample(B, wl.n_obs, seed=4049, keep_lane0=False)
             eng2.fit()
@@ -381,71 +558,98 @@ def main():
         per_rank_ms = [float(x[0]) for x in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         step_ms, e2e_step_ms = float(t[0]), float(t[1])
-        c = torch.tensor([converged, launches], dtype=torch.int64, device="cuda")
+        c = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        converged, launches = int(c[0]), int(c[1])
+        launches = int(c[0])
+    line = None
+    nit_cfg2 = None
     if rank == 0:
-        total_lanes = B * world
-        value = total_lanes / (step_ms * 1e-3)
+        value = total / (step_ms * 1e-3)
         peak, peak_src = measured_peaks()
         # algorithmic bytes of the pass-kernel launches of the profiled steps (SURVEY.md 8d figure at each launch's width)
         alg_bytes = (8.0 * wl.nnz + 4.0 * (wl.R + 1)) * prof["passes"] + (4.0 * wl.R + 16.0 * wl.V) * prof["lane_passes"]
         pass_s = prof["pass_ms"] * 1e-3
-        achieved = alg_bytes / pass_s / 1e9 if pass_s > 0 else 0.0
+        hbm_achieved = alg_bytes / pass_s / 1e9 if pass_s > 0 else 0.0
         flops = 4.0 * wl.nnz * prof["lane_passes"] + 6.0 * wl.R * prof["lane_passes"]
+        tflops = flops / pass_s / 1e12 if pass_s > 0 else 0.0
         # shared-memory operand bytes: every FMA of the two sparse products reads one 8-byte operand from shared memory
         smem_bytes = 2.0 * 8.0 * wl.nnz * prof["lane_passes"]
-        sm_count, smem_bw = 148, 128.0 * 1.965e9          # 128 B/clk/SM at the 1965 MHz boost clock
+        traffic, traffic_src = ncu_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "ms_per_step_by_rank": [round(x, 3) for x in per_rank_ms], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, wl),
-            "e2e": {"value": total_lanes / (e2e_step_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(wl.R) * B * 2,
+            "e2e": {"value": total / (e2e_step_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(wl.R) * B * 2 * world,
                     "step_ms_p50": float(np.median(e2e_ms)), "step_ms_max": float(np.max(e2e_ms)),
-                    "d2h_bytes_per_step": int(wl.V) * B * 8 + B * (8 + 16 + 4 + 4)},
+                    "d2h_bytes_per_step": (int(wl.V) * total * 8 + total * (8 + 16 + 4 + 4)) * world,
+                    "api": "LaneContext.fit_weights(pinned uint16 weights) -> result arrays of all lanes on every rank"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "pass3_kernel (fused p = A x, w/p, w log p, t = A^T(w/p))",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                         "traffic": 76.2e6,
-                         "traffic_note": "dram read+write of ONE full-width (1000-lane) launch, ncu --set full (profiles/r1_end_pass3_full.csv); "
-                                         "algorithmic bytes of that launch: 74.3e6",
+            "collective": {"op": "all_gather_into_tensor (NCCL) of the packed per-lane results, from the device buffers tvs_fit wrote"
+                                 if world > 1 else "none (single GPU)",
+                           "per_step": (g1[1] - g0[1]) / args.steps, "bytes_received_per_rank_per_step": (g1[0] - g0[0]) / args.steps,
+                           "inside_timed_region": True,
+                           "plus": "one 16-byte all_gather per batch: every rank holds the same batch (size, digest)" if world > 1 else None},
+            "roofline": {"bound": "fp64", "kernel": "pass3_kernel (fused p = A x, w/p, w log p, t = A^T(w/p))",
+                         "achieved": tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tflops / fp64_peak if fp64_peak > 0 else None,
+                         "peak_source": "tvs_measure_fp64_peak (DFMA micro-benchmark on this GPU; MEASURED_PEAKS.json has no fp64 entry)",
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_full_width_launch": 8.0 * wl.nnz + 4.0 * (wl.R + 1) + (4.0 * wl.R + 16.0 * wl.V) * B,
                          "avg_launch_us": 1e3 * prof["pass_ms"] / max(prof["passes"], 1), "launches_profiled": prof["passes"],
                          "pass_share_of_step": prof["pass_ms"] / prof["total_ms"] if prof["total_ms"] > 0 else None,
-                         "binding_roof_note": "at this lane count the pass is NOT HBM-bound (SURVEY F8): the weights are L2-resident (72 MB) "
-                                              "and every FMA of the sparse products needs an 8-byte shared-memory operand; see fp64 / smem below",
-                         "fp64": {"achieved_tflops": flops / pass_s / 1e12 if pass_s > 0 else 0.0, "peak_tflops": fp64_peak,
-                                  "frac": (flops / pass_s / 1e12 / fp64_peak) if pass_s > 0 and fp64_peak > 0 else None,
-                                  "peak_source": "tvs_measure_fp64_peak (DFMA micro-benchmark on this GPU)"},
-                         "smem_operand": {"achieved_gbs": smem_bytes / pass_s / 1e9 if pass_s > 0 else 0.0,
-                                          "peak_gbs": sm_count * smem_bw / 1e9,
-                                          "frac": (smem_bytes / pass_s) / (sm_count * smem_bw) if pass_s > 0 else None,
-                                          "peak_source": "128 B/clk/SM x 148 SMs x 1.965 GHz (B300_MICROARCH.md shared-memory figure)"}},
-            "solver": {"converged_lanes": converged, "lanes": total_lanes, "mean_iters": iters_mean,
+                         "binding_roof_note": "the weights are 16-bit and L2-resident, the pass is not HBM-bound (SURVEY F8); the design reads one 8-byte "
+                                              "shared-memory operand per DFMA, which caps it at 16 DFMA/clk/SM = 25 % of the fp64 pipe",
+                         "hbm": {"achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak, "peak_source": peak_src},
+                         "smem_operand": {"achieved_gbs": smem_bytes / pass_s / 1e9 if pass_s > 0 else 0.0, "peak_gbs": smem_peak,
+                                          "frac": (smem_bytes / pass_s / 1e9) / smem_peak if pass_s > 0 and smem_peak > 0 else None,
+                                          "peak_source": "tvs_measure_smem_peak (LDS.128 micro-benchmark on this GPU)"}},
+            "solver": {"converged_lanes": converged, "lanes": total, "mean_iters": iters_mean,
                        "kkt_tol": 1e-9, "passes_per_step": passes / args.steps, "lane_passes_per_step": lane_passes / args.steps,
-                       "wall_ms_per_step": 1e3 * wall / args.steps},
+                       "tvs_fit_ms_per_step": float(np.mean(fit_ms)), "wall_ms_per_step": 1e3 * wall / args.steps},
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = 1
             n_sample = 120                     # ~14 s of single-core CPU work
-            rate, wall_cpu, lls = cpu_reference_rate(wl, n_sample, cores, seed=5)
+            rate, wall_cpu, lls, nits = cpu_reference_rate(wl, n_sample, cores, seed=5)
+            nit_cfg2 = float(np.mean(nits))
             line["cpu_baseline"] = {
                 "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": "%d of the %d bootstrap lanes, one process (the reference's default -p 1; its bootstrap loop is "
                           "serial), %.1f s of CPU work" % (n_sample, B, wall_cpu),
+                "mean_slsqp_iterations_per_restart": nit_cfg2,
                 "note": "restated reference driver (scipy SLSQP multistart) + numpy closure of the reference objective; "
                         "omits the reference's symengine build + LLVM JIT, i.e. faster than the true reference"}
         if two_streams is not None:
             line["two_streams"] = two_streams
+    ctx.close()
+    del flush
+    torch.cuda.empty_cache()
+    # ---- the other BASELINE configs (each guarded: a secondary figure must never cost the headline line)
+    configs = {}
+    if not args.no_extra:
+        try:
+            r4 = run_cfg4(torch, dist, local_rank, rank, world, sharder, args.cfg4_lanes, fp64_peak, measured_peaks()[0], nit_cfg2)
+            if rank == 0:
+                configs["cfg4"] = r4
+        except Exception as e:
+            if rank == 0:
+                configs["cfg4"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    if rank == 0:
         if world == 1 and not args.no_selection:
             try:
-                line["selection"] = selection_rate(local_rank)
-            except Exception as e:                       # a secondary figure must never cost the headline line
-                line["selection"] = {"error": "%s: %s" % (type(e).__name__, e)}
+                configs["cfg3"] = selection_rate(local_rank, nit_cfg2=nit_cfg2)
+            except Exception as e:
+                configs["cfg3"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        if world == 1 and not args.no_extra:
+            try:
+                configs["cfg5"] = run_cfg5(torch, local_rank, fp64_peak, measured_peaks()[0], nit_cfg2)
+            except Exception as e:
+                configs["cfg5"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        line["configs"] = configs
         print(json.dumps(line), flush=True)
-    eng.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -28,6 +28,11 @@
  *   - a handle owns one CUDA stream on one device; calls on one handle are serialised by the
  *     caller; different handles are independent (re-entrant per handle).
  *   - there is NO CPU fallback: without a usable CUDA device tvs_create fails with TVS_ECUDA.
+ *   - output arrays of tvs_fit / tvs_loglik may be DEVICE pointers too: a multi-GPU caller gathers the per-lane results
+ *     with NCCL straight from them (traversome_b200/lanes.py: LaneSharder).
+ *   - candidate sets too wide for the shared-memory tiles of the staged kernel (V > ~330) and sparse (< 12 % of A
+ *     non-zero) run the blocked kernel of csrc/tvs_blk.cuh: register accumulators, operand tiles fetched by bulk
+ *     asynchronous copies (TMA); TVS_BLK=0 in the environment forbids it (falls back to the round-1 L2-gather kernel).
  *   - shapes with more than ~400 variants of which at least 12 % of A is non-zero keep a dense fp64 copy of A
  *     (R*V*8 bytes) and run the likelihood pass as two cuBLAS DGEMMs (the library links libcublas); TVS_DENSE=0
  *     in the environment forbids that, TVS_DENSE=1 forces it.
@@ -98,8 +103,11 @@ int tvs_destroy(tvs_handle h);
  * C[B] or NULL (= 0).  Computes N_b = sum_r w[r,b] on the device. */
 int tvs_set_lanes(tvs_handle h, int64_t B, const int32_t* w, const uint8_t* mask, const double* C);
 
-/* same with 16-bit weights (counts <= 65535, e.g. bootstrap replicates): halves the host->device traffic of a batch;
- * widened to the int32 lane-minor matrix on the device. */
+/* same with 16-bit weights (counts <= 65535, e.g. bootstrap replicates): halves the host->device traffic of a batch.
+ * The weights STAY 16-bit on the device (the likelihood pass reads them in that form; whenever every count of a batch
+ * fits, the other tvs_set_lanes* / tvs_resample entry points make the same 16-bit copy on the device).  This call does
+ * not synchronise: the copy is queued on the handle's stream and tvs_fit / tvs_loglik follow on it, so `w` (when it is
+ * pinned host memory) must stay unchanged until the next call on the handle has returned. */
 int tvs_set_lanes_u16(tvs_handle h, int64_t B, const uint16_t* w, const uint8_t* mask, const double* C);
 
 /* same, for batches in which many lanes share one weight column (all candidate subsets of one
@@ -109,6 +117,20 @@ int tvs_set_lanes_u16(tvs_handle h, int64_t B, const uint16_t* w, const uint8_t*
  * cross PCIe. */
 int tvs_set_lanes_indexed(tvs_handle h, int64_t B, int64_t n_cols, const int32_t* w_cols, const int32_t* col_of_lane,
                           const uint8_t* mask, const double* C);
+
+/* Device-resident weight columns.  The distinct weight vectors of a bootstrap / model selection (one per replicate:
+ * traversome.py:515-545 rebuilds them, and the objective, for every fit) are registered ONCE in a column store on the
+ * device; every later batch names its lanes' columns by slot, so no weights cross PCIe per batch.
+ *   tvs_columns_reserve     capacity of the store (columns); growing keeps the registered columns
+ *   tvs_columns_upload[_u16] w_cols[R*n] (element (r, c) at [r*n + c], host or device) -> slots first .. first+n-1
+ *   tvs_columns_resample    slots first .. first+n-1 <- bootstrap replicates drawn on the device as in tvs_resample; the
+ *                           Philox stream of slot first+j is keyed by first_id + j (a column depends on its id only)
+ *   tvs_set_lanes_columns   lane b uses slot col_of_lane[b]; mask / C as in tvs_set_lanes */
+int tvs_columns_reserve(tvs_handle h, int64_t n_cols);
+int tvs_columns_upload(tvs_handle h, int64_t first, int64_t n, const int32_t* w_cols);
+int tvs_columns_upload_u16(tvs_handle h, int64_t first, int64_t n, const uint16_t* w_cols);
+int tvs_columns_resample(tvs_handle h, int64_t first, int64_t n, const int32_t* n_obs, uint64_t seed, uint64_t first_id);
+int tvs_set_lanes_columns(tvs_handle h, int64_t B, const int32_t* col_of_lane, const uint8_t* mask, const double* C);
 
 /* device-side bootstrap: lane b's w[.,b] ~ Multinomial(N, n_obs/N), N = sum n_obs, drawn record by
  * record with Philox4x32-10(key=(seed, b), counter=draw index) -- the batched equivalent of
@@ -141,6 +163,9 @@ int tvs_dims(tvs_handle h, int64_t* R, int64_t* V, int64_t* nnz, int64_t* B);
 /* fp64 FMA peak micro-benchmark (MEASURED_PEAKS.json has no fp64 entry; SURVEY.md 8d asks for one).
  * Returns TFLOP/s of dependent-chain-free DFMA on `device`. */
 int tvs_measure_fp64_peak(int device, double* tflops_out);
+/* shared-memory read peak: GB/s of conflict-free 16-byte loads (LDS.128) summed over all SMs -- the roof that bounds the
+ * sparse products of the likelihood pass (one 8-byte shared-memory operand per DFMA). */
+int tvs_measure_smem_peak(int device, double* gbs_out);
 
 /* self-test of the device reciprocal / logarithm used inside the likelihood pass (they replace the
  * IEEE division and libdevice log there): log_out[i] = log(p[i]), rcp_out[i] = 1/p[i], host arrays. */

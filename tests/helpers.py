@@ -125,6 +125,20 @@ class OracleEngine(object):
         self.C = np.zeros(self.w.shape[1]) if C is None else np.asarray(C)
         self.B = self.w.shape[1]
 
+    # device-resident column store of the real engine (tvs_columns_*), host arrays here
+    def columns_reserve(self, n_cols):
+        old = getattr(self, "cols", None)
+        self.cols = np.zeros((self.R, int(n_cols)), dtype=np.int64)
+        if old is not None:
+            self.cols[:, :old.shape[1]] = old
+
+    def columns_upload(self, first, w_cols):
+        w_cols = np.asarray(w_cols)
+        self.cols[:, first:first + w_cols.shape[1]] = w_cols
+
+    def set_lanes_columns(self, col_of_lane, mask=None, C=None):
+        self.set_lanes_indexed(self.cols, col_of_lane, mask=mask, C=C)
+
     def fit(self, tol=0.0, max_iter=0, history=0, **_kw):
         from oracle import exact
         self.calls += 1

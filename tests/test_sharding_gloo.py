@@ -98,3 +98,53 @@ def test_two_rank_lane_sharding_matches_single_process():
     assert all(o[2] for o in out), "ragged sharded batch differs from the single-process run"
     assert out[0][3] == out[1][3], "ranks disagree on the selected models"
     assert all(o[5] is False for o in out)          # the uncovered lane fails identically everywhere
+
+
+def _worker_shuffle(rank, world, port, q):
+    """The DEFAULT shuffle (no pinned permutation) with more candidates than one chunk holds: every rank must draw the
+    same permutations (seed broadcast by rank 0), and a rank that holds a different batch must be caught."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        np.random.seed(1000 + 17 * rank)                     # the process-global generator differs per rank on purpose
+        from tests.helpers import OracleEngine, fit_context, model_from_workload
+        from traversome_b200 import synthetic
+        from traversome_b200.ModelFitMaxLike import ModelFitMaxLike
+        from traversome_b200.lanes import LaneBatch, LaneContext, LaneSharder
+        wl = synthetic.make_workload(9, 260, 0.45, seed=77, n_true=3)
+        model = model_from_workload(wl)
+        kw = fit_context(model)
+        ctx = LaneContext(wl.V, wl.L, sharder=LaneSharder())
+        ctx.engine_factory = OracleEngine
+        f = ModelFitMaxLike(context=ctx, **kw)
+        res = f.reverse_model_selection(n_proc=1, criterion="BIC", random_size=3)     # 9 candidates in chunks of 3: shuffled
+        seeds_equal = ctx.shuffle_seed is not None
+        # a rank-dependent batch must raise on every rank instead of pairing lanes with the wrong results
+        col = f._lane[0]
+        caught = False
+        try:
+            ctx.fit_batch(LaneBatch([col, col], mask=np.eye(wl.V, 2, k=-rank, dtype=np.uint8) + np.eye(wl.V, 2, k=-3, dtype=np.uint8)))
+        except RuntimeError as e:
+            caught = "different lane batches" in str(e)
+        q.put((rank, sorted(res[0]), [float(res[0][k]) for k in sorted(res[0])], float(res[1]), float(res[2]), seeds_equal, caught,
+               ctx.shuffle_seed))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_default_shuffle_is_rank_independent_and_batch_mismatch_is_caught():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_shuffle, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out[0][1:5] == out[1][1:5], "ranks selected different models / proportions with the default shuffle"
+    assert out[0][7] == out[1][7] and all(o[5] for o in out), "the shuffle seed was not shared"
+    assert all(o[6] for o in out), "a rank-dependent batch was not detected"

@@ -137,6 +137,7 @@ class ModelFitMaxLike(object):
         self._own_context = False
         self._lane = (int(lane[0]), float(lane[1]), int(lane[2]))
         self._shuffle = np.random.shuffle
+        self._pin_shuffle()
         self.n_gpu_fits = 0
         observed = np.zeros(pattern.shape[0], dtype=bool)
         observed[list(self.observed_sbp_id_set)] = True
@@ -161,7 +162,16 @@ class ModelFitMaxLike(object):
                 self._context = LaneContext(self.num_put_variants, self.model.variant_sizes, device=self.device,
                                             tol=self.tol, max_iter=self.max_iter, history=self.history)
             self._lane = self._context.add_model(self.model)
+            self._pin_shuffle()
         return self._context
+
+    def _pin_shuffle(self):
+        """Inside a sharded job every rank replays the selection of every replicate and the lanes of a batch are matched
+        by POSITION, so the candidate permutation (ModelFitMaxLike.py:203, process-global np.random in the reference) must
+        be the same on all ranks: a generator seeded with the context's broadcast seed and this model's column id."""
+        seed = getattr(self._context, "shuffle_seed", None)
+        if seed is not None and self._shuffle is np.random.shuffle:
+            self._shuffle = np.random.default_rng([int(seed), int(self._lane[0])]).shuffle
 
     def close(self):
         if self._context is not None and self._own_context:

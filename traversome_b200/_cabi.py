@@ -16,8 +16,9 @@ LIB_PATH = os.path.join(_HERE, "libtvs.so")
 # every symbol include/tvs.h declares (tests check that the library exports all of them)
 SYMBOLS = (
     "tvs_version", "tvs_last_error", "tvs_device_count", "tvs_create", "tvs_destroy", "tvs_set_lanes",
-    "tvs_set_lanes_u16", "tvs_set_lanes_indexed", "tvs_resample", "tvs_get_weights", "tvs_loglik", "tvs_fit", "tvs_last_fit_stats", "tvs_dims",
-    "tvs_measure_fp64_peak", "tvs_selftest_math", "tvs_selftest_table_log",
+    "tvs_set_lanes_u16", "tvs_set_lanes_indexed", "tvs_columns_reserve", "tvs_columns_upload", "tvs_columns_upload_u16",
+    "tvs_columns_resample", "tvs_set_lanes_columns", "tvs_resample", "tvs_get_weights", "tvs_loglik", "tvs_fit", "tvs_last_fit_stats", "tvs_dims",
+    "tvs_measure_fp64_peak", "tvs_measure_smem_peak", "tvs_selftest_math", "tvs_selftest_table_log",
     # include/tvs_subpaths.h
     "tvs_subpaths_count", "tvs_subpaths_fetch", "tvs_subpaths_destroy",
 )
@@ -63,6 +64,11 @@ def load():
     lib.tvs_set_lanes.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     lib.tvs_set_lanes_u16.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     lib.tvs_set_lanes_indexed.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.tvs_columns_reserve.argtypes = [c_void_p, c_int64]
+    lib.tvs_columns_upload.argtypes = [c_void_p, c_int64, c_int64, c_void_p]
+    lib.tvs_columns_upload_u16.argtypes = [c_void_p, c_int64, c_int64, c_void_p]
+    lib.tvs_columns_resample.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_uint64, c_uint64]
+    lib.tvs_set_lanes_columns.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     lib.tvs_resample.argtypes = [c_void_p, c_int64, c_void_p, c_uint64, c_int, c_void_p, c_void_p]
     lib.tvs_get_weights.argtypes = [c_void_p, c_void_p]
     lib.tvs_loglik.argtypes = [c_void_p, c_void_p, c_void_p]
@@ -70,6 +76,7 @@ def load():
     lib.tvs_last_fit_stats.argtypes = [c_void_p, POINTER(FitStats)]
     lib.tvs_dims.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]
     lib.tvs_measure_fp64_peak.argtypes = [c_int, POINTER(c_double)]
+    lib.tvs_measure_smem_peak.argtypes = [c_int, POINTER(c_double)]
     lib.tvs_selftest_math.argtypes = [c_int, c_int64, c_void_p, c_void_p, c_void_p]
     lib.tvs_selftest_table_log.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
     lib.tvs_subpaths_count.argtypes = [POINTER(c_void_p), c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -190,6 +197,35 @@ class Engine(object):
         _check(self._lib.tvs_set_lanes_indexed(self._h, B, n_cols, _ptr(w_cols), _ptr(col_of_lane), _ptr(mask), _ptr(C)))
         self.B = B
 
+    # ---- device-resident weight columns
+    def columns_reserve(self, n_cols):
+        _check(self._lib.tvs_columns_reserve(self._h, int(n_cols)))
+
+    def columns_upload(self, first, w_cols):
+        """w_cols [R, n] int32 or uint16 (numpy / torch, host or device) -> slots first .. first+n-1."""
+        is_u16 = (isinstance(w_cols, np.ndarray) and w_cols.dtype == np.uint16) or str(getattr(w_cols, "dtype", "")) == "torch.uint16"
+        if not is_u16:
+            w_cols = _as(w_cols, np.int32)
+        elif isinstance(w_cols, np.ndarray):
+            w_cols = np.ascontiguousarray(w_cols)
+        n = int(w_cols.shape[1]) if len(w_cols.shape) == 2 else int((w_cols.size if isinstance(w_cols, np.ndarray) else w_cols.numel()) // self.R)
+        fn = self._lib.tvs_columns_upload_u16 if is_u16 else self._lib.tvs_columns_upload
+        _check(fn(self._h, int(first), n, _ptr(w_cols)))
+
+    def columns_resample(self, first, n, n_obs, seed, first_id):
+        n_obs = _as(n_obs, np.int32)
+        _check(self._lib.tvs_columns_resample(self._h, int(first), int(n), _ptr(n_obs), c_uint64(int(seed)), c_uint64(int(first_id))))
+
+    def set_lanes_columns(self, col_of_lane, mask=None, C=None):
+        """lane b <- slot col_of_lane[b] of the column store (no weights cross PCIe)."""
+        col_of_lane = _as(col_of_lane, np.int32)
+        B = int(col_of_lane.shape[0])
+        mask = _as(mask, np.uint8)
+        C = _as(C, np.float64)
+        self._keep = (col_of_lane, mask, C)
+        _check(self._lib.tvs_set_lanes_columns(self._h, B, _ptr(col_of_lane), _ptr(mask), _ptr(C)))
+        self.B = B
+
     def resample(self, B, n_obs, seed, keep_lane0=False, mask=None, C=None):
         n_obs = _as(n_obs, np.int32)
         mask = _as(mask, np.uint8)
@@ -243,6 +279,13 @@ class Engine(object):
 def measure_fp64_peak(device=0):
     v = c_double(0.0)
     _check(load().tvs_measure_fp64_peak(int(device), ctypes.byref(v)))
+    return v.value
+
+
+def measure_smem_peak(device=0):
+    """GB/s of conflict-free 16-byte shared-memory loads (LDS.128) over all SMs: the roof of the sparse products' operand."""
+    v = c_double(0.0)
+    _check(load().tvs_measure_smem_peak(int(device), ctypes.byref(v)))
     return v.value
 
 

@@ -109,6 +109,24 @@ class ReadPathMatrix(object):
         return True
 
 
+class CsrMatrix(object):
+    """A read-path x variant matrix given directly as CSR arrays (synthetic workloads, array-form replicates): the
+    same `R` / `arrays()` surface as ReadPathMatrix without one Python tuple per non-zero."""
+
+    def __init__(self, n_variants, row_ptr, col, val):
+        self.V = int(n_variants)
+        self._row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
+        self._col = np.ascontiguousarray(col, dtype=np.int32)
+        self._val = np.ascontiguousarray(val, dtype=np.int32)
+
+    @property
+    def R(self):
+        return int(self._row_ptr.shape[0] - 1)
+
+    def arrays(self):
+        return self._row_ptr, self._col, self._val
+
+
 def lane_from_bins(bins_list, matrix, add_rows=True):
     """One lane (= one model / replicate) -> (w {row: count}, C, N).
 

@@ -63,12 +63,13 @@ static void free_csr(Csr& c) {
     c.has_blk = false;
 }
 static void free_lanes(Lanes& l) {
-    dev_free(l.w); dev_free(l.mask); dev_free(l.C); dev_free(l.N); dev_free(l.w16);
+    dev_free(l.w); dev_free(l.mask); dev_free(l.C); dev_free(l.N); dev_free(l.w16); dev_free(l.flag); dev_free(l.cols); dev_free(l.slot);
     if (l.acc) cudaFree(l.acc);
     l = Lanes();
 }
 static void free_fit(FitState& f) {
     for (void* p : f.owned) cudaFree(p);
+    for (int i = 0; i < 2; ++i) { if (f.wbuf[i]) cudaFree(f.wbuf[i]); if (f.wbuf16[i]) cudaFree(f.wbuf16[i]); }
     if (f.h_nactive) cudaFreeHost(f.h_nactive);
     if (f.Hpart) cudaFree(f.Hpart);
     if (f.cr) cudaFree(f.cr);
@@ -337,7 +338,7 @@ static int make_plan(const tvs_problem* h, int64_t B, PassPlan* out) {
 //   P^T [W x R] = X^T [W x V] * A^T [V x R]      (lane-minor arrays are column-major matrices with ld = W)
 //   rr = w / p, ll += w log p                     (dense_mid_kernel, fixed summation order)
 //   T^T [W x V] = RR^T [W x R] * A [R x V]
-__global__ void dense_mid_kernel(double* __restrict__ P, const int32_t* __restrict__ w, const int32_t* __restrict__ done,
+__global__ void dense_mid_kernel(double* __restrict__ P, const int32_t* __restrict__ w, const uint16_t* __restrict__ w16, const int32_t* __restrict__ done,
                                  int64_t W, int64_t R, int64_t rows_per_split, double* __restrict__ llpart, int backward) {
     const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (lane >= W) return;
@@ -346,7 +347,7 @@ __global__ void dense_mid_kernel(double* __restrict__ P, const int32_t* __restri
     double ll = 0.0;
     for (int64_t r = r0; r < r1; ++r) {
         const int64_t i = r * W + lane;
-        const int32_t wv = w[i];
+        const int32_t wv = w16 != nullptr ? (int32_t)w16[i] : w[i];
         double rr = 0.0;
         if (live && wv != 0) {
             const double p = P[i];
@@ -396,7 +397,7 @@ static int launch_dense(tvs_problem* h, const PassArgs& a, bool backward) {
     cublasStatus_t cs = cublasDgemm(hd, CUBLAS_OP_N, CUBLAS_OP_N, (int)W, (int)R, (int)V, &one, a.x, (int)W, c.dense, (int)V, &zero,
                                     h->dense_p, (int)W);
     if (cs != CUBLAS_STATUS_SUCCESS) { set_error("cublasDgemm (p = A x) failed: %d", (int)cs); return TVS_ECUDA; }
-    dense_mid_kernel<<<dim3((unsigned)((W + 127) / 128), (unsigned)S), 128, 0, h->stream>>>(h->dense_p, a.w, a.done, W, R, rows_per_split,
+    dense_mid_kernel<<<dim3((unsigned)((W + 127) / 128), (unsigned)S), 128, 0, h->stream>>>(h->dense_p, a.w, a.w16, a.done, W, R, rows_per_split,
                                                                                           h->dense_ll, backward ? 1 : 0);
     dense_ll_reduce_kernel<<<(unsigned)((W + 127) / 128), 128, 0, h->stream>>>(h->dense_ll, S, W, a.llpart);
     TVS_CUDA(cudaGetLastError());
@@ -435,7 +436,7 @@ static int launch_blk(tvs_problem* h, const PassPlan& pl, const PassArgs& a) {
     BlkArgs f{};
     f.m.seg_off = c.blk_f.seg_off; f.m.blob = (const uint4*)c.blk_f.blob; f.m.n_chunks = c.blk_f.n_chunks;
     f.m.n_panels = c.blk_f.n_panels; f.m.max_seg_bytes = c.blk_f.max_seg_bytes;
-    f.src = a.x; f.n_minor = V; f.n_major = R; f.W = W; f.done = a.done; f.w32 = a.w; f.w16 = nullptr;
+    f.src = a.x; f.n_minor = V; f.n_major = R; f.W = W; f.done = a.done; f.w32 = a.w; f.w16 = a.w16;
     f.rr = BW ? h->blk_rr : nullptr; f.llpart = a.llpart; f.tpart = nullptr; f.stages = pl.stages;
     f.logc = a.logc; f.logtab = a.logtab;
     const dim3 gf((unsigned)pl.tiles, (unsigned)pl.splits);
@@ -496,7 +497,7 @@ static PassArgs base_args(const tvs_problem* h) {
     PassArgs a{};
     const Csr& c = h->csr;
     a.row_ptr = c.row_ptr; a.ent = c.ent; a.chunk_row0 = c.chunk_row0; a.ccol_ptr = c.ccol_ptr; a.ccol_id = c.ccol_id;
-    a.ccol_start = c.ccol_start; a.cent = c.cent; a.w = h->lanes.w; a.B = h->lanes.B; a.V = (int)c.V;
+    a.ccol_start = c.ccol_start; a.cent = c.cent; a.w = h->lanes.w; a.w16 = h->lanes.has16 ? h->lanes.w16 : nullptr; a.B = h->lanes.B; a.V = (int)c.V;
     a.n_chunks = c.n_chunks; a.rows_per_chunk = c.rows_per_chunk;
     a.stage_cap = std::max(c.max_chunk_nnz, 1);
     a.desc = (const ChunkDesc*)c.desc; a.logc = make_log_coef();
@@ -533,7 +534,7 @@ static int ensure_fit_state(tvs_problem* h, int m) {
     }
     f.half = B / 2 + 4;            // +3: compacted widths are padded to a multiple of 4 (vector loads of w)
     for (int i = 0; i < 2; ++i) {
-        A_(f.wbuf[i], (size_t)R * f.half) A_(f.mbuf[i], (size_t)V * f.half) A_(f.nbuf[i], f.half) A_(f.cbuf[i], f.half)
+        A_(f.mbuf[i], (size_t)V * f.half) A_(f.nbuf[i], f.half) A_(f.cbuf[i], f.half)      // wbuf / wbuf16: on first compaction
     }
     A_(f.gt, vb) A_(f.gh, vb)
     // partial buffers: splits*width never exceeds (resident CTAs)*(lanes per tile) + width
@@ -827,6 +828,7 @@ int tvs_destroy(tvs_handle h) {
     if (h->dense_p) cudaFree(h->dense_p);
     if (h->dense_ll) cudaFree(h->dense_ll);
     if (h->blk_rr) cudaFree(h->blk_rr);
+    if (h->ll_scratch) cudaFree(h->ll_scratch);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evp0) cudaEventDestroy(h->evp0);
@@ -845,11 +847,16 @@ int tvs_dims(tvs_handle h, int64_t* R, int64_t* V, int64_t* nnz, int64_t* B) {
     return TVS_OK;
 }
 
-static int reserve_lanes(tvs_problem* h, int64_t B, bool with_mask, bool with_C) {
+// Lane weights live on the device in one or both of two forms: int32 (`w`, has32) and 16-bit counts (`w16`, has16).  The
+// pass kernels read the 16-bit form when it exists (half the traffic of the only HBM stream of a pass: a 1000-lane cfg2
+// pass reads 36 MB instead of 72 MB and the solver state stays in L2 between the pass and the update kernel).
+static int reserve_lanes(tvs_problem* h, int64_t B, bool with_mask, bool with_C, bool need32) {
     Lanes& l = h->lanes;
     const int64_t R = h->csr.R, V = h->csr.V;
     int rc;
-    if (l.cap_w < R * B) { dev_free(l.w); if ((rc = dev_alloc(&l.w, (size_t)(R * B))) != TVS_OK) return rc; l.cap_w = R * B; }
+    if (need32 && l.cap_w < R * B) { dev_free(l.w); l.cap_w = 0; if ((rc = dev_alloc(&l.w, (size_t)(R * B))) != TVS_OK) return rc; l.cap_w = R * B; }
+    if (l.cap_w16 < R * B) { dev_free(l.w16); l.cap_w16 = 0; if ((rc = dev_alloc(&l.w16, (size_t)(R * B))) != TVS_OK) return rc; l.cap_w16 = R * B; }
+    if (!l.flag && (rc = dev_alloc(&l.flag, 1)) != TVS_OK) return rc;
     if (with_mask) {
         if (l.cap_mask < V * B || !l.mask) { dev_free(l.mask); if ((rc = dev_alloc(&l.mask, (size_t)(V * B))) != TVS_OK) return rc; l.cap_mask = V * B; }
     } else { dev_free(l.mask); l.cap_mask = 0; }
@@ -860,15 +867,34 @@ static int reserve_lanes(tvs_problem* h, int64_t B, bool with_mask, bool with_C)
     }
     if (with_C) { if (!l.C && (rc = dev_alloc(&l.C, (size_t)l.cap_b)) != TVS_OK) return rc; }
     else dev_free(l.C);
-    l.B = B;
+    l.B = B; l.has32 = false; l.has16 = false;
     return TVS_OK;
 }
 
-static int finish_lanes(tvs_problem* h, const uint8_t* mask, const double* C) {
+// the int32 form on demand (tvs_get_weights after a 16-bit upload)
+static int ensure_w32(tvs_problem* h) {
     Lanes& l = h->lanes;
-    const int64_t V = h->csr.V, B = l.B;
+    if (l.has32) return TVS_OK;
+    const int64_t n = h->csr.R * l.B;
+    int rc;
+    if (l.cap_w < n) { dev_free(l.w); l.cap_w = 0; if ((rc = dev_alloc(&l.w, (size_t)n)) != TVS_OK) return rc; l.cap_w = n; }
+    widen_u16_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, h->stream>>>(l.w16, l.w, n);
+    TVS_CUDA(cudaGetLastError());
+    l.has32 = true;
+    return TVS_OK;
+}
+
+// `from16`: the weights were uploaded as 16-bit counts (l.w16); otherwise l.w holds them and the 16-bit copy is made here.
+static int finish_lanes(tvs_problem* h, const uint8_t* mask, const double* C, bool from16) {
+    Lanes& l = h->lanes;
+    const int64_t V = h->csr.V, B = l.B, n = h->csr.R * B;
     if (mask) TVS_CUDA(cudaMemcpyAsync(l.mask, mask, (size_t)(V * B), cudaMemcpyDefault, h->stream));
     if (C) TVS_CUDA(cudaMemcpyAsync(l.C, C, (size_t)B * sizeof(double), cudaMemcpyDefault, h->stream));
+    const bool narrow = !from16 && env_int("TVS_W16", 1) != 0;
+    if (narrow) {
+        cudaMemsetAsync(l.flag, 0, sizeof(int32_t), h->stream);
+        narrow_u16_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, h->stream>>>(l.w, l.w16, n, l.flag);
+    }
     {   // N_b = sum_r w[r,b] (exact integer sums; the solver state is not allocated yet, so use a scratch buffer)
         if (l.cap_acc < B) {
             if (l.acc) cudaFree(l.acc);
@@ -880,11 +906,21 @@ static int finish_lanes(tvs_problem* h, const uint8_t* mask, const double* C) {
         cudaMemsetAsync(acc, 0, (size_t)B * sizeof(unsigned long long), h->stream);
         const unsigned tiles = (unsigned)((B + 31) / 32);
         const unsigned slices = (unsigned)std::max<int64_t>(1, std::min<int64_t>(h->csr.R / 64 + 1, (int64_t)(4 * h->sm_count) / tiles + 1));
-        lane_sum_kernel<<<dim3(tiles, slices), 256, 0, h->stream>>>(l.w, h->csr.R, B, acc);
+        if (from16) lane_sum_kernel<uint16_t><<<dim3(tiles, slices), 256, 0, h->stream>>>(l.w16, h->csr.R, B, acc);
+        else lane_sum_kernel<int32_t><<<dim3(tiles, slices), 256, 0, h->stream>>>(l.w, h->csr.R, B, acc);
         lane_sum_finish_kernel<<<(unsigned)((B + 255) / 256), 256, 0, h->stream>>>(acc, B, l.N);
     }
     TVS_CUDA(cudaGetLastError());
-    TVS_CUDA(cudaStreamSynchronize(h->stream));
+    l.has32 = !from16; l.has16 = from16;
+    if (narrow) {          // the host needs the overflow flag to choose the form the pass kernels read
+        int32_t overflow = 0;
+        TVS_CUDA(cudaMemcpyAsync(&overflow, l.flag, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        TVS_CUDA(cudaStreamSynchronize(h->stream));
+        l.has16 = overflow == 0;
+    }
+    // 16-bit uploads do not synchronise: the copy of the caller's buffer and the kernels above are queued on the handle's
+    // stream, tvs_fit / tvs_loglik follow on the same stream (include/tvs.h: the buffer must stay valid until the next
+    // call on the handle has returned)
     h->lanes_set = true;
     return TVS_OK;
 }
@@ -893,25 +929,28 @@ int tvs_set_lanes(tvs_handle h, int64_t B, const int32_t* w, const uint8_t* mask
     if (!h || B <= 0 || !w) { set_error("tvs_set_lanes: null handle/weights or B<=0"); return TVS_EINVAL; }
     TVS_CUDA(cudaSetDevice(h->device));
     h->lanes_set = false;
-    int rc = reserve_lanes(h, B, mask != nullptr, C != nullptr);
+    int rc = reserve_lanes(h, B, mask != nullptr, C != nullptr, true);
     if (rc != TVS_OK) return rc;
     TVS_CUDA(cudaMemcpyAsync(h->lanes.w, w, (size_t)(h->csr.R * B) * sizeof(int32_t), cudaMemcpyDefault, h->stream));
-    return finish_lanes(h, mask, C);
+    return finish_lanes(h, mask, C, false);
 }
 
 int tvs_set_lanes_u16(tvs_handle h, int64_t B, const uint16_t* w, const uint8_t* mask, const double* C) {
     if (!h || B <= 0 || !w) { set_error("tvs_set_lanes_u16: null handle/weights or B<=0"); return TVS_EINVAL; }
     TVS_CUDA(cudaSetDevice(h->device));
     h->lanes_set = false;
-    int rc = reserve_lanes(h, B, mask != nullptr, C != nullptr);
+    int rc = reserve_lanes(h, B, mask != nullptr, C != nullptr, false);
     if (rc != TVS_OK) return rc;
-    const int64_t n = h->csr.R * B;
-    Lanes& l = h->lanes;
-    if (l.cap_w16 < n) { dev_free(l.w16); if ((rc = dev_alloc(&l.w16, (size_t)n)) != TVS_OK) return rc; l.cap_w16 = n; }
-    TVS_CUDA(cudaMemcpyAsync(l.w16, w, (size_t)n * sizeof(uint16_t), cudaMemcpyDefault, h->stream));
-    widen_u16_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, h->stream>>>(l.w16, l.w, n);
-    cudaError_t e = cudaGetLastError();
-    return (e == cudaSuccess) ? finish_lanes(h, mask, C) : cuda_fail(e, "widen_u16_kernel", __FILE__, __LINE__);
+    TVS_CUDA(cudaMemcpyAsync(h->lanes.w16, w, (size_t)(h->csr.R * B) * sizeof(uint16_t), cudaMemcpyDefault, h->stream));
+    return finish_lanes(h, mask, C, true);
+}
+
+static int check_slots(const int32_t* ids, int64_t B, int64_t limit, const char* who, std::vector<int32_t>* out) {
+    out->resize((size_t)B);
+    TVS_CUDA(cudaMemcpy(out->data(), ids, (size_t)B * sizeof(int32_t), cudaMemcpyDefault));
+    for (int64_t b = 0; b < B; ++b)
+        if ((*out)[(size_t)b] < 0 || (*out)[(size_t)b] >= limit) { set_error("%s: column %d of lane %lld out of range (0..%lld)", who, (*out)[(size_t)b], (long long)b, (long long)limit - 1); return TVS_EINVAL; }
+    return TVS_OK;
 }
 
 int tvs_set_lanes_indexed(tvs_handle h, int64_t B, int64_t n_cols, const int32_t* w_cols, const int32_t* col_of_lane,
@@ -920,12 +959,10 @@ int tvs_set_lanes_indexed(tvs_handle h, int64_t B, int64_t n_cols, const int32_t
     TVS_CUDA(cudaSetDevice(h->device));
     h->lanes_set = false;
     const int64_t R = h->csr.R;
-    std::vector<int32_t> idx((size_t)B);
-    TVS_CUDA(cudaMemcpy(idx.data(), col_of_lane, (size_t)B * sizeof(int32_t), cudaMemcpyDefault));
-    for (int64_t b = 0; b < B; ++b)
-        if (idx[b] < 0 || idx[b] >= n_cols) { set_error("tvs_set_lanes_indexed: col_of_lane[%lld]=%d out of range", (long long)b, idx[b]); return TVS_EINVAL; }
-    int rc = reserve_lanes(h, B, mask != nullptr, C != nullptr);
+    std::vector<int32_t> idx;
+    int rc = check_slots(col_of_lane, B, n_cols, "tvs_set_lanes_indexed", &idx);
     if (rc != TVS_OK) return rc;
+    if ((rc = reserve_lanes(h, B, mask != nullptr, C != nullptr, true)) != TVS_OK) return rc;
     int32_t *d_cols = nullptr, *d_idx = nullptr;
     if ((rc = dev_alloc(&d_cols, (size_t)(R * n_cols))) != TVS_OK) return rc;
     if ((rc = dev_alloc(&d_idx, (size_t)B)) != TVS_OK) { cudaFree(d_cols); return rc; }
@@ -933,48 +970,148 @@ int tvs_set_lanes_indexed(tvs_handle h, int64_t B, int64_t n_cols, const int32_t
     cudaMemcpyAsync(d_idx, idx.data(), (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream);
     gather_rows(h->stream, (const int32_t*)d_cols, h->lanes.w, R, n_cols, B, d_idx);
     cudaError_t e = cudaGetLastError();
-    rc = (e == cudaSuccess) ? finish_lanes(h, mask, C) : cuda_fail(e, "expand weight columns", __FILE__, __LINE__);
+    rc = (e == cudaSuccess) ? finish_lanes(h, mask, C, false) : cuda_fail(e, "expand weight columns", __FILE__, __LINE__);
     cudaFree(d_cols); cudaFree(d_idx);
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------ column store
+int tvs_columns_reserve(tvs_handle h, int64_t n_cols) {
+    if (!h || n_cols <= 0) { set_error("tvs_columns_reserve: null handle or n_cols<=0"); return TVS_EINVAL; }
+    TVS_CUDA(cudaSetDevice(h->device));
+    Lanes& l = h->lanes;
+    if (n_cols <= l.col_cap) return TVS_OK;
+    const int64_t R = h->csr.R;
+    int32_t* fresh = nullptr;
+    int rc = dev_alloc(&fresh, (size_t)(R * n_cols));
+    if (rc != TVS_OK) return rc;
+    if (l.cols) {      // keep the registered columns: row pitch changes from col_cap to n_cols
+        cudaMemcpy2DAsync(fresh, (size_t)n_cols * 4, l.cols, (size_t)l.col_cap * 4, (size_t)l.col_cap * 4, (size_t)R, cudaMemcpyDeviceToDevice, h->stream);
+        cudaStreamSynchronize(h->stream);
+        cudaFree(l.cols);
+    }
+    l.cols = fresh; l.col_cap = n_cols;
+    TVS_CUDA(cudaGetLastError());
+    return TVS_OK;
+}
+
+static int columns_range_ok(tvs_problem* h, int64_t first, int64_t n, const char* who) {
+    if (first < 0 || n <= 0 || first + n > h->lanes.col_cap) {
+        set_error("%s: columns %lld..%lld outside the reserved store (%lld)", who, (long long)first, (long long)(first + n - 1), (long long)h->lanes.col_cap);
+        return TVS_EINVAL;
+    }
+    return TVS_OK;
+}
+
+int tvs_columns_upload(tvs_handle h, int64_t first, int64_t n, const int32_t* w_cols) {
+    if (!h || !w_cols) { set_error("tvs_columns_upload: null argument"); return TVS_EINVAL; }
+    TVS_CUDA(cudaSetDevice(h->device));
+    int rc = columns_range_ok(h, first, n, "tvs_columns_upload");
+    if (rc != TVS_OK) return rc;
+    Lanes& l = h->lanes;
+    TVS_CUDA(cudaMemcpy2DAsync(l.cols + first, (size_t)l.col_cap * 4, w_cols, (size_t)n * 4, (size_t)n * 4, (size_t)h->csr.R, cudaMemcpyDefault, h->stream));
+    TVS_CUDA(cudaStreamSynchronize(h->stream));
+    return TVS_OK;
+}
+
+int tvs_columns_upload_u16(tvs_handle h, int64_t first, int64_t n, const uint16_t* w_cols) {
+    if (!h || !w_cols) { set_error("tvs_columns_upload_u16: null argument"); return TVS_EINVAL; }
+    TVS_CUDA(cudaSetDevice(h->device));
+    int rc = columns_range_ok(h, first, n, "tvs_columns_upload_u16");
+    if (rc != TVS_OK) return rc;
+    Lanes& l = h->lanes;
+    const int64_t R = h->csr.R, cnt = R * n;
+    uint16_t* tmp = nullptr;
+    if ((rc = dev_alloc(&tmp, (size_t)cnt)) != TVS_OK) return rc;
+    cudaMemcpyAsync(tmp, w_cols, (size_t)cnt * 2, cudaMemcpyDefault, h->stream);
+    widen_columns_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(tmp, n, R, l.cols, l.col_cap, first);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    return e == cudaSuccess ? TVS_OK : cuda_fail(e, "tvs_columns_upload_u16", __FILE__, __LINE__);
+}
+
+static int resample_into(tvs_problem* h, int32_t* dst, int64_t ld, int64_t n, const int32_t* n_obs, uint64_t seed, int keep_first, uint32_t id0);
+
+int tvs_columns_resample(tvs_handle h, int64_t first, int64_t n, const int32_t* n_obs, uint64_t seed, uint64_t first_id) {
+    if (!h || !n_obs) { set_error("tvs_columns_resample: null argument"); return TVS_EINVAL; }
+    TVS_CUDA(cudaSetDevice(h->device));
+    int rc = columns_range_ok(h, first, n, "tvs_columns_resample");
+    if (rc != TVS_OK) return rc;
+    if (first_id + (uint64_t)n > 0xffffffffull) { set_error("tvs_columns_resample: column ids beyond 2^32"); return TVS_ELIMIT; }
+    rc = resample_into(h, h->lanes.cols + first, h->lanes.col_cap, n, n_obs, seed, 0, (uint32_t)first_id);
+    if (rc != TVS_OK) return rc;
+    TVS_CUDA(cudaStreamSynchronize(h->stream));
+    return TVS_OK;
+}
+
+int tvs_set_lanes_columns(tvs_handle h, int64_t B, const int32_t* col_of_lane, const uint8_t* mask, const double* C) {
+    if (!h || B <= 0 || !col_of_lane) { set_error("tvs_set_lanes_columns: null argument or B<=0"); return TVS_EINVAL; }
+    TVS_CUDA(cudaSetDevice(h->device));
+    Lanes& l = h->lanes;
+    if (!l.cols) { set_error("tvs_set_lanes_columns: no columns registered (tvs_columns_reserve / _upload)"); return TVS_ESTATE; }
+    h->lanes_set = false;
+    std::vector<int32_t> idx;
+    int rc = check_slots(col_of_lane, B, l.col_cap, "tvs_set_lanes_columns", &idx);
+    if (rc != TVS_OK) return rc;
+    if ((rc = reserve_lanes(h, B, mask != nullptr, C != nullptr, true)) != TVS_OK) return rc;
+    if (l.cap_slot < B) { dev_free(l.slot); l.cap_slot = 0; if ((rc = dev_alloc(&l.slot, (size_t)B)) != TVS_OK) return rc; l.cap_slot = B; }
+    TVS_CUDA(cudaMemcpyAsync(l.slot, idx.data(), (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    const int64_t R = h->csr.R;
+    dim3 grid((unsigned)((B + 127) / 128), (unsigned)std::min<int64_t>(R, 4096));
+    gather_columns_kernel<<<grid, 128, 0, h->stream>>>(l.cols, l.col_cap, l.slot, R, B, l.w);
+    TVS_CUDA(cudaGetLastError());
+    return finish_lanes(h, mask, C, false);
+}
+
+// n bootstrap columns into dst[r*ld + j] (j < n): column j ~ Multinomial(N, n_obs/N) from the Philox stream id0 + j
+static int resample_into(tvs_problem* h, int32_t* dst, int64_t ld, int64_t n, const int32_t* n_obs, uint64_t seed, int keep_first, uint32_t id0) {
+    const int64_t R = h->csr.R;
+    std::vector<int32_t> nn((size_t)R);
+    TVS_CUDA(cudaMemcpy(nn.data(), n_obs, (size_t)R * sizeof(int32_t), cudaMemcpyDefault));
+    std::vector<int64_t> cum((size_t)R);
+    int64_t tot = 0;
+    for (int64_t r = 0; r < R; ++r) {
+        if (nn[r] < 0) { set_error("resample: negative count at row %lld", (long long)r); return TVS_EINVAL; }
+        tot += nn[r]; cum[r] = tot;
+    }
+    if (tot <= 0) { set_error("resample: no records"); return TVS_EINVAL; }
+    int64_t* d_cum = nullptr; int32_t* d_n = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&d_cum, (size_t)R)) != TVS_OK) return rc;
+    if ((rc = dev_alloc(&d_n, (size_t)R)) != TVS_OK) { cudaFree(d_cum); return rc; }
+    cudaMemcpyAsync(d_cum, cum.data(), (size_t)R * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(d_n, nn.data(), (size_t)R * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream);
+    cudaMemset2DAsync(dst, (size_t)ld * 4, 0, (size_t)n * 4, (size_t)R, h->stream);
+    const int threads = 256;
+    const int bx = (int)std::min<int64_t>((tot + threads - 1) / threads, 64);
+    for (int64_t j0 = 0; j0 < n; j0 += 32768) {
+        const int64_t nj = std::min<int64_t>(32768, n - j0);
+        resample_kernel<<<dim3(bx, (unsigned)nj), threads, 0, h->stream>>>(d_cum, R, tot, ld, seed, keep_first, d_n, dst + j0, id0 + (uint32_t)j0);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);          // the host vectors and the scratch arrays die here
+    cudaFree(d_cum); cudaFree(d_n);
+    return e == cudaSuccess ? TVS_OK : cuda_fail(e, "resample_kernel", __FILE__, __LINE__);
 }
 
 int tvs_resample(tvs_handle h, int64_t B, const int32_t* n_obs, uint64_t seed, int keep_lane0, const uint8_t* mask,
                  const double* C) {
     if (!h || B <= 0 || !n_obs) { set_error("tvs_resample: null handle/n_obs or B<=0"); return TVS_EINVAL; }
-    if (B > 65535) { set_error("tvs_resample: B > 65535 lanes per call unsupported"); return TVS_ELIMIT; }
     TVS_CUDA(cudaSetDevice(h->device));
     h->lanes_set = false;
-    const int64_t R = h->csr.R;
-    int rc = reserve_lanes(h, B, mask != nullptr, C != nullptr);
+    int rc = reserve_lanes(h, B, mask != nullptr, C != nullptr, true);
     if (rc != TVS_OK) return rc;
-    std::vector<int32_t> n((size_t)R);
-    TVS_CUDA(cudaMemcpy(n.data(), n_obs, (size_t)R * sizeof(int32_t), cudaMemcpyDefault));
-    std::vector<int64_t> cum((size_t)R);
-    int64_t tot = 0;
-    for (int64_t r = 0; r < R; ++r) {
-        if (n[r] < 0) { set_error("tvs_resample: negative count at row %lld", (long long)r); return TVS_EINVAL; }
-        tot += n[r]; cum[r] = tot;
-    }
-    if (tot <= 0) { set_error("tvs_resample: no records"); return TVS_EINVAL; }
-    int64_t* d_cum = nullptr; int32_t* d_n = nullptr;
-    if ((rc = dev_alloc(&d_cum, (size_t)R)) != TVS_OK) return rc;
-    if ((rc = dev_alloc(&d_n, (size_t)R)) != TVS_OK) { cudaFree(d_cum); return rc; }
-    cudaMemcpyAsync(d_cum, cum.data(), (size_t)R * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream);
-    cudaMemcpyAsync(d_n, n.data(), (size_t)R * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream);
-    cudaMemsetAsync(h->lanes.w, 0, (size_t)(R * B) * sizeof(int32_t), h->stream);
-    const int threads = 256;
-    int bx = (int)std::min<int64_t>((tot + threads - 1) / threads, 64);
-    resample_kernel<<<dim3(bx, (unsigned)B), threads, 0, h->stream>>>(d_cum, R, tot, B, seed, keep_lane0, d_n, h->lanes.w);
-    cudaError_t e = cudaGetLastError();
-    rc = (e == cudaSuccess) ? finish_lanes(h, mask, C) : cuda_fail(e, "resample_kernel", __FILE__, __LINE__);
-    cudaFree(d_cum); cudaFree(d_n);
-    return rc;
+    if ((rc = resample_into(h, h->lanes.w, B, B, n_obs, seed, keep_lane0, 0u)) != TVS_OK) return rc;
+    return finish_lanes(h, mask, C, false);
 }
 
 int tvs_get_weights(tvs_handle h, int32_t* w_out) {
     if (!h || !w_out) { set_error("tvs_get_weights: null argument"); return TVS_EINVAL; }
     if (!h->lanes_set) { set_error("tvs_get_weights: lanes not set"); return TVS_ESTATE; }
     TVS_CUDA(cudaSetDevice(h->device));
+    int rc = ensure_w32(h);
+    if (rc != TVS_OK) return rc;
     TVS_CUDA(cudaMemcpyAsync(w_out, h->lanes.w, (size_t)(h->csr.R * h->lanes.B) * sizeof(int32_t), cudaMemcpyDefault, h->stream));
     TVS_CUDA(cudaStreamSynchronize(h->stream));
     return TVS_OK;
@@ -988,11 +1125,17 @@ int tvs_loglik(tvs_handle h, const double* theta, double* ll_out) {
     PassPlan pl;
     int rc = make_plan<false>(h, B, &pl);
     if (rc != TVS_OK) return rc;
-    double *d_theta = nullptr, *d_x = nullptr, *d_den = nullptr, *d_llp = nullptr, *d_out = nullptr;
-    auto cleanup = [&]() { cudaFree(d_theta); cudaFree(d_x); cudaFree(d_den); cudaFree(d_llp); cudaFree(d_out); };
-    if ((rc = dev_alloc(&d_theta, (size_t)(V * B))) != TVS_OK || (rc = dev_alloc(&d_x, (size_t)(V * B))) != TVS_OK ||
-        (rc = dev_alloc(&d_den, (size_t)B)) != TVS_OK || (rc = dev_alloc(&d_llp, (size_t)B * pl.splits)) != TVS_OK ||
-        (rc = dev_alloc(&d_out, (size_t)B)) != TVS_OK) { cleanup(); return rc; }
+    // one pooled scratch block per handle (was five cudaMalloc / cudaFree per call)
+    const size_t need = (size_t)(2 * V * B) + (size_t)B * (size_t)(pl.splits + 2);
+    if (h->ll_scratch_cap < need) {
+        if (h->ll_scratch) cudaFree(h->ll_scratch);
+        h->ll_scratch = nullptr; h->ll_scratch_cap = 0;
+        TVS_CUDA(cudaMalloc((void**)&h->ll_scratch, need * sizeof(double)));
+        h->ll_scratch_cap = need;
+    }
+    double* d_theta = h->ll_scratch; double* d_x = d_theta + V * B; double* d_den = d_x + V * B; double* d_out = d_den + B;
+    double* d_llp = d_out + B;
+    auto cleanup = [&]() {};
     cudaMemcpyAsync(d_theta, theta, (size_t)(V * B) * sizeof(double), cudaMemcpyDefault, h->stream);
     const unsigned gb = (unsigned)((B + 127) / 128);
     prep_theta_kernel<<<gb, 128, 0, h->stream>>>(d_theta, h->lanes.mask, h->csr.Ld, (int)V, B, d_x, d_den);
@@ -1033,24 +1176,33 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
     cudaStream_t st = h->stream;
     const size_t vb0 = (size_t)V * B0;
 
-    TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Vl2Layout<4>::doubles * 8)));
-    TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Vl2Layout<8>::doubles * 8)));
-    TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Vl2Layout<16>::doubles * 8)));
-    TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl2_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Vl2Layout<12>::doubles * 8)));
+    if (!h->attrs_set) {                                           // once per handle (the attribute is per device)
+        TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Vl2Layout<4>::doubles * 8)));
+        TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Vl2Layout<8>::doubles * 8)));
+        TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Vl2Layout<16>::doubles * 8)));
+        TVS_CUDA(cudaFuncSetAttribute(lbfgs_update_vl2_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Vl2Layout<12>::doubles * 8)));
+        h->attrs_set = true;
+    }
     TVS_CUDA(cudaEventRecord(h->ev0, st));
     int cur = 0;
     {   // ---- reset set 0 (full width, views the caller's lanes)
         LaneSet& s = f.set[0];
-        s.width = B0; s.w = h->lanes.w; s.mask = h->lanes.mask; s.N = h->lanes.N; s.C = h->lanes.C;
-        cudaMemsetAsync(s.z, 0, vb0 * 8, st); cudaMemsetAsync(s.g, 0, vb0 * 8, st); cudaMemsetAsync(s.d, 0, vb0 * 8, st);
-        cudaMemsetAsync(f.gt, 0, vb0 * 8, st);
-        cudaMemsetAsync(s.F, 0, B0 * 8, st); cudaMemsetAsync(s.dg, 0, B0 * 8, st); cudaMemsetAsync(s.alpha, 0, B0 * 8, st);
-        cudaMemsetAsync(s.llsum, 0, B0 * 8, st); cudaMemsetAsync(s.kkt, 0, 2 * B0 * 8, st); cudaMemsetAsync(s.sumphi, 0, B0 * 8, st);
-        cudaMemsetAsync(s.gamma, 0, B0 * 8, st); cudaMemsetAsync(s.rho, 0, (size_t)B0 * m * 8, st);
-        cudaMemsetAsync(s.gram, 0, (size_t)B0 * ((2 * m + 1) * (2 * m + 2) / 2) * 8, st);
-        cudaMemsetAsync(s.S, 0, vb0 * m * 8, st); cudaMemsetAsync(s.Y, 0, vb0 * m * 8, st);
-        cudaMemsetAsync(s.ls, 0, B0 * 4, st); cudaMemsetAsync(s.iters, 0xFF, B0 * 4, st); cudaMemsetAsync(s.status, 0, B0 * 4, st);
-        cudaMemsetAsync(s.head, 0, B0 * 4, st); cudaMemsetAsync(s.cnt, 0, B0 * 4, st); cudaMemsetAsync(s.done, 0, B0 * 4, st);
+        s.width = B0; s.mask = h->lanes.mask; s.N = h->lanes.N; s.C = h->lanes.C;
+        s.w16 = h->lanes.has16 ? h->lanes.w16 : nullptr; s.w = h->lanes.has16 ? nullptr : h->lanes.w;   // the 16-bit form when the lanes carry it
+        FillArgs fa{};
+        auto fill = [&](void* ptr, size_t bytes, uint32_t v) { fa.t[fa.n].p = ptr; fa.t[fa.n].bytes = bytes; fa.t[fa.n].fill = v; ++fa.n; };
+        fill(s.z, vb0 * 8, 0); fill(s.g, vb0 * 8, 0); fill(s.d, vb0 * 8, 0); fill(f.gt, vb0 * 8, 0);
+        fill(s.F, B0 * 8, 0); fill(s.dg, B0 * 8, 0); fill(s.alpha, B0 * 8, 0); fill(s.llsum, B0 * 8, 0); fill(s.kkt, 2 * B0 * 8, 0);
+        fill(s.sumphi, B0 * 8, 0); fill(s.gamma, B0 * 8, 0); fill(s.rho, (size_t)B0 * m * 8, 0);
+        fill(s.gram, (size_t)B0 * ((2 * m + 1) * (2 * m + 2) / 2) * 8, 0);
+        fill(s.S, vb0 * m * 8, 0); fill(s.Y, vb0 * m * 8, 0);
+        fill(s.ls, B0 * 4, 0); fill(s.iters, B0 * 4, 0xFFFFFFFFu); fill(s.status, B0 * 4, 0);
+        fill(s.head, B0 * 4, 0); fill(s.cnt, B0 * 4, 0); fill(s.done, B0 * 4, 0);
+        {
+            const size_t big = vb0 * m * 8 / 16;                  // 16-byte words of the largest array
+            const unsigned gx = (unsigned)std::max<size_t>(1, std::min<size_t>((big + 255) / 256, (size_t)h->sm_count * 4));
+            fill_many_kernel<<<dim3(gx, (unsigned)fa.n), 256, 0, st>>>(fa);
+        }
         iota_kernel<<<(unsigned)((B0 + 255) / 256), 256, 0, st>>>(s.orig, B0);
         const double* d_theta0 = nullptr;
         if (theta0) { cudaMemcpyAsync(f.theta_io, theta0, vb0 * 8, cudaMemcpyDefault, st); d_theta0 = f.theta_io; }
@@ -1132,7 +1284,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         newton_init_kernel<<<(unsigned)((W + 127) / 128), 128, 0, st>>>(s.z, s.g, s.mask, h->csr.invL, (int)V, W, f.gha, s.x, f.lam, f.need, s.ls);
         ++launches;
         PassArgs pa = base_args(h);
-        pa.w = s.w; pa.B = W; pa.x = s.x; pa.done = s.done; pa.tpart = f.tpart; pa.llpart = f.llpart;
+        pa.w = s.w; pa.w16 = s.w16; pa.B = W; pa.x = s.x; pa.done = s.done; pa.tpart = f.tpart; pa.llpart = f.llpart;
         pa.cr = wide ? nullptr : f.cr; pa.crf = wide ? f.crf : nullptr;
         {   // refresh pass at the accepted point: c_r = w_r / p_r^2 for the first Hessian
             int lrc = launch_pass<true>(h, pl, pa);
@@ -1229,7 +1381,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
                 while (pl.splits > 1 && (size_t)pl.splits * (size_t)W > f.llpart_cap) --pl.splits;
             }
             PassArgs pa = base_args(h);
-            pa.w = s.w; pa.B = W; pa.x = s.x; pa.done = s.done; pa.tpart = f.tpart; pa.llpart = f.llpart;
+            pa.w = s.w; pa.w16 = s.w16; pa.B = W; pa.x = s.x; pa.done = s.done; pa.tpart = f.tpart; pa.llpart = f.llpart;
             UpdArgs ua{};
             ua.invL = h->csr.invL; ua.N = s.N; ua.mask = s.mask;
             ua.z = s.z; ua.zt = s.zt; ua.g = s.g; ua.gt = f.gt; ua.gh = f.gh; ua.d = s.d; ua.x = s.x; ua.Sh = s.S; ua.Yh = s.Y;
@@ -1291,7 +1443,14 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
             const int bi = (int)(compactions & 1);
             // new width: survivors + up to 3 padding lanes (index -1 -> zeros, flagged done, no original id)
             const int64_t A = (active + 3) & ~(int64_t)3;
-            n.w = f.wbuf[bi]; n.mask = s.mask ? f.mbuf[bi] : nullptr; n.N = f.nbuf[bi]; n.C = s.C ? f.cbuf[bi] : nullptr;
+            {   // compaction buffer of the weights, in the form the lane set carries (allocated on first use)
+                cudaError_t ae = cudaSuccess;
+                if (s.w16 && !f.wbuf16[bi]) ae = cudaMalloc((void**)&f.wbuf16[bi], (size_t)R * f.half * sizeof(uint16_t));
+                if (!s.w16 && !f.wbuf[bi]) ae = cudaMalloc((void**)&f.wbuf[bi], (size_t)R * f.half * sizeof(int32_t));
+                if (ae != cudaSuccess) { rc = cuda_fail(ae, "compaction buffer", __FILE__, __LINE__); break; }
+            }
+            n.w = s.w16 ? nullptr : f.wbuf[bi]; n.w16 = s.w16 ? f.wbuf16[bi] : nullptr;
+            n.mask = s.mask ? f.mbuf[bi] : nullptr; n.N = f.nbuf[bi]; n.C = s.C ? f.cbuf[bi] : nullptr;
             {   // one launch gathers every per-lane matrix (the L-BFGS history only while that phase is still running)
                 GatherArgs ga{};
                 int64_t row0 = 0;
@@ -1301,7 +1460,8 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
                     row0 += rows; ++ga.n;
                 };
                 const int64_t ng = (int64_t)((2 * m + 1) * (2 * m + 2) / 2);
-                add(s.w, f.wbuf[bi], R, 4); add(s.mask, f.mbuf[bi], V, 1); add(s.N, f.nbuf[bi], 1, 8); add(s.C, f.cbuf[bi], 1, 8);
+                if (s.w16) add(s.w16, f.wbuf16[bi], R, 2); else add(s.w, f.wbuf[bi], R, 4);
+                add(s.mask, f.mbuf[bi], V, 1); add(s.N, f.nbuf[bi], 1, 8); add(s.C, f.cbuf[bi], 1, 8);
                 add(s.orig, n.orig, 1, 4); add(s.z, n.z, V, 8); add(s.zt, n.zt, V, 8); add(s.g, n.g, V, 8); add(s.d, n.d, V, 8); add(s.x, n.x, V, 8);
                 if (!in_newton && !to_newton) {
                     add(s.S, n.S, (int64_t)m * V, 8); add(s.Y, n.Y, (int64_t)m * V, 8); add(s.rho, n.rho, m, 8); add(s.gamma, n.gamma, 1, 8);
@@ -1446,6 +1606,33 @@ int tvs_measure_fp64_peak(int device, double* tflops_out) {
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     *tflops_out = best;
+    return TVS_OK;
+}
+
+int tvs_measure_smem_peak(int device, double* gbs_out) {
+    if (!gbs_out) { set_error("gbs_out is null"); return TVS_EINVAL; }
+    TVS_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    TVS_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 2, threads = 512, iters = 1 << 14;
+    double* d = nullptr;
+    TVS_CUDA(cudaMalloc((void**)&d, (size_t)blocks * threads * 8));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        smem_peak_kernel<<<blocks, threads>>>(d, iters);
+        cudaEventRecord(e1);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e, "smem_peak_kernel", __FILE__, __LINE__); }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double bytes = 16.0 * 8.0 * (double)iters * blocks * threads;
+        best = std::max(best, bytes / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *gbs_out = best;
     return TVS_OK;
 }
 

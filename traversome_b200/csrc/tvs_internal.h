@@ -65,8 +65,14 @@ struct Lanes {
     double*  C = nullptr;      // [B]
     double*  N = nullptr;      // [B]
     int64_t  cap_w = 0, cap_mask = 0, cap_b = 0;
-    uint16_t* w16 = nullptr;   // staging of tvs_set_lanes_u16
+    uint16_t* w16 = nullptr;   // [R*B] the same weights as 16-bit counts (valid when has16)
     int64_t  cap_w16 = 0;
+    bool     has32 = false;    // w holds the current lanes
+    bool     has16 = false;    // w16 holds the current lanes (every count <= 65535); the pass kernels prefer it
+    int32_t* flag = nullptr;   // device word: overflow flag of the narrowing kernel
+    // device-resident column store (tvs_columns_*): [R x col_cap] int32, element (r, c) at [r*col_cap + c]
+    int32_t* cols = nullptr; int64_t col_cap = 0;
+    int32_t* slot = nullptr; int64_t cap_slot = 0;   // staging of the lanes' column slots
     unsigned long long* acc = nullptr;   // integer lane sums (finish_lanes)
     int64_t  cap_acc = 0;
 };
@@ -77,7 +83,8 @@ struct Lanes {
 struct LaneSet {
     int64_t width = 0;
     // inputs (set 0 views the arrays of Lanes; after the first compaction they are owned copies)
-    const int32_t* w = nullptr; const uint8_t* mask = nullptr; const double* N = nullptr; const double* C = nullptr;
+    const int32_t* w = nullptr; const uint16_t* w16 = nullptr;   // weights: the 16-bit form when the lanes carry it, else int32
+    const uint8_t* mask = nullptr; const double* N = nullptr; const double* C = nullptr;
     int32_t* orig = nullptr;      // [cap] original lane id of each column
     // solver state, all lane-minor [rows * width]
     double *z = nullptr, *zt = nullptr, *g = nullptr, *d = nullptr, *x = nullptr;          // V rows
@@ -92,7 +99,8 @@ struct LaneSet {
 struct FitState {               // all device, sized for (V, B, history)
     int64_t V = 0, B = 0, R = 0; int m = 0;
     LaneSet set[2];
-    int32_t* wbuf[2] = {nullptr, nullptr}; uint8_t* mbuf[2] = {nullptr, nullptr};
+    int32_t* wbuf[2] = {nullptr, nullptr}; uint16_t* wbuf16[2] = {nullptr, nullptr};   // compaction buffers of the weights (allocated on first use)
+    uint8_t* mbuf[2] = {nullptr, nullptr};
     double* nbuf[2] = {nullptr, nullptr}; double* cbuf[2] = {nullptr, nullptr};
     int64_t half = 0;           // capacity (lanes) of the compaction buffers above
     double *gt = nullptr, *gh = nullptr;            // scratch, V rows at full width
@@ -120,10 +128,12 @@ struct tvs_problem {
     tvs::FitState fs;
     tvs_fit_stats stats{};
     bool lanes_set = false;
+    bool attrs_set = false;     // cudaFuncSetAttribute of the update kernels done
     // dense (DGEMM) pass: cuBLAS handle bound to `stream`, p / w/p matrix [R x width], per-split log-likelihood partials
     void* cublas = nullptr;
     double* dense_p = nullptr; size_t dense_p_cap = 0;
     double* dense_ll = nullptr; size_t dense_ll_cap = 0;
     // blk pass: w/p of the forward product [R x width], read back by the backward product
     double* blk_rr = nullptr; size_t blk_rr_cap = 0;
+    double* ll_scratch = nullptr; size_t ll_scratch_cap = 0;     // tvs_loglik: theta, x, denominators, partials, result
 };

@@ -29,6 +29,7 @@ struct PassArgs {
     const int32_t* chunk_row0; const int32_t* ccol_ptr; const int32_t* ccol_id; const int32_t* ccol_start;
     const uint32_t* cent;
     const int32_t* w; const double* x; const int32_t* done;
+    const uint16_t* w16;  // the same weights as 16-bit counts (preferred by pass3_kernel / blk_kernel when not null: half the traffic)
     double* tpart; double* llpart;
     int64_t B; int V; int n_chunks; int rows_per_chunk;
     int stage_cap;       // capacity (entries) of the shared-memory staging buffers of pass3_kernel
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kThreads) pass_kernel(const PassArgs a) {
             }
 #pragma unroll
             for (int j = 0; j < LPT; ++j) {
-                const int wv = lv[j] ? __ldg(a.w + (int64_t)r * B + lane[j]) : 0;
+                const int wv = !lv[j] ? 0 : (a.w16 != nullptr ? (int)__ldg(a.w16 + (int64_t)r * B + lane[j]) : __ldg(a.w + (int64_t)r * B + lane[j]));
                 double rr = 0.0;
                 if (wv > 0) {
                     const double wd = (double)wv;
@@ -193,7 +194,8 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
 // ------------------------------------------------------------------------------------------------
 // N_b = sum_r w[r,b]: grid.x = lane tiles of 32, grid.y = row slices; exact integer partial sums, one atomicAdd
 // (64-bit integer: order-independent) per (slice, lane).  lane_sum_finish_kernel converts to double.
-__global__ void __launch_bounds__(256) lane_sum_kernel(const int32_t* __restrict__ w, int64_t R, int64_t B, unsigned long long* __restrict__ acc) {
+template <typename T>
+__global__ void __launch_bounds__(256) lane_sum_kernel(const T* __restrict__ w, int64_t R, int64_t B, unsigned long long* __restrict__ acc) {
     __shared__ long long red[8][32];
     const int t = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const int64_t b = (int64_t)blockIdx.x * 32 + t;
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(256) lane_sum_kernel(const int32_t* __restrict
     const int64_t r0 = (int64_t)blockIdx.y * rows, r1 = min(R, r0 + rows);
     long long s = 0;
     if (b < B)
-        for (int64_t r = r0 + wi; r < r1; r += 8) s += w[r * B + b];
+        for (int64_t r = r0 + wi; r < r1; r += 8) s += (long long)w[r * B + b];
     red[wi][t] = s;
     __syncthreads();
     if (wi == 0 && b < B) {
@@ -740,6 +742,9 @@ __global__ void __launch_bounds__(128) gather_all_kernel(const GatherArgs a) {
         } else if (a.t[k].elem == 4) {
             const int32_t v = (sj >= 0) ? static_cast<const int32_t*>(a.t[k].src)[r * a.Bs + sj] : 0;
             static_cast<int32_t*>(a.t[k].dst)[r * a.Bd + j] = v;
+        } else if (a.t[k].elem == 2) {
+            const uint16_t v = (sj >= 0) ? static_cast<const uint16_t*>(a.t[k].src)[r * a.Bs + sj] : (uint16_t)0;
+            static_cast<uint16_t*>(a.t[k].dst)[r * a.Bd + j] = v;
         } else {
             const uint8_t v = (sj >= 0) ? static_cast<const uint8_t*>(a.t[k].src)[r * a.Bs + sj] : (uint8_t)0;
             static_cast<uint8_t*>(a.t[k].dst)[r * a.Bd + j] = v;
@@ -755,6 +760,52 @@ __global__ void widen_u16_kernel(const uint16_t* __restrict__ src, int32_t* __re
     } else {
         for (int64_t k = i; k < n; ++k) dst[k] = src[k];
     }
+}
+
+// int32 -> uint16 copy of the weights; *overflow is set when a count does not fit (the 16-bit copy is then not used)
+__global__ void narrow_u16_kernel(const int32_t* __restrict__ src, uint16_t* __restrict__ dst, int64_t n, int32_t* __restrict__ overflow) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    bool bad = false;
+    if (i + 4 <= n) {
+        const int4 v = *reinterpret_cast<const int4*>(src + i);
+        bad = ((unsigned)v.x | (unsigned)v.y | (unsigned)v.z | (unsigned)v.w) > 65535u;
+        *reinterpret_cast<ushort4*>(dst + i) = make_ushort4((unsigned short)v.x, (unsigned short)v.y, (unsigned short)v.z, (unsigned short)v.w);
+    } else {
+        for (int64_t k = i; k < n; ++k) { bad = bad || (unsigned)src[k] > 65535u; dst[k] = (uint16_t)src[k]; }
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(overflow, 1);
+}
+
+// lane columns from the device-resident column store: dst[r, b] = store[r, slot[b]]  (replaces the per-batch rebuild of the
+// replicate weights, traversome.py:515-545)
+__global__ void gather_columns_kernel(const int32_t* __restrict__ store, int64_t cap, const int32_t* __restrict__ slot, int64_t R, int64_t B,
+                                      int32_t* __restrict__ dst) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int64_t sj = slot[b];
+    for (int64_t r = blockIdx.y; r < R; r += gridDim.y) dst[r * B + b] = store[r * cap + sj];
+}
+__global__ void widen_columns_kernel(const uint16_t* __restrict__ src, int64_t n, int64_t R, int32_t* __restrict__ store, int64_t cap, int64_t first) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // src [R x n] lane-minor
+    if (i >= R * n) return;
+    const int64_t r = i / n, c = i - r * n;
+    store[r * cap + first + c] = src[i];
+}
+
+// All the solver-state arrays of a fit reset in ONE launch (tvs_fit issued ~25 memsets before): task k fills `bytes`
+// (a multiple of 4) at p with the 32-bit pattern `fill`.  grid.y = task.
+struct FillTask { void* p; size_t bytes; uint32_t fill; };
+constexpr int kMaxFillTasks = 28;
+struct FillArgs { FillTask t[kMaxFillTasks]; int n; };
+__global__ void __launch_bounds__(256) fill_many_kernel(const FillArgs a) {
+    const FillTask k = a.t[blockIdx.y];
+    const size_t n16 = k.bytes / 16;
+    const uint4 v = make_uint4(k.fill, k.fill, k.fill, k.fill);
+    uint4* p16 = static_cast<uint4*>(k.p);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p16[i] = v;
+    uint32_t* p4 = static_cast<uint32_t*>(k.p) + n16 * 4;
+    const size_t rest = (k.bytes - n16 * 16) / 4;
+    if (blockIdx.x == 0 && threadIdx.x < rest) p4[threadIdx.x] = k.fill;
 }
 
 __global__ void iota_kernel(int32_t* p, int64_t n) {
@@ -780,18 +831,19 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__global__ void resample_kernel(const int64_t* __restrict__ cum, int64_t R, int64_t Ntot, int64_t B, uint64_t seed,
-                                int keep_lane0, const int32_t* __restrict__ n_obs, int32_t* __restrict__ w) {
-    // grid.y = lane, grid-stride over draws
+// Lane b (grid.y) is written with stride `ld` (element (r, b) at w[r*ld + b]); its Philox stream is keyed by id0 + b, so a
+// column of the column store (tvs_columns_resample) depends on its id only.  keep_lane0: stream 0 is the observed data.
+__global__ void resample_kernel(const int64_t* __restrict__ cum, int64_t R, int64_t Ntot, int64_t ld, uint64_t seed,
+                                int keep_lane0, const int32_t* __restrict__ n_obs, int32_t* __restrict__ w, uint32_t id0) {
     const int64_t b = blockIdx.y;
-    if (keep_lane0 && b == 0) {
+    if (keep_lane0 && b == 0 && id0 == 0) {
         for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x)
-            w[r * B] = n_obs[r];
+            w[r * ld] = n_obs[r];
         return;
     }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Ntot; i += (int64_t)gridDim.x * blockDim.x) {
         uint32_t o[4];
-        philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)b, 0x54565321u, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+        philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)b + id0, 0x54565321u, (uint32_t)seed, (uint32_t)(seed >> 32), o);
         const uint64_t u = ((uint64_t)o[1] << 32) | o[0];
         const uint64_t idx = __umul64hi(u, (uint64_t)Ntot);
         int64_t lo = 0, hi = R - 1;                 // first r with cum[r] > idx
@@ -799,7 +851,7 @@ __global__ void resample_kernel(const int64_t* __restrict__ cum, int64_t R, int6
             const int64_t mid = (lo + hi) >> 1;
             if (__ldg(cum + mid) > (int64_t)idx) hi = mid; else lo = mid + 1;
         }
-        atomicAdd(w + lo * B + b, 1);
+        atomicAdd(w + lo * ld + b, 1);
     }
 }
 
@@ -812,6 +864,30 @@ __global__ void fp64_peak_kernel(double* out, int iters, double seed) {
         a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
     }
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// shared-memory read peak: every thread streams 16-byte words of a 32 KB tile, conflict-free (a warp reads 512 contiguous
+// bytes per instruction), 8 independent loads in flight
+__global__ void __launch_bounds__(512) smem_peak_kernel(double* out, int iters) {
+    __shared__ double2 tile[2048];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) tile[i] = make_double2(1.0 + i, 2.0);
+    __syncthreads();
+    double2 acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = make_double2(0.0, 0.0);
+    unsigned idx = threadIdx.x;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double2 v = tile[(idx + 256u * j) & 2047u];     // 8 distinct rows of 32 x 16 bytes
+            acc[j].x += v.x; acc[j].y += v.y;
+        }
+        idx = (idx + 32u) & 2047u;
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += acc[j].x + acc[j].y;
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 }  // namespace tvs

@@ -139,6 +139,21 @@ template <> struct WVec<1> { int v[1]; };
 template <> struct __align__(8) WVec<2> { int v[2]; };
 template <> struct __align__(16) WVec<4> { int v[4]; };
 
+// K consecutive lanes' weights of one row: 16-bit counts when the lane set carries them, else int32
+template <int K>
+__device__ __forceinline__ WVec<K> load_w(const PassArgs& a, int64_t idx) {
+    WVec<K> o;
+    if (a.w16 != nullptr) {
+        if (K == 1) o.v[0] = a.w16[idx];
+        else if (K == 2) { const unsigned u = *reinterpret_cast<const unsigned*>(a.w16 + idx); o.v[0] = (int)(u & 0xffffu); o.v[K - 1] = (int)(u >> 16); }
+        else {
+            const uint2 u = *reinterpret_cast<const uint2*>(a.w16 + idx);
+            o.v[0] = (int)(u.x & 0xffffu); o.v[1 % K] = (int)(u.x >> 16); o.v[2 % K] = (int)(u.y & 0xffffu); o.v[3 % K] = (int)(u.y >> 16);
+        }
+    } else o = *reinterpret_cast<const WVec<K>*>(a.w + idx);
+    return o;
+}
+
 template <int K>
 __device__ __forceinline__ void lds_lanes(const double* row, int t, double* out) {   // out[K] = lanes K*t .. K*t+K-1
     if (K == 1) out[0] = row[t];
@@ -206,7 +221,7 @@ __global__ void __launch_bounds__(kThreads2, 1) pass2_kernel(const PassArgs a) {
         for (int r = row0 + wi; r < row1; r += kWarps2) {
             const int k0 = __ldg(a.row_ptr + r), k1 = __ldg(a.row_ptr + r + 1);
             WVec<K> wv;
-            if (lv) wv = *reinterpret_cast<const WVec<K>*>(a.w + (int64_t)r * B + mylane);
+            if (lv) wv = load_w<K>(a, (int64_t)r * B + mylane);
             else {
 #pragma unroll
                 for (int j = 0; j < K; ++j) wv.v[j] = 0;
@@ -426,7 +441,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
         WVec<K> wnext;
         {
             const int r = row0 + wi;
-            if (lv && r < row1) wnext = *reinterpret_cast<const WVec<K>*>(a.w + (int64_t)r * B + mylane);
+            if (lv && r < row1) wnext = load_w<K>(a, (int64_t)r * B + mylane);
             else {
 #pragma unroll
                 for (int j = 0; j < K; ++j) wnext.v[j] = 0;
@@ -434,7 +449,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
         }
         for (int r = row0 + wi; r < row1; r += NW) {
             const WVec<K> wv = wnext;
-            if (lv && r + NW < row1) wnext = *reinterpret_cast<const WVec<K>*>(a.w + (int64_t)(r + NW) * B + mylane);
+            if (lv && r + NW < row1) wnext = load_w<K>(a, (int64_t)(r + NW) * B + mylane);
             const int k0 = rp[r - row0] - e0, k1 = rp[r - row0 + 1] - e0;
             double p[K];
 #pragma unroll

@@ -3,16 +3,19 @@
 The reference fits one subset of one replicate at a time (ModelFitMaxLike.py:349-370 inside the
 loops of :199-322, repeated per replicate by traversome.py:515-556).  Here every such fit is a
 "lane" = (weight column, candidate subset); a `LaneContext` owns the read-path x variant CSR on one
-GPU and turns a list of lane requests into one `tvs_set_lanes_indexed` + `tvs_fit`.  With a
+GPU, keeps the weight columns RESIDENT on the device (registered once, named by slot afterwards:
+`tvs_columns_*`, `tvs_set_lanes_columns`) and turns a batch of lanes into one `tvs_fit`.  With a
 `LaneSharder` the lanes of a batch are split over the ranks of a torch.distributed job (one process
-per GPU) and only the per-lane results are gathered.
+per GPU); every rank fits its slice and ONE all_gather of the per-lane results -- straight from the
+device buffers `tvs_fit` wrote -- returns all of them to all ranks.
 """
 import threading
+import zlib
 
 import numpy as np
 
 from . import _cabi
-from .csr import ReadPathMatrix, lane_from_bins
+from .csr import CsrMatrix, ReadPathMatrix, lane_from_bins
 
 
 class FitResult(object):
@@ -34,18 +37,84 @@ class LaneRequest(object):
         self.theta0 = None if theta0 is None else np.asarray(theta0, dtype=np.float64)
 
 
+class LaneBatch(object):
+    """Array form of a list of lanes: `cols` int64[B], `C` float64[B], `mask` uint8[V,B] or None (= every variant in
+    every lane), `theta0` float64[V,B] or None (= uniform starts).  Built once when the same batch is fitted again and
+    again (bootstrap of a fixed candidate set), otherwise by `from_requests`."""
+    __slots__ = ("cols", "C", "mask", "theta0")
+
+    def __init__(self, cols, C=None, mask=None, theta0=None):
+        self.cols = np.ascontiguousarray(cols, dtype=np.int64)
+        B = self.cols.shape[0]
+        self.C = np.zeros(B, dtype=np.float64) if C is None else np.ascontiguousarray(C, dtype=np.float64)
+        self.mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self.theta0 = None if theta0 is None else np.ascontiguousarray(theta0, dtype=np.float64)
+
+    def __len__(self):
+        return int(self.cols.shape[0])
+
+    @classmethod
+    def from_requests(cls, requests, V):
+        B = len(requests)
+        cols = np.fromiter((rq.col for rq in requests), dtype=np.int64, count=B)
+        C = np.fromiter((rq.C for rq in requests), dtype=np.float64, count=B)
+        sizes = np.fromiter((len(rq.ids) for rq in requests), dtype=np.int64, count=B)
+        mask = None
+        flat = lane = None
+        if B and (sizes != V).any():
+            # one scatter for the whole batch instead of a Python loop over lanes
+            flat = np.concatenate([np.asarray(rq.ids, dtype=np.int64) for rq in requests]) if sizes.sum() else np.zeros(0, np.int64)
+            lane = np.repeat(np.arange(B, dtype=np.int64), sizes)
+            mask = np.zeros((V, B), dtype=np.uint8)
+            mask[flat, lane] = 1
+        theta0 = None
+        if any(rq.theta0 is not None for rq in requests):
+            if flat is None:
+                flat = np.concatenate([np.asarray(rq.ids, dtype=np.int64) for rq in requests])
+                lane = np.repeat(np.arange(B, dtype=np.int64), sizes)
+            vals = np.concatenate([rq.theta0 if rq.theta0 is not None else np.full(len(rq.ids), 1.0 / max(len(rq.ids), 1))
+                                   for rq in requests])
+            theta0 = np.zeros((V, B), dtype=np.float64)
+            theta0[flat, lane] = vals
+        return cls(cols, C, mask, theta0)
+
+    def slice(self, lo, hi):
+        return LaneBatch(self.cols[lo:hi], self.C[lo:hi], None if self.mask is None else self.mask[:, lo:hi],
+                         None if self.theta0 is None else self.theta0[:, lo:hi])
+
+    def digest(self):
+        """32-bit digest of what the lanes ARE (columns, subsets): ranks of a sharded job compare it before they split a
+        batch by position."""
+        d = zlib.crc32(self.cols.tobytes())
+        if self.mask is not None:
+            d = zlib.crc32(np.packbits(self.mask, axis=0).tobytes(), d)
+        return d & 0x7fffffff
+
+
+_RESULT_KEYS = ("theta", "loglike", "kkt", "iters", "status")
+
+
 class LaneSharder(object):
     """Contiguous split of a batch of lanes over the ranks of a process group + result gather.
 
     No data-path collective: every rank holds the whole CSR and fits its own slice; one
-    all_gather of {theta, loglike, kkt, iters, status} per batch (NCCL on GPUs, gloo in CPU tests)."""
+    all_gather of {theta, loglike, kkt, iters, status} per batch (NCCL on GPUs, gloo in CPU tests).
+    With NCCL the solver writes its results into views of ONE packed device buffer per rank (tvs_fit accepts device
+    pointers), the collective runs on that buffer and a single device->host copy of the gathered block follows."""
 
     def __init__(self, group=None):
+        import torch
         import torch.distributed as dist
+        self._torch = torch
         self._dist = dist
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        self.backend = dist.get_backend(group)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if self.backend == "nccl" else torch.device("cpu")
+        self._bufs = {}
+        self.bytes_gathered = 0          # total bytes received by this rank's all_gathers (diagnostics / bench)
+        self.n_gathers = 0
 
     @staticmethod
     def bounds(B, rank, world):
@@ -57,36 +126,108 @@ class LaneSharder(object):
     def my_slice(self, B):
         return self.bounds(B, self.rank, self.world)
 
+    # ---- packed per-rank result block: [theta V*cap f64][loglike cap f64][kkt 2*cap f64][iters cap i32][status cap i32]
+    @staticmethod
+    def _layout(cap, V):
+        o_ll = V * cap * 8
+        o_kkt = o_ll + cap * 8
+        o_it = o_kkt + cap * 16
+        o_st = o_it + cap * 4
+        return o_ll, o_kkt, o_it, o_st, o_st + cap * 4
+
+    def _buffers(self, cap, V):
+        key = (cap, V)
+        if key not in self._bufs:
+            torch = self._torch
+            nbytes = self._layout(cap, V)[-1]
+            mine = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            every = torch.zeros(self.world * nbytes, dtype=torch.uint8, device=self.device)
+            host = torch.zeros(self.world * nbytes, dtype=torch.uint8, pin_memory=True) if self.device.type == "cuda" else None
+            if len(self._bufs) > 8:
+                self._bufs.clear()
+            self._bufs[key] = (mine, every, host)
+        return self._bufs[key]
+
+    def views(self, n, B, V):
+        """Views of this rank's packed block for its `n` lanes of a batch of B, keyed like Engine.fit's result
+        (torch tensors; on the CPU their .numpy() share the memory)."""
+        torch = self._torch
+        cap = (int(B) + self.world - 1) // self.world
+        mine = self._buffers(cap, V)[0]
+        o_ll, o_kkt, o_it, o_st, _ = self._layout(cap, V)
+        return {"theta": mine[0:V * n * 8].view(torch.float64).view(V, n),
+                "loglike": mine[o_ll:o_ll + n * 8].view(torch.float64),
+                "kkt": mine[o_kkt:o_kkt + n * 16].view(torch.float64).view(n, 2),
+                "iters": mine[o_it:o_it + n * 4].view(torch.int32),
+                "status": mine[o_st:o_st + n * 4].view(torch.int32)}
+
+    def check_same_batch(self, B, digest):
+        """All ranks must hold the same batch before it is split by position (a rank-dependent permutation of the
+        candidates would silently pair lanes with the wrong results): one tiny all_gather, raises on mismatch."""
+        torch, dist = self._torch, self._dist
+        t = torch.tensor([int(B), int(digest)], dtype=torch.int64, device=self.device)
+        every = torch.empty(self.world * 2, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(every, t, group=self.group)
+        every = every.cpu().view(self.world, 2)
+        if not bool((every == every[0]).all()):
+            raise RuntimeError("LaneSharder: ranks hold different lane batches (sizes/digests %s): the candidate order must not "
+                               "depend on the rank -- seed or broadcast every permutation" % every.tolist())
+
     def gather(self, local, B, V):
-        """local: dict of this rank's arrays (theta [V,b], loglike [b], kkt [b,2], iters [b], status [b]);
-        returns the same dict for all B lanes, identical on every rank."""
-        import torch
-        dist = self._dist
-        backend = dist.get_backend(self.group)
-        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-        cap = (B + self.world - 1) // self.world
-        width = V + 5                                     # theta | loglike | kkt0 | kkt1 | iters | status
-        buf = torch.zeros((cap, width), dtype=torch.float64)
+        """local: this rank's result dict (arrays or the `views` themselves) for its slice of a batch of B lanes;
+        returns the dict (numpy) for all B lanes, identical on every rank."""
+        torch, dist = self._torch, self._dist
+        cap = (int(B) + self.world - 1) // self.world
+        mine, every, host = self._buffers(cap, V)
         lo, hi = self.my_slice(B)
         n = hi - lo
         if n:
-            buf[:n, :V] = torch.from_numpy(np.ascontiguousarray(local["theta"].T))
-            buf[:n, V] = torch.from_numpy(np.asarray(local["loglike"], dtype=np.float64))
-            buf[:n, V + 1:V + 3] = torch.from_numpy(np.asarray(local["kkt"], dtype=np.float64))
-            buf[:n, V + 3] = torch.from_numpy(np.asarray(local["iters"], dtype=np.float64))
-            buf[:n, V + 4] = torch.from_numpy(np.asarray(local["status"], dtype=np.float64))
-        buf = buf.to(dev)
-        out = torch.empty((self.world * cap, width), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(out, buf, group=self.group)
-        out = out.cpu().numpy().reshape(self.world, cap, width)
-        rows = []
+            mv = self.views(n, B, V)
+            for k in _RESULT_KEYS:
+                src = local[k]
+                if isinstance(src, torch.Tensor) and src.data_ptr() == mv[k].data_ptr():
+                    continue                                   # the solver wrote straight into the packed block
+                mv[k].copy_(torch.as_tensor(np.ascontiguousarray(src)).to(mv[k].dtype))
+        dist.all_gather_into_tensor(every, mine, group=self.group)
+        if host is not None:
+            host.copy_(every, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            flat = host.numpy()
+        else:
+            flat = every.numpy()
+        self.bytes_gathered += int(every.numel())
+        self.n_gathers += 1
+        nbytes = mine.numel()
+        o_ll, o_kkt, o_it, o_st, _ = self._layout(cap, V)
+        out = {"theta": np.empty((V, B), dtype=np.float64), "loglike": np.empty(B, dtype=np.float64),
+               "kkt": np.empty((B, 2), dtype=np.float64), "iters": np.empty(B, dtype=np.int32), "status": np.empty(B, dtype=np.int32)}
         for r in range(self.world):
             a, b = self.bounds(B, r, self.world)
-            rows.append(out[r, :b - a])
-        full = np.concatenate(rows, axis=0)
-        return {"theta": np.ascontiguousarray(full[:, :V].T), "loglike": full[:, V].copy(),
-                "kkt": full[:, V + 1:V + 3].copy(), "iters": full[:, V + 3].astype(np.int32),
-                "status": full[:, V + 4].astype(np.int32)}
+            m = b - a
+            if not m:
+                continue
+            blk = flat[r * nbytes:(r + 1) * nbytes]
+            out["theta"][:, a:b] = blk[0:V * m * 8].view(np.float64).reshape(V, m)
+            out["loglike"][a:b] = blk[o_ll:o_ll + m * 8].view(np.float64)
+            out["kkt"][a:b] = blk[o_kkt:o_kkt + m * 16].view(np.float64).reshape(m, 2)
+            out["iters"][a:b] = blk[o_it:o_it + m * 4].view(np.int32)
+            out["status"][a:b] = blk[o_st:o_st + m * 4].view(np.int32)
+        return out
+
+    def broadcast_seed(self):
+        """One 63-bit seed chosen by rank 0 for everything that must be random but identical on all ranks."""
+        torch, dist = self._torch, self._dist
+        t = torch.tensor([int(np.random.SeedSequence().entropy % (1 << 62))], dtype=torch.int64, device=self.device)
+        dist.broadcast(t, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        return int(t.item())
+
+
+class _Residency(object):
+    """Which weight columns of a LaneContext live in which slot of one engine's column store."""
+    __slots__ = ("slot_of", "used", "cap")
+
+    def __init__(self):
+        self.slot_of, self.used, self.cap = {}, 0, 0
 
 
 class LaneContext(object):
@@ -97,6 +238,9 @@ class LaneContext(object):
     # streams, two host threads): the narrow tail of one half overlaps the wide phase of the other.  Measured on cfg2:
     # 4000 lanes 40.9 -> 35.7 ms (1.15x), no gain at 1000 lanes (tools/two_handles.py).  0 disables.
     concurrent_min_lanes = 3000
+    # STALLED lanes (line search exhausted at fp64 resolution) are accepted only when their KKT residuals are within this
+    # factor of the tolerances (complementarity tol, dual 100 tol); otherwise they are reported like MAXITER
+    stalled_slack = 1e3
 
     def __init__(self, n_variants, variant_sizes, device=0, sharder=None, tol=1e-9, max_iter=2000, history=16):
         self.V = int(n_variants)
@@ -105,13 +249,26 @@ class LaneContext(object):
         self.sharder = sharder
         self.tol, self.max_iter, self.history = tol, max_iter, history
         self.matrix = ReadPathMatrix(self.V)
-        self._cols = []               # list of (rows, counts): sparse weight columns
+        self._cols = []               # per column: (rows, counts) sparse host copy, or ("resample", n_obs, seed, id)
         self._engine = None
         self._engine2 = None          # second handle for concurrent halves (created on first use)
         self._engine_R = -1
+        self._resident = {}           # id(engine) -> _Residency
         self.n_lanes_fitted = 0
         self.n_batches = 0
+        self.check_consistency = True
+        self.time_passes = False      # CUDA events around every pass launch (roofline figures; ~1 ms per fit)
         self.engine_factory = _cabi.Engine     # tests of the host logic inject a stand-in here
+        # permutations drawn inside a sharded job must not depend on the rank (ModelFitMaxLike.py:203 shuffles the
+        # candidates with the process-global np.random): one seed from rank 0
+        self.shuffle_seed = sharder.broadcast_seed() if sharder is not None else None
+
+    @classmethod
+    def from_csr(cls, n_variants, variant_sizes, row_ptr, col, val, **kw):
+        """A context over a matrix given as CSR arrays (rows = read paths in the caller's order)."""
+        self = cls(n_variants, variant_sizes, **kw)
+        self.matrix = CsrMatrix(n_variants, row_ptr, col, val)
+        return self
 
     # ---- models -> weight columns
     def add_model(self, model):
@@ -126,45 +283,56 @@ class LaneContext(object):
     def add_weights(self, w):
         """Register a dense weight column w[R] (synthetic workloads)."""
         w = np.asarray(w)
+        if w.size and int(w.min()) < 0:
+            raise ValueError("LaneContext.add_weights: negative weight")
         rows = np.nonzero(w)[0]
         self._cols.append((rows.astype(np.int64), w[rows].astype(np.int32)))
         return len(self._cols) - 1
+
+    def add_resampled(self, n_obs, n, seed):
+        """Register n bootstrap replicates of the observed counts n_obs[R] that are DRAWN ON THE DEVICE when first used
+        (tvs_columns_resample: Philox stream = column id, so a column is the same on whichever rank draws it).
+        Returns the list of column ids."""
+        n_obs = np.ascontiguousarray(n_obs, dtype=np.int32)
+        first = len(self._cols)
+        for j in range(int(n)):
+            self._cols.append(("resample", n_obs, int(seed), first + j))
+        return list(range(first, first + int(n)))
 
     @staticmethod
     def _sparse_column(w_map):
         """{row: count} -> (rows int64[], counts int32[]): columns are scattered with numpy, not Python loops."""
         rows = np.fromiter(w_map.keys(), dtype=np.int64, count=len(w_map))
         vals = np.fromiter(w_map.values(), dtype=np.int32, count=len(w_map))
+        if vals.size and int(vals.min()) < 0:
+            raise ValueError("LaneContext: negative weight")
         return rows, vals
+
+    def _new_engine(self):
+        row_ptr, col, val = self.matrix.arrays()
+        return self.engine_factory(row_ptr, col, val, self.L, n_variants=self.V, device=self.device)
 
     def engine(self):
         if self._engine is None or self._engine_R != self.matrix.R:
-            if self._engine is not None:
-                self._engine.close()
-            if self._engine2 is not None:
-                self._engine2.close()
-                self._engine2 = None
+            self.close()
             if self.matrix.R == 0:
                 raise Exception("Likelihood maximization failed.")        # nothing to fit
-            row_ptr, col, val = self.matrix.arrays()
-            self._engine = self.engine_factory(row_ptr, col, val, self.L, n_variants=self.V, device=self.device)
+            self._engine = self._new_engine()
             self._engine_R = self.matrix.R
         return self._engine
 
     def second_engine(self):
         self.engine()
         if self._engine2 is None:
-            row_ptr, col, val = self.matrix.arrays()
-            self._engine2 = self.engine_factory(row_ptr, col, val, self.L, n_variants=self.V, device=self.device)
+            self._engine2 = self._new_engine()
         return self._engine2
 
     def close(self):
-        if self._engine is not None:
-            self._engine.close()
-            self._engine = None
-        if self._engine2 is not None:
-            self._engine2.close()
-            self._engine2 = None
+        for e in (self._engine, self._engine2):
+            if e is not None:
+                e.close()
+        self._engine = self._engine2 = None
+        self._resident = {}
 
     def dense_columns(self, cols):
         w = np.zeros((self.matrix.R, len(cols)), dtype=np.int32)
@@ -173,21 +341,83 @@ class LaneContext(object):
             w[rows, j] = vals
         return w
 
+    def _slots(self, eng, cols):
+        """Slots of `cols` (array of column ids) in the column store of `eng`; columns seen for the first time are
+        uploaded (host copies, one dense block) or drawn on the device (add_resampled) now."""
+        res = self._resident.setdefault(id(eng), _Residency())
+        uniq = np.unique(cols)
+        missing = [int(c) for c in uniq if int(c) not in res.slot_of]
+        if missing:
+            need = res.used + len(missing)
+            if need > res.cap:
+                res.cap = max(need, 2 * res.cap, 16)
+                eng.columns_reserve(res.cap)
+            host = [c for c in missing if not (isinstance(self._cols[c][0], str))]
+            if host:
+                eng.columns_upload(res.used, self.dense_columns(host))
+                for j, c in enumerate(host):
+                    res.slot_of[c] = res.used + j
+                res.used += len(host)
+            drawn = [c for c in missing if isinstance(self._cols[c][0], str)]
+            i = 0
+            while i < len(drawn):                        # runs of consecutive ids with the same source -> one call each
+                j = i
+                _, n_obs, seed, cid = self._cols[drawn[i]]
+                while (j + 1 < len(drawn) and self._cols[drawn[j + 1]][3] == self._cols[drawn[j]][3] + 1
+                       and self._cols[drawn[j + 1]][1] is n_obs and self._cols[drawn[j + 1]][2] == seed):
+                    j += 1
+                n = j - i + 1
+                eng.columns_resample(res.used, n, n_obs, seed, cid)
+                for k in range(n):
+                    res.slot_of[drawn[i + k]] = res.used + k
+                res.used += n
+                i = j + 1
+        lut = res.slot_of
+        return np.fromiter((lut[int(c)] for c in cols), dtype=np.int32, count=len(cols))
+
     # ---- the batched fit
     def fit(self, requests):
         """requests: list of LaneRequest -> list of FitResult (same order)."""
         B = len(requests)
         if B == 0:
             return []
-        lo, hi = (0, B) if self.sharder is None else self.sharder.my_slice(B)
+        out = self.fit_batch(LaneBatch.from_requests(requests, self.V))
+        results = []
+        status_all, ll_all, kkt_all = out["status"], out["loglike"], out["kkt"]
+        ok_all = self.lane_ok(out)
+        for b, rq in enumerate(requests):
+            results.append(FitResult(x=np.array(out["theta"][rq.ids, b], dtype=np.float64), fun=-float(ll_all[b]), success=bool(ok_all[b]),
+                                     status=int(status_all[b]), kkt=tuple(kkt_all[b]), nit=int(out["iters"][b])))
+        return results
+
+    def lane_ok(self, out):
+        """success flag per lane: CONVERGED, or STALLED with KKT residuals within `stalled_slack` of the tolerances (a lane
+        whose line search gave up far from the optimum is a failure, like MAXITER), and a finite log-likelihood."""
+        status = np.asarray(out["status"])
+        kkt = np.asarray(out["kkt"])
+        near = (kkt[:, 0] <= self.stalled_slack * self.tol) & (kkt[:, 1] <= self.stalled_slack * 100.0 * self.tol)
+        return ((status == _cabi.CONVERGED) | ((status == _cabi.STALLED) & near)) & np.isfinite(np.asarray(out["loglike"]))
+
+    def fit_batch(self, batch):
+        """LaneBatch -> dict(theta [V,B], loglike [B], kkt [B,2], iters [B], status [B]) for ALL lanes of the batch (with
+        a sharder: this rank fits its slice, one all_gather returns the rest)."""
+        B = len(batch)
+        sh = self.sharder
+        if sh is not None and self.check_consistency:
+            sh.check_same_batch(B, batch.digest())
+        lo, hi = (0, B) if sh is None else sh.my_slice(B)
+        n = hi - lo
         local = None
-        if hi > lo and self.concurrent_min_lanes and hi - lo >= self.concurrent_min_lanes:
-            mid = lo + (hi - lo) // 2
+        views = None
+        if sh is not None and n and sh.device.type == "cuda":
+            views = sh.views(n, B, self.V)                      # the solver writes into the packed block that is gathered
+        if n and self.concurrent_min_lanes and n >= self.concurrent_min_lanes:
+            mid = lo + n // 2
             halves = [None, None]
 
             def work(i, a, b, eng):
                 try:
-                    halves[i] = self._fit_on(eng, requests[a:b])
+                    halves[i] = self._fit_on(eng, batch.slice(a, b))
                 except BaseException as e:                      # re-raised in the calling thread
                     halves[i] = e
             t = threading.Thread(target=work, args=(1, mid, hi, self.second_engine()))
@@ -198,37 +428,46 @@ class LaneContext(object):
                 if isinstance(h, BaseException):
                     raise h
             local = {k: np.concatenate([halves[0][k], halves[1][k]], axis=(1 if k == "theta" else 0)) for k in halves[0]}
-        elif hi > lo:
-            local = self._fit_on(self.engine(), requests[lo:hi])
-        out = local if self.sharder is None else self.sharder.gather(local, B, self.V)
+        elif n:
+            local = self._fit_on(self.engine(), batch.slice(lo, hi), out=views)
+        out = local if sh is None else sh.gather(local, B, self.V)
         self.n_lanes_fitted += B
         self.n_batches += 1
-        results = []
-        for b, rq in enumerate(requests):
-            status = int(out["status"][b])
-            ll = float(out["loglike"][b])
-            ok = status in (_cabi.CONVERGED, _cabi.STALLED) and np.isfinite(ll)
-            results.append(FitResult(x=np.array(out["theta"][rq.ids, b], dtype=np.float64), fun=-ll, success=bool(ok),
-                                     status=status, kkt=tuple(out["kkt"][b]), nit=int(out["iters"][b])))
-        return results
+        return out
 
-    def _fit_on(self, eng, mine):
-        """Fit the lanes `mine` on one handle; returns the engine's result dict."""
-        n = len(mine)
-        used = sorted({rq.col for rq in mine})
-        pos = {c: j for j, c in enumerate(used)}
-        w_cols = self.dense_columns(used)
-        col_of_lane = np.array([pos[rq.col] for rq in mine], dtype=np.int32)
-        mask = np.zeros((self.V, n), dtype=np.uint8)
-        for b, rq in enumerate(mine):
-            mask[rq.ids, b] = 1
-        eng.set_lanes_indexed(w_cols, col_of_lane, mask=mask, C=np.array([rq.C for rq in mine]))
-        theta0 = None
-        if any(rq.theta0 is not None for rq in mine):
-            theta0 = np.zeros((self.V, n), dtype=np.float64)
-            for b, rq in enumerate(mine):
-                theta0[rq.ids, b] = rq.theta0 if rq.theta0 is not None else 1.0 / len(rq.ids)
-        return eng.fit(theta0=theta0, tol=self.tol, max_iter=self.max_iter, history=self.history)
+    def _fit_on(self, eng, mine, out=None):
+        """Fit the lanes `mine` (LaneBatch) on one handle; returns the engine's result dict."""
+        slots = self._slots(eng, mine.cols)
+        eng.set_lanes_columns(slots, mask=mine.mask, C=mine.C)
+        return eng.fit(theta0=mine.theta0, tol=self.tol, max_iter=self.max_iter, history=self.history, out=out,
+                       time_passes=self.time_passes)
+
+    def make_resident(self, cols):
+        """Upload / draw the given columns on this rank's device now (otherwise it happens at their first fit)."""
+        self._slots(self.engine(), np.asarray(cols, dtype=np.int64))
+
+    def fit_weights(self, w_local, B=None, C=None):
+        """One-shot lanes: the full-candidate-set ML fit of replicates whose weights are used once (a plain bootstrap):
+        `w_local` [R, n] (uint16 or int32; numpy or pinned torch) are the weights of THIS rank's lanes of a batch of B
+        (default n: single process), uploaded as lanes directly -- no column registration.  Returns the result dict of
+        all B lanes (gathered when the context has a sharder)."""
+        n = int(w_local.shape[1])
+        sh = self.sharder
+        B = n if B is None else int(B)
+        if sh is not None:
+            lo, hi = sh.my_slice(B)
+            if hi - lo != n:
+                raise ValueError("fit_weights: this rank owns %d lanes of a batch of %d, got %d" % (hi - lo, B, n))
+        eng = self.engine()
+        views = sh.views(n, B, self.V) if (sh is not None and n and sh.device.type == "cuda") else None
+        local = None
+        if n:
+            eng.set_lanes(w_local, C=C, B=n)
+            local = eng.fit(tol=self.tol, max_iter=self.max_iter, history=self.history, out=views)
+        out = local if sh is None else sh.gather(local, B, self.V)
+        self.n_lanes_fitted += B
+        self.n_batches += 1
+        return out
 
     def loglik(self, request, theta_of_ids):
         """-LL at given proportions of request.ids (single lane)."""
@@ -237,6 +476,6 @@ class LaneContext(object):
         mask = np.zeros((self.V, 1), dtype=np.uint8)
         mask[request.ids, 0] = 1
         eng = self.engine()
-        eng.set_lanes(self.dense_columns([request.col]), mask=mask, C=np.array([request.C]))
+        eng.set_lanes_columns(self._slots(eng, np.array([request.col])), mask=mask, C=np.array([request.C]))
         with np.errstate(invalid="ignore"):
             return -eng.loglik(theta)
