@@ -204,7 +204,7 @@ def test_do_subsampling_from_records_reproduces_the_reference_run(plastome):
     from traversome_b200.resample import RecordPool
     L = plastome["variant_sizes"]
     model0 = model_from_tables(L, plastome["models"][0]["bins_list"])
-    pool = RecordPool.from_golden(plastome)
+    pool = RecordPool.from_tables(plastome)
     pattern = np.zeros((pool.n_rows, len(L)), dtype=bool)
     ctx = _ctx(L)
     for r, rp in enumerate(plastome["read_paths"]):
@@ -234,7 +234,7 @@ def test_jackknife_from_records_equals_serial_fits(plastome):
     from traversome_b200.resample import RecordPool
     from traversome_b200.lanes import LaneRequest
     L = plastome["variant_sizes"]
-    pool = RecordPool.from_golden(plastome)
+    pool = RecordPool.from_tables(plastome)
     pattern = np.zeros((pool.n_rows, len(L)), dtype=bool)
     ctx = _ctx(L)
     for r, rp in enumerate(plastome["read_paths"]):

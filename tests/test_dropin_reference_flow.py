@@ -1,9 +1,11 @@
 """CPU, build container only: the UNMODIFIED reference driver (`traversome.traversome.Traversome.run`, the `thorough`
-flow of BASELINE configs[0]) with this package's classes swapped in exactly as INTEGRATION.md sections 1 and 4 say:
+flow of BASELINE configs[0]) after `traversome_b200.install(traversome.traversome)` -- the shipped entry point that
+performs the swaps of INTEGRATION.md:
 
     traversome.traversome.ModelFitMaxLike          <- traversome_b200.ModelFitMaxLike.ModelFitMaxLike
     traversome.traversome.VariantSubPathsGenerator <- traversome_b200.subpaths.VariantSubPathsGenerator
     Traversome.generate_read_paths                 <- traversome_b200.readpaths.generate_read_paths
+    Traversome.do_subsampling                      <- all replicates in lock step (traversome_b200.bootstrap)
 
 There is no GPU here, so the two device calls are replaced by their test stand-ins (the oracle-backed engine of
 tests/helpers.py and the contract emulation of tests/subpath_helpers.py); everything above the C ABI -- constructor
@@ -56,20 +58,21 @@ def test_reference_thorough_flow_with_the_swapped_classes(plastome, tmp_path, mo
             created["generators"] += 1
             super().__init__(*a, **k)
 
-    from traversome_b200 import readpaths
+    import traversome_b200
+    from traversome_b200 import dropin
     created["read_path_calls"] = 0
+    installed_grp = dropin._generate_read_paths
 
     def generate_read_paths(self, graph_alignment, filter_by_graph=True, min_alignment_counts=1):
         created["read_path_calls"] += 1
         assert not self.read_paths                                         # the reference starts from an empty table
-        table = readpaths.generate_read_paths(self.graph, graph_alignment.raw_records, filter_by_graph=filter_by_graph,
-                                              min_alignment_counts=min_alignment_counts)
-        readpaths.install_on(self, table)
+        installed_grp(self, graph_alignment, filter_by_graph, min_alignment_counts)
 
-    monkeypatch.setattr(tvm.Traversome, "generate_read_paths", generate_read_paths)
-    monkeypatch.setattr(lanes._cabi, "Engine", OracleEngine)               # no GPU in this container
-    monkeypatch.setattr(tvm, "ModelFitMaxLike", CountingMirror)
-    monkeypatch.setattr(tvm, "VariantSubPathsGenerator", CountingGenerator)
+    monkeypatch.setattr(dropin, "_generate_read_paths", generate_read_paths)
+    traversome_b200.install(tvm)                                           # the four swaps (INTEGRATION.md sections 1, 2, 4, 6)
+    monkeypatch.setattr(lanes._cabi, "Engine", OracleEngine)               # no GPU in this container: device calls -> stand-ins
+    monkeypatch.setattr(tvm, "ModelFitMaxLike", CountingMirror)            # the installed class, counted
+    monkeypatch.setattr(tvm, "VariantSubPathsGenerator", CountingGenerator)  # contract emulation of tvs_subpaths_count
 
     gfa, gaf = str(tmp_path / "plastome.gfa"), str(tmp_path / "sim.gaf")
     _gunzip(os.path.join(GOLDEN, "plastome.gfa.gz"), gfa)
@@ -90,9 +93,12 @@ def test_reference_thorough_flow_with_the_swapped_classes(plastome, tmp_path, mo
         trv.run()
     finally:
         logger.remove()
+        traversome_b200.uninstall()
 
-    assert created["generators"] == 1 and created["fitters"] >= 101        # full data + 100 replicates
+    assert created["generators"] == 1 and created["fitters"] >= 1          # the whole-data fitter comes from the swapped name
     assert created["read_path_calls"] >= 1
+    ctx = trv.max_like_fit._ensure_lane()
+    assert ctx.n_batches <= 8 and ctx.n_lanes_fitted >= 101                # 100 replicates in a handful of lock-step batches
     # what the reference's own objects hold afterwards
     assert [int(s) for s in trv.variant_sizes] == plastome["variant_sizes"]
     assert [[int(k), int(v)] for k, v in trv.be_unidentifiable_to.items()] == plastome["be_unidentifiable_to"]

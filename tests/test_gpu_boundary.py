@@ -249,7 +249,7 @@ def test_cfg1_bootstrap_from_record_pool_on_gpu(gpu, plastome):
     import random
     from traversome_b200.resample import RecordPool
     L = plastome["variant_sizes"]
-    pool = RecordPool.from_golden(plastome)
+    pool = RecordPool.from_tables(plastome)
     pattern = np.zeros((pool.n_rows, len(L)), dtype=bool)
     ctx = LaneContext(len(L), L)
     for r, rp in enumerate(plastome["read_paths"]):

@@ -30,14 +30,14 @@ def _check_bins(pool, fixture, got, ref_bins_list):
 
 
 def test_whole_data_bins_bit_exact(plastome):
-    pool = RecordPool.from_golden(plastome)
+    pool = RecordPool.from_tables(plastome)
     bins, observed = pool.bins_of(np.arange(pool.n_records))
     _check_bins(pool, plastome, bins, plastome["models"][0]["bins_list"])
     assert sorted(observed.tolist()) == plastome["models"][0]["observed_sub_path_ids"]
 
 
 def test_bootstrap_replay_reproduces_every_reference_replicate(plastome):
-    pool = RecordPool.from_golden(plastome)
+    pool = RecordPool.from_tables(plastome)
     rng = random.Random(12345)                       # traversome.py:142-143 with the CLI default --rs 12345
     for k in range(1, len(plastome["models"])):
         sample = pool.sample_bootstrap(rng, plastome["num_valid_records"])
@@ -48,7 +48,7 @@ def test_bootstrap_replay_reproduces_every_reference_replicate(plastome):
 
 def test_lane_of_equals_lane_from_reference_bins(plastome):
     """(w, C, N) from the arrays == (w, C, N) from the reference's bin objects (csr.lane_from_bins)."""
-    pool = RecordPool.from_golden(plastome)
+    pool = RecordPool.from_tables(plastome)
     rng = random.Random(12345)
     L = plastome["variant_sizes"]
     row_sig = [_sig(r["from_variants"]) for r in plastome["read_paths"]]
@@ -67,7 +67,7 @@ def test_lane_of_equals_lane_from_reference_bins(plastome):
 
 
 def test_jackknife_draw_replays_random_sample(plastome):
-    pool = RecordPool.from_golden(plastome)
+    pool = RecordPool.from_tables(plastome)
     a = pool.sample_jackknife(random.Random(7), 17)
     b = random.Random(7).sample(range(pool.n_records), k=pool.n_records - 17)
     assert a.tolist() == b and len(set(a.tolist())) == pool.n_records - 17

@@ -18,7 +18,7 @@ groups = {int(k): [int(x) for x in v] for k, v in plastome["repr_to_merged_varia
 unid = {int(k): int(v) for k, v in plastome["be_unidentifiable_to"]}
 for trial in range(3):
     t0 = time.time()
-    pool = RecordPool.from_golden(plastome)
+    pool = RecordPool.from_tables(plastome)
     pattern = np.zeros((pool.n_rows, len(L)), dtype=bool)
     ctx = LaneContext(len(L), L)
     for r, rp in enumerate(plastome["read_paths"]):

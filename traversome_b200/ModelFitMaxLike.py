@@ -21,7 +21,7 @@ from typing import Set, Union
 import numpy as np
 from loguru import logger
 
-from .lanes import FitResult, LaneContext, LaneRequest  # noqa: F401  (FitResult re-exported)
+from .lanes import FitResult, IdSet, LaneContext, LaneRequest  # noqa: F401  (FitResult re-exported)
 from .utils import Criterion, LogLikeFuncInfo, aic, bic
 
 
@@ -53,6 +53,24 @@ def prune_model_bins(model):
         if bins.rp_bins:
             kept.append(bins)
     model.bins_list[:] = kept
+
+
+def _debug_logging():
+    """True when a DEBUG record written from this module would reach some loguru handler.  The reference writes several
+    DEBUG lines per candidate subset (each O(candidates) to format); when nobody listens the selection loop skips
+    building them -- and builds the proportion dictionaries of the ACCEPTED candidate only -- without changing any
+    decision."""
+    try:
+        core = logger._core
+        if core.min_level > 10:                              # no handler at DEBUG or below
+            return False
+        dotted = __name__ + "."                              # logger.disable("traversome_b200") and friends
+        for dotted_module_name, status in core.activation_list:
+            if dotted[: len(dotted_module_name)] == dotted_module_name:
+                return bool(status)
+        return True
+    except Exception:
+        return True
 
 
 class ModelFitMaxLike(object):
@@ -107,6 +125,7 @@ class ModelFitMaxLike(object):
         # backward selection starts each candidate subset from the accepted model's optimum (see _start_point)
         self.warm_start = os.environ.get("TVS_WARM_START", "1") != "0"
         self._warm = None            # {representative id: proportion} of the accepted model, inside a selection only
+        self._warm_vec = None
         self._batch_x = None
 
     @classmethod
@@ -150,6 +169,7 @@ class ModelFitMaxLike(object):
         self._cover_base = None
         self.warm_start = os.environ.get("TVS_WARM_START", "1") != "0"
         self._warm = None
+        self._warm_vec = None
         self._batch_x = None
         self._array_form = True
         return self
@@ -178,7 +198,7 @@ class ModelFitMaxLike(object):
             self._context.close()
 
     def lane_requests(self, subsets):
-        """Lane descriptions of ML fits restricted to subsets[b] (sets of representative ids)."""
+        """Lane descriptions of ML fits restricted to subsets[b] (sets of representative ids, or IdSet)."""
         self._ensure_lane()
         col, C, _N = self._lane
         return [LaneRequest(col, C, ids, self._start_point(ids)) for ids in subsets]
@@ -190,7 +210,12 @@ class ModelFitMaxLike(object):
         warm = self._warm
         if not warm or not self.warm_start:
             return None
-        x = np.array([warm.get(v, 0.0) for v in sorted(ids)], dtype=np.float64)
+        if self._warm_vec is None or self._warm_vec[0] is not warm:      # dense copy of the accepted optimum, once per accept
+            vec = np.zeros(self.num_put_variants, dtype=np.float64)
+            vec[np.fromiter(warm.keys(), dtype=np.int64, count=len(warm))] = np.fromiter(warm.values(), dtype=np.float64, count=len(warm))
+            self._warm_vec = (warm, vec)
+        arr = ids.arr if isinstance(ids, IdSet) else np.array(sorted(ids), dtype=np.int64)
+        x = self._warm_vec[1][arr]
         total = x.sum()
         if not np.isfinite(total) or total <= 0.0:
             return None
@@ -293,46 +318,43 @@ class ModelFitMaxLike(object):
             self._shuffle(chosen_rd_list)
             changed = False
             rs = random_size if random_size > 0 else len(chosen_rd_list)
+            verbose = _debug_logging()
+            chosen_arr = np.array(chosen_ids_sorted, dtype=np.int64)
             for go_rd_sp in range(0, len(chosen_rd_list), rs):
                 this_rd_ids = chosen_rd_list[go_rd_sp: go_rd_sp + rs]
-                test_id_res = OrderedDict()
                 # -- which candidates of this chunk get a fit (same screening as __test_one_drop, :349-370)
                 to_fit = []
+                label = ", ".join([self.__str_rep_id(_c_i) for _c_i in chosen_ids_sorted]) if verbose else None
                 for rd_id in this_rd_ids:
                     var_id = chosen_ids_sorted[rd_id]
-                    label = ", ".join([self.__str_rep_id(_c_i) for _c_i in chosen_ids_sorted])
                     if var_id not in indispensable_ids:
-                        testing_ids = chosen_ids - {var_id}
-                        if self.cover_all_observed_subpaths(testing_ids):
-                            logger.debug("Test variants [{}] - {}".format(label, self.__str_rep_id(var_id)))
-                            to_fit.append((var_id, testing_ids))
+                        if self._cover_without(var_id):
+                            if verbose:
+                                logger.debug("Test variants [{}] - {}".format(label, self.__str_rep_id(var_id)))
+                            # leave-one-out subset = the sorted accepted set with one element deleted
+                            to_fit.append((var_id, IdSet(np.delete(chosen_arr, rd_id))))
                         else:
                             indispensable_ids[var_id] = True
-                            logger.debug("Test variants [{}] - {}: skipped for necessary subpath(s) (case *)"
-                                         .format(label, self.__str_rep_id(var_id)))
-                    else:
+                            if verbose:
+                                logger.debug("Test variants [{}] - {}: skipped for necessary subpath(s) (case *)"
+                                             .format(label, self.__str_rep_id(var_id)))
+                    elif verbose:
                         logger.debug("Test variants [{}] - {}: skipped for necessary subpath(s) (case **)"
                                      .format(label, self.__str_rep_id(var_id)))
-                # -- one batch of lanes for the whole chunk
-                batch_x = {}
+                # -- one batch of lanes for the whole chunk; the criterion of every candidate, the proportion tables of
+                #    the best one only (the reference builds them per candidate, :448-510, and reads the best's)
                 if to_fit:
                     id_sets = [ids for _, ids in to_fit]
-                    batch = self.__summarize_batch(id_sets, (yield id_sets), criterion)
-                    for (var_id, _), res_list, x in zip(to_fit, batch, self._batch_x):
-                        test_id_res[var_id] = {"prop": res_list[0], "echo": res_list[1], "loglike": res_list[2],
-                                               criterion: res_list[3]}
-                        batch_x[var_id] = x
-                if test_id_res:
-                    best_drop_id, best_val = sorted([[_go_var_, test_id_res[_go_var_][criterion]]
-                                                     for _go_var_ in test_id_res],
-                                                    key=lambda x: x[1])[0]
+                    results = (yield id_sets)
+                    crit_vals = self.__criteria_of_batch(id_sets, results, criterion, verbose)
+                    best = min(range(len(to_fit)), key=crit_vals.__getitem__)      # first minimum = sorted(...)[0] of the reference
+                    best_drop_id, best_val = to_fit[best][0], crit_vals[best]
                     if best_val < previous_criteria:
                         previous_criteria = best_val
-                        previous_like = test_id_res[best_drop_id]["loglike"]
-                        previous_prop = test_id_res[best_drop_id]["prop"]
-                        previous_echo = test_id_res[best_drop_id]["echo"]
+                        previous_like = -results[best].fun
+                        previous_prop, previous_echo = self.__summarize_run_prop(results[best], id_sets[best])
                         chosen_ids.remove(best_drop_id)
-                        self._warm = batch_x.get(best_drop_id) or self._warm
+                        self._warm = dict(zip(id_sets[best].arr.tolist(), (float(v) for v in results[best].x))) or self._warm
                         log = logger.debug if self.bootstrap_mode else logger.info
                         log("Drop {}".format(self.__str_rep_id(best_drop_id)))
                         log("Proportions: " + ", ".join(["%s:%.4f" % (_id, _p) for _id, _p, in previous_echo.items()]))
@@ -391,11 +413,53 @@ class ModelFitMaxLike(object):
             out.append(self.__summarize_like_and_criteria(res if res.success else False, ids, criteria, info))
         return out
 
+    def __criteria_of_batch(self, id_sets, results, criteria, verbose):
+        """AIC / BIC of every lane of a batch (ModelFitMaxLike.py:472-497 per lane).  Raises like the reference when a fit
+        failed.  With DEBUG logging on, the reference's per-candidate lines are written as well."""
+        _col, _C, sample_size = self._lane
+        if criteria not in ("AIC", "BIC"):
+            raise Exception("Invalid criterion {}".format(criteria))
+        if verbose:
+            logger.debug("Generating the likelihood function .. ")
+        vals = []
+        for ids, res in zip(id_sets, results):
+            if verbose or not self.bootstrap_mode:
+                msg = "Maximizing the likelihood function for {} variants".format(len(ids))
+                if self.bootstrap_mode:
+                    logger.debug(msg)
+                else:
+                    logger.info(msg)
+            if not res.success:
+                raise Exception("Likelihood maximization failed.")
+            this_like = -res.fun
+            k = self.__variable_size(ids)
+            this_criteria = aic(loglike=this_like, len_param=k) if criteria == "AIC" else bic(loglike=this_like, len_param=k, len_data=sample_size)
+            if verbose:
+                _use, echo_prop = self.__summarize_run_prop(res, ids)
+                logger.debug("Proportions: " + ", ".join(["%s:%.4f" % (_id, _p) for _id, _p, in echo_prop.items()]))
+                logger.debug("Log-likelihood: %s" % this_like)
+                logger.debug("len_param: %s" % k)
+                if criteria == "BIC":
+                    logger.debug("len_data: %s" % sample_size)
+                logger.debug("%s: %s" % (criteria, this_criteria))
+            vals.append(this_criteria)
+        return vals
+
+    def _cover_without(self, var_id):
+        """cover_all_observed_subpaths(accepted set - {var_id}) from the round's cached cover counts (_set_cover_base):
+        uncovered iff some observed read path is held by `var_id` alone."""
+        base = self._cover_base
+        if base[1]:
+            return False
+        sole = base[3]
+        return not (sole.size and bool(self._cover_cache[3][int(var_id), sole].any()))
+
     def __variable_size(self, ids):
         # ModelGenerator.py:125-126,175: an empty subset or the full set counts every variant
-        if not ids or set(ids) == set(range(self.num_put_variants)):
+        n = len(ids)
+        if n == 0 or n >= self.num_put_variants and set(ids) == set(range(self.num_put_variants)):
             return self.num_put_variants
-        return len(ids)
+        return n
 
     def __summarize_like_and_criteria(self, success_run, chosen_id_set, criteria, neg_loglike_func_obj):
         if success_run:
@@ -547,5 +611,13 @@ class ModelFitMaxLike(object):
         self._cover_tables()
         ids = frozenset(int(v) for v in variant_ids)
         observed = self._cover_cache[2]
-        counts = self._cover_cache[3][sorted(ids)].sum(axis=0, dtype=np.int32)
-        self._cover_base = (ids, bool(np.any((counts == 0) & observed)), (counts == 1) & observed)
+        by_variant = self._cover_cache[3]
+        prev = self._cover_base
+        if prev is not None and len(prev) > 4 and prev[5] is by_variant and ids <= prev[0] and len(prev[0]) - len(ids) <= 8:
+            counts = prev[4].copy()                            # the previous round's set minus the variants dropped since
+            for v in prev[0] - ids:
+                counts -= by_variant[v]
+        else:
+            counts = by_variant[sorted(ids)].sum(axis=0, dtype=np.int32)
+        sole = (counts == 1) & observed
+        self._cover_base = (ids, bool(np.any((counts == 0) & observed)), sole, np.nonzero(sole)[0], counts, by_variant)

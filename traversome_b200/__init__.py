@@ -9,3 +9,14 @@ __version__ = "0.1.0"
 
 from .utils import Bins, BinInfo, SubPathInfo, LogLikeFormulaInfo, LogLikeFuncInfo, Criterion, aic, bic  # noqa: F401
 from .ModelGenerator import PathMultinomialModel  # noqa: F401
+
+
+def install(module=None, **kw):
+    """Swap this package's classes into the reference's orchestrator (see traversome_b200.dropin)."""
+    from .dropin import install as _install
+    return _install(module, **kw)
+
+
+def uninstall():
+    from .dropin import uninstall as _uninstall
+    return _uninstall()

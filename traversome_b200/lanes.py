@@ -20,11 +20,38 @@ from .csr import CsrMatrix, ReadPathMatrix, lane_from_bins
 
 class FitResult(object):
     """What the reference reads off scipy's OptimizeResult: ``x`` (proportions of the fitted ids in
-    increasing id order), ``fun`` (= -loglike), ``success``."""
-    __slots__ = ("x", "fun", "success", "status", "kkt", "nit")
+    increasing id order), ``fun`` (= -loglike), ``success``.  ``x`` is cut out of the batch's theta matrix on first
+    use: a selection round reads it for the accepted candidate only."""
+    __slots__ = ("_x", "_theta", "_ids", "_b", "fun", "success", "status", "kkt", "nit")
 
-    def __init__(self, x, fun, success, status, kkt, nit):
-        self.x, self.fun, self.success, self.status, self.kkt, self.nit = x, fun, success, status, kkt, nit
+    def __init__(self, x, fun, success, status, kkt, nit, theta=None, ids=None, b=0):
+        self._x, self._theta, self._ids, self._b = x, theta, ids, b
+        self.fun, self.success, self.status, self.kkt, self.nit = fun, success, status, kkt, nit
+
+    @property
+    def x(self):
+        if self._x is None:
+            self._x = np.array(self._theta[self._ids, self._b], dtype=np.float64)
+        return self._x
+
+
+class IdSet(object):
+    """A candidate subset as a SORTED int64 array: what the selection loop hands to `lane_requests` (a leave-one-out
+    subset is the accepted set with one element deleted -- no per-lane sort, no per-lane Python set)."""
+    __slots__ = ("arr",)
+
+    def __init__(self, arr):
+        self.arr = arr
+
+    def __iter__(self):
+        return iter(self.arr.tolist())
+
+    def __len__(self):
+        return int(self.arr.shape[0])
+
+    def __contains__(self, v):
+        i = int(np.searchsorted(self.arr, v))
+        return i < self.arr.shape[0] and int(self.arr[i]) == int(v)
 
 
 class LaneRequest(object):
@@ -33,7 +60,8 @@ class LaneRequest(object):
     __slots__ = ("col", "C", "ids", "theta0")
 
     def __init__(self, col, C, ids, theta0=None):
-        self.col, self.C, self.ids = int(col), float(C), sorted(int(v) for v in ids)
+        self.col, self.C = int(col), float(C)
+        self.ids = ids.arr if isinstance(ids, IdSet) else sorted(int(v) for v in ids)
         self.theta0 = None if theta0 is None else np.asarray(theta0, dtype=np.float64)
 
 
@@ -382,13 +410,12 @@ class LaneContext(object):
         if B == 0:
             return []
         out = self.fit_batch(LaneBatch.from_requests(requests, self.V))
-        results = []
-        status_all, ll_all, kkt_all = out["status"], out["loglike"], out["kkt"]
-        ok_all = self.lane_ok(out)
-        for b, rq in enumerate(requests):
-            results.append(FitResult(x=np.array(out["theta"][rq.ids, b], dtype=np.float64), fun=-float(ll_all[b]), success=bool(ok_all[b]),
-                                     status=int(status_all[b]), kkt=tuple(kkt_all[b]), nit=int(out["iters"][b])))
-        return results
+        theta = out["theta"]
+        fun = (-out["loglike"]).tolist()
+        ok = self.lane_ok(out).tolist()
+        status, iters, kkt = out["status"].tolist(), out["iters"].tolist(), out["kkt"].tolist()
+        return [FitResult(None, fun[b], ok[b], status[b], tuple(kkt[b]), iters[b], theta=theta, ids=rq.ids, b=b)
+                for b, rq in enumerate(requests)]
 
     def lane_ok(self, out):
         """success flag per lane: CONVERGED, or STALLED with KKT residuals within `stalled_slack` of the tolerances (a lane

@@ -71,8 +71,10 @@ class RecordPool(object):
                    multi, inner, full, lroom, rroom)
 
     @classmethod
-    def from_golden(cls, fixture):
-        """From the JSON tables written by oracle/make_golden.py (tests)."""
+    def from_tables(cls, fixture):
+        """From plain tables (JSON-able): fixture["read_paths"] = per read path {path, inner_len, full_len, left_len,
+        left_overlap, right_len, right_overlap}, fixture["records"] = {pool_sorted, row_of_record, align_len} -- the
+        array form of what `from_traversome` reads off the reference's objects."""
         rp = fixture["read_paths"]
         multi = [len(r["path"]) > 1 for r in rp]
         lroom = [r.get("left_len", 0) - r.get("left_overlap", 0) for r in rp]
