@@ -165,7 +165,7 @@ class ModelFitMaxLike(object):
         shared = getattr(context, "_pattern_by_variant", None)
         if shared is None or shared[0] is not pattern:
             shared = context._pattern_by_variant = (pattern, np.ascontiguousarray(pattern.T))
-        self._cover_cache = (len(self.observed_sbp_id_set), pattern, observed, shared[1])
+        self._cover_cache = (self._cover_key(), pattern, observed, shared[1])
         self._cover_base = None
         self.warm_start = os.environ.get("TVS_WARM_START", "1") != "0"
         self._warm = None
@@ -532,13 +532,20 @@ class ModelFitMaxLike(object):
                 logger.trace("Drop subpath without observation: {}: {}".format(go_sp, this_sub_path))
         self._cover_cache = None
 
+    def _cover_key(self):
+        """What the cover tables were built from: the reference keeps observed_sbp_id_set and sbp_to_sbp_id as public,
+        replaceable attributes, so the cache is keyed on their identity and size (a same-sized replacement rebuilds)."""
+        obs, sbp = self.observed_sbp_id_set, self.sbp_to_sbp_id
+        return (id(obs), len(obs), id(sbp), len(sbp) if sbp is not None else -1)
+
     def _cover_tables(self):
         """Matrix form of the tables cover_all_observed_subpaths walks (ModelFitMaxLike.py:568-580):
         contains[s, v] = sub-path id s occurs in variant v (through variant_subpath_counters and sbp_to_sbp_id),
         observed[s] = s is in observed_sbp_id_set.  Same sets, evaluated with numpy instead of Python set unions
         (the reference spends O(sub-paths) dict operations per variant per candidate)."""
         cache = getattr(self, "_cover_cache", None)
-        if cache is not None and cache[0] == len(self.observed_sbp_id_set):
+        key = self._cover_key()
+        if cache is not None and cache[0] == key:
             return cache[1], cache[2]
         n_sbp = (max(self.sbp_to_sbp_id.values()) + 1) if self.sbp_to_sbp_id else 0
         n_sbp = max(n_sbp, (max(self.observed_sbp_id_set) + 1) if self.observed_sbp_id_set else 0)
@@ -558,7 +565,7 @@ class ModelFitMaxLike(object):
         observed = np.zeros(n_sbp, dtype=bool)
         observed[list(self.observed_sbp_id_set)] = True
         # variant-major copy: a candidate set is a gather of contiguous rows
-        self._cover_cache = (len(self.observed_sbp_id_set), contains, observed, np.ascontiguousarray(contains.T))
+        self._cover_cache = (key, contains, observed, np.ascontiguousarray(contains.T))
         self._cover_base = None
         return contains, observed
 

@@ -170,12 +170,17 @@ def do_subsampling_from_records(pool, pattern, context, full_fit, raw_result, rn
     go_bs = 0
     while go_bs < n_replicate and bs_eligible:
         fitters = []
-        for k in range(min(batch, n_replicate - go_bs)):
+        states = []                                   # rng state after each replicate's draws (see the early stop below)
+        while len(fitters) < min(batch, n_replicate - go_bs):
+            k = len(fitters)
             if jackknife:
                 sample = pool.sample_jackknife(rng, int(pool.n_records / float(n_replicate)))
             else:
                 sample = pool.sample_bootstrap(rng, pool.n_records)
             w, C, N, observed = pool.lane_of(sample, masked_rows)
+            if N == 0 or not np.any(observed):            # traversome.py:528-529 `if not sampled_sub_paths: continue`: draw again
+                continue
+            states.append(rng.getstate() if hasattr(rng, "getstate") else None)
             col = context.add_weights(w)
             f = ModelFitMaxLike.from_lane(context, (col, C, N), pattern, np.nonzero(observed)[0], full_fit.repr_to_merged_variants,
                                           full_fit.be_unidentifiable_to, loglevel=loglevel,
@@ -183,6 +188,7 @@ def do_subsampling_from_records(pool, pattern, context, full_fit, raw_result, rn
             f._shuffle = full_fit._shuffle
             fitters.append(f)
         results = run_selections(fitters, criterion=criterion, n_proc=n_proc, user_fixed_ids=user_fixed_ids)
+        batch_first = len(reps)
         for res in results:
             if isinstance(res, Exception):
                 raise res
@@ -193,6 +199,11 @@ def do_subsampling_from_records(pool, pattern, context, full_fit, raw_result, rn
                     logger.info("Sampling terminates due to divergence in bootstraps (see '--bs-threshold'). "
                                 "No convincing support can be found given the dataset and parameters. ")
                 bs_eligible = False
+                # the serial loop stops drawing here: leave the shared generator where it would be (the draws of the
+                # replicates of this batch that come after the stop are undone)
+                st = states[len(reps) - 1 - batch_first] if len(reps) - 1 - batch_first < len(states) else None
+                if st is not None:
+                    rng.setstate(st)
                 break
             go_bs += 1
     logger.info("Summarizing the replicates ..")

@@ -289,7 +289,7 @@ static int plan_blk(const tvs_problem* h, int64_t W, PassPlan* out) {
     }
     // backward: CTA (tile, variant chunk, split) walks the row panels split, split + S, ...; tpart[split][V][W]
     if (BW) {
-        int s = fill_waves(out->tiles * c.blk_b.n_chunks, std::min(24, std::max(1, c.blk_b.n_panels / 4)));
+        int s = fill_waves(out->tiles * c.blk_b.n_chunks, std::min(std::max(24, slots / std::max(1, out->tiles * c.blk_b.n_chunks)), std::max(1, c.blk_b.n_panels / 4)));
         const int forced = env_int("TVS_BSPLITS", 0);
         if (forced > 0) s = forced;
         out->bsplits = std::max(1, std::min(s, c.blk_b.n_panels));
@@ -311,7 +311,16 @@ static int make_plan(const tvs_problem* h, int64_t B, PassPlan* out) {
     }
     if (env_int("TVS_PASS_V1", 0) == 0) {
         const int rc2 = make_plan_v2<BW>(h, B, out);
-        if (rc2 == TVS_OK || rc2 == TVS_ECUDA) return rc2;       // otherwise: tiles too large for shared memory
+        if (rc2 == TVS_ECUDA) return rc2;
+        if (rc2 == TVS_OK) {
+            // staged kernel with one lane per thread only (its x / t tiles leave no room for more): on a wide lane set the
+            // blocked kernel wins (it keeps no whole-V tile); narrow sets are latency-bound and stay on the staged kernel
+            if (want_blk != 0 && out->lpt == 1 && h->csr.has_blk && B >= env_int("TVS_BLK_MIN_LANES", 192)) {
+                PassPlan pb;
+                if (plan_blk<BW>(h, B, &pb) == TVS_OK) *out = pb;
+            }
+            return TVS_OK;
+        }                                                        // otherwise: tiles too large for shared memory
     }
     if (want_blk != 0) {
         const int rcb = plan_blk<BW>(h, B, out);
@@ -806,7 +815,9 @@ int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, c
     }
     {   // blocked copies of A and A^T for blk_kernel: candidate sets too wide for the staged kernel's shared-memory tiles
         const int want = env_int("TVS_BLK", -1);
-        if (nnz > 0 && want != 0 && (want == 1 || V > env_int("TVS_BLK_MIN_V", 256)) && c.dense == nullptr) {
+        // (V > ~330), or whose staged kernel is left with one lane per thread (V > ~160: the blocked kernel is 1.46x faster on
+        // wide lane sets there -- cfg3, 1,024 lanes: 1.21 ms against 1.76 ms per pass)
+        if (nnz > 0 && want != 0 && (want == 1 || V > env_int("TVS_BLK_MIN_V", 160)) && c.dense == nullptr) {
             BlkHost hf, hb;
             const bool ok = build_blk<int32_t>(R, V, row_ptr, col, val, &hf) && build_blk_transposed(R, V, nnz, row_ptr, col, val, &hb);
             if (ok) {
@@ -917,6 +928,7 @@ static int finish_lanes(tvs_problem* h, const uint8_t* mask, const double* C, bo
         TVS_CUDA(cudaMemcpyAsync(&overflow, l.flag, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
         TVS_CUDA(cudaStreamSynchronize(h->stream));
         l.has16 = overflow == 0;
+        if (overflow & 2) { h->lanes_set = false; set_error("negative weight in the lane matrix (weights are record counts: w >= 0)"); return TVS_EINVAL; }
     }
     // 16-bit uploads do not synchronise: the copy of the caller's buffer and the kernels above are queued on the handle's
     // stream, tvs_fit / tvs_loglik follow on the same stream (include/tvs.h: the buffer must stay valid until the next

@@ -765,15 +765,17 @@ __global__ void widen_u16_kernel(const uint16_t* __restrict__ src, int32_t* __re
 // int32 -> uint16 copy of the weights; *overflow is set when a count does not fit (the 16-bit copy is then not used)
 __global__ void narrow_u16_kernel(const int32_t* __restrict__ src, uint16_t* __restrict__ dst, int64_t n, int32_t* __restrict__ overflow) {
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    bool bad = false;
+    bool bad = false, neg = false;                        // flag bit 0: a count above 65535, bit 1: a NEGATIVE weight
     if (i + 4 <= n) {
         const int4 v = *reinterpret_cast<const int4*>(src + i);
         bad = ((unsigned)v.x | (unsigned)v.y | (unsigned)v.z | (unsigned)v.w) > 65535u;
+        neg = (v.x | v.y | v.z | v.w) < 0;
         *reinterpret_cast<ushort4*>(dst + i) = make_ushort4((unsigned short)v.x, (unsigned short)v.y, (unsigned short)v.z, (unsigned short)v.w);
     } else {
-        for (int64_t k = i; k < n; ++k) { bad = bad || (unsigned)src[k] > 65535u; dst[k] = (uint16_t)src[k]; }
+        for (int64_t k = i; k < n; ++k) { bad = bad || (unsigned)src[k] > 65535u; neg = neg || src[k] < 0; dst[k] = (uint16_t)src[k]; }
     }
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(overflow, 1);
+    if (__any_sync(0xffffffffu, neg) && (threadIdx.x & 31) == 0) atomicOr(overflow, 2);
 }
 
 // lane columns from the device-resident column store: dst[r, b] = store[r, slot[b]]  (replaces the per-batch rebuild of the
