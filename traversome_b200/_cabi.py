@@ -21,6 +21,8 @@ SYMBOLS = (
     "tvs_measure_fp64_peak", "tvs_measure_smem_peak", "tvs_selftest_math", "tvs_selftest_table_log",
     # include/tvs_subpaths.h
     "tvs_subpaths_count", "tvs_subpaths_fetch", "tvs_subpaths_destroy",
+    # include/tvs_pool.h
+    "tvs_pool_create", "tvs_pool_lanes", "tvs_pool_destroy",
 )
 
 TVS_OK, TVS_EINVAL, TVS_ECUDA, TVS_ENOMEM, TVS_ELIMIT, TVS_ESTATE = 0, -1, -2, -3, -4, -5
@@ -84,6 +86,9 @@ def load():
                                        POINTER(c_int64), POINTER(c_int64), POINTER(c_double)]
     lib.tvs_subpaths_fetch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.tvs_subpaths_destroy.argtypes = [c_void_p]
+    lib.tvs_pool_create.argtypes = [POINTER(c_void_p), c_int, c_int64, c_int64] + [c_void_p] * 8
+    lib.tvs_pool_lanes.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.tvs_pool_destroy.argtypes = [c_void_p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("tvs_last_error",):
@@ -336,3 +341,41 @@ def count_subpaths(var_ptr, var_tok, var_step, var_circular, n_rows, key_ptr, ke
     finally:
         lib.tvs_subpaths_destroy(h)
     return row_ptr, col, val, first, {"n_windows": n_windows.value, "kernel_ms": ms.value, "nnz": nnz.value}
+
+
+class DevicePool(object):
+    """The record pool of one run on the device (include/tvs_pool.h): per-replicate bin statistics -> lanes, batched."""
+
+    def __init__(self, record_ids, row_of, align_len, multi, inner_len, full_len, left_room, right_room, device=0):
+        lib = load()
+        self._lib = lib
+        self._h = c_void_p(None)
+        self._keep = (np.ascontiguousarray(record_ids, dtype=np.int64), np.ascontiguousarray(row_of, dtype=np.int32),
+                      np.ascontiguousarray(align_len, dtype=np.int64), np.ascontiguousarray(multi, dtype=np.uint8),
+                      np.ascontiguousarray(inner_len, dtype=np.int64), np.ascontiguousarray(full_len, dtype=np.int64),
+                      np.ascontiguousarray(left_room, dtype=np.int64), np.ascontiguousarray(right_room, dtype=np.int64))
+        self.n_records, self.n_rows = int(self._keep[0].size), int(self._keep[3].size)
+        _check(lib.tvs_pool_create(ctypes.byref(self._h), int(device), self.n_records, self.n_rows, *[_ptr(a) for a in self._keep]))
+
+    def lanes(self, samples, masked_rows=None):
+        """samples int32 [B, n_draw] (-1 = no draw) -> (w int32 [R, B], C float64 [B], N int64 [B], observed bool [R, B])."""
+        samples = np.ascontiguousarray(samples, dtype=np.int32)
+        B, n_draw = samples.shape
+        masked = None if masked_rows is None else np.ascontiguousarray(masked_rows, dtype=np.uint8)
+        w = np.empty((self.n_rows, B), dtype=np.int32)
+        obs = np.empty((self.n_rows, B), dtype=np.uint8)
+        C = np.empty(B, dtype=np.float64)
+        N = np.empty(B, dtype=np.int64)
+        _check(self._lib.tvs_pool_lanes(self._h, B, n_draw, _ptr(samples), _ptr(masked), _ptr(w), _ptr(C), _ptr(N), _ptr(obs)))
+        return w, C, N, obs.astype(bool)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.tvs_pool_destroy(self._h)
+            self._h = c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -63,7 +63,7 @@ static void free_csr(Csr& c) {
     c.has_blk = false;
 }
 static void free_lanes(Lanes& l) {
-    dev_free(l.w); dev_free(l.mask); dev_free(l.C); dev_free(l.N); dev_free(l.w16); dev_free(l.flag); dev_free(l.cols); dev_free(l.slot);
+    dev_free(l.w); dev_free(l.mask); dev_free(l.C); dev_free(l.N); dev_free(l.w16); dev_free(l.flag); dev_free(l.cols); dev_free(l.cols16); dev_free(l.slot);
     if (l.acc) cudaFree(l.acc);
     l = Lanes();
 }
@@ -995,14 +995,18 @@ int tvs_columns_reserve(tvs_handle h, int64_t n_cols) {
     if (n_cols <= l.col_cap) return TVS_OK;
     const int64_t R = h->csr.R;
     int32_t* fresh = nullptr;
+    uint16_t* fresh16 = nullptr;
     int rc = dev_alloc(&fresh, (size_t)(R * n_cols));
     if (rc != TVS_OK) return rc;
+    if ((rc = dev_alloc(&fresh16, (size_t)(R * n_cols))) != TVS_OK) { cudaFree(fresh); return rc; }
+    if (!l.flag && (rc = dev_alloc(&l.flag, 1)) != TVS_OK) { cudaFree(fresh); cudaFree(fresh16); return rc; }
     if (l.cols) {      // keep the registered columns: row pitch changes from col_cap to n_cols
         cudaMemcpy2DAsync(fresh, (size_t)n_cols * 4, l.cols, (size_t)l.col_cap * 4, (size_t)l.col_cap * 4, (size_t)R, cudaMemcpyDeviceToDevice, h->stream);
+        cudaMemcpy2DAsync(fresh16, (size_t)n_cols * 2, l.cols16, (size_t)l.col_cap * 2, (size_t)l.col_cap * 2, (size_t)R, cudaMemcpyDeviceToDevice, h->stream);
         cudaStreamSynchronize(h->stream);
-        cudaFree(l.cols);
+        cudaFree(l.cols); cudaFree(l.cols16);
     }
-    l.cols = fresh; l.col_cap = n_cols;
+    l.cols = fresh; l.cols16 = fresh16; l.col_cap = n_cols;
     TVS_CUDA(cudaGetLastError());
     return TVS_OK;
 }
@@ -1015,6 +1019,20 @@ static int columns_range_ok(tvs_problem* h, int64_t first, int64_t n, const char
     return TVS_OK;
 }
 
+// 16-bit mirror of freshly registered columns; a count above 65,535 retires the mirror, a negative weight is an error
+static int mirror_columns(tvs_problem* h, int64_t first, int64_t n, const char* who) {
+    Lanes& l = h->lanes;
+    const int64_t cnt = h->csr.R * n;
+    cudaMemsetAsync(l.flag, 0, sizeof(int32_t), h->stream);
+    narrow_columns_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(l.cols, l.cols16, l.col_cap, first, n, h->csr.R, l.flag);
+    int32_t flag = 0;
+    TVS_CUDA(cudaMemcpyAsync(&flag, l.flag, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    TVS_CUDA(cudaStreamSynchronize(h->stream));
+    if (flag & 2) { set_error("%s: negative weight (weights are record counts: w >= 0)", who); return TVS_EINVAL; }
+    if (flag & 1) l.cols16_ok = false;
+    return TVS_OK;
+}
+
 int tvs_columns_upload(tvs_handle h, int64_t first, int64_t n, const int32_t* w_cols) {
     if (!h || !w_cols) { set_error("tvs_columns_upload: null argument"); return TVS_EINVAL; }
     TVS_CUDA(cudaSetDevice(h->device));
@@ -1022,8 +1040,7 @@ int tvs_columns_upload(tvs_handle h, int64_t first, int64_t n, const int32_t* w_
     if (rc != TVS_OK) return rc;
     Lanes& l = h->lanes;
     TVS_CUDA(cudaMemcpy2DAsync(l.cols + first, (size_t)l.col_cap * 4, w_cols, (size_t)n * 4, (size_t)n * 4, (size_t)h->csr.R, cudaMemcpyDefault, h->stream));
-    TVS_CUDA(cudaStreamSynchronize(h->stream));
-    return TVS_OK;
+    return mirror_columns(h, first, n, "tvs_columns_upload");
 }
 
 int tvs_columns_upload_u16(tvs_handle h, int64_t first, int64_t n, const uint16_t* w_cols) {
@@ -1037,6 +1054,7 @@ int tvs_columns_upload_u16(tvs_handle h, int64_t first, int64_t n, const uint16_
     if ((rc = dev_alloc(&tmp, (size_t)cnt)) != TVS_OK) return rc;
     cudaMemcpyAsync(tmp, w_cols, (size_t)cnt * 2, cudaMemcpyDefault, h->stream);
     widen_columns_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(tmp, n, R, l.cols, l.col_cap, first);
+    cudaMemcpy2DAsync(l.cols16 + first, (size_t)l.col_cap * 2, tmp, (size_t)n * 2, (size_t)n * 2, (size_t)R, cudaMemcpyDeviceToDevice, h->stream);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaFree(tmp);
@@ -1053,8 +1071,7 @@ int tvs_columns_resample(tvs_handle h, int64_t first, int64_t n, const int32_t* 
     if (first_id + (uint64_t)n > 0xffffffffull) { set_error("tvs_columns_resample: column ids beyond 2^32"); return TVS_ELIMIT; }
     rc = resample_into(h, h->lanes.cols + first, h->lanes.col_cap, n, n_obs, seed, 0, (uint32_t)first_id);
     if (rc != TVS_OK) return rc;
-    TVS_CUDA(cudaStreamSynchronize(h->stream));
-    return TVS_OK;
+    return mirror_columns(h, first, n, "tvs_columns_resample");
 }
 
 int tvs_set_lanes_columns(tvs_handle h, int64_t B, const int32_t* col_of_lane, const uint8_t* mask, const double* C) {
@@ -1066,14 +1083,17 @@ int tvs_set_lanes_columns(tvs_handle h, int64_t B, const int32_t* col_of_lane, c
     std::vector<int32_t> idx;
     int rc = check_slots(col_of_lane, B, l.col_cap, "tvs_set_lanes_columns", &idx);
     if (rc != TVS_OK) return rc;
-    if ((rc = reserve_lanes(h, B, mask != nullptr, C != nullptr, true)) != TVS_OK) return rc;
+    const bool use16 = l.cols16_ok && env_int("TVS_W16", 1) != 0;       // gather the 16-bit mirror: half the traffic, no flag to wait for
+    if ((rc = reserve_lanes(h, B, mask != nullptr, C != nullptr, !use16)) != TVS_OK) return rc;
     if (l.cap_slot < B) { dev_free(l.slot); l.cap_slot = 0; if ((rc = dev_alloc(&l.slot, (size_t)B)) != TVS_OK) return rc; l.cap_slot = B; }
     TVS_CUDA(cudaMemcpyAsync(l.slot, idx.data(), (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     const int64_t R = h->csr.R;
     dim3 grid((unsigned)((B + 127) / 128), (unsigned)std::min<int64_t>(R, 4096));
-    gather_columns_kernel<<<grid, 128, 0, h->stream>>>(l.cols, l.col_cap, l.slot, R, B, l.w);
+    if (use16) gather_columns_kernel<uint16_t><<<grid, 128, 0, h->stream>>>(l.cols16, l.col_cap, l.slot, R, B, l.w16);
+    else gather_columns_kernel<int32_t><<<grid, 128, 0, h->stream>>>(l.cols, l.col_cap, l.slot, R, B, l.w);
     TVS_CUDA(cudaGetLastError());
-    return finish_lanes(h, mask, C, false);
+    // (the slot ids come from a pageable host vector: cudaMemcpyAsync returns once they are staged, so the vector may die here)
+    return finish_lanes(h, mask, C, use16);
 }
 
 // n bootstrap columns into dst[r*ld + j] (j < n): column j ~ Multinomial(N, n_obs/N) from the Philox stream id0 + j

@@ -72,6 +72,7 @@ struct Lanes {
     int32_t* flag = nullptr;   // device word: overflow flag of the narrowing kernel
     // device-resident column store (tvs_columns_*): [R x col_cap] int32, element (r, c) at [r*col_cap + c]
     int32_t* cols = nullptr; int64_t col_cap = 0;
+    uint16_t* cols16 = nullptr; bool cols16_ok = true;   // 16-bit mirror of the store (valid while no registered count exceeded 65,535)
     int32_t* slot = nullptr; int64_t cap_slot = 0;   // staging of the lanes' column slots
     unsigned long long* acc = nullptr;   // integer lane sums (finish_lanes)
     int64_t  cap_acc = 0;

@@ -780,12 +780,23 @@ __global__ void narrow_u16_kernel(const int32_t* __restrict__ src, uint16_t* __r
 
 // lane columns from the device-resident column store: dst[r, b] = store[r, slot[b]]  (replaces the per-batch rebuild of the
 // replicate weights, traversome.py:515-545)
-__global__ void gather_columns_kernel(const int32_t* __restrict__ store, int64_t cap, const int32_t* __restrict__ slot, int64_t R, int64_t B,
-                                      int32_t* __restrict__ dst) {
+template <typename T>
+__global__ void gather_columns_kernel(const T* __restrict__ store, int64_t cap, const int32_t* __restrict__ slot, int64_t R, int64_t B,
+                                      T* __restrict__ dst) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int64_t sj = slot[b];
     for (int64_t r = blockIdx.y; r < R; r += gridDim.y) dst[r * B + b] = store[r * cap + sj];
+}
+// 16-bit mirror of columns first .. first+n-1 of the store; *flag bit 0 = a count above 65535, bit 1 = a negative weight
+__global__ void narrow_columns_kernel(const int32_t* __restrict__ store, uint16_t* __restrict__ store16, int64_t cap, int64_t first, int64_t n,
+                                      int64_t R, int32_t* __restrict__ flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R * n) return;
+    const int64_t r = i / n, c = i - r * n;
+    const int32_t v = store[r * cap + first + c];
+    store16[r * cap + first + c] = (uint16_t)v;
+    if ((unsigned)v > 65535u) atomicOr(flag, v < 0 ? 3 : 1);
 }
 __global__ void widen_columns_kernel(const uint16_t* __restrict__ src, int64_t n, int64_t R, int32_t* __restrict__ store, int64_t cap, int64_t first) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // src [R x n] lane-minor

@@ -252,10 +252,10 @@ class LaneSharder(object):
 
 class _Residency(object):
     """Which weight columns of a LaneContext live in which slot of one engine's column store."""
-    __slots__ = ("slot_of", "used", "cap")
+    __slots__ = ("slot_of", "used", "cap", "last")
 
     def __init__(self):
-        self.slot_of, self.used, self.cap = {}, 0, 0
+        self.slot_of, self.used, self.cap, self.last = {}, 0, 0, None
 
 
 class LaneContext(object):
@@ -285,6 +285,7 @@ class LaneContext(object):
         self.n_lanes_fitted = 0
         self.n_batches = 0
         self.check_consistency = True
+        self._checked = None
         self.time_passes = False      # CUDA events around every pass launch (roofline figures; ~1 ms per fit)
         self.engine_factory = _cabi.Engine     # tests of the host logic inject a stand-in here
         # permutations drawn inside a sharded job must not depend on the rank (ModelFitMaxLike.py:203 shuffles the
@@ -373,6 +374,9 @@ class LaneContext(object):
         """Slots of `cols` (array of column ids) in the column store of `eng`; columns seen for the first time are
         uploaded (host copies, one dense block) or drawn on the device (add_resampled) now."""
         res = self._resident.setdefault(id(eng), _Residency())
+        key = cols.tobytes()
+        if res.last is not None and res.last[0] == key:          # the same lanes as the previous batch (a bootstrap refit)
+            return res.last[1]
         uniq = np.unique(cols)
         missing = [int(c) for c in uniq if int(c) not in res.slot_of]
         if missing:
@@ -401,7 +405,9 @@ class LaneContext(object):
                 res.used += n
                 i = j + 1
         lut = res.slot_of
-        return np.fromiter((lut[int(c)] for c in cols), dtype=np.int32, count=len(cols))
+        slots = np.fromiter((lut[int(c)] for c in cols), dtype=np.int32, count=len(cols))
+        res.last = (key, slots)
+        return slots
 
     # ---- the batched fit
     def fit(self, requests):
@@ -430,8 +436,9 @@ class LaneContext(object):
         a sharder: this rank fits its slice, one all_gather returns the rest)."""
         B = len(batch)
         sh = self.sharder
-        if sh is not None and self.check_consistency:
-            sh.check_same_batch(B, batch.digest())
+        if sh is not None and self.check_consistency and batch is not self._checked:
+            sh.check_same_batch(B, batch.digest())              # once per batch object: a batch that is fitted again is the same
+            self._checked = batch
         lo, hi = (0, B) if sh is None else sh.my_slice(B)
         n = hi - lo
         local = None
@@ -464,7 +471,7 @@ class LaneContext(object):
 
     def _fit_on(self, eng, mine, out=None):
         """Fit the lanes `mine` (LaneBatch) on one handle; returns the engine's result dict."""
-        slots = self._slots(eng, mine.cols)
+        slots = self._slots(eng, np.ascontiguousarray(mine.cols))
         eng.set_lanes_columns(slots, mask=mine.mask, C=mine.C)
         return eng.fit(theta0=mine.theta0, tol=self.tol, max_iter=self.max_iter, history=self.history, out=out,
                        time_passes=self.time_passes)

@@ -188,6 +188,32 @@ class RecordPool(object):
                         "rows": uniq.astype(np.int64), "num_matched": counts.astype(np.int64), "X": X})
         return out, np.asarray(legal, dtype=np.int64)
 
+    # ------------------------------------------------------------------ the same on the device, a batch of replicates per call
+    def device_pool(self, device=0):
+        """The pool on the device (include/tvs_pool.h, csrc/tvs_pool.cu); created once, reused by `lanes_on_device`."""
+        from . import _cabi
+        pool = getattr(self, "_device_pool", None)
+        if pool is None or pool[0] != device:
+            if pool is not None:
+                pool[1].close()
+            pool = self._device_pool = (device, _cabi.DevicePool(self.record_ids, self.row_of, self.align_len, self.multi, self.inner_len,
+                                                                 self.full_len, self.left_room, self.right_room, device=device))
+        return pool[1]
+
+    def lanes_on_device(self, samples, masked_rows=(), device=0):
+        """`lane_of` for a BATCH of replicates in one device call: samples = list of index arrays (one per replicate, the
+        draws of sample_bootstrap / sample_jackknife).  Returns (w int32 [n_rows, B], C [B], N [B], observed bool [n_rows, B])
+        -- w, N and observed identical to `lane_of`, C equal to rounding (its terms are summed in another order)."""
+        n_draw = max(len(s) for s in samples)
+        block = np.full((len(samples), n_draw), -1, dtype=np.int32)
+        for b, s_ in enumerate(samples):
+            block[b, :len(s_)] = s_
+        masked = None
+        if len(masked_rows):
+            masked = np.zeros(self.n_rows, dtype=np.uint8)
+            masked[np.asarray(list(masked_rows), dtype=np.int64)] = 1
+        return self.device_pool(device).lanes(block, masked)
+
     def lane_of(self, sample, masked_rows=()):
         """(w int32[n_rows], C, N, observed bool[n_rows]) of one replicate: the pruning rule of
         ModelGenerator.py:138-151 (bins with num_possible_X < 1 dropped) applied to bins_of(sample)."""
