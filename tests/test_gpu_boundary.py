@@ -242,10 +242,12 @@ def test_backward_selection_decisions_equal_exact_replay(gpu, criterion):
     assert n_gpu >= 5 and len(gp) < wl.V                    # the selection did drop variants and tested candidates
 
 
-def test_cfg1_bootstrap_from_record_pool_on_gpu(gpu, plastome):
+@pytest.mark.parametrize("device_bins", [False, True])
+def test_cfg1_bootstrap_from_record_pool_on_gpu(gpu, plastome, device_bins):
     """cfg1 without any per-replicate object graph: records -> replayed draws -> bit-exact bins -> weight columns ->
     lock-step backward selection on the CUDA solver.  Same support table as the reference run; every replicate's
-    proportions within the reference's own SLSQP spread and within 1e-6 of the exact optimum of ITS replicate."""
+    proportions within the reference's own SLSQP spread and within 1e-6 of the exact optimum of ITS replicate.
+    device_bins: the bin statistics of all 100 replicates in one device call (include/tvs_pool.h)."""
     import random
     from traversome_b200.resample import RecordPool
     L = plastome["variant_sizes"]
@@ -262,7 +264,7 @@ def test_cfg1_bootstrap_from_record_pool_on_gpu(gpu, plastome):
     full = ModelFitMaxLike.from_lane(ctx, (ctx.add_weights(w0), C0, N0), pattern, np.nonzero(obs0)[0], groups, unid)
     raw = full.reverse_model_selection(n_proc=1)
     assert abs(raw[0][0] - 23 / 35.) < 1e-7 and abs(raw[1] - plastome["final"]["res_loglike"]) < 1e-9 * abs(raw[1])
-    s = bootstrap.do_subsampling_from_records(pool, pattern, ctx, full, raw, random.Random(12345), n_replicate=100)
+    s = bootstrap.do_subsampling_from_records(pool, pattern, ctx, full, raw, random.Random(12345), n_replicate=100, device_bins=device_bins)
     assert s.bs_eligible and s.n_replicates_run == 100
     got = [[list(k), s.vp_unique_results[k]["support"]] for k in s.vp_unique_results_sorted]
     assert got == plastome["final"]["support"]

@@ -156,12 +156,14 @@ def summarize_replicates(variant_proportions_reps, raw_variant_proportions, raw_
 
 def do_subsampling_from_records(pool, pattern, context, full_fit, raw_result, rng, n_replicate, criterion=Criterion.BIC,
                                 threshold=0.95, jackknife=0, n_proc=1, user_fixed_ids=None, masked_rows=(), batch=None,
-                                loglevel="INFO"):
+                                loglevel="INFO", device_bins=False):
     """``Traversome.do_subsampling`` from the record pool in array form (traversome_b200.resample.RecordPool): the
     replicates are drawn with the reference's own draws (`rng` = the reference's ``self.random``, e.g.
     ``random.Random(12345)``), binned bit-exactly, registered as weight columns of `context` and selected in lock
     step -- no per-replicate object graph.  `pattern` [rows, V] bool is the non-zero pattern of from_variants in
-    ``all_sub_paths`` order (the rows of `pool`); `context.matrix` must hold exactly those rows in that order."""
+    ``all_sub_paths`` order (the rows of `pool`); `context.matrix` must hold exactly those rows in that order.
+    device_bins: the bin statistics of a whole batch of replicates in ONE device call (include/tvs_pool.h) instead of the
+    host array code, replicate by replicate -- same weights, N and observed read paths, C equal to rounding."""
     n_digit = len(str(n_replicate))
     count_unique = {}
     reps = []
@@ -171,15 +173,15 @@ def do_subsampling_from_records(pool, pattern, context, full_fit, raw_result, rn
     while go_bs < n_replicate and bs_eligible:
         fitters = []
         states = []                                   # rng state after each replicate's draws (see the early stop below)
-        while len(fitters) < min(batch, n_replicate - go_bs):
-            k = len(fitters)
+        want = min(batch, n_replicate - go_bs)
+
+        def draw():
             if jackknife:
-                sample = pool.sample_jackknife(rng, int(pool.n_records / float(n_replicate)))
-            else:
-                sample = pool.sample_bootstrap(rng, pool.n_records)
-            w, C, N, observed = pool.lane_of(sample, masked_rows)
-            if N == 0 or not np.any(observed):            # traversome.py:528-529 `if not sampled_sub_paths: continue`: draw again
-                continue
+                return pool.sample_jackknife(rng, int(pool.n_records / float(n_replicate)))
+            return pool.sample_bootstrap(rng, pool.n_records)
+
+        def add(w, C, N, observed):
+            k = len(fitters)
             states.append(rng.getstate() if hasattr(rng, "getstate") else None)
             col = context.add_weights(w)
             f = ModelFitMaxLike.from_lane(context, (col, C, N), pattern, np.nonzero(observed)[0], full_fit.repr_to_merged_variants,
@@ -187,6 +189,27 @@ def do_subsampling_from_records(pool, pattern, context, full_fit, raw_result, rn
                                           bootstrap_mode=f"BS{go_bs + k + 1: 0{n_digit}d}")
             f._shuffle = full_fit._shuffle
             fitters.append(f)
+
+        if device_bins:
+            # draw the whole batch first (the generator state after each draw is kept for the early stop), then one device
+            # call; an empty replicate is drawn again like traversome.py:528-529, which costs one more (small) device call
+            while len(fitters) < want:
+                samples, after = [], []
+                for _ in range(want - len(fitters)):
+                    samples.append(draw())
+                    after.append(rng.getstate() if hasattr(rng, "getstate") else None)
+                w_all, C_all, N_all, obs_all = pool.lanes_on_device(samples, masked_rows=masked_rows, device=context.device)
+                for j in range(len(samples)):
+                    if int(N_all[j]) == 0 or not obs_all[:, j].any():
+                        continue
+                    add(w_all[:, j], float(C_all[j]), int(N_all[j]), obs_all[:, j])
+                    states[-1] = after[j]
+        else:
+            while len(fitters) < want:
+                w, C, N, observed = pool.lane_of(draw(), masked_rows)
+                if N == 0 or not np.any(observed):            # traversome.py:528-529 `if not sampled_sub_paths: continue`: draw again
+                    continue
+                add(w, C, N, observed)
         results = run_selections(fitters, criterion=criterion, n_proc=n_proc, user_fixed_ids=user_fixed_ids)
         batch_first = len(reps)
         for res in results:
