@@ -301,3 +301,61 @@ def test_lane_context_concurrent_halves_on_gpu(gpu):
     assert all(r.success for r in res[0]) and all(r.success for r in res[1])
     assert max(np.abs(a.x - b.x).max() for a, b in zip(*res)) < 1e-7
     assert max(abs(a.fun - b.fun) / abs(a.fun) for a, b in zip(*res)) < 1e-12
+
+
+def test_weight_forms_and_the_column_store(gpu):
+    """The lane weights live on the device as 16-bit counts when every count fits and as int32 otherwise; the column
+    store (tvs_columns_*) registers a replicate's weight vector once and batches name it by slot.  All forms give the
+    same fits; counts above 65,535 take the int32 path; a negative weight is refused."""
+    from traversome_b200 import synthetic
+    wl = synthetic.make_workload(12, 800, 0.3, seed=31)
+    B = 10
+    w = synthetic.bootstrap_weights(wl.n_obs, B, seed=6)
+    with _cabi.Engine(wl.row_ptr, wl.col, wl.val, wl.L) as eng:
+        eng.set_lanes(w)                                        # int32 upload, 16-bit copy made on the device
+        a = eng.fit()
+        eng.set_lanes(w.astype(np.uint16))                      # 16-bit upload, stays 16-bit
+        b = eng.fit()
+        assert np.array_equal(eng.get_weights(), w)             # widened on request
+        assert np.array_equal(a["theta"], b["theta"]) and np.array_equal(a["loglike"], b["loglike"])
+        # the column store: int32 and uint16 uploads, lanes by slot in any order and with repeats
+        eng.columns_reserve(4)
+        eng.columns_upload(0, w[:, :4])
+        eng.columns_reserve(B + 3)                              # growing keeps the registered columns
+        eng.columns_upload(4, w[:, 4:].astype(np.uint16))
+        order = np.array([3, 0, 9, 9, 5, 1, 2, 4, 6, 7, 8], dtype=np.int32)
+        eng.set_lanes_columns(order)
+        c = eng.fit()
+        assert np.array_equal(eng.get_weights(), w[:, order])
+        assert np.abs(c["theta"] - a["theta"][:, order]).max() < 1e-7       # same lanes in another batch geometry
+        assert np.array_equal(c["theta"][:, 2], c["theta"][:, 3])           # the repeated column: the same lane twice
+        # device-drawn columns depend on (seed, id) only, not on the slot or the call that drew them
+        eng.columns_resample(B, 3, wl.n_obs, seed=77, first_id=5)
+        eng.set_lanes_columns(np.array([B, B + 1, B + 2], dtype=np.int32))
+        d1 = eng.get_weights()
+        eng.columns_resample(0, 2, wl.n_obs, seed=77, first_id=6)
+        eng.set_lanes_columns(np.array([0, 1], dtype=np.int32))
+        d2 = eng.get_weights()
+        assert np.array_equal(d1[:, 1:3], d2) and np.all(d1.sum(0) == wl.N)
+        with pytest.raises(_cabi.TvsError):
+            eng.set_lanes_columns(np.array([B + 3], dtype=np.int32))        # slot outside the store
+        # counts above 65,535: int32 path, same optimum (theta is invariant under a scaling of the weights)
+        big = w.astype(np.int64) * 40000
+        assert big.max() > 65535 and big.max() < 2 ** 31
+        eng.set_lanes(big.astype(np.int32))
+        e = eng.fit()
+        assert np.all(e["status"] == _cabi.CONVERGED) and np.abs(e["theta"] - a["theta"]).max() < 1e-7
+        assert np.array_equal(eng.get_weights(), big.astype(np.int32))
+        neg = w.copy()
+        neg[5, 2] = -1
+        with pytest.raises(_cabi.TvsError):
+            eng.set_lanes(neg)
+    check_fit_against_exact_lane(wl, w, a, [0, 3, B - 1])
+
+
+def check_fit_against_exact_lane(wl, w, out, lanes):
+    A = wl.scipy_csr()
+    for b in lanes:
+        r = exact.exact_fit(A, wl.L, w[:, b])
+        assert np.abs(out["theta"][:, b] - r["theta"]).max() < 1e-6
+        assert abs(out["loglike"][b] - r["loglike_no_C"]) < 1e-9 * abs(r["loglike_no_C"])
