@@ -56,11 +56,11 @@ static void free_csr(Csr& c) {
     dev_free(c.slab_ptr); dev_free(c.h_row); dev_free(c.h_val); dev_free(c.h_slot);
     dev_free(c.wide_ptr); if (c.wide_rec) { cudaFree(c.wide_rec); c.wide_rec = nullptr; }
     dev_free(c.dense);
-    for (Csr::Blk* b : {&c.blk_f, &c.blk_b}) {
+    for (Csr::Blk* b : {&c.blk_f, &c.blk_b, &c.blk_h}) {
         dev_free(b->seg_off);
         if (b->blob) { cudaFree(b->blob); b->blob = nullptr; }
     }
-    c.has_blk = false;
+    c.has_blk = false; c.has_blk_h = false;
 }
 static void free_lanes(Lanes& l) {
     dev_free(l.w); dev_free(l.mask); dev_free(l.C); dev_free(l.N); dev_free(l.w16); dev_free(l.flag); dev_free(l.cols); dev_free(l.cols16); dev_free(l.slot);
@@ -426,6 +426,44 @@ __global__ void densify_kernel(const int32_t* __restrict__ row_ptr, const uint32
 }
 
 
+
+// geometry of ONE blocked product in backward mode for a lane set of width W (the Hessian product of the Newton phase)
+struct BlkOne { int K = 2; bool bulk = true; int stages = 2; size_t smem = 0; int tiles = 0; int splits = 1; };
+static int plan_blk_backward(const tvs_problem* h, int64_t W, const Csr::Blk& m, BlkOne* out) {
+    const size_t limit = 227 * 1024;
+    int K = (W % 2 == 0) ? 2 : 1;
+    const bool bulk = (W % 2 == 0);
+    auto stages_for = [&](int k) {
+        int n = std::min(kBlkMaxStages, std::max(2, env_int("TVS_BLK_STAGES", kBlkMaxStages)));
+        while (n >= 2 && blk_layout(32 * k, m.max_seg_bytes, n).total > limit) --n;
+        return n;
+    };
+    int ns = stages_for(K);
+    if (K == 2 && ns < 2) { K = 1; ns = stages_for(1); }
+    if (ns < 2) return TVS_ELIMIT;
+    const size_t smem = blk_layout(32 * K, m.max_seg_bytes, ns).total;
+    int occ = 0, rc;
+    if (K == 2) rc = blk_prepare<2, 1, true>(h, smem, &occ);
+    else if (bulk) rc = blk_prepare<1, 1, true>(h, smem, &occ);
+    else rc = blk_prepare<1, 1, false>(h, smem, &occ);
+    if (rc != TVS_OK) return rc;
+    if (occ < 1) return TVS_ELIMIT;
+    out->K = K; out->bulk = bulk; out->stages = ns; out->smem = smem;
+    out->tiles = (int)((W + 32 * K - 1) / (32 * K));
+    const int slots = h->sm_count, units = out->tiles * m.n_chunks;
+    int best_s = 1;
+    double best = -1.0;
+    const int s_max = std::min(std::max(8, slots / std::max(1, units)), std::max(1, m.n_panels / 4));
+    for (int cand = 1; cand <= std::max(1, s_max); ++cand) {
+        const int64_t total = (int64_t)units * cand;
+        const int64_t waves = (total + slots - 1) / slots;
+        const double eff = (double)total / (double)(waves * slots);
+        if (eff > best + 0.02) { best = eff; best_s = cand; }
+    }
+    out->splits = std::max(1, std::min(best_s, m.n_panels));
+    return TVS_OK;
+}
+
 template <int K, bool BULK>
 static void blk_launch_one(const BlkArgs& a, int mode, dim3 grid, size_t smem, cudaStream_t st) {
     if (mode == 0) blk_kernel<K, 0, BULK><<<grid, kBlkThreads, smem, st>>>(a);
@@ -787,6 +825,32 @@ int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, c
                     wcap = std::max(wcap, (int)(wp[(size_t)b * (NS + 1) + std::min(NS, s0 + kWideWarps)] - wp[(size_t)b * (NS + 1) + s0]));
             }
             c.w_HB = WB; c.w_nblk = wnblk; c.w_cap = wcap;
+            // the same products once more in blocked form, grouped by H entry (major) with the read path as minor index:
+            // the Hessian of every lane is then the blocked product G x (w / p^2), one launch of blk_kernel's backward mode
+            if (env_int("TVS_HESS_BLK", 1) != 0) {
+                bool small = true;
+                for (int64_t k = 0; k < nnz && small; ++k) small = val[k] <= 46340;       // products below 2^31
+                if (small) {
+                    std::vector<int64_t> gp((size_t)NPk + 1, 0);
+                    for (int64_t r = 0; r < R; ++r)
+                        for (int64_t i = row_ptr[r]; i < row_ptr[r + 1]; ++i)
+                            for (int64_t j = row_ptr[r]; j <= i; ++j) gp[(size_t)(col[i] * (col[i] + 1) / 2 + col[j]) + 1]++;
+                    for (int e = 0; e < NPk; ++e) gp[(size_t)e + 1] += gp[(size_t)e];
+                    std::vector<int32_t> gr((size_t)std::max<int64_t>(np, 1)), gv((size_t)std::max<int64_t>(np, 1));
+                    std::vector<int64_t> at(gp.begin(), gp.end() - 1);
+                    for (int64_t r = 0; r < R; ++r)                          // rows ascending inside every entry
+                        for (int64_t i = row_ptr[r]; i < row_ptr[r + 1]; ++i)
+                            for (int64_t j = row_ptr[r]; j <= i; ++j) {
+                                const int64_t q = at[(size_t)(col[i] * (col[i] + 1) / 2 + col[j])]++;
+                                gr[(size_t)q] = (int32_t)r; gv[(size_t)q] = val[i] * val[j];
+                            }
+                    BlkHost hg;
+                    if (build_blk<int64_t>(NPk, R, gp.data(), gr.data(), gv.data(), &hg)) {
+                        if ((rc = upload_blk(hg, &c.blk_h)) != TVS_OK) return fail(rc);
+                        c.has_blk_h = true;
+                    }
+                }
+            }
             UP_(wide_ptr, wp, int32_t)
             {
                 uint2* dd = nullptr;
@@ -1262,7 +1326,9 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
     };
 
     // ---- damped Newton phase (tvs_newton.cuh): runs the lanes of a small set to convergence
-    const int newton_lanes = (h->csr.slab_ptr != nullptr && V <= kNewtonMaxV) ? env_int("TVS_NEWTON_LANES", 128) : 0;
+    // Newton takes over once at most this many lanes are still iterating: 512 with the blocked Hessian product (one launch,
+    // 0.6 ms per 1,000 lanes: cfg2 11.7 -> 11.1 ms per 1000-lane fit), 128 with the round-1 Hessian kernels
+    const int newton_lanes = (h->csr.slab_ptr != nullptr && V <= kNewtonMaxV) ? env_int("TVS_NEWTON_LANES", h->csr.has_blk_h ? 512 : 128) : 0;
     int64_t newton_iters = 0;
     const bool newton_trace = env_int("TVS_NEWTON_TRACE", 0) != 0;
     bool newton_off = false;                                    // set when the shape has no staged pass kernel
@@ -1273,7 +1339,11 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         const int64_t W = s.width;
         const int NP = (int)(V * (V + 1) / 2);
         const Csr& c = h->csr;
-        const bool wide = c.wide_ptr != nullptr && W >= env_int("TVS_HESS_WIDE_MIN", 256) && W % 4 == 0;
+        // Hessian as a blocked product (blk_kernel, backward mode) when its matrix was built; else the round-1 kernels
+        BlkOne hb;
+        const bool hblk = c.has_blk_h && env_int("TVS_HESS_BLK", 1) != 0 && W >= env_int("TVS_HESS_BLK_MIN", 16) &&
+                          plan_blk_backward(h, W, c.blk_h, &hb) == TVS_OK;
+        const bool wide = !hblk && c.wide_ptr != nullptr && W >= env_int("TVS_HESS_WIDE_MIN", 256) && W % 4 == 0;
         // slab kernel: one CTA per (lane, range of row blocks), all CTAs resident at once
         const size_t hess_smem = ((size_t)NP + c.h_HB + 1 + c.h_NG + 1) * 8 + (size_t)c.h_NG * 32 * 2;
         const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(220 * 1024) / (hess_smem + 1024)));
@@ -1282,7 +1352,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         S_h = (c.h_nblk + blocks_per_split - 1) / blocks_per_split;
         const size_t wide_smem = (size_t)2 * c.w_HB * 32 * sizeof(float) + (size_t)2 * c.w_cap * 8 + (size_t)(2 * (kWideWarps + 1) + 2) * 4 +
                                  (size_t)kWideWarps * kWideEnt * 32 * sizeof(float);
-        const size_t need_cap = wide ? (size_t)W * (size_t)NP : (size_t)S_h * (size_t)W * (size_t)NP;
+        const size_t need_cap = hblk ? (size_t)hb.splits * (size_t)W * (size_t)NP : wide ? (size_t)W * (size_t)NP : (size_t)S_h * (size_t)W * (size_t)NP;
         if (f.Hpart_cap < need_cap) {
             if (f.Hpart) cudaFree(f.Hpart);
             f.Hpart = nullptr; f.Hpart_cap = 0;
@@ -1331,9 +1401,16 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         hw.wide_ptr = c.wide_ptr; hw.wide_rec = (const uint2*)c.wide_rec; hw.crf = f.crf; hw.H = f.Hpart;
         hw.W = W; hw.R = R; hw.V = (int)V; hw.HB = c.w_HB; hw.nblk = c.w_nblk; hw.cap = c.w_cap;
         const dim3 wide_grid((unsigned)((W + 31) / 32), (unsigned)((NP + kWideSet - 1) / kWideSet));
+        BlkArgs hbk{};                                           // blocked Hessian product: H[(u,v), lane] = sum_r G[(u,v), r] * cr[r, lane]
+        hbk.m.seg_off = c.blk_h.seg_off; hbk.m.blob = (const uint4*)c.blk_h.blob; hbk.m.n_chunks = c.blk_h.n_chunks;
+        hbk.m.n_panels = c.blk_h.n_panels; hbk.m.max_seg_bytes = c.blk_h.max_seg_bytes;
+        hbk.src = f.cr; hbk.n_minor = R; hbk.n_major = NP; hbk.W = W; hbk.done = s.done; hbk.need = f.need;
+        hbk.tpart = f.Hpart; hbk.stages = hb.stages; hbk.logc = pa.logc;
+        const dim3 hblk_grid((unsigned)c.blk_h.n_chunks, (unsigned)hb.tiles, (unsigned)hb.splits);
         SolveArgs sa{};
-        sa.Hpart = f.Hpart; sa.S = wide ? 1 : S_h;
-        sa.h_entry = wide ? W : 1; sa.h_lane = wide ? 1 : NP; sa.h_split = wide ? 0 : (int64_t)W * NP;
+        sa.Hpart = f.Hpart; sa.S = hblk ? hb.splits : wide ? 1 : S_h;
+        sa.h_entry = (wide || hblk) ? W : 1; sa.h_lane = (wide || hblk) ? 1 : NP;
+        sa.h_split = hblk ? (int64_t)W * NP : wide ? 0 : (int64_t)W * NP;
         sa.z = s.z; sa.g = s.g; sa.gha = f.gha; sa.invL = h->csr.invL; sa.N = s.N; sa.mask = s.mask;
         sa.done = s.done; sa.lam = f.lam; sa.d = s.d; sa.zt = s.zt; sa.x = s.x; sa.dg = s.dg; sa.alpha = s.alpha; sa.W = W; sa.V = (int)V;
         sa.sumphi = s.sumphi; sa.tol_dual = (double)env_int("TVS_DUAL_MULT", 100) * opt.tol; sa.ls = s.ls;
@@ -1348,7 +1425,11 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
             const int slot = (int)(n_polls % 16);
             cudaEvent_t eh0 = nullptr, eh1 = nullptr, eh2 = nullptr;
             if (time_passes) { cudaEventCreate(&eh0); cudaEventCreate(&eh1); cudaEventCreate(&eh2); cudaEventRecord(eh0, st); }
-            if (wide) hess_wide_kernel<<<wide_grid, 32 * kWideWarps, wide_smem, st>>>(hw);
+            if (hblk) {
+                if (hb.K == 2) blk_launch_one<2, true>(hbk, 1, hblk_grid, hb.smem, st);
+                else if (hb.bulk) blk_launch_one<1, true>(hbk, 1, hblk_grid, hb.smem, st);
+                else blk_launch_one<1, false>(hbk, 1, hblk_grid, hb.smem, st);
+            } else if (wide) hess_wide_kernel<<<wide_grid, 32 * kWideWarps, wide_smem, st>>>(hw);
             else hess_kernel<<<dim3((unsigned)W, (unsigned)S_h), 32 * kHessWarps, hess_smem, st>>>(ha);
             if (time_passes) cudaEventRecord(eh1, st);
             if (V <= 64) solve_kernel<64><<<(unsigned)W, kSolveThreads, solve_smem, st>>>(sa);

@@ -48,6 +48,8 @@ struct BlkArgs {
     const double* src;                              // dense operand [n_minor x W], lane-minor (x or rr)
     int64_t n_minor, n_major, W;
     const int32_t* done;
+    const int32_t* need;                            // backward, optional: lanes with need == 0 keep their previous output (Newton phase:
+                                                    // a lane whose trial point was rejected re-uses its Hessian)
     const int32_t* w32; const uint16_t* w16;        // forward: weights [R x W] (one of the two)
     double* rr;                                     // forward out: [R x W] (null: log-likelihood only)
     double* llpart;                                 // forward out: [splits x W]
@@ -321,13 +323,19 @@ __global__ void __launch_bounds__(kBlkThreads, 1) blk_kernel(const BlkArgs a) {
             // ---- backward epilogue: the chunk's block of t for this split
             const int64_t v0 = (int64_t)blockIdx.x * kBlkCH + wi * kBlkRPW;
             if (lv) {
+                bool on[K];
+#pragma unroll
+                for (int j = 0; j < K; ++j) on[j] = a.need == nullptr || (a.need[mylane + j] != 0 && (a.done == nullptr || a.done[mylane + j] == 0));
 #pragma unroll
                 for (int i = 0; i < kBlkRPW; ++i) {
                     const int64_t v = v0 + i;
                     if (v < a.n_major) {
                         double* dst = a.tpart + ((int64_t)split * a.n_major + v) * W + mylane;
-                        if (K == 2) *reinterpret_cast<double2*>(dst) = make_double2(acc[i][0], acc[i][K - 1]);
-                        else dst[0] = acc[i][0];
+                        if (K == 2 && on[0] && on[K - 1]) *reinterpret_cast<double2*>(dst) = make_double2(acc[i][0], acc[i][K - 1]);
+                        else {
+                            if (on[0]) dst[0] = acc[i][0];
+                            if (K == 2 && on[K - 1]) dst[K - 1] = acc[i][K - 1];
+                        }
                     }
                 }
             }

@@ -53,6 +53,10 @@ struct Csr {
     struct Blk { uint32_t* seg_off = nullptr; void* blob = nullptr; int n_chunks = 0, n_panels = 0, max_seg_bytes = 0; };
     Blk blk_f, blk_b;
     bool has_blk = false;
+    // Newton phase (V <= 128): the Hessian as ONE more blocked product -- G[(u,v), r] = A_ru A_rv (u >= v, packed index
+    // u(u+1)/2+v) times the dense w/p^2 [R x lanes] -- run by blk_kernel's backward mode
+    Blk blk_h;
+    bool has_blk_h = false;
     double*   invL = nullptr;        // [V] 1/L_v
     double*   Ld = nullptr;          // [V] L_v as double
     int64_t   n_ccol = 0;
