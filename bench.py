@@ -551,11 +551,14 @@ def main():
     step_ms = float(np.sum(dev_ms)) / args.steps
     e2e_step_ms = float(np.sum(e2e_ms)) / args.steps
     per_rank_ms = [step_ms]
+    per_rank_fit_ms = [float(np.mean(fit_ms))]
     if world > 1:
-        t = torch.tensor([step_ms, e2e_step_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([step_ms, e2e_step_ms, float(np.mean(fit_ms))], dtype=torch.float64, device="cuda")
         every = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(every, t)
         per_rank_ms = [float(x[0]) for x in every]
+        per_rank_fit_ms = [float(x[2]) for x in every]
+        t = t[:2].clone()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         step_ms, e2e_step_ms = float(t[0]), float(t[1])
         c = torch.tensor([launches], dtype=torch.int64, device="cuda")
@@ -577,7 +580,9 @@ def main():
         traffic, traffic_src = ncu_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_ms, "ms_per_step_by_rank": [round(x, 3) for x in per_rank_ms], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": step_ms, "ms_per_step_by_rank": [round(x, 3) for x in per_rank_ms],
+            "tvs_fit_ms_by_rank": [round(x, 3) for x in per_rank_fit_ms],      # the solver alone on each rank's lanes: the slowest rank sets the step
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, wl),
             "e2e": {"value": total / (e2e_step_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(wl.R) * B * 2 * world,
