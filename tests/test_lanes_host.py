@@ -1,0 +1,75 @@
+"""CPU: the host-side lane plumbing of traversome_b200.lanes -- array form of a batch, sorted id sets, the per-rank result
+blocks of a gathered batch, the success rule for stalled lanes, column residency -- without a GPU (stand-in engine)."""
+import numpy as np
+import pytest
+
+from tests.helpers import OracleEngine
+from traversome_b200 import _cabi, synthetic
+from traversome_b200.lanes import IdSet, LaneBatch, LaneContext, LaneRequest, LaneSharder, ShardedTheta
+
+
+def test_lane_batch_from_requests_builds_masks_and_starts_in_one_scatter():
+    V = 7
+    reqs = [LaneRequest(3, 1.5, {0, 2, 5}), LaneRequest(4, 0.0, range(V), theta0=np.full(V, 1.0 / V)),
+            LaneRequest(3, 2.5, IdSet(np.array([1, 6])), theta0=np.array([0.25, 0.75]))]
+    b = LaneBatch.from_requests(reqs, V)
+    assert b.cols.tolist() == [3, 4, 3] and b.C.tolist() == [1.5, 0.0, 2.5]
+    want = np.zeros((V, 3), np.uint8)
+    want[[0, 2, 5], 0] = 1
+    want[:, 1] = 1
+    want[[1, 6], 2] = 1
+    assert np.array_equal(b.mask, want)
+    assert np.allclose(b.theta0[:, 0], want[:, 0] / 3.0)                 # no start given: uniform over the subset
+    assert np.allclose(b.theta0[:, 1], 1.0 / V) and b.theta0[1, 2] == 0.25 and b.theta0[6, 2] == 0.75
+    full = LaneBatch.from_requests([LaneRequest(0, 0.0, range(V)), LaneRequest(1, 0.0, range(V))], V)
+    assert full.mask is None and full.theta0 is None                      # every variant in every lane: no mask at all
+    s = b.slice(1, 3)
+    assert len(s) == 2 and s.cols.tolist() == [4, 3] and np.array_equal(s.mask, want[:, 1:3])
+    assert b.digest() == LaneBatch.from_requests(reqs, V).digest() != b.slice(0, 2).digest()
+
+
+def test_id_set_behaves_like_a_sorted_set():
+    s = IdSet(np.array([2, 5, 9], dtype=np.int64))
+    assert list(s) == [2, 5, 9] and len(s) == 3 and 5 in s and 4 not in s and 10 not in s
+    assert LaneRequest(0, 0.0, s).ids is s.arr                            # no copy, no sort
+    assert LaneRequest(0, 0.0, {9, 2, 5}).ids == [2, 5, 9]
+
+
+def test_sharded_theta_indexing_and_materialisation():
+    rng = np.random.default_rng(0)
+    blocks = [rng.random((4, 3)), rng.random((4, 2)), rng.random((4, 3))]
+    full = np.concatenate(blocks, axis=1)
+    th = ShardedTheta(blocks, [0, 3, 5], 4, 8)
+    assert th.shape == (4, 8)
+    for b in range(8):
+        assert np.array_equal(th[:, b], full[:, b]) and np.array_equal(th[[1, 3], b], full[[1, 3], b])
+    assert np.array_equal(th[np.array([0, 2]), -1], full[[0, 2], -1])
+    assert np.array_equal(np.asarray(th), full) and np.array_equal(th[:, 2:6], full[:, 2:6])
+    assert np.array_equal(th - full, np.zeros_like(full)) and np.array_equal(th * 2.0, full * 2.0) and np.array_equal(th.T, full.T)
+
+
+def test_stalled_lanes_succeed_only_near_the_optimum():
+    ctx = LaneContext(3, [100, 100, 100])
+    out = {"status": np.array([_cabi.CONVERGED, _cabi.STALLED, _cabi.STALLED, _cabi.MAXITER, _cabi.CONVERGED]),
+           "kkt": np.array([[1e-10, 1e-8], [5e-7, 5e-5], [1e-3, 1e-2], [1e-10, 1e-9], [1e-10, 1e-9]]),
+           "loglike": np.array([-1.0, -2.0, -3.0, -4.0, -np.inf])}
+    assert ctx.lane_ok(out).tolist() == [True, True, False, False, False]
+
+
+def test_columns_are_uploaded_once_and_named_by_slot():
+    wl = synthetic.make_workload(5, 120, 0.5, seed=9)
+    W = synthetic.bootstrap_weights(wl.n_obs, 6, seed=2)
+    ctx = LaneContext.from_csr(wl.V, wl.L, wl.row_ptr, wl.col, wl.val)
+    ctx.engine_factory = OracleEngine
+    cols = [ctx.add_weights(W[:, b]) for b in range(6)]
+    with pytest.raises(ValueError):
+        ctx.add_weights(np.array([1, -1] + [0] * (wl.R - 2)))
+    r1 = ctx.fit([LaneRequest(cols[4], 0.0, range(wl.V)), LaneRequest(cols[1], 0.5, range(wl.V)), LaneRequest(cols[1], 0.0, {0})])
+    eng = ctx.engine()
+    res = ctx._resident[id(eng)]
+    assert sorted(res.slot_of) == [cols[1], cols[4]] and res.used == 2     # only what the batch needed
+    r2 = ctx.fit([LaneRequest(cols[1], 0.5, range(wl.V)), LaneRequest(cols[2], 0.0, range(wl.V))])
+    assert res.used == 3 and np.array_equal(eng.cols[:, res.slot_of[cols[2]]], W[:, 2])
+    assert np.array_equal(r1[1].x, r2[0].x) and r1[1].fun == r2[0].fun     # the same lane in another batch
+    assert r1[0].success and len(r1[0].x) == wl.V and len(r1[2].x) == 1 and not r1[2].success    # one variant cannot cover every read path
+    assert LaneSharder.bounds(10, 0, 4) == (0, 3) and LaneSharder.bounds(10, 3, 4) == (8, 10)
