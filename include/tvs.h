@@ -30,10 +30,10 @@
  *   - there is NO CPU fallback: without a usable CUDA device tvs_create fails with TVS_ECUDA.
  *   - output arrays of tvs_fit / tvs_loglik may be DEVICE pointers too: a multi-GPU caller gathers the per-lane results
  *     with NCCL straight from them (traversome_b200/lanes.py: LaneSharder).
- *   - candidate sets too wide for the shared-memory tiles of the staged kernel (V > ~330) and sparse (< 12 % of A
+ *   - candidate sets too wide for the shared-memory tiles of the staged kernel (V > ~330) and sparse (< 22 % of A
  *     non-zero) run the blocked kernel of csrc/tvs_blk.cuh: register accumulators, operand tiles fetched by bulk
  *     asynchronous copies (TMA); TVS_BLK=0 in the environment forbids it (falls back to the round-1 L2-gather kernel).
- *   - shapes with more than ~400 variants of which at least 12 % of A is non-zero keep a dense fp64 copy of A
+ *   - shapes with more than ~400 variants of which at least 22 % of A is non-zero keep a dense fp64 copy of A
  *     (R*V*8 bytes) and run the likelihood pass as two cuBLAS DGEMMs (the library links libcublas); TVS_DENSE=0
  *     in the environment forbids that, TVS_DENSE=1 forces it.
  */

@@ -117,7 +117,7 @@ def test_fit_medium_and_large_variant_counts(gpu, V, R, density, B):
 
 
 def test_dense_contraction_pass_equals_sparse_pass_and_exact_optimum(gpu, monkeypatch):
-    """Dense shapes (V > 400, >= 12 % of A non-zero: BASELINE configs[4]) run the likelihood pass as two fp64 GEMMs on a
+    """Dense shapes (V > 400, >= 22 % of A non-zero: BASELINE configs[4]) run the likelihood pass as two fp64 GEMMs on a
     dense copy of A (tvs_api.cu: launch_dense).  Same log-likelihoods as the sparse kernels to fp64 round-off, the
     same optimum, subset masks and finished lanes honoured; TVS_DENSE=0 keeps the sparse path."""
     V, B = 448, 24

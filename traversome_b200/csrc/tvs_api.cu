@@ -866,7 +866,7 @@ int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, c
         // V <= ~400) and the matrix is dense enough for a full contraction to win (TVS_DENSE=1 forces, 0 forbids)
         const int want = env_int("TVS_DENSE", -1);
         const double density = (double)nnz / ((double)R * (double)V);
-        const double min_density = env_int("TVS_DENSE_MIN_PCT", 12) / 100.0;   // measured crossover ~10 % (profiles/r1_dense_summary.md)
+        const double min_density = env_int("TVS_DENSE_MIN_PCT", 22) / 100.0;   // measured crossover against blk_kernel ~21 % (profiles/r2_summary.md; ~10 % against the round-1 sparse kernel)
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         const bool fits = (double)R * (double)V * 8.0 < 0.25 * (double)free_b;
