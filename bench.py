@@ -117,7 +117,7 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------ model selection
-def selection_rate(device, n_rep=256, nit_cfg2=None):
+def selection_rate(device, n_rep=256, nit_cfg2=None, n_groups=None):
     """SURVEY.md 8d asks for replicates/s too (one replicate = one complete backward model selection): BASELINE
     configs[2] -- 256 candidate variants (32 carry reads) x 50k read paths -- for `n_rep` bootstrap replicates advanced
     in lock step through the public classes (array-form fitters, traversome_b200.bootstrap.run_selections)."""
@@ -142,20 +142,20 @@ def selection_rate(device, n_rep=256, nit_cfg2=None):
         fitters.append(f)
     ctx.engine()
     solver = [0.0]
-    inner = ctx.fit
+    inner = ctx.fit_batch
 
-    def timed(requests):
+    def timed(batch):
         t = time.perf_counter()
-        out = inner(requests)
+        out = inner(batch)
         solver[0] += time.perf_counter() - t
         return out
-    ctx.fit = timed
+    ctx.fit_batch = timed
     walls = []
     for _ in range(3):                                   # one warm-up run, then the better of two (a 0.5 s figure on a shared host)
         solver[0] = 0.0
         lanes0, batches0 = ctx.n_lanes_fitted, ctx.n_batches
         t0 = time.perf_counter()
-        res = bootstrap.run_selections(fitters, criterion="BIC")
+        res = bootstrap.run_selections(fitters, criterion="BIC", groups=n_groups)
         walls.append((time.perf_counter() - t0, solver[0], ctx.n_lanes_fitted - lanes0, ctx.n_batches - batches0))
     wall, solver[0], n_lanes, n_batches = min(walls[1:])
     sizes = [len(r[0]) for r in res if not isinstance(r, Exception)]

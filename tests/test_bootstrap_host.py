@@ -91,6 +91,71 @@ def test_lock_step_selection_equals_serial(synthetic_small):
     assert ctx.n_lanes_fitted == sum(f.n_gpu_fits for f in fitters)
 
 
+@pytest.mark.parametrize("groups", [2, 3])
+def test_selection_in_groups_equals_one_group_and_is_reproducible(synthetic_small, groups):
+    """Replicates advanced as interleaved groups on host threads (their batches take the engine strictly in turn) select
+    the same models as one lock-step group; with the global generator seeded, two runs draw the same permutations."""
+    case = synthetic_small["cases"][2]
+    L = case["variant_sizes"]
+    rng = np.random.default_rng(1)
+    models = []
+    for k in range(7):
+        bins = [dict(b, rp_bins=[dict(rp, num_matched=int(rng.poisson(rp["num_matched"])) + 1) for rp in b["rp_bins"]])
+                for b in case["bins_list"]]
+        models.append(model_from_tables(L, bins))
+
+    def run(n_groups, pin):
+        ctx = _ctx(L)
+        fitters = []
+        for m in models:
+            f = ModelFitMaxLike(context=ctx, **fit_context(m, case["be_unidentifiable_to"], case["repr_to_merged_variants"]))
+            if pin:
+                f._shuffle = lambda x: None
+            fitters.append(f)
+        np.random.seed(11)
+        out = bootstrap.run_selections(fitters, groups=n_groups, random_size=2)
+        assert ctx.n_lanes_fitted == sum(f.n_gpu_fits for f in fitters)
+        assert all(f._shuffle is np.random.shuffle for f in fitters) or pin
+        return out, ctx.n_batches
+
+    one, nb1 = run(1, True)
+    many, nbg = run(groups, True)
+    assert nbg > nb1                                                        # each group has its own rounds
+    for (p0, l0, c0), (p1, l1, c1) in zip(one, many):
+        assert list(p0) == list(p1)
+        assert all(abs(p0[k] - p1[k]) < 1e-9 for k in p0) and abs(l0 - l1) < 1e-9 * abs(l0) and abs(c0 - c1) < 1e-9 * abs(c0)
+    a, _ = run(groups, False)
+    b, _ = run(groups, False)
+    for (p0, l0, c0), (p1, l1, c1) in zip(a, b):
+        assert list(p0) == list(p1) and l0 == l1 and c0 == c1
+
+
+def test_a_failing_group_does_not_hang_the_others():
+    from traversome_b200.bootstrap import _Turns
+    import threading
+    turns = _Turns(3)
+    order = []
+
+    def member(g, n):
+        try:
+            for k in range(n):
+                with turns.gate(g):
+                    order.append(g)
+                    if g == 1 and k == 1:
+                        raise RuntimeError("boom")
+        except RuntimeError:
+            pass
+        finally:
+            turns.finish(g)
+    ts = [threading.Thread(target=member, args=(g, n)) for g, n in ((0, 4), (1, 5), (2, 2))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=20)
+    assert not any(t.is_alive() for t in ts)
+    assert order == [0, 1, 2, 0, 1, 2, 0, 0]
+
+
 def test_support_tally_matches_reference_tables(plastome):
     """summarize_replicates / check_bs_threshold on the reference's own replicate results reproduce its
     support table (final.result.tab) -- traversome.py:561-617."""

@@ -5,7 +5,7 @@ import pytest
 
 from tests.helpers import OracleEngine
 from traversome_b200 import _cabi, synthetic
-from traversome_b200.lanes import IdSet, LaneBatch, LaneContext, LaneRequest, LaneSharder, ShardedTheta
+from traversome_b200.lanes import IdSet, LaneBatch, LaneBlock, LaneContext, LaneRequest, LaneSharder, LeaveOneOut, ShardedTheta
 
 
 def test_lane_batch_from_requests_builds_masks_and_starts_in_one_scatter():
@@ -33,6 +33,63 @@ def test_id_set_behaves_like_a_sorted_set():
     assert list(s) == [2, 5, 9] and len(s) == 3 and 5 in s and 4 not in s and 10 not in s
     assert LaneRequest(0, 0.0, s).ids is s.arr                            # no copy, no sort
     assert LaneRequest(0, 0.0, {9, 2, 5}).ids == [2, 5, 9]
+
+
+def _start_like_the_fitter(warm, ids):
+    """ModelFitMaxLike._start_point for one subset (the per-lane form the array form must reproduce)."""
+    x = warm[ids]
+    tot = x.sum()
+    if not np.isfinite(tot) or tot <= 0.0:
+        return None
+    x = np.maximum(x / tot, 1e-3 / len(ids))
+    return x / x.sum()
+
+
+@pytest.mark.parametrize("warm_kind", ["optimum", "none", "degenerate"])
+def test_leave_one_out_block_equals_the_per_lane_requests(warm_kind):
+    V = 11
+    rng = np.random.default_rng(5)
+    chosen = np.array([0, 2, 3, 6, 7, 10], dtype=np.int64)
+    lo = LeaveOneOut(chosen, [4, 0, 5, 2])
+    assert len(lo) == 4 and [list(s) for s in lo] == [[0, 2, 3, 6, 10], [2, 3, 6, 7, 10], [0, 2, 3, 6, 7], [0, 2, 6, 7, 10]]
+    warm = None
+    if warm_kind != "none":
+        warm = np.zeros(V)
+        warm[chosen] = rng.dirichlet(np.ones(len(chosen)))
+        warm[3] = 0.0                                                     # an exact zero in the accepted optimum: floored
+        if warm_kind == "degenerate":                                     # all the mass on the variant lane 0 leaves out
+            warm[:] = 0.0
+            warm[7] = 1.0
+    cols, C, mask, theta0 = LaneBlock(2, -3.5, lo, warm).arrays(V)
+    reqs = [LaneRequest(2, -3.5, ids, None if warm is None else _start_like_the_fitter(warm, ids.arr)) for ids in lo]
+    want = LaneBatch.from_requests(reqs, V)
+    assert cols.tolist() == want.cols.tolist() and C.tolist() == want.C.tolist() and np.array_equal(mask, want.mask)
+    if warm is None:
+        assert theta0 is None
+    else:
+        assert np.allclose(theta0, want.theta0, rtol=0, atol=1e-15) and np.allclose(theta0.sum(axis=0), 1.0)
+        assert np.all(theta0[mask == 0] == 0.0)
+
+
+def test_fit_items_mixes_blocks_and_request_lists_in_one_batch():
+    wl = synthetic.make_workload(6, 200, 0.8, seed=4)
+    A = wl.scipy_csr().toarray() > 0
+    ok_drop = [v for v in range(wl.V) if np.all(np.delete(A, v, axis=1).any(axis=1))]      # still covers every read path
+    assert len(ok_drop) >= 2
+    ctx = LaneContext.from_csr(wl.V, wl.L, wl.row_ptr, wl.col, wl.val)
+    ctx.engine_factory = OracleEngine
+    c0 = ctx.add_weights(wl.n_obs.astype(np.int64))
+    chosen = np.arange(wl.V, dtype=np.int64)
+    lo = LeaveOneOut(chosen, ok_drop[:2])
+    full = [LaneRequest(c0, 2.0, range(wl.V))]
+    res_full, res_blk = ctx.fit_items([full, LaneBlock(c0, 2.0, lo, None)])
+    assert ctx.n_batches == 1 and ctx.n_lanes_fitted == 3 and len(res_full) == 1 and len(res_blk) == 2
+    one_by_one = ctx.fit([LaneRequest(c0, 2.0, ids) for ids in lo])
+    for j in range(2):
+        assert abs(res_blk.fun[j] - one_by_one[j].fun) <= 1e-9 * abs(one_by_one[j].fun) and bool(res_blk.success[j])
+        assert np.allclose(res_blk.x(j), one_by_one[j].x, atol=1e-7) and np.allclose(res_blk[j].x, res_blk.x(j))
+        assert res_blk.ids(j).tolist() == list(lo[j])
+    assert res_full[0].fun <= res_blk.fun.min() + 1e-9
 
 
 def test_sharded_theta_indexing_and_materialisation():

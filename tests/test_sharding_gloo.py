@@ -34,7 +34,7 @@ def _replicates(case, n):
     return models
 
 
-def _run(ctx, case, models):
+def _run(ctx, case, models, groups=None):
     from tests.helpers import fit_context
     from traversome_b200 import bootstrap
     from traversome_b200.ModelFitMaxLike import ModelFitMaxLike
@@ -44,7 +44,7 @@ def _run(ctx, case, models):
         f = ModelFitMaxLike(context=ctx, **kw)
         f._shuffle = lambda x: None
         fitters.append(f)
-    return bootstrap.run_selections(fitters, criterion="BIC")
+    return bootstrap.run_selections(fitters, criterion="BIC", groups=groups)
 
 
 def _worker(rank, world, port, q):
@@ -68,6 +68,13 @@ def _worker(rank, world, port, q):
         got = _run(ctx2, case, models)
         same = all(list(a[0]) == list(b[0]) and all(abs(a[0][k] - b[0][k]) < 1e-12 for k in a[0]) and a[1] == b[1] and a[2] == b[2]
                    for a, b in zip(ref, got))
+        # the replicates as two groups on two host threads: their batches -- and collectives -- strictly in turn on every rank
+        ctx3 = LaneContext(len(L), L, sharder=LaneSharder())
+        ctx3.engine_factory = OracleEngine
+        got = _run(ctx3, case, models, groups=2)
+        same = same and ctx3.sharder.n_gathers > ctx2.sharder.n_gathers and all(
+            list(a[0]) == list(b[0]) and all(abs(a[0][k] - b[0][k]) < 1e-12 for k in a[0]) and a[1] == b[1] and a[2] == b[2]
+            for a, b in zip(ref, got))
         # a ragged batch: 7 lanes over 2 ranks, one of them infeasible (uncovered subset)
         col = ctx2.add_weights(ctx2.dense_columns([0])[:, 0])
         reqs = [LaneRequest(col, 1.5 * i, set(range(len(L))) - {i}) for i in range(6)] + [LaneRequest(col, 0.0, {0})]

@@ -33,17 +33,17 @@ for b in range(n_rep):
 t_models = time.time() - t0
 ctx = LaneContext(wl.V, wl.L)
 t_fit = [0.0]
-orig_fit = ctx.fit
+orig_fit = ctx.fit_batch
 
 
-def timed_fit(requests):
+def timed_fit(batch):
     t = time.time()
-    out = orig_fit(requests)
+    out = orig_fit(batch)
     t_fit[0] += time.time() - t
     return out
 
 
-ctx.fit = timed_fit
+ctx.fit_batch = timed_fit
 fitters = []
 kw0 = fit_context(models[0])
 for m in models:

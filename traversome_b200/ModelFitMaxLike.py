@@ -21,7 +21,7 @@ from typing import Set, Union
 import numpy as np
 from loguru import logger
 
-from .lanes import FitResult, IdSet, LaneContext, LaneRequest  # noqa: F401  (FitResult re-exported)
+from .lanes import BlockResult, FitResult, IdSet, LaneBlock, LaneContext, LaneRequest, LeaveOneOut  # noqa: F401  (FitResult re-exported)
 from .utils import Criterion, LogLikeFuncInfo, aic, bic
 
 
@@ -201,21 +201,30 @@ class ModelFitMaxLike(object):
         """Lane descriptions of ML fits restricted to subsets[b] (sets of representative ids, or IdSet)."""
         self._ensure_lane()
         col, C, _N = self._lane
+        if isinstance(subsets, LeaveOneOut):                    # a whole chunk of leave-one-out candidates: array form
+            return LaneBlock(col, C, subsets, self._warm_dense())
         return [LaneRequest(col, C, ids, self._start_point(ids)) for ids in subsets]
+
+    def _warm_dense(self):
+        """The accepted model's optimum as a dense [V] vector (None outside a selection / with warm starts off)."""
+        warm = self._warm
+        if not warm or not self.warm_start:
+            return None
+        if self._warm_vec is None or self._warm_vec[0] is not warm:
+            vec = np.zeros(self.num_put_variants, dtype=np.float64)
+            vec[np.fromiter(warm.keys(), dtype=np.int64, count=len(warm))] = np.fromiter(warm.values(), dtype=np.float64, count=len(warm))
+            self._warm_vec = (warm, vec)
+        return self._warm_vec[1]
 
     def _start_point(self, ids):
         """Starting proportions of a candidate subset during backward selection: the accepted model's optimum restricted
         to the subset (a leave-one-out optimum is close to it), floored so that no component starts at the stationary
         point z = 0 of the solver's parametrisation.  None (uniform start) outside a selection."""
-        warm = self._warm
-        if not warm or not self.warm_start:
+        vec = self._warm_dense()
+        if vec is None:
             return None
-        if self._warm_vec is None or self._warm_vec[0] is not warm:      # dense copy of the accepted optimum, once per accept
-            vec = np.zeros(self.num_put_variants, dtype=np.float64)
-            vec[np.fromiter(warm.keys(), dtype=np.int64, count=len(warm))] = np.fromiter(warm.values(), dtype=np.float64, count=len(warm))
-            self._warm_vec = (warm, vec)
         arr = ids.arr if isinstance(ids, IdSet) else np.array(sorted(ids), dtype=np.int64)
-        x = self._warm_vec[1][arr]
+        x = vec[arr]
         total = x.sum()
         if not np.isfinite(total) or total <= 0.0:
             return None
@@ -228,7 +237,7 @@ class ModelFitMaxLike(object):
         ctx = self._ensure_lane()
         if ctx.matrix.R == 0:
             raise Exception("Likelihood maximization failed.")   # nothing to fit
-        results = ctx.fit(self.lane_requests(subsets))
+        results = ctx.fit_items([self.lane_requests(subsets)])[0]
         self.n_gpu_fits += len(subsets)
         return results
 
@@ -331,8 +340,7 @@ class ModelFitMaxLike(object):
                         if self._cover_without(var_id):
                             if verbose:
                                 logger.debug("Test variants [{}] - {}".format(label, self.__str_rep_id(var_id)))
-                            # leave-one-out subset = the sorted accepted set with one element deleted
-                            to_fit.append((var_id, IdSet(np.delete(chosen_arr, rd_id))))
+                            to_fit.append((var_id, rd_id))           # leave-one-out subset = the sorted accepted set minus position rd_id
                         else:
                             indispensable_ids[var_id] = True
                             if verbose:
@@ -344,17 +352,38 @@ class ModelFitMaxLike(object):
                 # -- one batch of lanes for the whole chunk; the criterion of every candidate, the proportion tables of
                 #    the best one only (the reference builds them per candidate, :448-510, and reads the best's)
                 if to_fit:
-                    id_sets = [ids for _, ids in to_fit]
+                    id_sets = LeaveOneOut(chosen_arr, [rd for _, rd in to_fit])
                     results = (yield id_sets)
-                    crit_vals = self.__criteria_of_batch(id_sets, results, criterion, verbose)
-                    best = min(range(len(to_fit)), key=crit_vals.__getitem__)      # first minimum = sorted(...)[0] of the reference
-                    best_drop_id, best_val = to_fit[best][0], crit_vals[best]
+                    if isinstance(results, BlockResult) and not verbose:
+                        # the criterion of every candidate in one array expression (ModelFitMaxLike.py:472-497 per lane)
+                        if criterion not in ("AIC", "BIC"):
+                            raise Exception("Invalid criterion {}".format(criterion))
+                        if not self.bootstrap_mode:
+                            for _ in range(len(to_fit)):
+                                logger.info("Maximizing the likelihood function for {} variants".format(len(chosen_arr) - 1))
+                        if not bool(np.all(results.success)):
+                            raise Exception("Likelihood maximization failed.")
+                        k_par = self.__variable_size(id_sets[0])
+                        like = -results.fun
+                        crit_arr = aic(loglike=like, len_param=k_par) if criterion == "AIC" else \
+                            bic(loglike=like, len_param=k_par, len_data=self._lane[2])       # same expression, elementwise
+                        best = int(np.argmin(crit_arr))                              # first minimum = sorted(...)[0] of the reference
+                        best_val = float(crit_arr[best])
+                        best_res = results[best]
+                        best_ids = id_sets[best]
+                    else:
+                        per_lane = [results[j] for j in range(len(to_fit))]
+                        sets = [id_sets[j] for j in range(len(to_fit))]
+                        crit_vals = self.__criteria_of_batch(sets, per_lane, criterion, verbose)
+                        best = min(range(len(to_fit)), key=crit_vals.__getitem__)  # first minimum = sorted(...)[0] of the reference
+                        best_val, best_res, best_ids = crit_vals[best], per_lane[best], sets[best]
+                    best_drop_id = to_fit[best][0]
                     if best_val < previous_criteria:
                         previous_criteria = best_val
-                        previous_like = -results[best].fun
-                        previous_prop, previous_echo = self.__summarize_run_prop(results[best], id_sets[best])
+                        previous_like = -best_res.fun
+                        previous_prop, previous_echo = self.__summarize_run_prop(best_res, best_ids)
                         chosen_ids.remove(best_drop_id)
-                        self._warm = dict(zip(id_sets[best].arr.tolist(), (float(v) for v in results[best].x))) or self._warm
+                        self._warm = dict(zip(best_ids.arr.tolist(), (float(v) for v in best_res.x))) or self._warm
                         log = logger.debug if self.bootstrap_mode else logger.info
                         log("Drop {}".format(self.__str_rep_id(best_drop_id)))
                         log("Proportions: " + ", ".join(["%s:%.4f" % (_id, _p) for _id, _p, in previous_echo.items()]))

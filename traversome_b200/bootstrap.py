@@ -14,6 +14,8 @@ Two entry points: ``do_subsampling`` takes the replicate models the reference's 
 array form (``traversome_b200.resample``: the reference's draws replayed, its bins reproduced bit for bit), which
 removes the per-replicate Python object graph.
 """
+import sys
+import threading
 from collections import OrderedDict
 
 import numpy as np
@@ -24,24 +26,51 @@ from .lanes import LaneContext
 from .utils import Criterion
 
 
-def run_selections(fitters, criterion=Criterion.BIC, n_proc=1, random_size=20, user_fixed_ids=None, chosen_ids=None):
-    """Backward model selection of every fitter (one per replicate), lock step.
+class _Turns(object):
+    """Whose batch goes to the GPU next when the replicates advance as several groups: strictly in turn (group 0, 1, ..,
+    0, ..; a finished group is skipped), so the sequence of batches -- and with a LaneSharder the sequence of collectives --
+    is the same on every run and on every rank, whatever the thread timing."""
 
-    fitters: ModelFitMaxLike objects built on ONE shared LaneContext.  Returns a list of
-    (prop, loglike, criterion) -- or the Exception a replicate raised (the reference would have
-    propagated it out of its serial loop at that replicate)."""
-    if not fitters:
-        return []
-    ctx = fitters[0]._ensure_lane()
-    for f in fitters:
-        if f._ensure_lane() is not ctx:
-            raise ValueError("run_selections: all fitters must share one LaneContext")
-    steps = [f.selection_steps(n_proc, criterion, chosen_ids, random_size, user_fixed_ids) for f in fitters]
-    results = [None] * len(fitters)
+    def __init__(self, n):
+        self.cond = threading.Condition()
+        self.done = [False] * n
+        self.turn = 0
+
+    def _advance(self, g):
+        n = len(self.done)
+        for k in range(1, n + 1):
+            if not self.done[(g + k) % n]:
+                self.turn = (g + k) % n
+                break
+        self.cond.notify_all()
+
+    def gate(self, g):
+        turns = self
+
+        class _Gate(object):
+            def __enter__(self):
+                with turns.cond:
+                    while turns.turn != g:
+                        turns.cond.wait()
+
+            def __exit__(self, *exc):
+                with turns.cond:
+                    turns._advance(g)
+        return _Gate()
+
+    def finish(self, g):
+        with self.cond:
+            self.done[g] = True
+            if self.turn == g:
+                self._advance(g)
+
+
+def _advance_group(ctx, fitters, steps, results, members, gate=None):
+    """Lock-step rounds of the replicates `members`: one GPU batch per round for all their pending chunks."""
     pending = {}                                  # replicate -> subsets it waits for
-    for i, st in enumerate(steps):
+    for i in members:
         try:
-            pending[i] = next(st)
+            pending[i] = next(steps[i])
         except StopIteration as stop:             # cannot happen before the first fit, kept for symmetry
             results[i] = stop.value
         except Exception as e:
@@ -49,19 +78,10 @@ def run_selections(fitters, criterion=Criterion.BIC, n_proc=1, random_size=20, u
     n_rounds = 0
     while pending:
         order = sorted(pending)
-        requests, owner = [], []
-        for i in order:
-            rq = fitters[i].lane_requests(pending[i])
-            requests += rq
-            owner += [i] * len(rq)
-        fitted = ctx.fit(requests)
+        fitted = ctx.fit_items([fitters[i].lane_requests(pending[i]) for i in order], gate=gate)
         n_rounds += 1
-        pos = 0
-        for i in order:
-            n = len(pending[i])
-            mine = fitted[pos:pos + n]
-            pos += n
-            fitters[i].n_gpu_fits += n
+        for i, mine in zip(order, fitted):
+            fitters[i].n_gpu_fits += len(pending[i])
             try:
                 pending[i] = steps[i].send(mine)
             except StopIteration as stop:
@@ -70,8 +90,72 @@ def run_selections(fitters, criterion=Criterion.BIC, n_proc=1, random_size=20, u
             except Exception as e:
                 results[i] = e
                 del pending[i]
-    logger.debug("run_selections: {} replicates, {} lock-step rounds, {} lanes".format(
-        len(fitters), n_rounds, ctx.n_lanes_fitted))
+    return n_rounds
+
+
+def run_selections(fitters, criterion=Criterion.BIC, n_proc=1, random_size=20, user_fixed_ids=None, chosen_ids=None, groups=None):
+    """Backward model selection of every fitter (one per replicate), lock step.
+
+    fitters: ModelFitMaxLike objects built on ONE shared LaneContext.  Returns a list of
+    (prop, loglike, criterion) -- or the Exception a replicate raised (the reference would have
+    propagated it out of its serial loop at that replicate).
+
+    groups (default: the context's `selection_groups`, 2, when there are at least 64 replicates, else 1): the replicates
+    advance as that many interleaved groups, each in lock step on its own host thread, their batches taking the GPU
+    strictly in turn -- while the solver works on one group's batch (the C call releases the interpreter lock) the
+    decision logic and lane assembly of the other group run on the host."""
+    if not fitters:
+        return []
+    ctx = fitters[0]._ensure_lane()
+    for f in fitters:
+        if f._ensure_lane() is not ctx:
+            raise ValueError("run_selections: all fitters must share one LaneContext")
+    steps = [f.selection_steps(n_proc, criterion, chosen_ids, random_size, user_fixed_ids) for f in fitters]
+    results = [None] * len(fitters)
+    if groups is None:
+        groups = int(getattr(ctx, "selection_groups", 2)) if len(fitters) >= 64 else 1
+    groups = max(1, min(int(groups), len(fitters)))
+    if groups == 1:
+        n_rounds = _advance_group(ctx, fitters, steps, results, range(len(fitters)))
+    else:
+        # the candidate permutations come from the process-global generator in the reference (ModelFitMaxLike.py:203); with
+        # several host threads the order of its draws would depend on timing: one draw here, one generator per replicate
+        base = int(np.random.randint(0, 2 ** 31 - 1))
+        pinned = []
+        for i, f in enumerate(fitters):
+            if f._shuffle is np.random.shuffle:
+                f._shuffle = np.random.default_rng([base, i]).shuffle
+                pinned.append(f)
+        turns = _Turns(groups)
+        rounds = [0] * groups
+        errors = [None] * groups
+
+        def work(g):
+            try:
+                rounds[g] = _advance_group(ctx, fitters, steps, results, range(g, len(fitters), groups), gate=turns.gate(g))
+            except BaseException as e:            # re-raised in the calling thread
+                errors[g] = e
+            finally:
+                turns.finish(g)
+        interval = sys.getswitchinterval()
+        sys.setswitchinterval(min(interval, 2e-4))        # the thread that returns from the solver takes the interpreter back at once
+        threads = [threading.Thread(target=work, args=(g,)) for g in range(1, groups)]
+        try:
+            for t in threads:
+                t.start()
+            work(0)
+            for t in threads:
+                t.join()
+        finally:
+            sys.setswitchinterval(interval)
+            for f in pinned:
+                f._shuffle = np.random.shuffle
+        for e in errors:
+            if e is not None:
+                raise e
+        n_rounds = max(rounds)
+    logger.debug("run_selections: {} replicates in {} group(s), {} lock-step rounds, {} lanes".format(
+        len(fitters), groups, n_rounds, ctx.n_lanes_fitted))
     return results
 
 

@@ -72,6 +72,10 @@ static void free_fit(FitState& f) {
     for (int i = 0; i < 2; ++i) { if (f.wbuf[i]) cudaFree(f.wbuf[i]); if (f.wbuf16[i]) cudaFree(f.wbuf16[i]); }
     if (f.h_nactive) cudaFreeHost(f.h_nactive);
     if (f.Hpart) cudaFree(f.Hpart);
+    if (f.pad_w) cudaFree(f.pad_w);
+    if (f.pad_mask) cudaFree(f.pad_mask);
+    if (f.pad_N) cudaFree(f.pad_N);
+    if (f.pad_C) cudaFree(f.pad_C);
     if (f.cr) cudaFree(f.cr);
     if (f.crf) cudaFree(f.crf);
     f = FitState();
@@ -1283,26 +1287,78 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
     int cur = 0;
     {   // ---- reset set 0 (full width, views the caller's lanes)
         LaneSet& s = f.set[0];
-        s.width = B0; s.mask = h->lanes.mask; s.N = h->lanes.N; s.C = h->lanes.C;
+        s.mask = h->lanes.mask; s.N = h->lanes.N; s.C = h->lanes.C;
         s.w16 = h->lanes.has16 ? h->lanes.w16 : nullptr; s.w = h->lanes.has16 ? nullptr : h->lanes.w;   // the 16-bit form when the lanes carry it
+        // The 2- and 4-lane pass kernels load lane pairs / quads as vectors and need a width that is a multiple of their
+        // lane count (a 2,063-lane batch of a selection round ran 1.65x slower per lane than a 2,118-lane one).  A batch
+        // whose lane count is not a multiple of 4 is therefore re-laid once at the next multiple: its inputs are copied
+        // with the row stride A0, the 1..3 extra lanes are zeros, flagged done, without an original id -- the padding
+        // lanes a compaction makes.
+        const bool pad0 = B0 % 4 != 0 && B0 >= env_int("TVS_PAD_MIN_LANES", 6) && env_int("TVS_PAD", 1) != 0;
+        const int64_t A0 = pad0 ? ((B0 + 3) & ~(int64_t)3) : B0;
+        if (pad0) {
+            const size_t elem = s.w16 ? 2 : 4;
+            auto grow = [&](void** ptr, size_t* cap, size_t bytes) -> int {
+                if (*cap >= bytes) return TVS_OK;
+                if (*ptr) cudaFree(*ptr);
+                *ptr = nullptr; *cap = 0;
+                TVS_CUDA(cudaMalloc(ptr, bytes));
+                *cap = bytes;
+                return TVS_OK;
+            };
+            if ((rc = grow(&f.pad_w, &f.pad_w_cap, (size_t)R * A0 * elem)) != TVS_OK) return rc;
+            if (s.mask && (rc = grow((void**)&f.pad_mask, &f.pad_mask_cap, (size_t)V * A0)) != TVS_OK) return rc;
+            if (f.pad_b_cap < (size_t)A0) {
+                if (f.pad_N) cudaFree(f.pad_N);
+                if (f.pad_C) cudaFree(f.pad_C);
+                f.pad_N = f.pad_C = nullptr; f.pad_b_cap = 0;
+                TVS_CUDA(cudaMalloc((void**)&f.pad_N, (size_t)A0 * 8));
+                TVS_CUDA(cudaMalloc((void**)&f.pad_C, (size_t)A0 * 8));
+                f.pad_b_cap = (size_t)A0;
+            }
+            iota_kernel<<<(unsigned)((B0 + 255) / 256), 256, 0, st>>>(f.idx, B0);
+            cudaMemsetAsync(f.idx + B0, 0xFF, (size_t)(A0 - B0) * 4, st);           // -1: a column of zeros
+            GatherArgs ga{};
+            int64_t row0 = 0;
+            auto add = [&](const void* src, void* dst, int64_t rows, int el) {
+                if (!src || !dst || rows <= 0) return;
+                ga.t[ga.n].src = src; ga.t[ga.n].dst = dst; ga.t[ga.n].rows = rows; ga.t[ga.n].elem = el; ga.t[ga.n].row0 = (int32_t)row0;
+                row0 += rows; ++ga.n;
+            };
+            add(s.w16 ? (const void*)s.w16 : (const void*)s.w, f.pad_w, R, (int)elem);
+            add(s.mask, f.pad_mask, V, 1); add(s.N, f.pad_N, 1, 8); add(s.C, f.pad_C, 1, 8);
+            ga.total_rows = row0; ga.Bs = B0; ga.Bd = A0; ga.idx = f.idx;
+            dim3 grid((unsigned)((A0 + 127) / 128), (unsigned)std::min<int64_t>(row0, 8192));
+            gather_all_kernel<<<grid, 128, 0, st>>>(ga);
+            if (s.w16) s.w16 = (const uint16_t*)f.pad_w; else s.w = (const int32_t*)f.pad_w;
+            if (s.mask) s.mask = f.pad_mask;
+            s.N = f.pad_N;
+            if (s.C) s.C = f.pad_C;
+        }
+        s.width = A0;
+        const size_t vbA = (size_t)V * A0;
         FillArgs fa{};
         auto fill = [&](void* ptr, size_t bytes, uint32_t v) { fa.t[fa.n].p = ptr; fa.t[fa.n].bytes = bytes; fa.t[fa.n].fill = v; ++fa.n; };
-        fill(s.z, vb0 * 8, 0); fill(s.g, vb0 * 8, 0); fill(s.d, vb0 * 8, 0); fill(f.gt, vb0 * 8, 0);
-        fill(s.F, B0 * 8, 0); fill(s.dg, B0 * 8, 0); fill(s.alpha, B0 * 8, 0); fill(s.llsum, B0 * 8, 0); fill(s.kkt, 2 * B0 * 8, 0);
-        fill(s.sumphi, B0 * 8, 0); fill(s.gamma, B0 * 8, 0); fill(s.rho, (size_t)B0 * m * 8, 0);
-        fill(s.gram, (size_t)B0 * ((2 * m + 1) * (2 * m + 2) / 2) * 8, 0);
-        fill(s.S, vb0 * m * 8, 0); fill(s.Y, vb0 * m * 8, 0);
-        fill(s.ls, B0 * 4, 0); fill(s.iters, B0 * 4, 0xFFFFFFFFu); fill(s.status, B0 * 4, 0);
-        fill(s.head, B0 * 4, 0); fill(s.cnt, B0 * 4, 0); fill(s.done, B0 * 4, 0);
+        fill(s.z, vbA * 8, 0); fill(s.g, vbA * 8, 0); fill(s.d, vbA * 8, 0); fill(f.gt, vbA * 8, 0);
+        fill(s.F, A0 * 8, 0); fill(s.dg, A0 * 8, 0); fill(s.alpha, A0 * 8, 0); fill(s.llsum, A0 * 8, 0); fill(s.kkt, 2 * A0 * 8, 0);
+        fill(s.sumphi, A0 * 8, 0); fill(s.gamma, A0 * 8, 0); fill(s.rho, (size_t)A0 * m * 8, 0);
+        fill(s.gram, (size_t)A0 * ((2 * m + 1) * (2 * m + 2) / 2) * 8, 0);
+        fill(s.S, vbA * m * 8, 0); fill(s.Y, vbA * m * 8, 0);
+        fill(s.ls, A0 * 4, 0); fill(s.iters, A0 * 4, 0xFFFFFFFFu); fill(s.status, A0 * 4, 0);
+        fill(s.head, A0 * 4, 0); fill(s.cnt, A0 * 4, 0); fill(s.done, A0 * 4, 0);
         {
-            const size_t big = vb0 * m * 8 / 16;                  // 16-byte words of the largest array
+            const size_t big = vbA * m * 8 / 16;                  // 16-byte words of the largest array
             const unsigned gx = (unsigned)std::max<size_t>(1, std::min<size_t>((big + 255) / 256, (size_t)h->sm_count * 4));
             fill_many_kernel<<<dim3(gx, (unsigned)fa.n), 256, 0, st>>>(fa);
         }
         iota_kernel<<<(unsigned)((B0 + 255) / 256), 256, 0, st>>>(s.orig, B0);
+        if (A0 > B0) {
+            cudaMemsetAsync(s.orig + B0, 0xFF, (size_t)(A0 - B0) * 4, st);
+            cudaMemsetAsync(s.done + B0, 1, (size_t)(A0 - B0) * 4, st);
+        }
         const double* d_theta0 = nullptr;
         if (theta0) { cudaMemcpyAsync(f.theta_io, theta0, vb0 * 8, cudaMemcpyDefault, st); d_theta0 = f.theta_io; }
-        init_z_kernel<<<(unsigned)((B0 + 127) / 128), 128, 0, st>>>(d_theta0, s.mask, h->csr.Ld, h->csr.invL, (int)V, B0, s.zt, s.x);
+        init_z_kernel<<<(unsigned)((A0 + 127) / 128), 128, 0, st>>>(d_theta0, s.mask, h->csr.Ld, h->csr.invL, (int)V, A0, B0, s.zt, s.x);
     }
 
     std::vector<cudaEvent_t> pev, uev; // per-pass / per-update events when timing is requested

@@ -108,6 +108,9 @@ struct FitState {               // all device, sized for (V, B, history)
     uint8_t* mbuf[2] = {nullptr, nullptr};
     double* nbuf[2] = {nullptr, nullptr}; double* cbuf[2] = {nullptr, nullptr};
     int64_t half = 0;           // capacity (lanes) of the compaction buffers above
+    // inputs of a batch whose lane count is not a multiple of 4, re-laid at the padded width (tvs_fit, set 0)
+    void* pad_w = nullptr; size_t pad_w_cap = 0; uint8_t* pad_mask = nullptr; size_t pad_mask_cap = 0;
+    double *pad_N = nullptr, *pad_C = nullptr; size_t pad_b_cap = 0;
     double *gt = nullptr, *gh = nullptr;            // scratch, V rows at full width
     double *tpart = nullptr, *llpart = nullptr; size_t tpart_cap = 0, llpart_cap = 0;
     double *t_red = nullptr, *ll_red = nullptr;     // partials summed over the row splits

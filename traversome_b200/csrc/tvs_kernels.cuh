@@ -220,22 +220,25 @@ __global__ void lane_sum_finish_kernel(const unsigned long long* __restrict__ ac
 
 // z0 from theta0 (or uniform over the mask): phi_v ~ theta_v * L_v, z = sqrt(phi)
 __global__ void init_z_kernel(const double* __restrict__ theta0, const uint8_t* __restrict__ mask,
-                              const double* __restrict__ Ld, const double* __restrict__ invL, int V, int64_t B,
+                              const double* __restrict__ Ld, const double* __restrict__ invL, int V, int64_t B, int64_t B0,
                               double* __restrict__ zt, double* __restrict__ x) {
+    // B = width of the lane set (stride of mask / zt / x), B0 <= B = lanes of the caller's theta0 (its stride); lanes
+    // b >= B0 are the padding of a set whose width was rounded up
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    if (b >= B0) theta0 = nullptr;
     double s = 0.0;
     for (int v = 0; v < V; ++v) {
         const bool m = mask ? mask[(int64_t)v * B + b] != 0 : true;
         double ph = 0.0;
-        if (m) ph = theta0 ? fmax(theta0[(int64_t)v * B + b], 0.0) * Ld[v] : 1.0;
+        if (m) ph = theta0 ? fmax(theta0[(int64_t)v * B0 + b], 0.0) * Ld[v] : 1.0;
         s += ph;
     }
     for (int v = 0; v < V; ++v) {
         const bool m = mask ? mask[(int64_t)v * B + b] != 0 : true;
         double ph = 0.0;
         if (m) {
-            ph = theta0 ? fmax(theta0[(int64_t)v * B + b], 0.0) * Ld[v] : 1.0;
+            ph = theta0 ? fmax(theta0[(int64_t)v * B0 + b], 0.0) * Ld[v] : 1.0;
             ph = (s > 0.0) ? ph / s : 0.0;
             ph = fmax(ph, 1e-12);      // an exact zero inside the subset is a stationary point of the z-parametrisation
         }

@@ -54,6 +54,86 @@ class IdSet(object):
         return i < self.arr.shape[0] and int(self.arr[i]) == int(v)
 
 
+class LeaveOneOut(object):
+    """The candidate subsets of one chunk of a backward-selection round: the accepted set (sorted array) minus ONE of its
+    elements each (positions `drop_pos`).  Behaves like a sequence of IdSet, but the lane builder takes it whole: masks and
+    starting points of the chunk are built with array operations, not lane by lane."""
+    __slots__ = ("chosen", "drop_pos")
+
+    def __init__(self, chosen, drop_pos):
+        self.chosen = np.ascontiguousarray(chosen, dtype=np.int64)
+        self.drop_pos = np.ascontiguousarray(drop_pos, dtype=np.int64)
+
+    def __len__(self):
+        return int(self.drop_pos.shape[0])
+
+    def __getitem__(self, j):
+        return IdSet(np.delete(self.chosen, int(self.drop_pos[j])))
+
+    def __iter__(self):
+        return (self[j] for j in range(len(self)))
+
+
+class LaneBlock(object):
+    """The lanes of one LeaveOneOut chunk of one weight column: `col`, `C`, the subsets, and the accepted model's optimum
+    `warm` (dense [V] proportions, or None for uniform starts)."""
+    __slots__ = ("col", "C", "subsets", "warm")
+
+    def __init__(self, col, C, subsets, warm):
+        self.col, self.C, self.subsets, self.warm = int(col), float(C), subsets, warm
+
+    def __len__(self):
+        return len(self.subsets)
+
+    def arrays(self, V):
+        """(cols [n], C [n], mask uint8 [V, n], theta0 float64 [V, n] or None) -- same starts as
+        ModelFitMaxLike._start_point: the accepted optimum restricted to the subset, floored at 1e-3 / |subset|."""
+        lo = self.subsets
+        n, K = len(lo), int(lo.chosen.shape[0]) - 1
+        base = np.zeros(V, dtype=np.uint8)
+        base[lo.chosen] = 1
+        mask = np.repeat(base[:, None], n, axis=1)
+        dropped = lo.chosen[lo.drop_pos]
+        lane = np.arange(n)
+        mask[dropped, lane] = 0
+        theta0 = None
+        if self.warm is not None and K > 0:
+            T = np.repeat(self.warm[:, None], n, axis=1)
+            T[dropped, lane] = 0.0
+            T *= mask
+            tot = T.sum(axis=0)
+            bad = ~np.isfinite(tot) | (tot <= 0.0)
+            T /= np.where(bad, 1.0, tot)
+            T = np.where(mask != 0, np.maximum(T, 1e-3 / K), 0.0)
+            T /= T.sum(axis=0)
+            if bad.any():
+                T[:, bad] = mask[:, bad] / float(K)
+            theta0 = T
+        return np.full(n, self.col, dtype=np.int64), np.full(n, self.C, dtype=np.float64), mask, theta0
+
+
+class BlockResult(object):
+    """Results of one LaneBlock: `fun` (= -loglike) and `success` per lane as arrays, proportions of lane j on demand."""
+    __slots__ = ("fun", "success", "status", "_theta", "_lo", "_subsets")
+
+    def __init__(self, fun, success, status, theta, lo, subsets):
+        self.fun, self.success, self.status, self._theta, self._lo, self._subsets = fun, success, status, theta, lo, subsets
+
+    def __len__(self):
+        return int(self.fun.shape[0])
+
+    def ids(self, j):
+        return np.delete(self._subsets.chosen, int(self._subsets.drop_pos[j]))
+
+    def x(self, j):
+        return np.array(self._theta[self.ids(j), self._lo + j], dtype=np.float64)
+
+    def __getitem__(self, j):
+        """Lane j as a FitResult (compatibility with the per-lane protocol)."""
+        return FitResult(None, float(self.fun[j]), bool(self.success[j]), int(self.status[j]), (0.0, 0.0), 0,
+                         theta=self._theta, ids=self.ids(j), b=self._lo + j)
+
+
 class LaneRequest(object):
     """One lane: weight column `col` of the context, the theta-free constant C, candidate ids, and optionally a
     starting point `theta0` (proportions of `ids` in increasing id order; None = uniform)."""
@@ -324,6 +404,7 @@ class LaneContext(object):
     # streams, two host threads): the narrow tail of one half overlaps the wide phase of the other.  Measured on cfg2:
     # 4000 lanes 40.9 -> 35.7 ms (1.15x), no gain at 1000 lanes (tools/two_handles.py).  0 disables.
     concurrent_min_lanes = 3000
+    selection_groups = 2          # bootstrap.run_selections: replicate groups whose host logic overlaps the other group's solver call
     # STALLED lanes (line search exhausted at fp64 resolution) are accepted only when their KKT residuals are within this
     # factor of the tolerances (complementarity tol, dual 100 tol); otherwise they are reported like MAXITER
     stalled_slack = 1e3
@@ -480,6 +561,59 @@ class LaneContext(object):
         status, iters, kkt = out["status"].tolist(), out["iters"].tolist(), out["kkt"].tolist()
         return [FitResult(None, fun[b], ok[b], status[b], tuple(kkt[b]), iters[b], theta=theta, ids=rq.ids, b=b)
                 for b, rq in enumerate(requests)]
+
+    def fit_items(self, items, gate=None):
+        """items: a list whose elements are either a list of LaneRequest or a LaneBlock; ONE batch for all of them.
+        Returns, per item, a list of FitResult or a BlockResult.  `gate` (a context manager) is held around the solver
+        call only: several host threads may assemble and unpack their batches concurrently, the context's engine and
+        counters are touched by one at a time (bootstrap.run_selections)."""
+        V = self.V
+        parts, sizes = [], []
+        for it in items:
+            if isinstance(it, LaneBlock):
+                parts.append(it.arrays(V))
+            else:
+                b = LaneBatch.from_requests(it, V)
+                parts.append((b.cols, b.C, b.mask, b.theta0))
+            sizes.append(int(parts[-1][0].shape[0]))
+        B = int(sum(sizes))
+        if B == 0:
+            return [[] for _ in items]
+        cols = np.concatenate([p[0] for p in parts])
+        C = np.concatenate([p[1] for p in parts])
+        mask = None
+        if any(p[2] is not None for p in parts):
+            mask = np.concatenate([p[2] if p[2] is not None else np.ones((V, n), dtype=np.uint8) for p, n in zip(parts, sizes)], axis=1)
+        theta0 = None
+        if any(p[3] is not None for p in parts):
+            blocks = []
+            for p, n in zip(parts, sizes):
+                if p[3] is not None:
+                    blocks.append(p[3])
+                else:                                           # uniform over the lane's subset
+                    m = p[2].astype(np.float64) if p[2] is not None else np.ones((V, n))
+                    blocks.append(m / np.maximum(m.sum(axis=0), 1.0))
+            theta0 = np.concatenate(blocks, axis=1)
+        batch = LaneBatch(cols, C, mask, theta0)
+        if gate is None:
+            out = self.fit_batch(batch)
+        else:
+            with gate:
+                out = self.fit_batch(batch)
+        ok = self.lane_ok(out)
+        theta = out["theta"]
+        fun_all = -out["loglike"]
+        results, lo = [], 0
+        for it, n in zip(items, sizes):
+            if isinstance(it, LaneBlock):
+                results.append(BlockResult(fun_all[lo:lo + n], ok[lo:lo + n], out["status"][lo:lo + n], theta, lo, it.subsets))
+            else:
+                fun, okl = fun_all[lo:lo + n].tolist(), ok[lo:lo + n].tolist()
+                st, itr, kkt = out["status"][lo:lo + n].tolist(), out["iters"][lo:lo + n].tolist(), out["kkt"][lo:lo + n].tolist()
+                results.append([FitResult(None, fun[j], okl[j], st[j], tuple(kkt[j]), itr[j], theta=theta, ids=rq.ids, b=lo + j)
+                                for j, rq in enumerate(it)])
+            lo += n
+        return results
 
     def lane_ok(self, out):
         """success flag per lane: CONVERGED, or STALLED with KKT residuals within `stalled_slack` of the tolerances (a lane
