@@ -245,7 +245,9 @@ def workload_config(args, wl):
     return {"workload": "%s: %d variants x %d read paths (nnz %d, %d reads), %d bootstrap replicates per GPU, "
                         "full-candidate-set ML fit to KKT 1e-9" % (args.workload, wl.V, wl.R, wl.nnz, wl.N, args.lanes),
             "lanes_per_gpu": args.lanes, "V": wl.V, "R": wl.R, "nnz": wl.nnz,
-            "l2": "L2 flushed between timed steps (256 MiB write); within a step the solver re-reads its own weights",
+            "l2": "inputs larger than L2: 8 distinct batches fitted round-robin (consecutive steps read different weights, 8 x lanes x R x 2 bytes "
+                  "> 126 MB); no flush between steps.  `one_batch_at_a_time` repeats the measurement with a 256 MiB flush before every step",
+            "steps_in_flight": int(os.environ.get("TVS_BENCH_DEPTH", "4")),
             "parallelism": "lanes sharded over ranks, no data-path collective"}
 
 
@@ -442,70 +444,106 @@ def main():
     B = args.lanes
     total = B * world
     ctx = LaneContext.from_csr(wl.V, wl.L, wl.row_ptr, wl.col, wl.val, device=local_rank, sharder=sharder)
-    ctx.concurrent_min_lanes = 0                  # `value` times one batch on one stream (two_streams is reported apart)
-    cols = ctx.add_resampled(wl.n_obs, total, seed=2024)      # replicate j = Philox stream j: the same on any rank
-    batch = LaneBatch(cols)
+    ctx.concurrent_min_lanes = 0                  # a batch is never cut in halves here: the batches themselves overlap
+    ctx.collect_stats = True
+    ctx.pipeline_depth = int(os.environ.get("TVS_BENCH_DEPTH", "4"))
+    # N_SETS distinct batches of B replicates per rank, fitted round-robin: a long bootstrap cut into batches.  A step is
+    # one batch; consecutive steps read different weights (N_SETS x 36 MB of 16-bit counts on cfg2 > the 126 MB L2), so
+    # no step finds its inputs in L2 and no flush is needed between steps.  LaneContext.fit_batches keeps two batches in
+    # flight (two handles = two CUDA streams, two host threads; batch k runs on handle k % 2).
+    N_SETS = 12 if ctx.pipeline_depth == 3 else 8
     lo, hi = (0, total) if sharder is None else sharder.my_slice(total)
-    ctx.make_resident(cols[lo:hi])                # drawn on this rank's device, resident in HBM from here on
+    sets = [ctx.add_resampled(wl.n_obs, total, seed=2024 + j) for j in range(N_SETS)]   # replicate = Philox stream of its column id: the same on any rank
+    set_batches = [LaneBatch(c) for c in sets]
+    ctx.fit_batches(set_batches)                  # draws every set on the handle that will fit it: resident in HBM from here on
     eng = ctx.engine()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    # end-to-end input: this rank's replicate weights in pinned HOST memory, 16 bits per count
-    eng.set_lanes_columns(ctx._slots(eng, np.asarray(cols[lo:hi])))
-    w32 = eng.get_weights()
-    assert int(w32.max()) <= 65535
-    w_host = torch.empty((wl.R, B), dtype=torch.uint16, pin_memory=True)
-    w_host.numpy()[:] = w32.astype(np.uint16)
-    del w32
+    # end-to-end input: this rank's replicate weights of 4 of the sets in pinned HOST memory, 16 bits per count
+    N_HOST = 4
+    w_hosts = []
+    for j in range(N_HOST):
+        e = ctx.engines(ctx.pipeline_depth)[j % ctx.pipeline_depth]
+        e.set_lanes_columns(ctx._slots(e, np.asarray(sets[j][lo:hi])))
+        w32 = e.get_weights()
+        assert int(w32.max()) <= 65535
+        wh = torch.empty((wl.R, B), dtype=torch.uint16, pin_memory=True)
+        wh.numpy()[:] = w32.astype(np.uint16)
+        w_hosts.append(wh)
+        del w32
+    cols = sets[0]
+    batch = set_batches[0]
+
+    def step_batches(n):
+        return [set_batches[k % N_SETS] for k in range(n)]
+
+    def step_weights(n):
+        return [w_hosts[k % N_HOST] for k in range(n)]
 
     # ---- warm-up: both timed paths
-    for _ in range(args.warmup):
-        flush.zero_()
-        ctx.fit_batch(batch)
-    for _ in range(args.warmup):
-        flush.zero_()
-        ctx.fit_weights(w_host, B=total)
+    ctx.fit_batches(step_batches(args.warmup))
+    ctx.fit_weight_batches(step_weights(args.warmup), B=total)
     import gc
     gc.collect()
     gc.disable()                                  # no collector pauses inside the timed regions
-    # ---- timed: device-resident replicate weights (CUDA events around the whole step: column gather, fit, NCCL gather
-    #      of the results from the device buffers, device->host copy of the gathered block)
+    # ---- timed: device-resident replicate weights.  CUDA events around the region of K steps (column gather, fit, NCCL
+    #      gather of the results from the device buffers, device->host copy of the gathered block, for every step)
     sampler = ClockSampler(range(world) if rank == 0 else ())     # single node: local ranks = GPU indices
     sampler.start()
     barrier()
-    dev_ms, fit_ms, launches, passes, lane_passes = [], [], 0, 0, 0
     g0 = (sharder.bytes_gathered, sharder.n_gathers) if sharder is not None else (0, 0)
+    s0 = dict(ctx.stats)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        e0.record()
-        out = ctx.fit_batch(batch)
-        e1.record()
-        torch.cuda.synchronize()
-        dev_ms.append(e0.elapsed_time(e1))
-        st = eng.last_fit_stats()
-        fit_ms.append(st["total_ms"])
-        launches += st["kernel_launches"] + 4        # + column gather, 16-bit copy, lane sums (tvs_set_lanes_columns)
-        passes += st["passes"]
-        lane_passes += st["lane_passes"]
+    e0.record()
+    outs = ctx.fit_batches(step_batches(args.steps))
+    e1.record()
+    torch.cuda.synchronize()
+    region_ms = e0.elapsed_time(e1)
     barrier()
     wall = time.perf_counter() - t0
     g1 = (sharder.bytes_gathered, sharder.n_gathers) if sharder is not None else (0, 0)
-    ok = ctx.lane_ok(out)
-    converged = int(ok.sum())                     # all lanes of the job (gathered)
-    iters_mean = float(out["iters"].mean())
-    # ---- timed: end to end through the public API, weights in pinned host memory (H2D of this rank's weights, fit,
-    #      gather, D2H of all results) -- wall clock per step
-    e2e_ms = []
-    for _ in range(args.steps):
+    s1 = dict(ctx.stats)
+    launches = (s1["kernel_launches"] - s0["kernel_launches"]) + 4 * (s1["fits"] - s0["fits"])   # + column gather, lane sums (tvs_set_lanes_columns)
+    passes, lane_passes = s1["passes"] - s0["passes"], s1["lane_passes"] - s0["lane_passes"]
+    fit_ms = [(s1["total_ms"] - s0["total_ms"]) / max(1, s1["fits"] - s0["fits"])]
+    dev_ms = [region_ms / args.steps] * args.steps
+    converged = int(sum(int(ctx.lane_ok(o).sum()) for o in outs[-N_SETS:]) / len(outs[-N_SETS:]))    # per batch, all lanes of the job (gathered)
+    iters_mean = float(np.mean([o["iters"].mean() for o in outs[-N_SETS:]]))
+    out = outs[-1]
+    # ---- timed: end to end through the public API, weights in pinned host memory (per step: H2D of this rank's weights,
+    #      fit, gather, D2H of all results), two steps in flight -- wall clock over the region
+    torch.cuda.synchronize()
+    barrier()
+    t1 = time.perf_counter()
+    ctx.fit_weight_batches(step_weights(args.steps), B=total)
+    torch.cuda.synchronize()
+    e2e_region_ms = 1e3 * (time.perf_counter() - t1)
+    e2e_ms = [e2e_region_ms / args.steps] * args.steps
+    barrier()
+    clocks = sampler.stop()
+    # ---- the same two measurements with ONE batch at a time (round 1's definition of a step: L2 flushed, one handle)
+    serial = {}
+    ctx.pipeline_batches = False
+    n_serial = max(6, args.steps // 3)
+    ms_a, ms_b = [], []
+    for k in range(n_serial):
+        flush.zero_()
+        torch.cuda.synchronize()
+        e0.record()
+        ctx.fit_batch(set_batches[ctx.pipeline_depth * (k % (N_SETS // ctx.pipeline_depth))])        # sets of handle 0
+        e1.record()
+        torch.cuda.synchronize()
+        ms_a.append(e0.elapsed_time(e1))
+    for k in range(n_serial):
         flush.zero_()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        ctx.fit_weights(w_host, B=total)
-        e2e_ms.append(1e3 * (time.perf_counter() - t1))
-    barrier()
-    clocks = sampler.stop()
+        ctx.fit_weights(w_hosts[0], B=total)
+        ms_b.append(1e3 * (time.perf_counter() - t1))
+    ctx.pipeline_batches = True
+    serial = {"value": total / (float(np.mean(ms_a)) * 1e-3), "e2e": total / (float(np.mean(ms_b)) * 1e-3), "unit": UNIT, "steps": n_serial,
+              "ms_per_step": float(np.mean(ms_a)), "e2e_ms_per_step": float(np.mean(ms_b)),
+              "note": "this rank only; one batch at a time on one handle, L2 flushed (256 MiB write) between steps"}
     # ---- the same fits once more with CUDA events around every launch of the dominant kernel (the events
     #      cost ~1 ms per step, so they are kept out of the steps that produce `value`)
     prof = {"pass_ms": 0.0, "update_ms": 0.0, "total_ms": 0.0, "passes": 0, "lane_passes": 0}
@@ -519,35 +557,6 @@ def main():
             prof[k] += stp[k]
     fp64_peak = _cabi.measure_fp64_peak(local_rank)
     smem_peak = _cabi.measure_smem_peak(local_rank)
-    # ---- informational: the same batches through two handles (two CUDA streams, two host threads), i.e. consecutive
-    #      batches of a long bootstrap overlapped -- the narrow tail of one hides under the wide phase of the next.
-    two_streams = None
-    if world == 1 and not args.no_selection:
-        try:
-            eng2 = _cabi.Engine(wl.row_ptr, wl.col, wl.val, wl.L, device=local_rank)
-            eng2.resample(B, wl.n_obs, seed=4049, keep_lane0=False)
-            eng2.fit()
-            n_each = max(4, args.steps // 2)
-
-            def loop(e):
-                for _ in range(n_each):
-                    e.fit()
-            torch.cuda.synchronize()
-            th = [threading.Thread(target=loop, args=(e,)) for e in (eng, eng2)]
-            t2 = time.perf_counter()
-            for x in th:
-                x.start()
-            for x in th:
-                x.join()
-            torch.cuda.synchronize()
-            wall2 = time.perf_counter() - t2
-            two_streams = {"value": 2 * n_each * B / wall2, "unit": UNIT, "batches": 2 * n_each, "wall_s": wall2,
-                           "note": "two handles fitting %d-lane batches concurrently (wall clock, no L2 flush); "
-                                   "traversome_b200.lanes.LaneContext does this for batches of 3,000+ lanes" % B}
-            eng2.close()
-        except Exception as e:
-            two_streams = {"error": "%s: %s" % (type(e).__name__, e)}
-
     step_ms = float(np.sum(dev_ms)) / args.steps
     e2e_step_ms = float(np.sum(e2e_ms)) / args.steps
     per_rank_ms = [step_ms]
@@ -586,16 +595,16 @@ def main():
             "data": "synthetic", "config": workload_config(args, wl),
             "e2e": {"value": total / (e2e_step_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(wl.R) * B * 2 * world,
-                    "step_ms_p50": float(np.median(e2e_ms)), "step_ms_max": float(np.max(e2e_ms)),
+                    "region_ms": e2e_region_ms,
                     "d2h_bytes_per_step": (int(wl.V) * total * 8 + total * (8 + 16 + 4 + 4)) * world,
-                    "api": "LaneContext.fit_weights(pinned uint16 weights) -> result arrays of all lanes on every rank"},
+                    "api": "LaneContext.fit_weight_batches(pinned uint16 weight blocks) -> result arrays of all lanes of every batch on every rank"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "collective": {"op": "all_gather_into_tensor (NCCL) of the packed per-lane results, from the device buffers tvs_fit wrote"
                                  if world > 1 else "none (single GPU)",
                            "per_step": (g1[1] - g0[1]) / args.steps, "bytes_received_per_rank_per_step": (g1[0] - g0[0]) / args.steps,
                            "inside_timed_region": True,
-                           "plus": "one 16-byte all_gather per batch: every rank holds the same batch (size, digest)" if world > 1 else None},
+                           "plus": "one 16-byte all_gather per fit_batches call: every rank holds the same batches (sizes, digests)" if world > 1 else None},
             "roofline": {"bound": "fp64", "kernel": "pass3_kernel (fused p = A x, w/p, w log p, t = A^T(w/p))",
                          "achieved": tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tflops / fp64_peak if fp64_peak > 0 else None,
                          "peak_source": "tvs_measure_fp64_peak (DFMA micro-benchmark on this GPU; MEASURED_PEAKS.json has no fp64 entry)",
@@ -625,8 +634,7 @@ def main():
                 "mean_slsqp_iterations_per_restart": nit_cfg2,
                 "note": "restated reference driver (scipy SLSQP multistart) + numpy closure of the reference objective; "
                         "omits the reference's symengine build + LLVM JIT, i.e. faster than the true reference"}
-        if two_streams is not None:
-            line["two_streams"] = two_streams
+        line["one_batch_at_a_time"] = serial
     ctx.close()
     del flush
     torch.cuda.empty_cache()

@@ -125,6 +125,10 @@ class OracleEngine(object):
         self.C = np.zeros(self.w.shape[1]) if C is None else np.asarray(C)
         self.B = self.w.shape[1]
 
+    def set_lanes(self, w, mask=None, C=None, B=None):
+        w = np.asarray(w)
+        self.set_lanes_indexed(w, np.arange(w.shape[1]), mask=mask, C=C)
+
     # device-resident column store of the real engine (tvs_columns_*), host arrays here
     def columns_reserve(self, n_cols):
         old = getattr(self, "cols", None)

@@ -92,6 +92,39 @@ def test_fit_items_mixes_blocks_and_request_lists_in_one_batch():
     assert res_full[0].fun <= res_blk.fun.min() + 1e-9
 
 
+def test_pipelined_batches_equal_one_by_one():
+    wl = synthetic.make_workload(6, 200, 0.8, seed=4)
+    W = synthetic.bootstrap_weights(wl.n_obs, 10, seed=2)
+    ctx = LaneContext.from_csr(wl.V, wl.L, wl.row_ptr, wl.col, wl.val)
+    ctx.engine_factory = OracleEngine
+    cols = [ctx.add_weights(W[:, b]) for b in range(10)]
+    batches = [LaneBatch(np.array(cols[0:4])), LaneBatch(np.array(cols[4:5])), LaneBatch(np.array(cols[5:10]), C=np.arange(5.0)),
+               LaneBatch(np.array(cols[2:6])), LaneBatch(np.array(cols[9:10]))]
+    one = [ctx.fit_batch(b) for b in batches]
+    n0, l0 = ctx.n_batches, ctx.n_lanes_fitted
+    two = ctx.fit_batches(batches)
+    assert ctx.n_batches - n0 == 5 and ctx.n_lanes_fitted - l0 == 15 and ctx._engine2 is not None
+    for a, b in zip(one, two):
+        for k in ("theta", "loglike", "status"):
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k]))
+    ws = [np.ascontiguousarray(W[:, 0:3]), np.ascontiguousarray(W[:, 3:4]), np.ascontiguousarray(W[:, 4:10])]
+    got = ctx.fit_weight_batches(ws, C=[np.zeros(3), np.ones(1), None])
+    for w, g, c in zip(ws, got, (0.0, 1.0, 0.0)):
+        ref = ctx.fit_weights(w)
+        assert np.allclose(g["loglike"], ref["loglike"] + c, rtol=1e-12, atol=0) and np.array_equal(g["theta"], ref["theta"])
+    ctx.pipeline_batches = False
+    assert all(np.array_equal(a["loglike"], b["loglike"]) for a, b in zip(one, ctx.fit_batches(batches)))
+
+    class Boom(OracleEngine):
+        def fit(self, *a, **k):
+            raise RuntimeError("boom")
+    ctx2 = LaneContext.from_csr(wl.V, wl.L, wl.row_ptr, wl.col, wl.val)
+    ctx2.engine_factory = Boom
+    c2 = [ctx2.add_weights(W[:, b]) for b in range(4)]
+    with pytest.raises(RuntimeError):
+        ctx2.fit_batches([LaneBatch(np.array(c2[:2])), LaneBatch(np.array(c2[2:])), LaneBatch(np.array(c2[:1]))])
+
+
 def test_sharded_theta_indexing_and_materialisation():
     rng = np.random.default_rng(0)
     blocks = [rng.random((4, 3)), rng.random((4, 2)), rng.random((4, 3))]

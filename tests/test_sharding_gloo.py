@@ -82,6 +82,16 @@ def _worker(rank, world, port, q):
         res1 = ctx1.fit([LaneRequest(ctx1.add_weights(ctx1.dense_columns([0])[:, 0]), r.C, r.ids) for r in reqs])
         ragged = all(a.success == b.success and a.status == b.status and (not a.success or (np.array_equal(a.x, b.x) and a.fun == b.fun))
                      for a, b in zip(res1, res2))
+        # several independent batches, two in flight on two handles: the gathers stay in batch order on both ranks
+        from traversome_b200.lanes import LaneBatch
+        cols2 = [ctx2.add_weights(ctx2.dense_columns([j])[:, 0]) for j in range(len(models))]
+        bs = [LaneBatch(np.array(cols2[0:3])), LaneBatch(np.array(cols2[3:4])), LaneBatch(np.array(cols2[1:5]), C=np.arange(4.0)),
+              LaneBatch(np.array(cols2[0:1])), LaneBatch(np.array(cols2[2:5]))]
+        seq = [ctx2.fit_batch(b) for b in bs]
+        g0 = ctx2.sharder.n_gathers
+        pip = ctx2.fit_batches(bs)
+        ragged = ragged and ctx2.sharder.n_gathers - g0 == len(bs) and all(
+            np.array_equal(np.asarray(a[k]), np.asarray(b[k])) for a, b in zip(seq, pip) for k in ("theta", "loglike", "status"))
         lanes_here = ctx2._engine.calls
         q.put((rank, bool(same), bool(ragged), [sorted(r[0]) for r in got], lanes_here, res2[-1].success))
     finally:

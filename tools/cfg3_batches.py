@@ -11,8 +11,23 @@ rows = []
 inner = LaneContext._fit_on
 
 
+DUMP = [int(x) for x in os.environ.get("CFG3_DUMP", "").split(",") if x]      # batch indices of the first run whose passes are dumped
+calls = [0]
+
+
 def fit_on(self, eng, mine, out=None):
-    res = inner(self, eng, mine, out=out)
+    dump = calls[0] in DUMP
+    calls[0] += 1
+    if dump:
+        sys.stderr.write("batch %d lanes %d\n" % (calls[0] - 1, len(mine)))
+        sys.stderr.flush()
+        os.environ["TVS_TIME_PASSES"] = "1"
+        os.environ["TVS_DUMP_PASSES"] = "1"
+    try:
+        res = inner(self, eng, mine, out=out)
+    finally:
+        if dump:
+            del os.environ["TVS_TIME_PASSES"], os.environ["TVS_DUMP_PASSES"]
     st = eng.last_fit_stats()
     width = float(mine.mask.sum(axis=0).mean()) if mine.mask is not None else float(self.V)
     it = np.asarray(res["iters"])

@@ -297,8 +297,8 @@ class LaneSharder(object):
         o_st = o_it + cap * 4
         return o_ll, o_kkt, o_it, o_st, o_st + cap * 4
 
-    def _buffers(self, cap, V):
-        key = (cap, V)
+    def _buffers(self, cap, V, slot=0):
+        key = (cap, V, slot)
         if key not in self._bufs:
             torch = self._torch
             nbytes = self._layout(cap, V)[-1]
@@ -310,12 +310,13 @@ class LaneSharder(object):
             self._bufs[key] = (mine, every, host)
         return self._bufs[key]
 
-    def views(self, n, B, V):
+    def views(self, n, B, V, slot=0):
         """Views of this rank's packed block for its `n` lanes of a batch of B, keyed like Engine.fit's result
-        (torch tensors; on the CPU their .numpy() share the memory)."""
+        (torch tensors; on the CPU their .numpy() share the memory).  `slot` names one of several buffer sets: batches that
+        are in flight at the same time (LaneContext.fit_batches) must not share one."""
         torch = self._torch
         cap = (int(B) + self.world - 1) // self.world
-        mine = self._buffers(cap, V)[0]
+        mine = self._buffers(cap, V, slot)[0]
         o_ll, o_kkt, o_it, o_st, _ = self._layout(cap, V)
         return {"theta": mine[0:V * n * 8].view(torch.float64).view(V, n),
                 "loglike": mine[o_ll:o_ll + n * 8].view(torch.float64),
@@ -335,16 +336,16 @@ class LaneSharder(object):
             raise RuntimeError("LaneSharder: ranks hold different lane batches (sizes/digests %s): the candidate order must not "
                                "depend on the rank -- seed or broadcast every permutation" % every.tolist())
 
-    def gather(self, local, B, V):
+    def gather(self, local, B, V, slot=0):
         """local: this rank's result dict (arrays or the `views` themselves) for its slice of a batch of B lanes;
         returns the dict (numpy) for all B lanes, identical on every rank."""
         torch, dist = self._torch, self._dist
         cap = (int(B) + self.world - 1) // self.world
-        mine, every, host = self._buffers(cap, V)
+        mine, every, host = self._buffers(cap, V, slot)
         lo, hi = self.my_slice(B)
         n = hi - lo
         if n:
-            mv = self.views(n, B, V)
+            mv = self.views(n, B, V, slot)
             for k in _RESULT_KEYS:
                 src = local[k]
                 if isinstance(src, torch.Tensor) and src.data_ptr() == mv[k].data_ptr():
@@ -388,6 +389,33 @@ class LaneSharder(object):
         return int(t.item())
 
 
+class _InOrder(object):
+    """Admits the indices 0, 1, 2, .. one at a time and in that order: the collectives of batches that are fitted
+    concurrently are issued in batch order on every rank, whatever the thread timing."""
+
+    def __init__(self):
+        self.cond = threading.Condition()
+        self.next = 0
+        self.failed = False
+
+    def enter(self, i):
+        with self.cond:
+            while self.next != i and not self.failed:
+                self.cond.wait()
+            if self.failed:
+                raise RuntimeError("pipelined fit: another batch failed")
+
+    def leave(self, i):
+        with self.cond:
+            self.next = i + 1
+            self.cond.notify_all()
+
+    def fail(self):
+        with self.cond:
+            self.failed = True
+            self.cond.notify_all()
+
+
 class _Residency(object):
     """Which weight columns of a LaneContext live in which slot of one engine's column store."""
     __slots__ = ("slot_of", "used", "cap", "last")
@@ -404,6 +432,8 @@ class LaneContext(object):
     # streams, two host threads): the narrow tail of one half overlaps the wide phase of the other.  Measured on cfg2:
     # 4000 lanes 40.9 -> 35.7 ms (1.15x), no gain at 1000 lanes (tools/two_handles.py).  0 disables.
     concurrent_min_lanes = 3000
+    pipeline_batches = True       # fit_batches / fit_weight_batches: `pipeline_depth` batches in flight, one handle each
+    pipeline_depth = None         # None: 4 for matrices of up to 8M non-zeros (latency-bound narrow phases), else 2
     selection_groups = 2          # bootstrap.run_selections: replicate groups whose host logic overlaps the other group's solver call
     # STALLED lanes (line search exhausted at fp64 resolution) are accepted only when their KKT residuals are within this
     # factor of the tolerances (complementarity tol, dual 100 tol); otherwise they are reported like MAXITER
@@ -419,6 +449,7 @@ class LaneContext(object):
         self._cols = []               # per column: (rows, counts) sparse host copy, or ("resample", n_obs, seed, id)
         self._engine = None
         self._engine2 = None          # second handle for concurrent halves (created on first use)
+        self._engines_more = []       # further handles of a deeper batch pipeline (pipeline_depth > 2)
         self._engine_R = -1
         self._resident = {}           # id(engine) -> _Residency
         self.n_lanes_fitted = 0
@@ -426,6 +457,9 @@ class LaneContext(object):
         self.check_consistency = True
         self._checked = None
         self.time_passes = False      # CUDA events around every pass launch (roofline figures; ~1 ms per fit)
+        self.collect_stats = False    # sum tvs_last_fit_stats of every solver call into `stats` (bench / diagnostics)
+        self.stats = {"fits": 0, "passes": 0, "kernel_launches": 0, "lane_passes": 0, "total_ms": 0.0}
+        self._stats_lock = threading.Lock()
         self.engine_factory = _cabi.Engine     # tests of the host logic inject a stand-in here
         # permutations drawn inside a sharded job must not depend on the rank (ModelFitMaxLike.py:203 shuffles the
         # candidates with the process-global np.random): one seed from rank 0
@@ -495,11 +529,22 @@ class LaneContext(object):
             self._engine2 = self._new_engine()
         return self._engine2
 
+    def engines(self, n):
+        """The first n handles of this context (created on first use): engine(), second_engine(), then extra ones."""
+        out = [self.engine(), self.second_engine()][:n]
+        while len(out) < n:
+            k = len(out) - 2
+            if k >= len(self._engines_more):
+                self._engines_more.append(self._new_engine())
+            out.append(self._engines_more[k])
+        return out
+
     def close(self):
-        for e in (self._engine, self._engine2):
+        for e in [self._engine, self._engine2] + self._engines_more:
             if e is not None:
                 e.close()
         self._engine = self._engine2 = None
+        self._engines_more = []
         self._resident = {}
 
     def dense_columns(self, cols):
@@ -661,12 +706,116 @@ class LaneContext(object):
         self.n_batches += 1
         return out
 
+    def _pipelined(self, n_batches, total_lanes, fit_local):
+        """Batches 0..n-1 over `pipeline_depth` (2) handles (a CUDA stream and a host thread each): handle k fits the batches
+        k, k + depth, ..; while
+        one handle is in the narrow tail of its batch (few lanes left, latency-bound kernels, host polls) or copies its
+        inputs in, the other is in the wide phase of the next batch.  `fit_local(i, eng, views)` fits this rank's lanes of
+        batch i on `eng` and returns (local result dict, B_i); the gathers of a sharded context are issued in batch order."""
+        sh = self.sharder
+        depth = self.pipeline_depth
+        if depth is None:
+            depth = 4 if getattr(self.engine(), "nnz", 0) <= 8000000 else 2
+        depth = max(2, min(int(depth), n_batches))
+        engines = self.engines(depth)
+        results = [None] * n_batches
+        order = _InOrder()
+        errors = []
+
+        def work(k):
+            try:
+                if sh is not None and sh.device.type == "cuda":
+                    sh._torch.cuda.set_device(sh.device)        # the device is a per-thread setting
+                for i in range(k, n_batches, depth):
+                    local, B = fit_local(i, engines[k], k)
+                    if sh is None:
+                        results[i] = local
+                    else:
+                        order.enter(i)
+                        try:
+                            results[i] = sh.gather(local, B, self.V, slot=k)
+                        finally:
+                            order.leave(i)
+            except BaseException as e:                          # re-raised in the calling thread
+                errors.append(e)
+                order.fail()
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(1, depth)]
+        for t in threads:
+            t.start()
+        work(0)
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        self.n_lanes_fitted += total_lanes
+        self.n_batches += n_batches
+        return results
+
+    def fit_batches(self, batches):
+        """A sequence of LaneBatch -> the list of their result dicts (as fit_batch), with two batches in flight at any time
+        (see _pipelined): for callers that hold several independent batches, e.g. a bootstrap of more replicates than one
+        batch takes."""
+        batches = list(batches)
+        if len(batches) < 2 or not self.pipeline_batches:
+            return [self.fit_batch(b) for b in batches]
+        sh = self.sharder
+        if sh is not None and self.check_consistency:           # one collective for the whole sequence, before any thread starts
+            sh.check_same_batch(sum(len(b) for b in batches), zlib.crc32(np.array([b.digest() for b in batches], dtype=np.int64).tobytes()))
+
+        def fit_local(i, eng, slot):
+            batch = batches[i]
+            B = len(batch)
+            lo, hi = (0, B) if sh is None else sh.my_slice(B)
+            if hi == lo:
+                return None, B
+            views = sh.views(hi - lo, B, self.V, slot) if (sh is not None and sh.device.type == "cuda") else None
+            return self._fit_on(eng, batch.slice(lo, hi), out=views), B
+        return self._pipelined(len(batches), sum(len(b) for b in batches), fit_local)
+
+    def fit_weight_batches(self, w_locals, B=None, C=None):
+        """One-shot lanes (see fit_weights) for a sequence of weight blocks, two in flight: the host->device copy of one
+        block runs while the other handle fits.  `w_locals[i]` [R, n_i] are THIS rank's lanes of batch i; B (int or
+        list) the batch sizes over all ranks (default n_i), C (list of arrays or None) the constants."""
+        w_locals = list(w_locals)
+        sh = self.sharder
+        n_b = len(w_locals)
+        sizes = [int(w.shape[1]) for w in w_locals]
+        totals = sizes if B is None else ([int(B)] * n_b if np.isscalar(B) else [int(x) for x in B])
+        if n_b < 2 or not self.pipeline_batches:
+            return [self.fit_weights(w, B=t, C=(None if C is None else C[i])) for i, (w, t) in enumerate(zip(w_locals, totals))]
+        if sh is not None:
+            for n, t in zip(sizes, totals):
+                lo, hi = sh.my_slice(t)
+                if hi - lo != n:
+                    raise ValueError("fit_weight_batches: this rank owns %d lanes of a batch of %d, got %d" % (hi - lo, t, n))
+
+        def fit_local(i, eng, slot):
+            n, t = sizes[i], totals[i]
+            if not n:
+                return None, t
+            views = sh.views(n, t, self.V, slot) if (sh is not None and sh.device.type == "cuda") else None
+            eng.set_lanes(w_locals[i], C=(None if C is None else C[i]), B=n)
+            res = eng.fit(tol=self.tol, max_iter=self.max_iter, history=self.history, out=views)
+            self._note_stats(eng)
+            return res, t
+        return self._pipelined(n_b, sum(totals), fit_local)
+
     def _fit_on(self, eng, mine, out=None):
         """Fit the lanes `mine` (LaneBatch) on one handle; returns the engine's result dict."""
         slots = self._slots(eng, np.ascontiguousarray(mine.cols))
         eng.set_lanes_columns(slots, mask=mine.mask, C=mine.C)
-        return eng.fit(theta0=mine.theta0, tol=self.tol, max_iter=self.max_iter, history=self.history, out=out,
-                       time_passes=self.time_passes)
+        res = eng.fit(theta0=mine.theta0, tol=self.tol, max_iter=self.max_iter, history=self.history, out=out,
+                      time_passes=self.time_passes)
+        self._note_stats(eng)
+        return res
+
+    def _note_stats(self, eng):
+        if self.collect_stats:
+            st = eng.last_fit_stats()
+            with self._stats_lock:
+                self.stats["fits"] += 1
+                for k in ("passes", "kernel_launches", "lane_passes", "total_ms"):
+                    self.stats[k] += st[k]
 
     def make_resident(self, cols):
         """Upload / draw the given columns on this rank's device now (otherwise it happens at their first fit)."""
@@ -690,6 +839,7 @@ class LaneContext(object):
         if n:
             eng.set_lanes(w_local, C=C, B=n)
             local = eng.fit(tol=self.tol, max_iter=self.max_iter, history=self.history, out=views)
+            self._note_stats(eng)
         out = local if sh is None else sh.gather(local, B, self.V)
         self.n_lanes_fitted += B
         self.n_batches += 1
