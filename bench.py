@@ -144,9 +144,9 @@ def selection_rate(device, n_rep=256, nit_cfg2=None, n_groups=None):
     solver = [0.0]
     inner = ctx.fit_batch
 
-    def timed(batch):
+    def timed(batch, **kw):
         t = time.perf_counter()
-        out = inner(batch)
+        out = inner(batch, **kw)
         solver[0] += time.perf_counter() - t
         return out
     ctx.fit_batch = timed

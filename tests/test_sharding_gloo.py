@@ -144,6 +144,14 @@ def _worker_shuffle(rank, world, port, q):
             ctx.fit_batch(LaneBatch([col, col], mask=np.eye(wl.V, 2, k=-rank, dtype=np.uint8) + np.eye(wl.V, 2, k=-3, dtype=np.uint8)))
         except RuntimeError as e:
             caught = "different lane batches" in str(e)
+        # the same from a thread that fits through a gate (no collective before the fit): the digest inside the gathered block
+        import contextlib
+        try:
+            ctx.fit_batch(LaneBatch([col, col], mask=np.eye(wl.V, 2, k=-rank, dtype=np.uint8) + np.eye(wl.V, 2, k=-3, dtype=np.uint8)),
+                          handle=1, gate=contextlib.nullcontext())
+            caught = False
+        except RuntimeError as e:
+            caught = caught and "different lane batches" in str(e)
         q.put((rank, sorted(res[0]), [float(res[0][k]) for k in sorted(res[0])], float(res[1]), float(res[2]), seeds_equal, caught,
                ctx.shuffle_seed))
     finally:

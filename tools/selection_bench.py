@@ -36,9 +36,9 @@ t_fit = [0.0]
 orig_fit = ctx.fit_batch
 
 
-def timed_fit(batch):
+def timed_fit(batch, **kw):
     t = time.time()
-    out = orig_fit(batch)
+    out = orig_fit(batch, **kw)
     t_fit[0] += time.time() - t
     return out
 

@@ -78,7 +78,7 @@ def _advance_group(ctx, fitters, steps, results, members, gate=None):
     n_rounds = 0
     while pending:
         order = sorted(pending)
-        fitted = ctx.fit_items([fitters[i].lane_requests(pending[i]) for i in order], gate=gate)
+        fitted = ctx.fit_items([fitters[i].lane_requests(pending[i]) for i in order], turn=gate)   # the gate: around the solver call only
         n_rounds += 1
         for i, mine in zip(order, fitted):
             fitters[i].n_gpu_fits += len(pending[i])
@@ -102,8 +102,11 @@ def run_selections(fitters, criterion=Criterion.BIC, n_proc=1, random_size=20, u
 
     groups (default: the context's `selection_groups`, 2, when there are at least 64 replicates, else 1): the replicates
     advance as that many interleaved groups, each in lock step on its own host thread, their batches taking the GPU
-    strictly in turn -- while the solver works on one group's batch (the C call releases the interpreter lock) the
-    decision logic and lane assembly of the other group run on the host."""
+    strictly in turn (group 0, 1, .., 0, ..; with a LaneSharder this is also the order of the collectives on every rank):
+    while the solver works on one group's batch (the C call releases the interpreter lock) the decision logic and lane
+    assembly of the other group run on the host.  Measured on BASELINE configs[2], 256 replicates: 3.33 s as one group,
+    2.94 s as two; letting the groups' batches run concurrently on separate handles instead is slower (3.12 s: the pass
+    kernels of a wide batch fill the GPU, two of them only delay each other and both groups then need the host at once)."""
     if not fitters:
         return []
     ctx = fitters[0]._ensure_lane()

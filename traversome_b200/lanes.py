@@ -289,13 +289,15 @@ class LaneSharder(object):
         return self.bounds(B, self.rank, self.world)
 
     # ---- packed per-rank result block: [theta V*cap f64][loglike cap f64][kkt 2*cap f64][iters cap i32][status cap i32]
+    #      [batch size, batch digest: 2 x i64]
     @staticmethod
     def _layout(cap, V):
         o_ll = V * cap * 8
         o_kkt = o_ll + cap * 8
         o_it = o_kkt + cap * 16
         o_st = o_it + cap * 4
-        return o_ll, o_kkt, o_it, o_st, o_st + cap * 4
+        o_dg = (o_st + cap * 4 + 7) // 8 * 8                     # (batch size, batch digest) of the rank that packed the block
+        return o_ll, o_kkt, o_it, o_st, o_dg + 16
 
     def _buffers(self, cap, V, slot=0):
         key = (cap, V, slot)
@@ -336,9 +338,10 @@ class LaneSharder(object):
             raise RuntimeError("LaneSharder: ranks hold different lane batches (sizes/digests %s): the candidate order must not "
                                "depend on the rank -- seed or broadcast every permutation" % every.tolist())
 
-    def gather(self, local, B, V, slot=0):
+    def gather(self, local, B, V, slot=0, digest=None):
         """local: this rank's result dict (arrays or the `views` themselves) for its slice of a batch of B lanes;
-        returns the dict (numpy) for all B lanes, identical on every rank."""
+        returns the dict (numpy) for all B lanes, identical on every rank.  `digest` (of the batch, LaneBatch.digest)
+        travels in the block: a rank that fitted a different batch of the same size is caught here."""
         torch, dist = self._torch, self._dist
         cap = (int(B) + self.world - 1) // self.world
         mine, every, host = self._buffers(cap, V, slot)
@@ -351,6 +354,9 @@ class LaneSharder(object):
                 if isinstance(src, torch.Tensor) and src.data_ptr() == mv[k].data_ptr():
                     continue                                   # the solver wrote straight into the packed block
                 mv[k].copy_(torch.as_tensor(np.ascontiguousarray(src)).to(mv[k].dtype))
+        nbytes = mine.numel()
+        if digest is not None:
+            mine[nbytes - 16:].view(torch.int64).copy_(torch.tensor([int(B), int(digest)], dtype=torch.int64))
         dist.all_gather_into_tensor(every, mine, group=self.group)
         if host is not None:
             host.copy_(every, non_blocking=True)
@@ -360,8 +366,12 @@ class LaneSharder(object):
             flat = every.numpy()
         self.bytes_gathered += int(every.numel())
         self.n_gathers += 1
-        nbytes = mine.numel()
         o_ll, o_kkt, o_it, o_st, _ = self._layout(cap, V)
+        if digest is not None:
+            tails = np.stack([flat[(r + 1) * nbytes - 16:(r + 1) * nbytes].view(np.int64) for r in range(self.world)])
+            if not bool((tails == tails[0]).all()):
+                raise RuntimeError("LaneSharder: ranks hold different lane batches (sizes/digests %s): the candidate order must not "
+                                   "depend on the rank -- seed or broadcast every permutation" % tails.tolist())
         out = {"loglike": np.empty(B, dtype=np.float64),
                "kkt": np.empty((B, 2), dtype=np.float64), "iters": np.empty(B, dtype=np.int32), "status": np.empty(B, dtype=np.int32)}
         blocks, starts = [], []
@@ -531,6 +541,8 @@ class LaneContext(object):
 
     def engines(self, n):
         """The first n handles of this context (created on first use): engine(), second_engine(), then extra ones."""
+        if n <= 1:
+            return [self.engine()]
         out = [self.engine(), self.second_engine()][:n]
         while len(out) < n:
             k = len(out) - 2
@@ -607,11 +619,11 @@ class LaneContext(object):
         return [FitResult(None, fun[b], ok[b], status[b], tuple(kkt[b]), iters[b], theta=theta, ids=rq.ids, b=b)
                 for b, rq in enumerate(requests)]
 
-    def fit_items(self, items, gate=None):
+    def fit_items(self, items, handle=0, gate=None, turn=None):
         """items: a list whose elements are either a list of LaneRequest or a LaneBlock; ONE batch for all of them.
-        Returns, per item, a list of FitResult or a BlockResult.  `gate` (a context manager) is held around the solver
-        call only: several host threads may assemble and unpack their batches concurrently, the context's engine and
-        counters are touched by one at a time (bootstrap.run_selections)."""
+        Returns, per item, a list of FitResult or a BlockResult.  `turn` (a context manager) is held around the solver call
+        only -- lane assembly before it and the unpacking of the results after it run outside, so several host threads
+        overlap them with each other's solver calls (bootstrap.run_selections).  `handle`, `gate`: see fit_batch."""
         V = self.V
         parts, sizes = [], []
         for it in items:
@@ -640,11 +652,11 @@ class LaneContext(object):
                     blocks.append(m / np.maximum(m.sum(axis=0), 1.0))
             theta0 = np.concatenate(blocks, axis=1)
         batch = LaneBatch(cols, C, mask, theta0)
-        if gate is None:
-            out = self.fit_batch(batch)
+        if turn is None:
+            out = self.fit_batch(batch, handle=handle, gate=gate)
         else:
-            with gate:
-                out = self.fit_batch(batch)
+            with turn:
+                out = self.fit_batch(batch, handle=handle, gate=gate)
         ok = self.lane_ok(out)
         theta = out["theta"]
         fun_all = -out["loglike"]
@@ -668,21 +680,29 @@ class LaneContext(object):
         near = (kkt[:, 0] <= self.stalled_slack * self.tol) & (kkt[:, 1] <= self.stalled_slack * 100.0 * self.tol)
         return ((status == _cabi.CONVERGED) | ((status == _cabi.STALLED) & near)) & np.isfinite(np.asarray(out["loglike"]))
 
-    def fit_batch(self, batch):
+    def fit_batch(self, batch, handle=0, gate=None):
         """LaneBatch -> dict(theta [V,B], loglike [B], kkt [B,2], iters [B], status [B]) for ALL lanes of the batch (with
-        a sharder: this rank fits its slice, one all_gather returns the rest)."""
+        a sharder: this rank fits its slice, one all_gather returns the rest).
+
+        `handle` / `gate`: for callers that fit from several host threads (bootstrap.run_selections): the batch runs on the
+        context's handle number `handle` (own CUDA stream; a thread must keep to its handle) and `gate`, a context manager,
+        is held around the collective only -- the caller's gates must admit the threads in an order that is the same on
+        every rank."""
         B = len(batch)
         sh = self.sharder
-        if sh is not None and self.check_consistency and batch is not self._checked:
-            sh.check_same_batch(B, batch.digest())              # once per batch object: a batch that is fitted again is the same
-            self._checked = batch
+        digest = batch.digest() if (sh is not None and self.check_consistency) else None
+        if digest is not None and gate is None and batch is not self._checked:
+            sh.check_same_batch(B, digest)                      # BEFORE the fit, once per batch object (a batch fitted again is the same);
+            self._checked = batch                               # threads with a gate rely on the digest inside the gathered block
         lo, hi = (0, B) if sh is None else sh.my_slice(B)
         n = hi - lo
         local = None
         views = None
+        if sh is not None and gate is not None and sh.device.type == "cuda":
+            sh._torch.cuda.set_device(sh.device)                # the device is a per-thread setting
         if sh is not None and n and sh.device.type == "cuda":
-            views = sh.views(n, B, self.V)                      # the solver writes into the packed block that is gathered
-        if n and self.concurrent_min_lanes and n >= self.concurrent_min_lanes:
+            views = sh.views(n, B, self.V, handle)              # the solver writes into the packed block that is gathered
+        if n and handle == 0 and gate is None and self.concurrent_min_lanes and n >= self.concurrent_min_lanes:
             mid = lo + n // 2
             halves = [None, None]
 
@@ -700,10 +720,17 @@ class LaneContext(object):
                     raise h
             local = {k: np.concatenate([halves[0][k], halves[1][k]], axis=(1 if k == "theta" else 0)) for k in halves[0]}
         elif n:
-            local = self._fit_on(self.engine(), batch.slice(lo, hi), out=views)
-        out = local if sh is None else sh.gather(local, B, self.V)
-        self.n_lanes_fitted += B
-        self.n_batches += 1
+            local = self._fit_on(self.engines(handle + 1)[handle], batch.slice(lo, hi), out=views)
+        if sh is None:
+            out = local
+        elif gate is None:
+            out = sh.gather(local, B, self.V, handle, digest)
+        else:
+            with gate:
+                out = sh.gather(local, B, self.V, handle, digest)
+        with self._stats_lock:
+            self.n_lanes_fitted += B
+            self.n_batches += 1
         return out
 
     def _pipelined(self, n_batches, total_lanes, fit_local):
