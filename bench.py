@@ -491,6 +491,7 @@ def main():
     sampler.start()
     barrier()
     g0 = (sharder.bytes_gathered, sharder.n_gathers) if sharder is not None else (0, 0)
+    gs0 = dict(sharder.seconds) if sharder is not None else {}
     s0 = dict(ctx.stats)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -502,6 +503,7 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     g1 = (sharder.bytes_gathered, sharder.n_gathers) if sharder is not None else (0, 0)
+    gather_ms = {k: 1e3 * (sharder.seconds[k] - gs0[k]) / args.steps for k in gs0} if sharder is not None else None
     s1 = dict(ctx.stats)
     launches = (s1["kernel_launches"] - s0["kernel_launches"]) + 4 * (s1["fits"] - s0["fits"])   # + column gather, lane sums (tvs_set_lanes_columns)
     passes, lane_passes = s1["passes"] - s0["passes"], s1["lane_passes"] - s0["lane_passes"]
@@ -603,7 +605,7 @@ def main():
             "collective": {"op": "all_gather_into_tensor (NCCL) of the packed per-lane results, from the device buffers tvs_fit wrote"
                                  if world > 1 else "none (single GPU)",
                            "per_step": (g1[1] - g0[1]) / args.steps, "bytes_received_per_rank_per_step": (g1[0] - g0[0]) / args.steps,
-                           "inside_timed_region": True,
+                           "inside_timed_region": True, "host_ms_per_step_rank0": gather_ms,
                            "plus": "one 16-byte all_gather per fit_batches call: every rank holds the same batches (sizes, digests)" if world > 1 else None},
             "roofline": {"bound": "fp64", "kernel": "pass3_kernel (fused p = A x, w/p, w log p, t = A^T(w/p))",
                          "achieved": tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tflops / fp64_peak if fp64_peak > 0 else None,

@@ -9,7 +9,9 @@ GPU, keeps the weight columns RESIDENT on the device (registered once, named by 
 per GPU); every rank fits its slice and ONE all_gather of the per-lane results -- straight from the
 device buffers `tvs_fit` wrote -- returns all of them to all ranks.
 """
+import sys
 import threading
+import time
 import zlib
 
 import numpy as np
@@ -277,6 +279,7 @@ class LaneSharder(object):
         self._bufs = {}
         self.bytes_gathered = 0          # total bytes received by this rank's all_gathers (diagnostics / bench)
         self.n_gathers = 0
+        self.seconds = {"pack": 0.0, "all_gather_to_host": 0.0, "unpack": 0.0}   # host time of this rank inside gather()
 
     @staticmethod
     def bounds(B, rank, world):
@@ -342,7 +345,13 @@ class LaneSharder(object):
         """local: this rank's result dict (arrays or the `views` themselves) for its slice of a batch of B lanes;
         returns the dict (numpy) for all B lanes, identical on every rank.  `digest` (of the batch, LaneBatch.digest)
         travels in the block: a rank that fitted a different batch of the same size is caught here."""
+        return self.unpack(self.gather_raw(local, B, V, slot, digest), B, V, digest is not None)
+
+    def gather_raw(self, local, B, V, slot=0, digest=None):
+        """The collective half of `gather`: pack, all_gather, copy to the host; returns the gathered bytes (a private copy).
+        Threads that take turns at the collective call this inside their turn and `unpack` outside it."""
         torch, dist = self._torch, self._dist
+        t_0 = time.perf_counter()
         cap = (int(B) + self.world - 1) // self.world
         mine, every, host = self._buffers(cap, V, slot)
         lo, hi = self.my_slice(B)
@@ -357,17 +366,27 @@ class LaneSharder(object):
         nbytes = mine.numel()
         if digest is not None:
             mine[nbytes - 16:].view(torch.int64).copy_(torch.tensor([int(B), int(digest)], dtype=torch.int64))
+        t_1 = time.perf_counter()
         dist.all_gather_into_tensor(every, mine, group=self.group)
         if host is not None:
             host.copy_(every, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            flat = host.numpy()
+            flat = host.numpy().copy()                          # the pinned buffer is reused by the next gather of this slot
         else:
-            flat = every.numpy()
+            flat = every.numpy().copy()
+        t_2 = time.perf_counter()
         self.bytes_gathered += int(every.numel())
         self.n_gathers += 1
-        o_ll, o_kkt, o_it, o_st, _ = self._layout(cap, V)
-        if digest is not None:
+        self.seconds["pack"] += t_1 - t_0
+        self.seconds["all_gather_to_host"] += t_2 - t_1
+        return flat
+
+    def unpack(self, flat, B, V, check_digest=False):
+        """The gathered bytes of a batch of B lanes -> the result dict (numpy) of all lanes."""
+        t_2 = time.perf_counter()
+        cap = (int(B) + self.world - 1) // self.world
+        o_ll, o_kkt, o_it, o_st, nbytes = self._layout(cap, V)
+        if check_digest:
             tails = np.stack([flat[(r + 1) * nbytes - 16:(r + 1) * nbytes].view(np.int64) for r in range(self.world)])
             if not bool((tails == tails[0]).all()):
                 raise RuntimeError("LaneSharder: ranks hold different lane batches (sizes/digests %s): the candidate order must not "
@@ -375,7 +394,6 @@ class LaneSharder(object):
         out = {"loglike": np.empty(B, dtype=np.float64),
                "kkt": np.empty((B, 2), dtype=np.float64), "iters": np.empty(B, dtype=np.int32), "status": np.empty(B, dtype=np.int32)}
         blocks, starts = [], []
-        flat = flat.copy()                                      # the pinned buffer is reused by the next gather
         for r in range(self.world):
             a, b = self.bounds(B, r, self.world)
             m = b - a
@@ -389,6 +407,7 @@ class LaneSharder(object):
             out["iters"][a:b] = blk[o_it:o_it + m * 4].view(np.int32)
             out["status"][a:b] = blk[o_st:o_st + m * 4].view(np.int32)
         out["theta"] = ShardedTheta(blocks, starts, V, B)
+        self.seconds["unpack"] += time.perf_counter() - t_2
         return out
 
     def broadcast_seed(self):
@@ -727,7 +746,8 @@ class LaneContext(object):
             out = sh.gather(local, B, self.V, handle, digest)
         else:
             with gate:
-                out = sh.gather(local, B, self.V, handle, digest)
+                flat = sh.gather_raw(local, B, self.V, handle, digest)
+            out = sh.unpack(flat, B, self.V, digest is not None)
         with self._stats_lock:
             self.n_lanes_fitted += B
             self.n_batches += 1
@@ -760,18 +780,24 @@ class LaneContext(object):
                     else:
                         order.enter(i)
                         try:
-                            results[i] = sh.gather(local, B, self.V, slot=k)
+                            flat = sh.gather_raw(local, B, self.V, slot=k)
                         finally:
                             order.leave(i)
+                        results[i] = sh.unpack(flat, B, self.V)
             except BaseException as e:                          # re-raised in the calling thread
                 errors.append(e)
                 order.fail()
         threads = [threading.Thread(target=work, args=(k,)) for k in range(1, depth)]
-        for t in threads:
-            t.start()
-        work(0)
-        for t in threads:
-            t.join()
+        interval = sys.getswitchinterval()
+        sys.setswitchinterval(min(interval, 2e-4))              # a thread that returns from the solver gets the interpreter at once
+        try:
+            for t in threads:
+                t.start()
+            work(0)
+            for t in threads:
+                t.join()
+        finally:
+            sys.setswitchinterval(interval)
         if errors:
             raise errors[0]
         self.n_lanes_fitted += total_lanes
