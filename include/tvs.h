@@ -151,7 +151,10 @@ int tvs_loglik(tvs_handle h, const double* theta, double* ll_out);
  * theta0[V*B] or NULL (= uniform over the lane's mask).  A lane without any record (all weights zero) has a constant
  * likelihood: it is reported TVS_CONVERGED at its starting point with ll = C.  Outputs (any may be NULL):
  * theta_out[V*B] (sums to 1 over the mask, 0 outside), ll_out[B] (includes C), kkt_out[2*B]
- * (complementarity, dual residual), iters_out[B], status_out[B]. */
+ * (complementarity, dual residual), iters_out[B], status_out[B].
+ * Any B is served by the 2- and 4-lane kernels: a lane count that is not a multiple of 4 is re-laid once, inside the call,
+ * at the next multiple (1..3 inert padding lanes; one extra copy of the lane weights at that width stays allocated on
+ * the handle).  TVS_PAD=0 in the environment keeps the caller's width (1-lane kernels for odd B). */
 int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt,
             double* theta_out, double* ll_out, double* kkt_out, int32_t* iters_out, int32_t* status_out);
 
