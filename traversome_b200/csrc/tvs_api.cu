@@ -583,7 +583,7 @@ static int ensure_fit_state(tvs_problem* h, int m) {
         A_(s.gram, (size_t)B * ((2 * m + 1) * (2 * m + 2) / 2))
         A_(s.ls, B) A_(s.iters, B) A_(s.head, B) A_(s.cnt, B) A_(s.done, B) A_(s.status, B)
     }
-    f.half = B / 2 + 4;            // +3: compacted widths are padded to a multiple of 4 (vector loads of w)
+    f.half = B * 3 / 4 + 4;        // compaction keeps at most 75 % of a set; +3: compacted widths are padded to a multiple of 4
     for (int i = 0; i < 2; ++i) {
         A_(f.mbuf[i], (size_t)V * f.half) A_(f.nbuf[i], f.half) A_(f.cbuf[i], f.half)      // wbuf / wbuf16: on first compaction
     }
@@ -1531,9 +1531,10 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
 
     bool in_newton = false;
     int64_t newton_active = 0;
-    // compact when at most this fraction of the set's lanes is still iterating (one gather launch per compaction)
-    // (measured on cfg2: thresholds of 50..85 % all land within 2 % of each other, the buffers are sized for 50 %)
-    const double compact_frac = std::min(0.5, std::max(0.1, env_int("TVS_COMPACT_PCT", 50) / 100.0));
+    // compact when at most this fraction of the set's lanes is still iterating (one gather launch per compaction; the
+    // buffers are sized for 75 %).  Measured, fit time at 50 / 60-65 / 70 / 75 %: cfg2 1,000 lanes 11.64 / 11.53 / 11.52 / 11.54 ms,
+    // cfg3 2,048 lanes 438 / 430 / 424 / 427 ms, cfg4 1,248 lanes 4.31 / 4.14 / - / 4.07 s (tools/compact_sweep.py)
+    const double compact_frac = std::min(0.75, std::max(0.1, env_int("TVS_COMPACT_PCT", 70) / 100.0));
     while (!all_done && passes < max_passes && rc == TVS_OK) {
         LaneSet& s = f.set[cur];
         const int64_t W = s.width;

@@ -83,7 +83,7 @@ struct Lanes {
 };
 
 // One set of per-lane arrays at some width.  tvs_fit keeps two of them and "compacts" the lanes
-// that are still iterating from one into the other whenever at least half of the lanes have finished,
+// that are still iterating from one into the other whenever at least 30 % of the lanes have finished,
 // so that the pass kernel never spends time on converged lanes.
 struct LaneSet {
     int64_t width = 0;
