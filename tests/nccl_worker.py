@@ -6,6 +6,8 @@
 2. A synthetic bootstrap batch (device-drawn replicate columns, ragged over the ranks): the gathered results on every
    rank equal a single-GPU fit of the same columns bit for bit (the fit of a lane does not depend on its neighbours'
    rank), and LaneContext.fit_weights (host weights, the end-to-end path) agrees with it.
+3. Several batches in flight (LaneContext.fit_batches / fit_weight_batches, one handle and host thread per batch in
+   flight, gathers in batch order): every batch equals the same batch fitted alone, on every rank.
 Exit code 0 = all checks passed on this rank."""
 import gzip
 import json
@@ -78,6 +80,32 @@ try:
     print("rank %d/%d: sharded batch of %d lanes: own slice bitwise %s, all converged %s, ranks agree %s, fit_weights agrees %s" % (
         rank, world, n_lanes, same, conv, agree, e2e_same), flush=True)
     ok = ok and same and conv and agree and e2e_same
+    # ---- 3. several batches in flight on several handles (LaneContext.fit_batches / fit_weight_batches): gathers in batch
+    #         order on every rank, every batch equal to the same batch fitted alone
+    sizes = [32 * world + 1, 5, 48 * world, 16 * world + 2, 7 * world, 9]
+    col_sets = [ctx2.add_resampled(wl.n_obs, n, seed=300 + j) for j, n in enumerate(sizes)]
+    batches = [LaneBatch(c) for c in col_sets]
+    alone = [ctx2.fit_batch(b) for b in batches]
+    g0 = sharder.n_gathers
+    piped = ctx2.fit_batches(batches)
+    pipe_same = sharder.n_gathers - g0 == len(batches) and all(
+        np.array_equal(np.asarray(a[k]), np.asarray(b[k])) for a, b in zip(alone, piped) for k in ("theta", "loglike", "iters", "status"))
+    w_blocks = [sharder.my_slice(len(c)) for c in col_sets]
+    # this rank's weights of every batch, taken from the sharded context's own handle
+    eng2 = ctx2.engine()
+    w_locals = []
+    for c, (a, b) in zip(col_sets, w_blocks):
+        if b > a:
+            eng2.set_lanes_columns(ctx2._slots(eng2, np.asarray(c[a:b])))
+            w_locals.append(eng2.get_weights().astype(np.uint16))
+        else:
+            w_locals.append(np.zeros((wl.R, 0), dtype=np.uint16))
+    piped_w = ctx2.fit_weight_batches(w_locals, B=sizes)
+    pipe_w_same = all(np.abs(np.asarray(a["theta"]) - np.asarray(b["theta"])).max() < 1e-9 and
+                      np.abs(a["loglike"] - b["loglike"]).max() < 1e-6 and np.array_equal(a["status"], b["status"]) for a, b in zip(alone, piped_w))
+    print("rank %d/%d: %d batches pipelined over %d handles: equal to one at a time %s, from host weights %s" % (
+        rank, world, len(batches), 4, pipe_same, pipe_w_same), flush=True)
+    ok = ok and pipe_same and pipe_w_same
     ctx2.close()
     solo.close()
 finally:

@@ -303,6 +303,49 @@ def test_lane_context_concurrent_halves_on_gpu(gpu):
     assert max(abs(a.fun - b.fun) / abs(a.fun) for a, b in zip(*res)) < 1e-12
 
 
+def test_batches_in_flight_equal_batches_one_at_a_time(gpu):
+    """LaneContext.fit_batches / fit_weight_batches: several batches in flight on separate handles (own CUDA stream and
+    host thread each) give, batch for batch, bitwise the fits of the same batch alone; masks, constants, warm starts,
+    odd and tiny batches included."""
+    from traversome_b200 import synthetic
+    from traversome_b200.lanes import LaneBatch, LaneContext
+    wl = synthetic.make_workload(40, 2000, 0.2, seed=62)
+    ctx = LaneContext.from_csr(wl.V, wl.L, wl.row_ptr, wl.col, wl.val)
+    rng = np.random.default_rng(9)
+    sizes = [301, 64, 7, 500, 1, 130, 222, 33, 96]
+    batches, blocks = [], []
+    for j, n in enumerate(sizes):
+        cols = ctx.add_resampled(wl.n_obs, n, seed=70 + j)
+        mask = None
+        theta0 = None
+        if j % 3 == 1:                                          # subsets that keep every read path covered: drop one rare variant
+            mask = np.ones((wl.V, n), dtype=np.uint8)
+            theta0 = rng.random((wl.V, n))
+            theta0 /= theta0.sum(axis=0)
+        batches.append(LaneBatch(np.asarray(cols), C=rng.normal(size=n) if j % 2 else None, mask=mask, theta0=theta0))
+    alone = [ctx.fit_batch(b) for b in batches]
+    piped = ctx.fit_batches(batches)
+    assert ctx._engine2 is not None and len(ctx._engines_more) == 2            # four handles
+    for a, b in zip(alone, piped):
+        assert bool(ctx.lane_ok(a).all())
+        for k in ("theta", "loglike", "kkt", "iters", "status"):
+            assert np.array_equal(a[k], b[k]), k
+    eng = ctx.engine()
+    for b in batches[:5]:
+        eng.set_lanes_columns(ctx._slots(eng, b.cols))
+        blocks.append(eng.get_weights().astype(np.uint16))
+    got = ctx.fit_weight_batches(blocks, C=[b.C for b in batches[:5]])
+    for a, b, src in zip(alone, got, batches[:5]):
+        if src.theta0 is None:                                  # the same lanes from the same start: the same iterates
+            assert np.array_equal(a["theta"], b["theta"]) and np.array_equal(a["loglike"], b["loglike"])
+        else:
+            assert np.abs(a["theta"] - b["theta"]).max() < 1e-6 and np.all(np.abs(a["loglike"] - b["loglike"]) < 1e-9 * np.abs(a["loglike"]))
+    ctx.pipeline_depth = 2
+    again = ctx.fit_batches(batches[:3])
+    assert all(np.array_equal(a["theta"], b["theta"]) for a, b in zip(alone, again))
+    ctx.close()
+
+
 def test_weight_forms_and_the_column_store(gpu):
     """The lane weights live on the device as 16-bit counts when every count fits and as int32 otherwise; the column
     store (tvs_columns_*) registers a replicate's weight vector once and batches name it by slot.  All forms give the

@@ -37,3 +37,4 @@ def test_nccl_sharded_flow_and_gather(lib_built):
     assert out.returncode == 0, tail
     assert out.stdout.count("support table identical") == world, tail
     assert out.stdout.count("own slice bitwise True") == world, tail
+    assert out.stdout.count("equal to one at a time True, from host weights True") == world, tail

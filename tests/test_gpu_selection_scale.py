@@ -86,3 +86,24 @@ def test_lock_step_equals_serial_selection_with_more_than_20_candidates(gpu):
         assert abs(a[1] - b[1]) <= 1e-10 * abs(b[1]) and abs(a[2] - b[2]) <= 1e-10 * abs(b[2])
     ctx_a.close()
     ctx_b.close()
+
+
+def test_replicate_groups_select_the_same_models_as_one_group(gpu):
+    """run_selections(groups=2 / 3): the replicates advance on several host threads whose solver calls alternate; the
+    selected models, proportions and criteria are those of one lock-step group."""
+    wl = synthetic.make_workload(48, 2500, 0.15, seed=1005, n_true=12)
+    n_rep = 9
+    W = synthetic.bootstrap_weights(wl.n_obs, n_rep, seed=6, keep_lane0=True)
+    seeds = [200 + b for b in range(n_rep)]
+    ctx_a, fa = _fitters(wl, W, None, seeds)
+    one = bootstrap.run_selections(fa, criterion="BIC", random_size=20, groups=1)
+    for g in (2, 3):
+        ctx_b, fb = _fitters(wl, W, None, seeds)
+        many = bootstrap.run_selections(fb, criterion="BIC", random_size=20, groups=g)
+        assert ctx_b.n_batches > ctx_a.n_batches and ctx_b.n_lanes_fitted == ctx_a.n_lanes_fitted
+        for a, b in zip(one, many):
+            assert sorted(a[0]) == sorted(b[0])
+            assert all(abs(a[0][k] - b[0][k]) < 1e-7 for k in a[0])
+            assert abs(a[1] - b[1]) <= 1e-10 * abs(b[1]) and abs(a[2] - b[2]) <= 1e-10 * abs(b[2])
+        ctx_b.close()
+    ctx_a.close()
