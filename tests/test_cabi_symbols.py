@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def header_symbols():
     names = set()
-    for header in ("tvs.h", "tvs_subpaths.h", "tvs_pool.h"):
+    for header in ("tvs.h", "tvs_subpaths.h", "tvs_pool.h", "tvs_gaf.h"):
         src = open(os.path.join(ROOT, "include", header)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names |= set(re.findall(r"\b(tvs_[a-z0-9_]+)\s*\(", src))

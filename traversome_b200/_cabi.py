@@ -23,6 +23,8 @@ SYMBOLS = (
     "tvs_subpaths_count", "tvs_subpaths_fetch", "tvs_subpaths_destroy",
     # include/tvs_pool.h
     "tvs_pool_create", "tvs_pool_lanes", "tvs_pool_destroy",
+    # include/tvs_gaf.h (host code: alignment-file parser)
+    "tvs_gaf_parse", "tvs_gaf_parse_spa", "tvs_gaf_dims", "tvs_gaf_columns", "tvs_gaf_steps", "tvs_gaf_destroy",
 )
 
 TVS_OK, TVS_EINVAL, TVS_ECUDA, TVS_ENOMEM, TVS_ELIMIT, TVS_ESTATE = 0, -1, -2, -3, -4, -5
@@ -89,6 +91,12 @@ def load():
     lib.tvs_pool_create.argtypes = [POINTER(c_void_p), c_int, c_int64, c_int64] + [c_void_p] * 8
     lib.tvs_pool_lanes.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.tvs_pool_destroy.argtypes = [c_void_p]
+    lib.tvs_gaf_parse.argtypes = [c_char_p, c_int64, c_double, c_int, c_int, POINTER(c_void_p)]
+    lib.tvs_gaf_parse_spa.argtypes = [c_char_p, c_int64, c_int, POINTER(c_void_p)]
+    lib.tvs_gaf_dims.argtypes = [c_void_p] + [POINTER(c_int64)] * 6
+    lib.tvs_gaf_columns.argtypes = [c_void_p] + [c_void_p] * 17
+    lib.tvs_gaf_steps.argtypes = [c_void_p] + [c_void_p] * 6
+    lib.tvs_gaf_destroy.argtypes = [c_void_p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("tvs_last_error",):

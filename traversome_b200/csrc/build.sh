@@ -6,5 +6,5 @@ OUT="$HERE/../libtvs.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
     -Xcompiler -fPIC,-Wall,-Wno-unused-function -shared ${TVS_PTXAS_V:+-Xptxas -v} \
-    -o "$OUT" "$HERE/tvs_api.cu" "$HERE/tvs_subpaths.cu" "$HERE/tvs_pool.cu" -lcudart -lcublas -Xlinker -rpath=/usr/local/cuda/lib64
+    -o "$OUT" "$HERE/tvs_api.cu" "$HERE/tvs_subpaths.cu" "$HERE/tvs_pool.cu" "$HERE/tvs_gaf.cpp" -lcudart -lpthread -lcublas -Xlinker -rpath=/usr/local/cuda/lib64
 echo "built $OUT"

@@ -70,7 +70,7 @@ def _do_subsampling(self):
         self.variant_proportions_best = summary.variant_proportions_best
 
 
-def install(module=None, batch_bootstrap=True, read_paths=True, subpaths=True):
+def install(module=None, batch_bootstrap=True, read_paths=True, subpaths=True, parser=True):
     """Swap this package's classes into the reference's orchestrator module (default: ``traversome.traversome``,
     imported here).  Returns the module.  Idempotent."""
     if module is None:
@@ -93,6 +93,9 @@ def install(module=None, batch_bootstrap=True, read_paths=True, subpaths=True):
         trv_cls.generate_read_paths = _generate_read_paths                      # swap 3
     if batch_bootstrap:
         trv_cls.do_subsampling = _do_subsampling                                # swap 4
+    if parser and hasattr(module, "GraphAlignRecords"):
+        from . import gaf
+        gaf.install_on_records(module.GraphAlignRecords)                        # swap 5: alignment file -> raw_records
     return module
 
 
@@ -101,6 +104,8 @@ def uninstall():
     module = _SAVED.pop("module", None)
     if module is None:
         return
+    from . import gaf
+    gaf.uninstall_from_records()
     trv_cls = module.Traversome
     for name in ("ModelFitMaxLike", "VariantSubPathsGenerator"):
         if name in _SAVED.get("attrs", {}):
