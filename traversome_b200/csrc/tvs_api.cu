@@ -50,7 +50,7 @@ static void dev_free(T*& p) {
 
 static void free_csr(Csr& c) {
     dev_free(c.row_ptr); dev_free(c.ent); dev_free(c.chunk_row0); dev_free(c.ccol_ptr); dev_free(c.ccol_id);
-    dev_free(c.ccol_start); dev_free(c.cent); dev_free(c.invL); dev_free(c.Ld);
+    dev_free(c.ccol_start); dev_free(c.cent); dev_free(c.ent3); dev_free(c.cent3); dev_free(c.invL); dev_free(c.Ld);
     if (c.desc) { cudaFree(c.desc); c.desc = nullptr; }
     if (c.logtab) { cudaFree(c.logtab); c.logtab = nullptr; }
     dev_free(c.slab_ptr); dev_free(c.h_row); dev_free(c.h_val); dev_free(c.h_slot);
@@ -143,6 +143,7 @@ static int plan_v3(const tvs_problem* h, int64_t B, PassPlan* out) {
     const int LT = 32 * K;
     const Csr& c = h->csr;
     if (B % K != 0 || c.rows_per_chunk < NW) return TVS_ELIMIT;
+    if (!c.ent3_ok) return TVS_ELIMIT;                 // a count that is not exact in 16 bits of an fp64: pass2_kernel
     const Pass3Smem L = pass3_layout((int)c.V, LT, c.rows_per_chunk, std::max(c.max_chunk_nnz, 1), BW, NW);
     if (L.total > 225 * 1024) return TVS_ELIMIT;
     auto kern = pass3_kernel<K, NW, BW>;
@@ -548,7 +549,7 @@ static PassArgs base_args(const tvs_problem* h) {
     PassArgs a{};
     const Csr& c = h->csr;
     a.row_ptr = c.row_ptr; a.ent = c.ent; a.chunk_row0 = c.chunk_row0; a.ccol_ptr = c.ccol_ptr; a.ccol_id = c.ccol_id;
-    a.ccol_start = c.ccol_start; a.cent = c.cent; a.w = h->lanes.w; a.w16 = h->lanes.has16 ? h->lanes.w16 : nullptr; a.B = h->lanes.B; a.V = (int)c.V;
+    a.ccol_start = c.ccol_start; a.cent = c.cent; a.ent3 = c.ent3; a.cent3 = c.cent3; a.w = h->lanes.w; a.w16 = h->lanes.has16 ? h->lanes.w16 : nullptr; a.B = h->lanes.B; a.V = (int)c.V;
     a.n_chunks = c.n_chunks; a.rows_per_chunk = c.rows_per_chunk;
     a.stage_cap = std::max(c.max_chunk_nnz, 1);
     a.desc = (const ChunkDesc*)c.desc; a.logc = make_log_coef();
@@ -671,15 +672,22 @@ int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, c
 
     Csr& c = h->csr;
     c.R = R; c.V = V; c.nnz = nnz;
-    // rows per chunk: 80 when the widest staged kernel (4 lanes per thread, 16 warps) still fits shared memory with it
-    // (cfg2: 139.6 us per full-width pass against 143.7 us with 64; 96 no longer fits and falls back to 2 lanes per
-    // thread, 166 us), else 64
+    // rows per chunk (a multiple of the 16 warps, so that every warp owns the same number of rows: 136 rows cost 131 us
+    // per full-width cfg2 pass where 144 cost 121): the largest of 160, 144, ... 96 that the widest staged kernel
+    // (4 lanes per thread, 16 warps) holds in shared memory while the matrix still has >= 96 chunks to split over CTAs
+    // (cfg2, V = 64 with the t accumulators in registers: 144 -- 80 rows 139.8 us, 112 131.6, 144 127.5 before the other
+    // changes of the round); else 80 when that fits, else 64
     int rpc = env_int("TVS_RC", 0);
     if (rpc <= 0) {
+        auto fits = [&](int rows) {
+            int64_t cap = 1;
+            for (int64_t r0 = 0; r0 < R; r0 += rows) cap = std::max<int64_t>(cap, row_ptr[std::min<int64_t>(R, r0 + rows)] - row_ptr[r0]);
+            return pass3_layout((int)V, 128, rows, (int)cap, true, 16).total <= 225 * 1024;
+        };
         rpc = 64;
-        int64_t cap80 = 1;
-        for (int64_t r0 = 0; r0 < R; r0 += 80) cap80 = std::max<int64_t>(cap80, row_ptr[std::min<int64_t>(R, r0 + 80)] - row_ptr[r0]);
-        if (pass3_layout((int)V, 128, 80, (int)cap80, true, 16).total <= 225 * 1024) rpc = 80;
+        if (fits(80)) rpc = 80;
+        for (int cand = 160; cand >= 96; cand -= 16)
+            if (R / cand >= 96 && fits(cand)) { rpc = cand; break; }
     }
     rpc = std::max(kWarps2, std::min(rpc, 4096));
     c.rows_per_chunk = rpc;
@@ -750,6 +758,23 @@ int tvs_create(tvs_handle* out, int device, int64_t R, int64_t V, int64_t nnz, c
         c.desc = dd;
         if (cudaMemcpy(dd, descv.data(), descv.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice) != cudaSuccess)
             return fail(cuda_fail(cudaGetLastError(), "upload desc", __FILE__, __LINE__));
+    }
+    {   // pass3_kernel's entries: the count as the top 16 bits of its fp64 form (rebuilt without an fp64 instruction)
+        auto hi16 = [](uint32_t v, bool* ok) {
+            const double d = (double)v;
+            uint64_t bits;
+            memcpy(&bits, &d, 8);
+            if (bits & 0x0000ffffffffffffull) *ok = false;
+            return (uint32_t)(bits >> 48);
+        };
+        bool ok = true;
+        std::vector<uint32_t> ent3(ent.size()), cent3(cent.size());
+        for (size_t k = 0; k < (size_t)nnz; ++k) {
+            ent3[k] = (ent[k] & 0xffffu) | (hi16(ent[k] >> 16, &ok) << 16);
+            cent3[k] = (cent[k] & 0xffffu) | (hi16(cent[k] >> 16, &ok) << 16);
+        }
+        c.ent3_ok = ok;
+        UP_(ent3, ent3, uint32_t) UP_(cent3, cent3, uint32_t)
     }
     UP_(ent, ent, uint32_t) UP_(cent, cent, uint32_t) UP_(chunk_row0, chunk_row0, int32_t) UP_(ccol_ptr, ccol_ptr, int32_t)
     if (ccol_id.empty()) ccol_id.push_back(0);

@@ -35,6 +35,9 @@ struct Csr {
     int32_t*  ccol_id = nullptr;     // [n_ccol] column id of each non-empty (chunk, column)
     int32_t*  ccol_start = nullptr;  // [n_ccol+1] -> index into cent
     uint32_t* cent = nullptr;        // [nnz]  local_row | val<<16, column-major within chunk
+    uint32_t* ent3 = nullptr;        // [nnz]  col | (top 16 bits of the fp64 count) << 16: pass3_kernel's form (no conversion per entry)
+    uint32_t* cent3 = nullptr;       // [nnz]  the same for the column-major entries
+    bool      ent3_ok = false;       // every count is exact in 16 bits of an fp64 (1..32, even numbers to 64, ...)
     int       max_chunk_nnz = 0;     // largest number of entries in one chunk
     void*     desc = nullptr;        // [n_chunks] ChunkDesc (tvs_kernels.cuh)
     void*     logtab = nullptr;      // [128] double2 {c_i, -log c_i} (table_log_pos)

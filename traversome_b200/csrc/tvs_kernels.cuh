@@ -38,6 +38,7 @@ struct PassArgs {
     double* cr;          // optional [R*B]: w / p^2 per (row, lane) for the Newton phase's Hessian (pass3_kernel only)
     float* crf;          // the same in fp32 (wide lane sets: hess_wide_kernel)
     const double2* logtab;   // [128] {c_i, -log c_i} for table_log_pos, or null (atanh series)
+    const uint32_t* ent3; const uint32_t* cent3;   // entries with the count as the top 16 bits of its fp64 form (pass3_kernel)
 };
 
 template <int LPT, bool XS, bool BACKWARD>

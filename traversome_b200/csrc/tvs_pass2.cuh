@@ -134,6 +134,22 @@ __device__ __forceinline__ int lane_slot(int l) {               // position of t
     return l;
 }
 
+// entry decode of pass3_kernel: the count travels as the top 16 bits of its fp64 form (Csr::ent3 / cent3), so it is rebuilt
+// with one LOP3 and no fp64 instruction; operand address = the thread's base + index * row bytes.
+__device__ __forceinline__ double ent_count(unsigned e) { return __hiloint2double((int)(e & 0xffff0000u), 0); }
+template <int K>
+__device__ __forceinline__ void lds_lanes_at(const double* tbase, unsigned e, double* out) {   // tbase = tile + this thread's slot
+    constexpr int LT = 32 * K;
+    const char* row = reinterpret_cast<const char*>(tbase) + (e & 0xffffu) * (unsigned)(LT * 8);
+    if (K == 1) out[0] = *reinterpret_cast<const double*>(row);
+    else if (K == 2) { const double2 a = *reinterpret_cast<const double2*>(row); out[0] = a.x; out[1] = a.y; }
+    else {
+        const double2 a = *reinterpret_cast<const double2*>(row);
+        const double2 b = *reinterpret_cast<const double2*>(row + 512);
+        out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+    }
+}
+
 template <int K> struct WVec;
 template <> struct WVec<1> { int v[1]; };
 template <> struct __align__(8) WVec<2> { int v[2]; };
@@ -151,6 +167,33 @@ __device__ __forceinline__ WVec<K> load_w(const PassArgs& a, int64_t idx) {
             o.v[0] = (int)(u.x & 0xffffu); o.v[1 % K] = (int)(u.x >> 16); o.v[2 % K] = (int)(u.y & 0xffffu); o.v[3 % K] = (int)(u.y >> 16);
         }
     } else o = *reinterpret_cast<const WVec<K>*>(a.w + idx);
+    return o;
+}
+
+// The same in two steps, so that a load issued one row ahead is not waited for before the row it belongs to: the RAW
+// words travel across the loop trip and are unpacked where the weights are used.  (With the unpacking inside the load the
+// warp stalled on its own prefetch: 17 % of the stall samples of the pass, profiles/r2_pass3_full.csv.)
+template <int K>
+__device__ __forceinline__ WVec<K> load_w_raw(const PassArgs& a, int64_t idx) {
+    WVec<K> o;
+#pragma unroll
+    for (int j = 0; j < K; ++j) o.v[j] = 0;
+    if (a.w16 != nullptr) {
+        if (K == 1) o.v[0] = a.w16[idx];
+        else if (K == 2) o.v[0] = (int)*reinterpret_cast<const unsigned*>(a.w16 + idx);
+        else { const uint2 u = *reinterpret_cast<const uint2*>(a.w16 + idx); o.v[0] = (int)u.x; o.v[1 % K] = (int)u.y; }
+    } else o = *reinterpret_cast<const WVec<K>*>(a.w + idx);
+    return o;
+}
+template <int K>
+__device__ __forceinline__ WVec<K> unpack_w(const WVec<K>& raw, bool is16) {
+    if (!is16 || K == 1) return raw;
+    WVec<K> o;
+    if (K == 2) { const unsigned u = (unsigned)raw.v[0]; o.v[0] = (int)(u & 0xffffu); o.v[K - 1] = (int)(u >> 16); }
+    else {
+        const unsigned ux = (unsigned)raw.v[0], uy = (unsigned)raw.v[1 % K];
+        o.v[0] = (int)(ux & 0xffffu); o.v[1 % K] = (int)(ux >> 16); o.v[2 % K] = (int)(uy & 0xffffu); o.v[3 % K] = (int)(uy >> 16);
+    }
     return o;
 }
 
@@ -330,11 +373,14 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 struct Pass3Smem {            // byte offsets from the start of dynamic shared memory
     size_t x, t, rr, c1, c2, rp, cs, cid, tab, total;
 };
+// t accumulators in REGISTERS when every warp can own at most 4 columns for the whole launch (wi, wi + NW, wi + 2 NW,
+// wi + 3 NW): no t tile in shared memory, so a chunk can hold 144 rows instead of 80 at V = 64, 4 lanes per thread
+__host__ __device__ inline bool pass3_treg(int V, int nw) { return V <= 4 * nw; }
 __host__ __device__ inline Pass3Smem pass3_layout(int V, int LT, int RC, int cap, bool backward, int nw) {
     Pass3Smem L;
     size_t o = 0;
     L.x = o; o += (size_t)V * LT * 8;
-    L.t = o; o += backward ? (size_t)V * LT * 8 : 0;
+    L.t = o; o += (backward && !pass3_treg(V, nw)) ? (size_t)V * LT * 8 : 0;
     L.rr = o; o += (size_t)(RC > nw ? RC : nw) * LT * 8;
     L.c1 = o; o += (size_t)2 * cap * 4;
     L.c2 = o; o += backward ? (size_t)cap * 4 : 0;
@@ -370,6 +416,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
     }
 
     const Pass3Smem L = pass3_layout(V, LT, RC, cap, BACKWARD, NW);
+    const bool treg = BACKWARD && pass3_treg(V, NW);
     double* x_s = reinterpret_cast<double*>(smem3 + L.x);
     double* t_s = reinterpret_cast<double*>(smem3 + L.t);
     double* rr_s = reinterpret_cast<double*>(smem3 + L.rr);
@@ -379,6 +426,9 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
     int* cs_s = reinterpret_cast<int*>(smem3 + L.cs);
     int* cid_s = reinterpret_cast<int*>(smem3 + L.cid);
     double2* tab_s = reinterpret_cast<double2*>(smem3 + L.tab);
+    const double* x_t = x_s + (K == 1 ? t : 2 * t);      // this thread's slot inside an operand row (lds_lanes_at)
+    const double* rr_t = rr_s + (K == 1 ? t : 2 * t);
+    const bool is16 = a.w16 != nullptr;
     const bool use_tab = a.logtab != nullptr;
     if (use_tab)
         for (int i = threadIdx.x; i < 128; i += NT) tab_s[i] = a.logtab[i];
@@ -386,14 +436,14 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
     // row-major entries + row pointers of a chunk -> buffer `buf`
     auto stage_rows = [&](const ChunkDesc& d, int buf) {
         for (int i = threadIdx.x; i < d.nent; i += NT) {
-            cp_async4(c1_s + (size_t)buf * cap + i, a.ent + d.e0 + i);
+            cp_async4(c1_s + (size_t)buf * cap + i, a.ent3 + d.e0 + i);
         }
         for (int i = threadIdx.x; i <= d.nrows; i += NT) cp_async4(rp_s + buf * (RC + 1) + i, a.row_ptr + d.row0 + i);
     };
     // column-major entries + column starts / ids of a chunk
     auto stage_cols = [&](const ChunkDesc& d) {
         for (int i = threadIdx.x; i < d.ncent; i += NT) {
-            cp_async4(c2_s + i, a.cent + d.ce0 + i);
+            cp_async4(c2_s + i, a.cent3 + d.ce0 + i);
         }
         for (int i = threadIdx.x; i <= d.ncol; i += NT) cp_async4(cs_s + i, a.ccol_start + d.c0 + i);
         for (int i = threadIdx.x; i < d.ncol; i += NT) cp_async4(cid_s + i, a.ccol_id + d.c0 + i);
@@ -419,12 +469,17 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
         const int64_t b = lane0 + l;
         const bool live = b < B && (a.done == nullptr || a.done[b] == 0);
         x_s[v * LT + lane_slot<K>(l)] = live ? a.x[(int64_t)v * B + b] : 1.0;
-        if (BACKWARD) t_s[i] = 0.0;
+        if (BACKWARD && !treg) t_s[i] = 0.0;
     }
 
     double ll[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) ll[j] = 0.0;
+    double tacc[4][K];                                     // treg: t of this warp's columns, in registers for the whole launch
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < K; ++j) tacc[q][j] = 0.0;
 
     for (; c < a.n_chunks; c += S, buf ^= 1) {
         const ChunkDesc nx2 = load_desc(c + 2 * S);        // consumed two trips from now
@@ -438,47 +493,46 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
         const uint32_t* c1 = c1_s + (size_t)buf * cap;
         const int* rp = rp_s + buf * (RC + 1);
         const int e0 = rp[0];
-        WVec<K> wnext;
+        WVec<K> wnext;                                     // RAW words of the next row's weights (load_w_raw)
+#pragma unroll
+        for (int j = 0; j < K; ++j) wnext.v[j] = 0;
         {
             const int r = row0 + wi;
-            if (lv && r < row1) wnext = load_w<K>(a, (int64_t)r * B + mylane);
-            else {
-#pragma unroll
-                for (int j = 0; j < K; ++j) wnext.v[j] = 0;
-            }
+            if (lv && r < row1) wnext = load_w_raw<K>(a, (int64_t)r * B + mylane);
         }
         for (int r = row0 + wi; r < row1; r += NW) {
-            const WVec<K> wv = wnext;
-            if (lv && r + NW < row1) wnext = load_w<K>(a, (int64_t)(r + NW) * B + mylane);
+            const WVec<K> wraw = wnext;
+            if (lv && r + NW < row1) wnext = load_w_raw<K>(a, (int64_t)(r + NW) * B + mylane);
             const int k0 = rp[r - row0] - e0, k1 = rp[r - row0 + 1] - e0;
             double p[K];
 #pragma unroll
             for (int j = 0; j < K; ++j) p[j] = 0.0;
 #pragma unroll 4
             for (int k = k0; k < k1; ++k) {
-                const unsigned e = c1[k];                            // column | count << 16
-                const double f = u31_to_double((int)(e >> 16));
-                const int cidx = (int)(e & 0xffffu);
+                const unsigned e = c1[k];                            // column | top 16 bits of the fp64 count << 16
+                const double f = ent_count(e);
                 double xv[K];
-                lds_lanes<K>(x_s + cidx * LT, t, xv);
+                lds_lanes_at<K>(x_t, e, xv);
 #pragma unroll
                 for (int j = 0; j < K; ++j) p[j] = fma(f, xv[j], p[j]);
             }
             bool fast = true;
 #pragma unroll
             for (int j = 0; j < K; ++j) fast = fast && is_pos_normal(p[j]);
+            const WVec<K> wv = unpack_w<K>(wraw, is16);
             double rr[K];
             double c2[K];                                  // w / p^2 (Newton phase only)
             if (fast) {
+                // p is finite, normal and positive here, so 1/p and log p are finite: a zero weight gives rr = +0 and leaves
+                // ll unchanged without a select (weights are validated w >= 0 at upload; max() guards anyway)
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
-                    const bool on = wv.v[j] > 0;
-                    const double wd = u31_to_double(on ? wv.v[j] : 0);
+                    const double wd = u31_to_double(max(wv.v[j], 0));
                     const double rcp = fast_rcp(p[j]);
-                    rr[j] = on ? wd * rcp : 0.0;
+                    rr[j] = wd * rcp;
                     c2[j] = rr[j] * rcp;
                     const double lg = use_tab ? table_log_pos(p[j], tab_s, a.logc) : fast_log_pos(p[j], a.logc);
-                    ll[j] = on ? fma(wd, lg, ll[j]) : ll[j];
+                    ll[j] = fma(wd, lg, ll[j]);
                 }
             } else {
 #pragma unroll
@@ -513,22 +567,44 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
             // ------------ phase 2: t += A^T rr over the non-empty columns of the chunk
             const int ncol = cur.ncol;
             const int ce0 = cs_s[0];
-            for (int ci = wi; ci < ncol; ci += NW) {
-                const int v = cid_s[ci];
-                const int k0 = cs_s[ci] - ce0, k1 = cs_s[ci + 1] - ce0;
-                double acc[K];
-                lds_lanes<K>(t_s + v * LT, t, acc);
-#pragma unroll 4
-                for (int k = k0; k < k1; ++k) {
-                    const unsigned e = c2_s[k];                      // chunk-local row | count << 16
-                    const double f = u31_to_double((int)(e >> 16));
-                    const int ridx = (int)(e & 0xffffu);
-                    double rv[K];
-                    lds_lanes<K>(rr_s + ridx * LT, t, rv);
+            if (treg) {
 #pragma unroll
-                    for (int j = 0; j < K; ++j) acc[j] = fma(f, rv[j], acc[j]);
+                for (int q = 0; q < 4; ++q) {
+                    const int v = wi + NW * q;
+                    if (v < V && ncol > 0) {
+                        int ci = min(v, ncol - 1);                  // the chunk lists its non-empty columns in ascending order
+                        while (ci > 0 && cid_s[ci] > v) --ci;
+                        if (cid_s[ci] == v) {
+                            const int k0 = cs_s[ci] - ce0, k1 = cs_s[ci + 1] - ce0;
+#pragma unroll 4
+                            for (int k = k0; k < k1; ++k) {
+                                const unsigned e = c2_s[k];              // chunk-local row | top 16 bits of the fp64 count << 16
+                                const double f = ent_count(e);
+                                double rv[K];
+                                lds_lanes_at<K>(rr_t, e, rv);
+#pragma unroll
+                                for (int j = 0; j < K; ++j) tacc[q][j] = fma(f, rv[j], tacc[q][j]);
+                            }
+                        }
+                    }
                 }
-                sts_lanes<K>(t_s + v * LT, t, acc);
+            } else {
+                for (int ci = wi; ci < ncol; ci += NW) {
+                    const int v = cid_s[ci];
+                    const int k0 = cs_s[ci] - ce0, k1 = cs_s[ci + 1] - ce0;
+                    double acc[K];
+                    lds_lanes<K>(t_s + v * LT, t, acc);
+#pragma unroll 4
+                    for (int k = k0; k < k1; ++k) {
+                        const unsigned e = c2_s[k];
+                        const double f = ent_count(e);
+                        double rv[K];
+                        lds_lanes_at<K>(rr_t, e, rv);
+#pragma unroll
+                        for (int j = 0; j < K; ++j) acc[j] = fma(f, rv[j], acc[j]);
+                    }
+                    sts_lanes<K>(t_s + v * LT, t, acc);
+                }
             }
         }
         cur = nxt; nxt = nx2;
@@ -537,7 +613,21 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
     __syncthreads();
 
     // ---------------- epilogue
-    if (BACKWARD) {
+    if (BACKWARD && treg) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int v = wi + NW * q;
+            if (v < V && lv) {
+                double* dst = a.tpart + ((int64_t)split * V + v) * B + mylane;
+                if (K == 1) dst[0] = tacc[q][0];
+                else if (K == 2) *reinterpret_cast<double2*>(dst) = make_double2(tacc[q][0], tacc[q][1]);
+                else {
+                    reinterpret_cast<double2*>(dst)[0] = make_double2(tacc[q][0], tacc[q][1]);
+                    reinterpret_cast<double2*>(dst)[1] = make_double2(tacc[q][2], tacc[q][3]);
+                }
+            }
+        }
+    } else if (BACKWARD) {
         for (int i = threadIdx.x; i < V * LT; i += NT) {
             const int v = i / LT, l = i - v * LT;
             const int64_t b = lane0 + l;
