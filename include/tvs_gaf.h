@@ -71,6 +71,12 @@ int tvs_gaf_columns(tvs_gaf_handle t, int64_t* line_no, int64_t* query_len, int6
 int tvs_gaf_steps(tvs_gaf_handle t, char* names, int8_t* step_forward, int64_t* seg_ptr, char* segs, int64_t* extra,
                   char* cigars);
 
+/* Distinct segment names of the path steps, numbered in order of first appearance in the file (a graph has far fewer
+ * segments than the file has steps): counts first, then step_segment[n_steps] (the id of every step), dseg_ptr[n_distinct + 1]
+ * into dsegs[distinct_bytes].  tvs_gaf_segment_ids before tvs_gaf_segments is TVS_ESTATE. */
+int tvs_gaf_segments(tvs_gaf_handle t, int64_t* n_distinct, int64_t* distinct_bytes);
+int tvs_gaf_segment_ids(tvs_gaf_handle t, int64_t* step_segment, int64_t* dseg_ptr, char* dsegs);
+
 int tvs_gaf_destroy(tvs_gaf_handle t);
 
 #ifdef __cplusplus

@@ -2,7 +2,7 @@
 """Developer tool (GPU box): compare builds of libtvs.so made by tools/build_variant.sh.  For every name given, the variant
 is copied over traversome_b200/libtvs.so and a child process fits cfg2 (1,000 lanes; median of 7 fits, per-pass times of
 one more fit) and, with `--cfg3`, a 2,048-lane fit of the cfg3 matrix; prints fit time, full-width pass time and a hash of
-theta (bitwise guard).  usage: python tools/variant_probe.py [--cfg3] base W2 ..."""
+theta (bitwise guard).  usage: python tools/variant_probe.py [--cfg3] [--cfg4] [--only] base W2 ..."""
 import hashlib, json, os, re, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -27,10 +27,12 @@ if os.environ.get("_INNER") == "1":
     sys.exit(0)
 args = sys.argv[1:]
 cfg3 = "--cfg3" in args
+cfg4 = "--cfg4" in args
+only = "--only" in args          # skip cfg2
 names = [a for a in args if not a.startswith("--")]
 for name in names:
     shutil.copy(os.path.join(ROOT, "build", "variants", "libtvs_%s.so" % name), os.path.join(ROOT, "traversome_b200", "libtvs.so"))
-    for which, B, reps in [("cfg2", 1000, 7)] + ([("cfg3", 2048, 3)] if cfg3 else []):
+    for which, B, reps in ([] if only else [("cfg2", 1000, 7)]) + ([("cfg3", 2048, 3)] if cfg3 else []) + ([("cfg4", 1248, 1)] if cfg4 else []):
         env = dict(os.environ, _INNER="1", TVS_DUMP_PASSES="1", _REPS=str(reps))
         r = subprocess.run([sys.executable, __file__, which, str(B)], env=env, capture_output=True, text=True)
         txt = r.stdout + r.stderr

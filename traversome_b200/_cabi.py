@@ -24,7 +24,8 @@ SYMBOLS = (
     # include/tvs_pool.h
     "tvs_pool_create", "tvs_pool_lanes", "tvs_pool_destroy",
     # include/tvs_gaf.h (host code: alignment-file parser)
-    "tvs_gaf_parse", "tvs_gaf_parse_spa", "tvs_gaf_dims", "tvs_gaf_columns", "tvs_gaf_steps", "tvs_gaf_destroy",
+    "tvs_gaf_parse", "tvs_gaf_parse_spa", "tvs_gaf_dims", "tvs_gaf_columns", "tvs_gaf_steps", "tvs_gaf_segments", "tvs_gaf_segment_ids",
+    "tvs_gaf_destroy",
 )
 
 TVS_OK, TVS_EINVAL, TVS_ECUDA, TVS_ENOMEM, TVS_ELIMIT, TVS_ESTATE = 0, -1, -2, -3, -4, -5
@@ -96,6 +97,8 @@ def load():
     lib.tvs_gaf_dims.argtypes = [c_void_p] + [POINTER(c_int64)] * 6
     lib.tvs_gaf_columns.argtypes = [c_void_p] + [c_void_p] * 17
     lib.tvs_gaf_steps.argtypes = [c_void_p] + [c_void_p] * 6
+    lib.tvs_gaf_segments.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64)]
+    lib.tvs_gaf_segment_ids.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
     lib.tvs_gaf_destroy.argtypes = [c_void_p]
     for name in SYMBOLS:
         fn = getattr(lib, name)

@@ -14,6 +14,8 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <unordered_map>
+#include <string_view>
 
 #include "../../include/tvs_gaf.h"
 #include "tvs_internal.h"
@@ -264,6 +266,10 @@ struct tvs_gaf_table {
     std::vector<double> identity;
     std::vector<int64_t> step_ptr, name_ptr, cigar_ptr, seg_ptr, extra;
     std::string names, segs, cigars;
+    // distinct segment names in order of first appearance (built on first use by tvs_gaf_segments)
+    bool interned = false;
+    std::vector<int64_t> step_segment, dseg_ptr;
+    std::string dsegs;
 };
 
 namespace {
@@ -392,6 +398,47 @@ int tvs_gaf_steps(tvs_gaf_handle t, char* names, int8_t* step_forward, int64_t* 
     copy_out(step_forward, t->step_fw); copy_out(seg_ptr, t->seg_ptr); copy_out(extra, t->extra);
     if (segs && !t->segs.empty()) memcpy(segs, t->segs.data(), t->segs.size());
     if (cigars && !t->cigars.empty()) memcpy(cigars, t->cigars.data(), t->cigars.size());
+    return TVS_OK;
+}
+
+static void intern_segments(tvs_gaf_table* t) {
+    if (t->interned) return;
+    std::unordered_map<std::string_view, int64_t> ids;
+    ids.reserve(1024);
+    t->step_segment.resize((size_t)t->n_steps);
+    t->dseg_ptr.assign(1, 0);
+    const char* base = t->segs.data();
+    for (int64_t i = 0; i < t->n_steps; ++i) {
+        const std::string_view key(base + t->seg_ptr[(size_t)i], (size_t)(t->seg_ptr[(size_t)i + 1] - t->seg_ptr[(size_t)i]));
+        auto it = ids.find(key);
+        if (it == ids.end()) {
+            it = ids.emplace(key, (int64_t)ids.size()).first;
+            t->dsegs.append(key.data(), key.size());
+            t->dseg_ptr.push_back((int64_t)t->dsegs.size());
+        }
+        t->step_segment[(size_t)i] = it->second;
+    }
+    t->interned = true;
+}
+
+int tvs_gaf_segments(tvs_gaf_handle t, int64_t* n_distinct, int64_t* distinct_bytes) {
+    if (!t) { tvs::set_error("tvs_gaf_segments: null handle"); return TVS_EINVAL; }
+    try {
+        intern_segments(t);
+    } catch (const std::bad_alloc&) {
+        tvs::set_error("tvs_gaf_segments: out of host memory");
+        return TVS_ENOMEM;
+    }
+    if (n_distinct) *n_distinct = (int64_t)t->dseg_ptr.size() - 1;
+    if (distinct_bytes) *distinct_bytes = (int64_t)t->dsegs.size();
+    return TVS_OK;
+}
+
+int tvs_gaf_segment_ids(tvs_gaf_handle t, int64_t* step_segment, int64_t* dseg_ptr, char* dsegs) {
+    if (!t) { tvs::set_error("tvs_gaf_segment_ids: null handle"); return TVS_EINVAL; }
+    if (!t->interned) { tvs::set_error("tvs_gaf_segment_ids: call tvs_gaf_segments first"); return TVS_ESTATE; }
+    copy_out(step_segment, t->step_segment); copy_out(dseg_ptr, t->dseg_ptr);
+    if (dsegs && !t->dsegs.empty()) memcpy(dsegs, t->dsegs.data(), t->dsegs.size());
     return TVS_OK;
 }
 

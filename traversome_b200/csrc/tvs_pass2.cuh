@@ -464,12 +464,18 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
     stage_rows(cur, 0);
     cp_async_commit();
 
-    for (int i = threadIdx.x; i < V * LT; i += NT) {
-        const int v = i / LT, l = i - v * LT;
+    {   // x tile: NT is a multiple of LT, so a thread always fills the same lane of the tile (one liveness test per thread)
+        static_assert(NT % LT == 0, "threads per CTA must be a multiple of the lane tile");
+        const int l = threadIdx.x % LT;
         const int64_t b = lane0 + l;
         const bool live = b < B && (a.done == nullptr || a.done[b] == 0);
-        x_s[v * LT + lane_slot<K>(l)] = live ? a.x[(int64_t)v * B + b] : 1.0;
-        if (BACKWARD && !treg) t_s[i] = 0.0;
+        const int slot = lane_slot<K>(l);
+        const double* src = a.x + (live ? b : 0);
+#pragma unroll 4
+        for (int v = threadIdx.x / LT; v < V; v += NT / LT) {
+            x_s[v * LT + slot] = live ? src[(int64_t)v * B] : 1.0;
+            if (BACKWARD && !treg) t_s[v * LT + l] = 0.0;
+        }
     }
 
     double ll[K];

@@ -12,6 +12,7 @@ pools) and the record objects are made from the columns; the arrays themselves (
 follow (``build_read_records``, ``filter_read_records``, :920-1022) are the reference's and see the same objects.
 """
 import ctypes
+import gc
 import gzip
 import re
 
@@ -108,29 +109,24 @@ class GafTable(object):
             self.p_align_len = self.p_end - self.p_start
             names = np.empty(max(name_bytes, 1), dtype=np.uint8)
             step_fw = np.empty(n_steps, dtype=np.int8)
-            seg_ptr = np.empty(n_steps + 1, dtype=np.int64)
-            segs = np.empty(max(seg_bytes, 1), dtype=np.uint8)
             self.step_extra = np.empty(n_steps, dtype=np.int64)
             cigars = np.empty(max(cigar_bytes, 1), dtype=np.uint8)
-            _cabi._check(lib.tvs_gaf_steps(h, p(names), p(step_fw), p(seg_ptr), p(segs), p(self.step_extra), p(cigars)))
+            _cabi._check(lib.tvs_gaf_steps(h, p(names), p(step_fw), None, None, p(self.step_extra), p(cigars)))
+            # distinct segment names -> ids, numbered in order of first appearance (a graph has far fewer segments than the
+            # file has steps)
+            n_seg, dbytes = ctypes.c_int64(), ctypes.c_int64()
+            _cabi._check(lib.tvs_gaf_segments(h, ctypes.byref(n_seg), ctypes.byref(dbytes)))
+            self.step_segment = np.empty(n_steps, dtype=np.int64)
+            dptr = np.empty(n_seg.value + 1, dtype=np.int64)
+            dsegs = np.empty(max(dbytes.value, 1), dtype=np.uint8)
+            _cabi._check(lib.tvs_gaf_segment_ids(h, p(self.step_segment), p(dptr), p(dsegs)))
         finally:
             lib.tvs_gaf_destroy(h)
         self._names = names[:name_bytes].tobytes()
         self._cigars = cigars[:cigar_bytes].tobytes()
         self.step_forward = step_fw.astype(bool)
-        # distinct segment names -> ids (a graph has far fewer segments than the file has steps)
-        seg_bytes_all = segs[:seg_bytes].tobytes()
-        ptr = seg_ptr.tolist()
-        ids, names_list, step_segment = {}, [], np.empty(n_steps, dtype=np.int64)
-        for i in range(n_steps):
-            key = seg_bytes_all[ptr[i]:ptr[i + 1]]
-            j = ids.get(key)
-            if j is None:
-                j = ids[key] = len(names_list)
-                names_list.append(key.decode())
-            step_segment[i] = j
-        self.segment_names = names_list
-        self.step_segment = step_segment
+        raw, dp = dsegs[:dbytes.value].tobytes(), dptr.tolist()
+        self.segment_names = [raw[dp[i]:dp[i + 1]].decode() for i in range(n_seg.value)]
 
     @classmethod
     def from_file(cls, path, alignment_format="GAF", **kw):
@@ -148,41 +144,57 @@ class GafTable(object):
     def query_names(self):
         ptr = self._name_ptr.tolist()
         raw = self._names
-        return [raw[ptr[i]:ptr[i + 1]].decode() for i in range(self.n_records)]
+        if raw.isascii():                       # one decode for the whole pool, then string slices
+            txt = raw.decode("ascii")
+            return [txt[a:b] for a, b in zip(ptr, ptr[1:])]
+        return [raw[a:b].decode() for a, b in zip(ptr, ptr[1:])]
 
     def paths(self):
         """Per record the path as the reference's tuple of (segment name, forward) pairs; equal steps share one tuple."""
-        names, seg, fw = self.segment_names, self.step_segment.tolist(), self.step_forward.tolist()
-        pair = {}
-        steps = []
-        for s, f in zip(seg, fw):
-            k = (s, f)
-            t = pair.get(k)
-            if t is None:
-                t = pair[k] = (names[s], f)
-            steps.append(t)
+        n_seg = len(self.segment_names)
+        pair = [(name, False) for name in self.segment_names] + [(name, True) for name in self.segment_names]
+        code = (self.step_segment + n_seg * self.step_forward.astype(np.int64)).tolist()
+        steps = list(map(pair.__getitem__, code))
         ptr = self.step_ptr.tolist()
-        return [tuple(steps[ptr[i]:ptr[i + 1]]) for i in range(self.n_records)]
+        return [tuple(steps[a:b]) for a, b in zip(ptr, ptr[1:])]
 
     def records(self, parse_cigar=False):
-        """The reference's ``raw_records``: a list of record objects in file order."""
+        """The reference's ``raw_records``: a list of record objects in file order.  The cyclic garbage collector is paused
+        while the objects are made (none of them can be garbage; with it running, its generation scans are 60 % of the time
+        at 300k records)."""
+        was_on = gc.isenabled()
+        gc.disable()
+        try:
+            return self._records(parse_cigar)
+        finally:
+            if was_on:
+                gc.enable()
+
+    def _records(self, parse_cigar):
         n = self.n_records
         names, paths = self.query_names(), self.paths()
         if self.alignment_format == "GAF":
             text = self._text
             tag_off, tag_end = self._tag_off.tolist(), self._tag_end.tolist()
+            if text.isascii():
+                whole = text.decode("ascii")
+                tags = [whole[a:b] if a >= 0 else "" for a, b in zip(tag_off, tag_end)]
+            else:
+                tags = [text[a:b].decode() if a >= 0 else "" for a, b in zip(tag_off, tag_end)]
             cols = [getattr(self, k).tolist() for k in ("query_len", "q_start", "q_end", "q_strand", "p_len", "p_start", "p_end",
                                                          "p_align_len", "num_match", "align_len", "align_quality", "identity")]
             out = []
-            for i in range(n):
+            add = out.append
+            for (name, path, tg, ql, qs, qe, st, pl, ps, pe, pal, nm, al, aq, idn) in zip(names, paths, tags, *cols):
                 r = GAFRecord()
-                r.query_name, r.path = names[i], paths[i]
-                (r.query_len, r.q_start, r.q_end, r.q_strand, r.p_len, r.p_start, r.p_end, r.p_align_len, r.num_match, r.align_len,
-                 r.align_quality, r.identity) = [c[i] for c in cols]
-                r._tags = text[tag_off[i]:tag_end[i]].decode() if tag_off[i] >= 0 else ""
-                r._fields = None
-                r.cigar = r.split_cigar_str() if (parse_cigar and "cg" in r.optional_fields) else None
-                out.append(r)
+                r.query_name = name; r.path = path; r.query_len = ql; r.q_start = qs; r.q_end = qe; r.q_strand = st
+                r.p_len = pl; r.p_start = ps; r.p_end = pe; r.p_align_len = pal; r.num_match = nm; r.align_len = al
+                r.align_quality = aq; r.identity = idn; r._tags = tg; r._fields = None; r.cigar = None
+                add(r)
+            if parse_cigar:
+                for r in out:
+                    if "cg" in r.optional_fields:
+                        r.cigar = r.split_cigar_str()
             return out
         ptr = self.step_ptr.tolist()
         extra = self.step_extra.tolist()
