@@ -226,21 +226,19 @@ __global__ void __launch_bounds__(kBlkThreads, 1) blk_kernel(const BlkArgs a) {
         unsigned round = 0;
         for (; valid(c, p); advance(c, p)) {
             const unsigned o0 = a.m.seg_off[(int64_t)c * NP + p], o1 = a.m.seg_off[(int64_t)c * NP + p + 1];
-#ifdef TVS_EXP_BLKW
-            // forward, 16-bit weights: the chunk's weights are requested BEFORE its last segment is consumed and travel as
-            // packed words, so the epilogue does not start with an exposed global-memory latency
-            constexpr int NPRE = TVS_EXP_BLKW;
-            unsigned wraw[NPRE];
+            // forward, 16-bit weights, 2 lanes per thread: the chunk's weights are requested BEFORE its last segment is consumed
+            // and travel as packed words, so the epilogue does not start with an exposed global-memory latency
+            // (cfg3, 2,048 lanes: 2.26 -> 2.08 ms per pass; cfg4, 16 panels per chunk: unchanged)
+            unsigned wraw[kBlkRPW];
             const bool pre = MODE == 0 && K == 2 && a.w16 != nullptr;
             if (MODE == 0 && K == 2 && p == NP - 1 && pre) {
                 const int64_t r0 = (int64_t)c * kBlkCH + wi * kBlkRPW;
 #pragma unroll
-                for (int i = 0; i < NPRE; ++i) {
+                for (int i = 0; i < kBlkRPW; ++i) {
                     const int64_t r = r0 + i;
                     wraw[i] = (lv && r < a.n_major) ? *reinterpret_cast<const unsigned*>(a.w16 + r * W + mylane) : 0u;
                 }
             }
-#endif
             if (o1 != o0) {
                 mbar_wait(full_s + 8u * st, round & 1u);
                 // ---- the segment: warp wi owns major indices wi*RPW .. +RPW of the chunk; entry lists have even
@@ -288,11 +286,8 @@ __global__ void __launch_bounds__(kBlkThreads, 1) blk_kernel(const BlkArgs a) {
                     const int64_t r = r0 + i;
 #pragma unroll
                     for (int j = 0; j < K; ++j) wv[i][j] = 0;
-#ifdef TVS_EXP_BLKW
-                    if (pre && i < NPRE) { wv[i][0] = (int)(wraw[i < NPRE ? i : 0] & 0xffffu); wv[i][K - 1] = (int)(wraw[i < NPRE ? i : 0] >> 16); }
-                    else
-#endif
-                    if (lv && r < a.n_major) {
+                    if (pre) { wv[i][0] = (int)(wraw[i] & 0xffffu); wv[i][K - 1] = (int)(wraw[i] >> 16); }
+                    else if (lv && r < a.n_major) {
                         if (a.w16 != nullptr) {
                             if (K == 2) { const unsigned u = *reinterpret_cast<const unsigned*>(a.w16 + r * W + mylane); wv[i][0] = (int)(u & 0xffffu); wv[i][K - 1] = (int)(u >> 16); }
                             else wv[i][0] = a.w16[r * W + mylane];
@@ -311,13 +306,12 @@ __global__ void __launch_bounds__(kBlkThreads, 1) blk_kernel(const BlkArgs a) {
                     for (int j = 0; j < K; ++j) fast = fast && is_pos_normal(acc[i][j]);
                     if (fast) {
 #pragma unroll
-                        for (int j = 0; j < K; ++j) {
-                            const bool on = wv[i][j] > 0;
-                            const double wd = u31_to_double(on ? wv[i][j] : 0);
+                        for (int j = 0; j < K; ++j) {        // p finite, normal, > 0: a zero weight needs no select (pass3_kernel)
+                            const double wd = u31_to_double(max(wv[i][j], 0));
                             const double rcp = fast_rcp(acc[i][j]);
-                            rr[j] = on ? wd * rcp : 0.0;
+                            rr[j] = wd * rcp;
                             const double lg = use_tab ? table_log_pos(acc[i][j], tab_s, a.logc) : fast_log_pos(acc[i][j], a.logc);
-                            ll[j] = on ? fma(wd, lg, ll[j]) : ll[j];
+                            ll[j] = fma(wd, lg, ll[j]);
                         }
                     } else {
 #pragma unroll
