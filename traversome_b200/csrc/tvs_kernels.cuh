@@ -316,7 +316,7 @@ __device__ __forceinline__ double sum_splits(const double* __restrict__ src, int
     return s0;
 }
 
-constexpr int kU2Lanes = 8;
+constexpr int kU2Lanes = 8;                                // lanes per CTA (4: 41.0 us per full-width cfg2 update against 38.9)
 constexpr int kU2Slots = 32;
 constexpr int kU2Threads = kU2Lanes * kU2Slots;
 constexpr int kU2Warps = kU2Threads / 32;
@@ -336,10 +336,11 @@ __device__ __forceinline__ void cta_reduce(double* vals, int first_max, double* 
 #pragma unroll
     for (int q = 0; q < N; ++q) {
         double v = vals[q];
-        const double o1 = __shfl_xor_sync(0xffffffffu, v, 8);
-        v = (q >= first_max) ? fmax(v, o1) : v + o1;
-        const double o2 = __shfl_xor_sync(0xffffffffu, v, 16);
-        v = (q >= first_max) ? fmax(v, o2) : v + o2;
+#pragma unroll
+        for (int off = kU2Lanes; off < 32; off <<= 1) {          // over the slots of this warp (thread = slot * lanes + lane)
+            const double o = __shfl_xor_sync(0xffffffffu, v, off);
+            v = (q >= first_max) ? fmax(v, o) : v + o;
+        }
         if (t < kU2Lanes) part[((size_t)w * N + q) * kU2Lanes + l] = v;
     }
     __syncthreads();
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(kU2Threads) lbfgs_update_vl2_kernel(const UpdA
     double (*misc)[kU2Lanes] = reinterpret_cast<double (*)[kU2Lanes]>(part + (size_t)kU2Warps * (NACC + 4) * kU2Lanes);   // [4]
 
     const int tid = threadIdx.x, t = tid & 31, w = tid >> 5;
-    const int l = tid & (kU2Lanes - 1), vs = tid >> 3;
+    const int l = tid & (kU2Lanes - 1), vs = tid / kU2Lanes;
     const int64_t B = a.B;
     const int64_t b = (int64_t)blockIdx.x * kU2Lanes + l;
     const bool valid = b < B;

@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(kU2Threads) newton_update_kernel(const NewtonU
     __shared__ double accs[4][kU2Lanes];
     double (*acc)[kU2Lanes] = accs;
     const int tid = threadIdx.x, t = tid & 31, w = tid >> 5;
-    const int l = tid & (kU2Lanes - 1), vs = tid >> 3;
+    const int l = tid & (kU2Lanes - 1), vs = tid / kU2Lanes;
     const int64_t B = a.B;
     const int64_t b = (int64_t)blockIdx.x * kU2Lanes + l;
     const bool valid = b < B;

@@ -53,10 +53,8 @@ __device__ __forceinline__ double i32_to_double(int v) {        // any int32
 __device__ __forceinline__ double fast_rcp(double p) {          // p finite, normal, > 0
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));        // MUFU.RCP64H, ~2^-20
-    double e = fma(-p, r, 1.0);
-    r = fma(r, e, r);                                            // ~2^-40
-    e = fma(-p, r, 1.0);
-    return fma(r, e, r);                                         // ~1 ulp
+    const double e = fma(-p, r, 1.0);                            // |e| <= ~2^-20 (the low 32 mantissa bits of p are ignored)
+    return fma(r, fma(e, e, e), r);                              // r (1 + e + e^2) = (1 - e^3) / p: ~1 ulp in 3 FMAs (was 2 Newton steps, 4)
 }
 
 // natural logarithm for finite normal p > 0: p = 2^e m, m in [sqrt(1/2), sqrt(2)),
