@@ -34,6 +34,10 @@ namespace tvs {
 constexpr int kBlkWarps = 15;                       // consumer warps; one more warp only issues the copies (16 warps: 128 registers each)
 constexpr int kBlkThreads = (kBlkWarps + 1) * 32;
 constexpr int kBlkRPW = kBlkCH / kBlkWarps;         // major indices (accumulator rows) per warp
+static_assert(kBlkWarps == kBlkCW && kBlkRPW == kBlkRW, "host layout (tvs_blk_host.h) and kernel disagree");
+__device__ __forceinline__ int64_t blk_major(int c, int wi, int i, int n_chunks) {   // = blk_major_of (tvs_blk_host.h)
+    return ((int64_t)i * kBlkWarps + wi) * n_chunks + c;
+}
 constexpr int kBlkMaxStages = 6;
 
 struct BlkMat {                                     // device view of one blocked matrix
@@ -232,10 +236,9 @@ __global__ void __launch_bounds__(kBlkThreads, 1) blk_kernel(const BlkArgs a) {
             unsigned wraw[kBlkRPW];
             const bool pre = MODE == 0 && K == 2 && a.w16 != nullptr;
             if (MODE == 0 && K == 2 && p == NP - 1 && pre) {
-                const int64_t r0 = (int64_t)c * kBlkCH + wi * kBlkRPW;
 #pragma unroll
                 for (int i = 0; i < kBlkRPW; ++i) {
-                    const int64_t r = r0 + i;
+                    const int64_t r = blk_major(c, wi, i, a.m.n_chunks);
                     wraw[i] = (lv && r < a.n_major) ? *reinterpret_cast<const unsigned*>(a.w16 + r * W + mylane) : 0u;
                 }
             }
@@ -279,11 +282,10 @@ __global__ void __launch_bounds__(kBlkThreads, 1) blk_kernel(const BlkArgs a) {
             }
             if (MODE == 0 && p == NP - 1) {
                 // ---- forward epilogue of chunk c: rr = w / p, ll += w log p; the accumulators start over
-                const int64_t r0 = (int64_t)c * kBlkCH + wi * kBlkRPW;
                 int wv[kBlkRPW][K];
 #pragma unroll
                 for (int i = 0; i < kBlkRPW; ++i) {
-                    const int64_t r = r0 + i;
+                    const int64_t r = blk_major(c, wi, i, a.m.n_chunks);
 #pragma unroll
                     for (int j = 0; j < K; ++j) wv[i][j] = 0;
                     if (pre) { wv[i][0] = (int)(wraw[i] & 0xffffu); wv[i][K - 1] = (int)(wraw[i] >> 16); }
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(kBlkThreads, 1) blk_kernel(const BlkArgs a) {
                 }
 #pragma unroll
                 for (int i = 0; i < kBlkRPW; ++i) {
-                    const int64_t r = r0 + i;
+                    const int64_t r = blk_major(c, wi, i, a.m.n_chunks);
                     double rr[K];
                     bool fast = true;
 #pragma unroll
@@ -334,14 +336,13 @@ __global__ void __launch_bounds__(kBlkThreads, 1) blk_kernel(const BlkArgs a) {
 
         if (MODE == 1) {
             // ---- backward epilogue: the chunk's block of t for this split
-            const int64_t v0 = (int64_t)blockIdx.x * kBlkCH + wi * kBlkRPW;
             if (lv) {
                 bool on[K];
 #pragma unroll
                 for (int j = 0; j < K; ++j) on[j] = a.need == nullptr || (a.need[mylane + j] != 0 && (a.done == nullptr || a.done[mylane + j] == 0));
 #pragma unroll
                 for (int i = 0; i < kBlkRPW; ++i) {
-                    const int64_t v = v0 + i;
+                    const int64_t v = blk_major((int)blockIdx.x, wi, i, a.m.n_chunks);
                     if (v < a.n_major) {
                         double* dst = a.tpart + ((int64_t)split * a.n_major + v) * W + mylane;
                         if (K == 2 && on[0] && on[K - 1]) *reinterpret_cast<double2*>(dst) = make_double2(acc[i][0], acc[i][K - 1]);

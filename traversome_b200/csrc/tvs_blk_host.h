@@ -9,6 +9,16 @@
 namespace tvs {
 
 constexpr int kBlkCH = 240;                         // major indices per chunk = 15 consumer warps x 16 accumulator rows
+constexpr int kBlkCW = 15;                          // consumer warps of blk_kernel (tvs_blk.cuh: kBlkWarps)
+constexpr int kBlkRW = kBlkCH / kBlkCW;             // accumulator rows per warp
+
+// Which major index sits in accumulator row `i` of consumer warp `wi` of chunk `c`: the major indices are dealt out round
+// robin, first over the chunks, then over the warps of a chunk, so that every chunk and every warp holds the same number
+// (+-1).  With contiguous ranges 256 variants were a chunk of 240 and a chunk of 16: half of the backward CTAs of cfg3 kept
+// one warp of 15 busy while they streamed every panel (26 % of the launch's stall samples on the ring's wait).
+static inline int64_t blk_major_of(int c, int wi, int i, int n_chunks) { return ((int64_t)i * kBlkCW + wi) * n_chunks + c; }
+// the inverse: slot (= wi * rows per warp + i) of the j-th major index of a chunk
+static inline int blk_slot_of(int64_t j) { return (int)(j % kBlkCW) * kBlkRW + (int)(j / kBlkCW); }
 constexpr int kBlkPN = 128;                         // minor indices per panel (rows of the operand tile)
 constexpr int kBlkPtrBytes = ((kBlkCH + 1) * 2 + 15) & ~15;
 
@@ -54,11 +64,15 @@ inline bool build_blk(int64_t n_major, int64_t n_minor, const PtrT* ptr, const i
     const int ptr_words = kBlkPtrBytes / 4;
     uint32_t terms[8];
     for (int ch = 0; ch < n_chunks; ++ch) {
-        const int64_t m0 = (int64_t)ch * CH, m1 = std::min<int64_t>(n_major, m0 + CH);
+        // the chunk's major indices: ch, ch + n_chunks, ch + 2 n_chunks, ... (j-th of them in slot blk_slot_of(j))
+        const int64_t n_here = n_major > ch ? (n_major - ch + n_chunks - 1) / n_chunks : 0;
         std::fill(cnt.begin(), cnt.end(), 0);
-        for (int64_t m = m0; m < m1; ++m)
+        for (int64_t j = 0; j < n_here; ++j) {
+            const int64_t m = j * n_chunks + ch;
+            const int slot = blk_slot_of(j);
             for (int64_t k = (int64_t)ptr[m]; k < (int64_t)ptr[m + 1]; ++k)
-                cnt[(size_t)(idx[k] / PN) * (CH + 1) + (m - m0) + 1] += blk_terms((uint32_t)val[k], terms);
+                cnt[(size_t)(idx[k] / PN) * (CH + 1) + slot + 1] += blk_terms((uint32_t)val[k], terms);
+        }
         // per panel: prefix sums over the major index (every list padded to an even length: the kernel reads entries in
         // 8-byte pairs; a padding entry is 0 = offset 0 with count +0.0), segment sizes
         for (int pn = 0; pn < n_panels; ++pn) {
@@ -78,15 +92,18 @@ inline bool build_blk(int64_t n_major, int64_t n_minor, const PtrT* ptr, const i
             out->max_seg_bytes = std::max(out->max_seg_bytes, (int)(words * 4));
         }
         // fill: entries of a major index in increasing minor order (cp[i] = running write position)
-        for (int64_t m = m0; m < m1; ++m)
+        for (int64_t j = 0; j < n_here; ++j) {
+            const int64_t m = j * n_chunks + ch;
+            const int slot = blk_slot_of(j);
             for (int64_t k = (int64_t)ptr[m]; k < (int64_t)ptr[m + 1]; ++k) {
                 const int pn = idx[k] / PN;
                 int32_t* cp = &cnt[(size_t)pn * (CH + 1)];
                 const int nt = blk_terms((uint32_t)val[k], terms);
                 uint32_t* ent = &out->blob[(size_t)base[pn] + ptr_words];
                 for (int q = 0; q < nt; ++q)
-                    ent[cp[m - m0]++] = (uint32_t)((idx[k] - pn * PN) * 512) | (blk_hi16(terms[q]) << 16);
+                    ent[cp[slot]++] = (uint32_t)((idx[k] - pn * PN) * 512) | (blk_hi16(terms[q]) << 16);
             }
+        }
     }
     out->seg_off[(size_t)n_chunks * n_panels] = (uint32_t)(out->blob.size() / 4);
     if (out->blob.empty()) out->blob.resize(4, 0u);
@@ -122,7 +139,7 @@ inline void blk_multiply_host(const BlkHost& b, int64_t n_major, const double* x
             const uint16_t* p16 = reinterpret_cast<const uint16_t*>(words);
             const uint32_t* ent = words + kBlkPtrBytes / 4;
             for (int i = 0; i < kBlkCH; ++i) {
-                const int64_t m = (int64_t)ch * kBlkCH + i;
+                const int64_t m = blk_major_of(ch, i / kBlkRW, i % kBlkRW, b.n_chunks);
                 for (int k = p16[i]; k < p16[i + 1]; ++k) {
                     const uint32_t e = ent[k];
                     const uint64_t bits = (uint64_t)(e & 0xffff0000u) << 32;
