@@ -218,7 +218,7 @@ static int upload_blk(const BlkHost& hb, Csr::Blk* d) {
     d->blob = blob;
     TVS_CUDA(cudaMemcpy(d->seg_off, hb.seg_off.data(), hb.seg_off.size() * 4, cudaMemcpyHostToDevice));
     TVS_CUDA(cudaMemcpy(blob, hb.blob.data(), hb.blob.size() * 4, cudaMemcpyHostToDevice));
-    d->n_chunks = hb.n_chunks; d->n_panels = hb.n_panels; d->max_seg_bytes = hb.max_seg_bytes;
+    d->n_chunks = hb.n_chunks; d->n_panels = hb.n_panels; d->max_seg_bytes = hb.max_seg_bytes; d->dealt = hb.dealt ? 1 : 0;
     return TVS_OK;
 }
 
@@ -487,7 +487,7 @@ static int launch_blk(tvs_problem* h, const PassPlan& pl, const PassArgs& a) {
     }
     BlkArgs f{};
     f.m.seg_off = c.blk_f.seg_off; f.m.blob = (const uint4*)c.blk_f.blob; f.m.n_chunks = c.blk_f.n_chunks;
-    f.m.n_panels = c.blk_f.n_panels; f.m.max_seg_bytes = c.blk_f.max_seg_bytes;
+    f.m.n_panels = c.blk_f.n_panels; f.m.max_seg_bytes = c.blk_f.max_seg_bytes; f.m.dealt = c.blk_f.dealt;
     f.src = a.x; f.n_minor = V; f.n_major = R; f.W = W; f.done = a.done; f.w32 = a.w; f.w16 = a.w16;
     f.rr = BW ? h->blk_rr : nullptr; f.llpart = a.llpart; f.tpart = nullptr; f.stages = pl.stages;
     f.logc = a.logc; f.logtab = a.logtab;
@@ -499,7 +499,7 @@ static int launch_blk(tvs_problem* h, const PassPlan& pl, const PassArgs& a) {
     if (BW) {
         BlkArgs b = f;
         b.m.seg_off = c.blk_b.seg_off; b.m.blob = (const uint4*)c.blk_b.blob; b.m.n_chunks = c.blk_b.n_chunks;
-        b.m.n_panels = c.blk_b.n_panels; b.m.max_seg_bytes = c.blk_b.max_seg_bytes;
+        b.m.n_panels = c.blk_b.n_panels; b.m.max_seg_bytes = c.blk_b.max_seg_bytes; b.m.dealt = c.blk_b.dealt;
         b.src = h->blk_rr; b.n_minor = R; b.n_major = V; b.rr = nullptr; b.llpart = nullptr; b.tpart = a.tpart; b.stages = pl.bstages;
         const dim3 gb((unsigned)c.blk_b.n_chunks, (unsigned)pl.tiles, (unsigned)pl.bsplits);   // the chunks of one (tile, split) are neighbours: they stream the same rr panels
         if (pl.lpt == 2) blk_launch_one<2, true>(b, 1, gb, pl.bsmem, h->stream);
@@ -1484,7 +1484,7 @@ int tvs_fit(tvs_handle h, const double* theta0, const tvs_fit_options* opt_in, d
         const dim3 wide_grid((unsigned)((W + 31) / 32), (unsigned)((NP + kWideSet - 1) / kWideSet));
         BlkArgs hbk{};                                           // blocked Hessian product: H[(u,v), lane] = sum_r G[(u,v), r] * cr[r, lane]
         hbk.m.seg_off = c.blk_h.seg_off; hbk.m.blob = (const uint4*)c.blk_h.blob; hbk.m.n_chunks = c.blk_h.n_chunks;
-        hbk.m.n_panels = c.blk_h.n_panels; hbk.m.max_seg_bytes = c.blk_h.max_seg_bytes;
+        hbk.m.n_panels = c.blk_h.n_panels; hbk.m.max_seg_bytes = c.blk_h.max_seg_bytes; hbk.m.dealt = c.blk_h.dealt;
         hbk.src = f.cr; hbk.n_minor = R; hbk.n_major = NP; hbk.W = W; hbk.done = s.done; hbk.need = f.need;
         hbk.tpart = f.Hpart; hbk.stages = hb.stages; hbk.logc = pa.logc;
         const dim3 hblk_grid((unsigned)c.blk_h.n_chunks, (unsigned)hb.tiles, (unsigned)hb.splits);

@@ -35,8 +35,8 @@ constexpr int kBlkWarps = 15;                       // consumer warps; one more 
 constexpr int kBlkThreads = (kBlkWarps + 1) * 32;
 constexpr int kBlkRPW = kBlkCH / kBlkWarps;         // major indices (accumulator rows) per warp
 static_assert(kBlkWarps == kBlkCW && kBlkRPW == kBlkRW, "host layout (tvs_blk_host.h) and kernel disagree");
-__device__ __forceinline__ int64_t blk_major(int c, int wi, int i, int n_chunks) {   // = blk_major_of (tvs_blk_host.h)
-    return ((int64_t)i * kBlkWarps + wi) * n_chunks + c;
+__device__ __forceinline__ int64_t blk_major(int c, int wi, int i, int n_chunks, int dealt) {   // = blk_major_of (tvs_blk_host.h)
+    return dealt ? ((int64_t)i * kBlkWarps + wi) * n_chunks + c : (int64_t)c * kBlkCH + wi * kBlkRPW + i;
 }
 constexpr int kBlkMaxStages = 6;
 
@@ -45,6 +45,7 @@ struct BlkMat {                                     // device view of one blocke
     const uint4* blob;
     int n_chunks, n_panels;
     int max_seg_bytes;
+    int dealt;                                      // major indices dealt round robin over chunks and warps (blk_major)
 };
 
 struct BlkArgs {
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(kBlkThreads, 1) blk_kernel(const BlkArgs a) {
             if (MODE == 0 && K == 2 && p == NP - 1 && pre) {
 #pragma unroll
                 for (int i = 0; i < kBlkRPW; ++i) {
-                    const int64_t r = blk_major(c, wi, i, a.m.n_chunks);
+                    const int64_t r = blk_major(c, wi, i, a.m.n_chunks, a.m.dealt);
                     wraw[i] = (lv && r < a.n_major) ? *reinterpret_cast<const unsigned*>(a.w16 + r * W + mylane) : 0u;
                 }
             }
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(kBlkThreads, 1) blk_kernel(const BlkArgs a) {
                 int wv[kBlkRPW][K];
 #pragma unroll
                 for (int i = 0; i < kBlkRPW; ++i) {
-                    const int64_t r = blk_major(c, wi, i, a.m.n_chunks);
+                    const int64_t r = blk_major(c, wi, i, a.m.n_chunks, a.m.dealt);
 #pragma unroll
                     for (int j = 0; j < K; ++j) wv[i][j] = 0;
                     if (pre) { wv[i][0] = (int)(wraw[i] & 0xffffu); wv[i][K - 1] = (int)(wraw[i] >> 16); }
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(kBlkThreads, 1) blk_kernel(const BlkArgs a) {
                 }
 #pragma unroll
                 for (int i = 0; i < kBlkRPW; ++i) {
-                    const int64_t r = blk_major(c, wi, i, a.m.n_chunks);
+                    const int64_t r = blk_major(c, wi, i, a.m.n_chunks, a.m.dealt);
                     double rr[K];
                     bool fast = true;
 #pragma unroll
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(kBlkThreads, 1) blk_kernel(const BlkArgs a) {
                 for (int j = 0; j < K; ++j) on[j] = a.need == nullptr || (a.need[mylane + j] != 0 && (a.done == nullptr || a.done[mylane + j] == 0));
 #pragma unroll
                 for (int i = 0; i < kBlkRPW; ++i) {
-                    const int64_t v = blk_major((int)blockIdx.x, wi, i, a.m.n_chunks);
+                    const int64_t v = blk_major((int)blockIdx.x, wi, i, a.m.n_chunks, a.m.dealt);
                     if (v < a.n_major) {
                         double* dst = a.tpart + ((int64_t)split * a.n_major + v) * W + mylane;
                         if (K == 2 && on[0] && on[K - 1]) *reinterpret_cast<double2*>(dst) = make_double2(acc[i][0], acc[i][K - 1]);

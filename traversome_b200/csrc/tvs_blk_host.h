@@ -16,8 +16,14 @@ constexpr int kBlkRW = kBlkCH / kBlkCW;             // accumulator rows per warp
 // robin, first over the chunks, then over the warps of a chunk, so that every chunk and every warp holds the same number
 // (+-1).  With contiguous ranges 256 variants were a chunk of 240 and a chunk of 16: half of the backward CTAs of cfg3 kept
 // one warp of 15 busy while they streamed every panel (26 % of the launch's stall samples on the ring's wait).
-static inline int64_t blk_major_of(int c, int wi, int i, int n_chunks) { return ((int64_t)i * kBlkCW + wi) * n_chunks + c; }
-// the inverse: slot (= wi * rows per warp + i) of the j-th major index of a chunk
+// A matrix of many chunks keeps contiguous ranges (dealt = false: chunk c holds c * 240 ... + 239, warp wi rows wi * 16 ...):
+// there the last chunk hardly matters and neighbouring rows of the weights / rr stay neighbours in memory (cfg4: dealing
+// cost 2 % per pass).  blk_dealt() is the rule.
+static inline bool blk_dealt(int64_t n_major) { return (n_major + kBlkCH - 1) / kBlkCH <= 4 && n_major % kBlkCH != 0; }
+static inline int64_t blk_major_of(int c, int wi, int i, int n_chunks, bool dealt) {
+    return dealt ? ((int64_t)i * kBlkCW + wi) * n_chunks + c : (int64_t)c * kBlkCH + wi * kBlkRW + i;
+}
+// the inverse: slot (= wi * rows per warp + i) of the j-th major index of a dealt chunk
 static inline int blk_slot_of(int64_t j) { return (int)(j % kBlkCW) * kBlkRW + (int)(j / kBlkCW); }
 constexpr int kBlkPN = 128;                         // minor indices per panel (rows of the operand tile)
 constexpr int kBlkPtrBytes = ((kBlkCH + 1) * 2 + 15) & ~15;
@@ -31,6 +37,7 @@ struct BlkHost {
     std::vector<uint32_t> seg_off;     // 16-byte units
     std::vector<uint32_t> blob;        // 32-bit words
     int n_chunks = 0, n_panels = 0, max_seg_bytes = 0;
+    bool dealt = false;                // major indices dealt round robin (blk_major_of)
 };
 
 static inline int blk_terms(uint32_t c, uint32_t* out) {
@@ -57,6 +64,7 @@ inline bool build_blk(int64_t n_major, int64_t n_minor, const PtrT* ptr, const i
     const int n_chunks = (int)((n_major + CH - 1) / CH), n_panels = (int)((n_minor + PN - 1) / PN);
     if ((int64_t)n_chunks * n_panels > ((int64_t)1 << 28)) return false;
     out->n_chunks = n_chunks; out->n_panels = n_panels; out->max_seg_bytes = 0;
+    const bool dealt = out->dealt = blk_dealt(n_major);
     out->seg_off.assign((size_t)n_chunks * n_panels + 1, 0);
     out->blob.clear();
     std::vector<int32_t> cnt((size_t)n_panels * (CH + 1));
@@ -64,12 +72,14 @@ inline bool build_blk(int64_t n_major, int64_t n_minor, const PtrT* ptr, const i
     const int ptr_words = kBlkPtrBytes / 4;
     uint32_t terms[8];
     for (int ch = 0; ch < n_chunks; ++ch) {
-        // the chunk's major indices: ch, ch + n_chunks, ch + 2 n_chunks, ... (j-th of them in slot blk_slot_of(j))
-        const int64_t n_here = n_major > ch ? (n_major - ch + n_chunks - 1) / n_chunks : 0;
+        // the chunk's major indices: dealt -- ch, ch + n_chunks, ch + 2 n_chunks, ... (j-th of them in slot blk_slot_of(j));
+        // else the contiguous range ch * CH ... (j-th in slot j)
+        const int64_t n_here = dealt ? (n_major > ch ? (n_major - ch + n_chunks - 1) / n_chunks : 0)
+                                     : std::max<int64_t>(0, std::min<int64_t>(n_major, (int64_t)(ch + 1) * CH) - (int64_t)ch * CH);
         std::fill(cnt.begin(), cnt.end(), 0);
         for (int64_t j = 0; j < n_here; ++j) {
-            const int64_t m = j * n_chunks + ch;
-            const int slot = blk_slot_of(j);
+            const int64_t m = dealt ? j * n_chunks + ch : (int64_t)ch * CH + j;
+            const int slot = dealt ? blk_slot_of(j) : (int)j;
             for (int64_t k = (int64_t)ptr[m]; k < (int64_t)ptr[m + 1]; ++k)
                 cnt[(size_t)(idx[k] / PN) * (CH + 1) + slot + 1] += blk_terms((uint32_t)val[k], terms);
         }
@@ -93,8 +103,8 @@ inline bool build_blk(int64_t n_major, int64_t n_minor, const PtrT* ptr, const i
         }
         // fill: entries of a major index in increasing minor order (cp[i] = running write position)
         for (int64_t j = 0; j < n_here; ++j) {
-            const int64_t m = j * n_chunks + ch;
-            const int slot = blk_slot_of(j);
+            const int64_t m = dealt ? j * n_chunks + ch : (int64_t)ch * CH + j;
+            const int slot = dealt ? blk_slot_of(j) : (int)j;
             for (int64_t k = (int64_t)ptr[m]; k < (int64_t)ptr[m + 1]; ++k) {
                 const int pn = idx[k] / PN;
                 int32_t* cp = &cnt[(size_t)pn * (CH + 1)];
@@ -139,7 +149,7 @@ inline void blk_multiply_host(const BlkHost& b, int64_t n_major, const double* x
             const uint16_t* p16 = reinterpret_cast<const uint16_t*>(words);
             const uint32_t* ent = words + kBlkPtrBytes / 4;
             for (int i = 0; i < kBlkCH; ++i) {
-                const int64_t m = blk_major_of(ch, i / kBlkRW, i % kBlkRW, b.n_chunks);
+                const int64_t m = blk_major_of(ch, i / kBlkRW, i % kBlkRW, b.n_chunks, b.dealt);
                 for (int k = p16[i]; k < p16[i + 1]; ++k) {
                     const uint32_t e = ent[k];
                     const uint64_t bits = (uint64_t)(e & 0xffff0000u) << 32;

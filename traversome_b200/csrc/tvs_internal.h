@@ -53,7 +53,7 @@ struct Csr {
     int64_t   h_steps = 0;
     double*   dense = nullptr;       // [R*V] row-major fp64 copy of A for the DGEMM pass (dense shapes only, see tvs_create)
     // blocked copies of A (major = read path) and A^T (major = variant) for blk_kernel (wide candidate sets, tvs_blk.cuh)
-    struct Blk { uint32_t* seg_off = nullptr; void* blob = nullptr; int n_chunks = 0, n_panels = 0, max_seg_bytes = 0; };
+    struct Blk { uint32_t* seg_off = nullptr; void* blob = nullptr; int n_chunks = 0, n_panels = 0, max_seg_bytes = 0, dealt = 0; };
     Blk blk_f, blk_b;
     bool has_blk = false;
     // Newton phase (V <= 128): the Hessian as ONE more blocked product -- G[(u,v), r] = A_ru A_rv (u >= v, packed index
