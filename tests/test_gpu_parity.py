@@ -53,6 +53,34 @@ def test_loglik_matches_oracle(gpu, V, R, density, B):
             assert rel(got[b], ref) < 1e-12, (b, got[b], ref)
 
 
+@pytest.mark.parametrize("counts", [(1, 2, 3, 40, 64), (1, 33, 47, 1000, 65535)])
+def test_loglik_and_fit_with_large_occurrence_counts(gpu, counts):
+    """Counts that are exact in the top 16 bits of an fp64 (1..32, 40, 64: pass3_kernel's packed entries) and counts that
+    are not (33, 47, 1000, 65535: the handle falls back to the unstaged kernel; blk_kernel splits such a count into
+    several entries).  Reference: from_variants counts are arbitrary positive integers (utils.py:416-501)."""
+    wl = synthetic.make_workload(48, 1500, 0.15, seed=77)
+    rng = np.random.default_rng(5)
+    val = wl.val.copy()
+    val[:] = rng.choice(np.asarray(counts, dtype=val.dtype), size=val.size)
+    B = 12
+    w = synthetic.bootstrap_weights(wl.n_obs, B, seed=9)
+    theta = rng.dirichlet(np.ones(48), size=B).T.copy()
+    import scipy.sparse as sp
+    A = sp.csr_matrix((val.astype(np.float64), wl.col, wl.row_ptr), shape=(wl.row_ptr.size - 1, 48))
+    with _cabi.Engine(wl.row_ptr, wl.col, val, wl.L) as eng:
+        eng.set_lanes(w)
+        got = eng.loglik(theta)
+        for b in range(B):
+            ref = loglik.loglik_rows(A, wl.L, w[:, b], 0.0, theta[:, b], np.ones(48, dtype=bool))
+            assert rel(got[b], ref) < 1e-12, (b, got[b], ref)
+        out = eng.fit()
+    assert (out["status"] == 0).all()
+    for b in (0, B - 1):
+        ref = exact.exact_fit(A, wl.L, w[:, b])
+        assert np.abs(out["theta"][:, b] - ref["theta"]).max() < TOL_THETA
+        assert rel(out["loglike"][b], ref["loglike_no_C"]) < TOL_LL
+
+
 def test_loglik_known_answers_from_reference(gpu, plastome, synthetic_small):
     cases = [(plastome["variant_sizes"], plastome["models"][0]["bins_list"], plastome["known_answer_ll"])]
     cases += [(c["variant_sizes"], c["bins_list"], c["known_answer_ll"]) for c in synthetic_small["cases"]]
