@@ -231,16 +231,15 @@ __global__ void __launch_bounds__(kBlkThreads, 1) blk_kernel(const BlkArgs a) {
         unsigned round = 0;
         for (; valid(c, p); advance(c, p)) {
             const unsigned o0 = a.m.seg_off[(int64_t)c * NP + p], o1 = a.m.seg_off[(int64_t)c * NP + p + 1];
-            // forward, 16-bit weights, 2 lanes per thread: the chunk's weights are requested BEFORE its last segment is consumed
-            // and travel as packed words, so the epilogue does not start with an exposed global-memory latency
-            // (cfg3, 2,048 lanes: 2.26 -> 2.08 ms per pass; cfg4, 16 panels per chunk: unchanged)
-            unsigned wraw[kBlkRPW];
-            const bool pre = MODE == 0 && K == 2 && a.w16 != nullptr;
-            if (MODE == 0 && K == 2 && p == NP - 1 && pre) {
+            // forward, 16-bit weights: the chunk's weight lines are requested into L2 when its first segment starts (one request
+            // per row and warp, no registers), so the elementwise part at the end of the chunk does not wait for DRAM
+            // (cfg3, 2,048 lanes: 2.26 -> 2.06 ms per pass; carrying the 16 packed words in registers instead measured the same
+            // and spilled; cfg4, 16 panels per chunk: unchanged)
+            if (MODE == 0 && p == 0 && a.w16 != nullptr && t == 0) {
 #pragma unroll
                 for (int i = 0; i < kBlkRPW; ++i) {
                     const int64_t r = blk_major(c, wi, i, a.m.n_chunks, a.m.dealt);
-                    wraw[i] = (lv && r < a.n_major) ? *reinterpret_cast<const unsigned*>(a.w16 + r * W + mylane) : 0u;
+                    if (r < a.n_major) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.w16 + r * W + lane0));
                 }
             }
             if (o1 != o0) {
@@ -289,8 +288,7 @@ __global__ void __launch_bounds__(kBlkThreads, 1) blk_kernel(const BlkArgs a) {
                     const int64_t r = blk_major(c, wi, i, a.m.n_chunks, a.m.dealt);
 #pragma unroll
                     for (int j = 0; j < K; ++j) wv[i][j] = 0;
-                    if (pre) { wv[i][0] = (int)(wraw[i] & 0xffffu); wv[i][K - 1] = (int)(wraw[i] >> 16); }
-                    else if (lv && r < a.n_major) {
+                    if (lv && r < a.n_major) {
                         if (a.w16 != nullptr) {
                             if (K == 2) { const unsigned u = *reinterpret_cast<const unsigned*>(a.w16 + r * W + mylane); wv[i][0] = (int)(u & 0xffffu); wv[i][K - 1] = (int)(u >> 16); }
                             else wv[i][0] = a.w16[r * W + mylane];
