@@ -10,7 +10,7 @@
 //   * K consecutive lanes per thread (K = 1, 2, 4): one entry decode / address computation feeds K
 //     FMAs, the x / rr operands come from shared memory as 128-bit loads (conflict-free layout),
 //     the weights from global memory as one K*4-byte load per thread.
-//   * 1/p from `rcp.approx.ftz.f64` + two Newton steps (5 instructions instead of the ~40 of an
+//   * 1/p from `rcp.approx.ftz.f64` + one third-order step (4 instructions instead of the ~40 of an
 //     IEEE division) and log p from an inlined atanh series on the reduced mantissa (no table: the
 //     binding resource of the sparse product is shared-memory operand bandwidth, so the logarithm
 //     is kept on the fp64 pipe).  Both are accurate to ~1 ulp; tests/test_gpu_parity.py pins them.
@@ -348,14 +348,16 @@ __global__ void __launch_bounds__(kThreads2, 1) pass2_kernel(const PassArgs a) {
 // ------------------------------------------------------------------------------------------------
 // pass3_kernel: pass2 + the CSR entries of each chunk staged in shared memory by cp.async
 // (profiles/r1_v2_summary.md: pass2 stalls on the dependent LDG(entry) -> LDS(x) -> DFMA chain).
-//   * entries stay packed (column or chunk-local row | count << 16, one 32-bit word): the inner loops are
-//     LDS.32 (broadcast) + unpack (the count goes into the mantissa of 2^52, one DADD: no XU conversion) +
-//     K/2 x LDS.128 + K x DFMA.  One broadcast read per non-zero instead of two took 3 % off the pass;
+//   * entries stay packed (column or chunk-local row | top 16 bits of the fp64 count << 16, one 32-bit word; Csr::ent3 /
+//     cent3): the inner loops are LDS.32 (broadcast) + one LOP3 for the count (no fp64 conversion) + K/2 x LDS.128 + K x DFMA;
 //   * the row-major entries of the NEXT chunk and the column-major entries of THIS chunk are in flight
 //     while phase 1 runs (double buffer / single buffer);
-//   * the weights of a warp's next row are loaded one row ahead (the only HBM stream of the pass).
-// shared: x_s[V][LT] t_s[V][LT] rr_s[RC][LT] | c1[2][cap] c2[cap] (packed entries) rp[2][RC+1]
-//         cs[V+1] cid[V] (int32)
+//   * the weights of a warp's next row are loaded one row ahead (the only HBM stream of the pass) and travel across
+//     the loop trip as RAW words (load_w_raw / unpack_w);
+//   * V <= 4 * NW: the t accumulators of a warp's columns (wi, wi + NW, wi + 2 NW, wi + 3 NW) stay in registers for the
+//     whole launch (pass3_treg): no t tile, so the chunks are longer (144 rows at V = 64, K = 4).
+// shared: x_s[V][LT] (t_s[V][LT] unless pass3_treg) rr_s[RC][LT] | c1[2][cap] c2[cap] (packed entries) rp[2][RC+1]
+//         cs[V+1] cid[V] (int32) | log table
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
