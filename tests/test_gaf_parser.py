@@ -214,3 +214,86 @@ def test_reference_class_with_the_native_parser_keeps_its_read_records(golden, t
             assert getattr(a, k) == getattr(b, k), k
     assert list(ours.read_records) == list(ref.read_records)
     assert [r.raw_ids for r in ours.read_records.values()] == [r.raw_ids for r in ref.read_records.values()]
+
+
+class ReadRecord(object):
+    """Stand-in with the fields of the reference's ReadRecord (GraphAlignRecords.py:200-216): build_read_records looks the
+    class up in the module of the object it is bound to -- here this test module."""
+
+    def __init__(self):
+        self.raw_ids, self.records, self.p_align_len, self._p_identity_sum, self.p_identity, self.q_seq = [], [], 0, 0., 0., None
+
+
+def _multi_hit_gaf():
+    """GAF text whose reads have one to three alignments, listed out of query order and interleaved with other reads."""
+    rows = []
+    for i in range(60):
+        n_hits = 1 + i % 3
+        for h in range(n_hits):
+            q_start = (n_hits - 1 - h) * 1000 + 7 * i                       # later hits first
+            length = 400 + 13 * ((i * 7 + h * 3) % 50)
+            n_match = length - (i + 2 * h) % 9
+            rows.append((i, h, "read%d\t5000\t%d\t%d\t+\t>s%d<s%d\t9000\t%d\t%d\t%d\t%d\t60" % (
+                i, q_start, q_start + length, 1 + i % 4, 2 + h, 100 + h, 100 + h + length, n_match, length)))
+    rows.sort(key=lambda r: (r[1], r[0]))                                    # all first hits, then all second hits, ...
+    return "".join(r[2] + "\n" for r in rows)
+
+
+def test_build_read_records_follows_the_reference_loop():
+    """The swapped build_read_records against a restatement of the reference's loop (GraphAlignRecords.py:225-230 append,
+    :252-256 sort_by, :936-950): grouping in order of first appearance, sums in raw order, records sorted by
+    (q_start, q_end, cigar)."""
+    text = _multi_hit_gaf().encode()
+    obj = _Records("unused")
+    obj.raw_records = gaf.GafTable(text, n_threads=1).records()
+    gaf.build_read_records(obj)
+    want = {}
+    for go_r, rec in enumerate(obj.raw_records):
+        rr = want.setdefault(rec.query_name, ReadRecord())
+        rr.raw_ids.append(go_r); rr.records.append(rec)
+        rr.p_align_len += rec.p_align_len
+        rr._p_identity_sum += rec.p_align_len * rec.identity
+        rr.p_identity = rr._p_identity_sum / rr.p_align_len
+    for rr in want.values():
+        order = sorted(range(len(rr.raw_ids)), key=lambda x: [rr.records[x].q_start, rr.records[x].q_end, rr.records[x].cigar])
+        rr.records, rr.raw_ids = [rr.records[x] for x in order], [rr.raw_ids[x] for x in order]
+    got = obj.read_records
+    assert list(got) == list(want) and len(got) == 60
+    assert sum(len(r.raw_ids) > 1 for r in got.values()) == 40
+    for name in want:
+        a, b = got[name], want[name]
+        assert isinstance(a, ReadRecord) and a.raw_ids == b.raw_ids and [id(r) for r in a.records] == [id(r) for r in b.records]
+        assert a.p_align_len == b.p_align_len and a._p_identity_sum == b._p_identity_sum and a.p_identity == b.p_identity
+        assert a.q_seq is None
+        assert [r.q_start for r in a.records] == sorted(r.q_start for r in a.records)
+
+
+def test_reference_read_records_with_and_without_the_swaps(tmp_path):
+    """The reference's own build_read_records / filter_read_records on a file with multi-hit reads: identical read
+    records (ids, order, sums, identities) and identical reads kept.  Needs /root/reference."""
+    if not os.path.isdir("/root/reference/traversome"):
+        pytest.skip("reference not present")
+    import sys
+    sys.path.insert(0, "/root/reference")
+    try:
+        from traversome.GraphAlignRecords import GraphAlignRecords
+    finally:
+        sys.path.remove("/root/reference")
+    path = str(tmp_path / "multi.gaf")
+    with open(path, "w") as h:
+        h.write(_multi_hit_gaf())
+    for min_identity in (0.9, 0.992):
+        ref = GraphAlignRecords(path, alignment_format="GAF", min_align_len=450, min_identity=min_identity)
+        gaf.install_on_records(GraphAlignRecords)
+        try:
+            ours = GraphAlignRecords(path, alignment_format="GAF", min_align_len=450, min_identity=min_identity)
+        finally:
+            gaf.uninstall_from_records()
+        assert GraphAlignRecords.build_read_records is not gaf.build_read_records
+        assert len(ours.raw_records) == len(ref.raw_records) and list(ours.read_records) == list(ref.read_records)
+        assert list(ref.read_records) != ["read%d" % i for i in range(60)]      # the filters did drop / split reads
+        for a, b in zip(ours.read_records.values(), ref.read_records.values()):
+            assert a.raw_ids == b.raw_ids and a.p_align_len == b.p_align_len
+            assert a._p_identity_sum == b._p_identity_sum and a.p_identity == b.p_identity
+            assert [(r.query_name, r.q_start, r.q_end, r.p_start, r.p_end) for r in a.records] == \
+                   [(r.query_name, r.q_start, r.q_end, r.p_start, r.p_end) for r in b.records]

@@ -8,8 +8,9 @@ to the native parser of ``libtvs.so`` once (``include/tvs_gaf.h``: threads over 
 pools) and the record objects are made from the columns; the arrays themselves (``GafTable``) are what
 ``traversome_b200.readpaths.generate_read_paths`` needs.
 
-``install_on_records(GraphAlignRecords)`` swaps ``parse_alignment_file`` of the reference's class; the per-read filters that
-follow (``build_read_records``, ``filter_read_records``, :920-1022) are the reference's and see the same objects.
+``install_on_records(GraphAlignRecords)`` swaps ``parse_alignment_file`` and ``build_read_records`` (:936-950) of the
+reference's class; the per-read filter that follows (``filter_read_records``, :952-1022) is the reference's and sees the same
+objects.
 """
 import ctypes
 import gc
@@ -223,23 +224,81 @@ def parse_alignment_file(self, num_proc=1, _num_block_lines=10000):
     self.gaf_table = table
 
 
+def build_read_records(self):
+    """Replacement for ``GraphAlignRecords.build_read_records`` (GraphAlignRecords.py:936-950): ``self.read_records`` =
+    OrderedDict query name -> ReadRecord (the reference's class) holding the read's alignment records sorted by
+    (q_start, q_end, cigar), its raw ids, the summed ``p_align_len`` and the length-weighted identity.
+
+    The reference makes one ``ReadRecord.append`` call per alignment (three attribute updates and a division each,
+    :225-230) and one ``sort_by`` per read (:252-256).  Here the raw ids are grouped by name in one pass and every
+    ReadRecord is filled once; the sums run in raw order, so ``_p_identity_sum`` and ``p_identity`` are the same floats.
+    ``filter_read_records`` (:952-1022) stays the reference's and calls this twice."""
+    import sys
+    from collections import OrderedDict
+    from loguru import logger
+    logger.debug("Build reads records ..")
+    read_record_cls = sys.modules[type(self).__module__].ReadRecord
+    raw = self.raw_records
+    groups = OrderedDict()
+    for go_r, record in enumerate(raw):
+        ids = groups.get(record.query_name)
+        if ids is None:
+            groups[record.query_name] = [go_r]
+        else:
+            ids.append(go_r)
+    new = read_record_cls.__new__
+    was_on = gc.isenabled()
+    gc.disable()                                   # as in GafTable.records: nothing made here can be garbage
+    try:
+        for name, ids in groups.items():
+            rr = new(read_record_cls)
+            rr.q_seq = None
+            if len(ids) == 1:
+                record = raw[ids[0]]
+                rr.raw_ids = ids
+                rr.records = [record]
+                rr.p_align_len = 0 + record.p_align_len
+                rr._p_identity_sum = 0. + record.p_align_len * record.identity
+            else:
+                records = [raw[i] for i in ids]
+                p_align_len, identity_sum = 0, 0.
+                for record in records:
+                    p_align_len += record.p_align_len
+                    identity_sum += record.p_align_len * record.identity
+                rr.p_align_len = p_align_len
+                rr._p_identity_sum = identity_sum
+                order = sorted(range(len(ids)), key=lambda x: [records[x].q_start, records[x].q_end, records[x].cigar])
+                rr.records = [records[x] for x in order]
+                rr.raw_ids = [ids[x] for x in order]
+            rr.p_identity = rr._p_identity_sum / rr.p_align_len
+            groups[name] = rr
+    finally:
+        if was_on:
+            gc.enable()
+    self.read_records = groups
+
+
 _SAVED = {}
+_SWAPPED = ("parse_alignment_file", "build_read_records")
 
 
 def install_on_records(cls=None):
-    """Swap ``parse_alignment_file`` of the reference's GraphAlignRecords class (default: imported here)."""
+    """Swap ``parse_alignment_file`` and ``build_read_records`` of the reference's GraphAlignRecords class (default:
+    imported here)."""
     if cls is None:
         from traversome.GraphAlignRecords import GraphAlignRecords as cls
     if cls not in _SAVED:
-        _SAVED[cls] = cls.__dict__.get("parse_alignment_file")
+        _SAVED[cls] = {name: cls.__dict__.get(name) for name in _SWAPPED}
     cls.parse_alignment_file = parse_alignment_file
+    cls.build_read_records = build_read_records
     return cls
 
 
 def uninstall_from_records():
-    for cls, fn in list(_SAVED.items()):
-        if fn is not None:
-            cls.parse_alignment_file = fn
-        elif "parse_alignment_file" in cls.__dict__:
-            del cls.parse_alignment_file
+    for cls, saved in list(_SAVED.items()):
+        for name, fn in saved.items():
+            if fn is not None:
+                setattr(cls, name, fn)
+            elif name in cls.__dict__:
+                delattr(cls, name)
         del _SAVED[cls]
