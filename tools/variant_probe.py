@@ -2,7 +2,8 @@
 """Developer tool (GPU box): compare builds of libtvs.so made by tools/build_variant.sh.  For every name given, the variant
 is copied over traversome_b200/libtvs.so and a child process fits cfg2 (1,000 lanes; median of 7 fits, per-pass times of
 one more fit) and, with `--cfg3`, a 2,048-lane fit of the cfg3 matrix; prints fit time, full-width pass time and a hash of
-theta (bitwise guard).  usage: python tools/variant_probe.py [--cfg3] [--cfg4] [--only] base W2 ..."""
+theta (bitwise guard).  NOTE: it overwrites traversome_b200/libtvs.so with the last variant -- meant for the scratch copy
+on the GPU box; rebuild (traversome_b200/csrc/build.sh) after running it anywhere else.  usage: python tools/variant_probe.py [--cfg3] [--cfg4] [--only] base W2 ..."""
 import hashlib, json, os, re, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
