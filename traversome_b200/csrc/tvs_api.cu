@@ -553,7 +553,7 @@ static PassArgs base_args(const tvs_problem* h) {
     a.n_chunks = c.n_chunks; a.rows_per_chunk = c.rows_per_chunk;
     a.stage_cap = std::max(c.max_chunk_nnz, 1);
     a.desc = (const ChunkDesc*)c.desc; a.logc = make_log_coef();
-    a.logtab = env_int("TVS_LOG_TABLE", 1) ? (const double2*)c.logtab : nullptr;
+    a.logtab = (const double2*)c.logtab;
     return a;
 }
 

@@ -171,8 +171,8 @@ __global__ void __launch_bounds__(kBlkThreads, 1) blk_kernel(const BlkArgs a) {
     // operand lanes beyond W are never copied: give them a defined value once (generic-proxy writes, then a proxy
     // fence so that the bulk copies are ordered after them)
     for (int i = tid; i < NST * kBlkPN * LT; i += kBlkThreads) reinterpret_cast<double*>(smb + L.tile0)[i] = 1.0;
-    if (MODE == 0 && a.logtab != nullptr)
-        for (int i = tid; i < 128; i += kBlkThreads) tab_s[i] = a.logtab[i];
+    if (MODE == 0)
+        for (int i = tid; i < 128; i += kBlkThreads) tab_s[i] = a.logtab[i];        // the log table (tvs_create always uploads it)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
@@ -224,7 +224,6 @@ __global__ void __launch_bounds__(kBlkThreads, 1) blk_kernel(const BlkArgs a) {
         double ll[K];
 #pragma unroll
         for (int j = 0; j < K; ++j) ll[j] = 0.0;
-        const bool use_tab = a.logtab != nullptr;
         const unsigned tK = (unsigned)t * (8u * K);                // this thread's bytes inside a tile row (bits 3..8)
 
         int st = 0;
@@ -311,7 +310,7 @@ __global__ void __launch_bounds__(kBlkThreads, 1) blk_kernel(const BlkArgs a) {
                             const double wd = u31_to_double(max(wv[i][j], 0));
                             const double rcp = fast_rcp(acc[i][j]);
                             rr[j] = wd * rcp;
-                            const double lg = use_tab ? table_log_pos(acc[i][j], tab_s, a.logc) : fast_log_pos(acc[i][j], a.logc);
+                            const double lg = table_log_pos(acc[i][j], tab_s, a.logc);
                             ll[j] = fma(wd, lg, ll[j]);
                         }
                     } else {

@@ -429,9 +429,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
     const double* x_t = x_s + (K == 1 ? t : 2 * t);      // this thread's slot inside an operand row (lds_lanes_at)
     const double* rr_t = rr_s + (K == 1 ? t : 2 * t);
     const bool is16 = a.w16 != nullptr;
-    const bool use_tab = a.logtab != nullptr;
-    if (use_tab)
-        for (int i = threadIdx.x; i < 128; i += NT) tab_s[i] = a.logtab[i];
+    for (int i = threadIdx.x; i < 128; i += NT) tab_s[i] = a.logtab[i];        // the log table (tvs_create always uploads it)
 
     // row-major entries + row pointers of a chunk -> buffer `buf`
     auto stage_rows = [&](const ChunkDesc& d, int buf) {
@@ -537,7 +535,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pass3_kernel(const PassArgs a) {
                     const double rcp = fast_rcp(p[j]);
                     rr[j] = wd * rcp;
                     c2[j] = rr[j] * rcp;
-                    const double lg = use_tab ? table_log_pos(p[j], tab_s, a.logc) : fast_log_pos(p[j], a.logc);
+                    const double lg = table_log_pos(p[j], tab_s, a.logc);
                     ll[j] = fma(wd, lg, ll[j]);
                 }
             } else {
